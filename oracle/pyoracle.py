@@ -1,0 +1,144 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (gd-slam_b200) never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build() -> None:
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        L = _LIB
+        L.gdo_gray_u8.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, C.c_int, u8p]
+        L.gdo_inv3_f32.argtypes = [f32p, f32p]
+        L.gdo_inv3_f64.argtypes = [f64p, f64p]
+        L.gdo_depth_edge.argtypes = [f32p, C.c_int, C.c_int, f32p, u8p]
+        L.gdo_mahalanobis.argtypes = [f32p, f32p, f32p, u8p, u8p, C.c_void_p, C.c_int, C.c_int, f32p, f32p, f32p,
+                                      f32p, C.c_void_p, C.c_void_p]
+        L.gdo_normalize_threshold.argtypes = [f32p, C.c_int, C.c_int, u8p, C.c_void_p, C.c_void_p]
+        L.gdo_depth2std.argtypes = [C.c_float, C.c_float]
+        L.gdo_depth2std.restype = C.c_float
+        L.gdo_farneback.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, f32p]
+        L.gdo_farneback_polyexp_level.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                                  f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.gdo_geomask_pair.argtypes = [u8p, u8p, f32p, f32p, C.c_int, C.c_int, f32p, f32p, f32p, u8p, C.c_void_p,
+                                       C.c_void_p]
+    return _LIB
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def gray(bgr: np.ndarray, order: int = 0) -> np.ndarray:
+    bgr = _c(bgr, np.uint8)
+    h, w = bgr.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    lib().gdo_gray_u8(bgr.reshape(-1), w * 3, w, h, order, out.reshape(-1))
+    return out
+
+
+def inv3(m: np.ndarray) -> np.ndarray:
+    if m.dtype == np.float64:
+        out = np.empty(9, np.float64)
+        lib().gdo_inv3_f64(_c(m, np.float64).reshape(-1), out)
+    else:
+        out = np.empty(9, np.float32)
+        lib().gdo_inv3_f32(_c(m, np.float32).reshape(-1), out)
+    return out.reshape(3, 3)
+
+
+def depth_edge(depth: np.ndarray, K: np.ndarray) -> np.ndarray:
+    depth = _c(depth, np.float32)
+    h, w = depth.shape
+    out = np.empty((h, w), np.uint8)
+    lib().gdo_depth_edge(depth.reshape(-1), w, h, _c(K, np.float32).reshape(-1), out.reshape(-1))
+    return out
+
+
+def mahalanobis(flow, depth_ref, depth_cur, edge_ref, edge_cur, K, R, T, lut=None):
+    flow = _c(flow, np.float32)
+    h, w = flow.shape[:2]
+    dist = np.empty((h, w), np.float32)
+    written = np.empty((h, w), np.uint8)
+    src = np.empty((h, w), np.int32)
+    lut_p = None
+    if lut is not None:
+        lut = _c(lut, np.float32)
+        lut_p = lut.ctypes.data_as(C.c_void_p)
+    lib().gdo_mahalanobis(flow.reshape(-1), _c(depth_ref, np.float32).reshape(-1),
+                          _c(depth_cur, np.float32).reshape(-1), _c(edge_ref, np.uint8).reshape(-1),
+                          _c(edge_cur, np.uint8).reshape(-1), lut_p, w, h, _c(K, np.float32).reshape(-1),
+                          _c(R, np.float32).reshape(-1), _c(T, np.float32).reshape(-1), dist.reshape(-1),
+                          written.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p))
+    return dist, written, src
+
+
+def normalize_threshold(dist):
+    dist = _c(dist, np.float32)
+    h, w = dist.shape
+    mask = np.empty((h, w), np.uint8)
+    d8 = np.empty((h, w), np.uint8)
+    mm = np.empty(2, np.float32)
+    lib().gdo_normalize_threshold(dist.reshape(-1), w, h, mask.reshape(-1), d8.ctypes.data_as(C.c_void_p),
+                                  mm.ctypes.data_as(C.c_void_p))
+    return mask, d8, mm
+
+
+def farneback(prev, nxt, pyr_scale=0.5, levels=3, winsize=15, iterations=3, poly_n=5, poly_sigma=1.2):
+    prev = _c(prev, np.uint8)
+    nxt = _c(nxt, np.uint8)
+    h, w = prev.shape
+    flow = np.empty((h, w, 2), np.float32)
+    lib().gdo_farneback(prev.reshape(-1), nxt.reshape(-1), w, h, pyr_scale, levels, winsize, iterations, poly_n,
+                        poly_sigma, flow.reshape(-1))
+    return flow
+
+
+def polyexp_level(img, k, pyr_scale=0.5, poly_n=5, poly_sigma=1.2):
+    img = _c(img, np.uint8)
+    h, w = img.shape
+    out = np.empty(h * w * 5, np.float32)
+    lw, lh = C.c_int(0), C.c_int(0)
+    lib().gdo_farneback_polyexp_level(img.reshape(-1), w, h, pyr_scale, k, poly_n, poly_sigma, out, C.byref(lw),
+                                      C.byref(lh))
+    return out[: lw.value * lh.value * 5].reshape(lh.value, lw.value, 5).copy()
+
+
+def geomask_pair(bgr_ref, bgr_cur, depth_ref, depth_cur, K, R, T, want_debug=False):
+    bgr_ref = _c(bgr_ref, np.uint8)
+    h, w = bgr_ref.shape[:2]
+    mask = np.empty((h, w), np.uint8)
+    flow = np.empty((h, w, 2), np.float32) if want_debug else None
+    dist = np.empty((h, w), np.float32) if want_debug else None
+    lib().gdo_geomask_pair(bgr_ref.reshape(-1), _c(bgr_cur, np.uint8).reshape(-1),
+                           _c(depth_ref, np.float32).reshape(-1), _c(depth_cur, np.float32).reshape(-1), w, h,
+                           _c(K, np.float32).reshape(-1), _c(R, np.float32).reshape(-1),
+                           _c(T, np.float32).reshape(-1), mask.reshape(-1),
+                           flow.ctypes.data_as(C.c_void_p) if want_debug else None,
+                           dist.ctypes.data_as(C.c_void_p) if want_debug else None)
+    return (mask, flow, dist) if want_debug else mask
