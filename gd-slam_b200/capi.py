@@ -1,0 +1,279 @@
+"""ctypes binding of include/gdslam_cuda.h (libgdslam_cuda.so).
+
+Used by the parity tests and bench.py to drive the C ABI exactly the way the C++ shim does.  There is no
+fallback of any kind: if the shared library is missing or a call fails, GdError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgdslam_cuda.so")
+
+GD_OK, GD_EINVAL, GD_ENODEVICE, GD_ECUDA, GD_ENOMEM, GD_ECAPACITY = 0, -1, -2, -3, -4, -5
+DBG_FLOW, DBG_DIST, DBG_EDGE_REF, DBG_EDGE_CUR, DBG_GRAY_CUR, DBG_MINMAX = range(6)
+
+
+class GdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgdslam_cuda error {code}: {msg}")
+        self.code = code
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class FrontendConfig(C.Structure):
+    _fields_ = [("K", C.c_float * 9), ("dist", C.c_float * 5), ("ndist", C.c_int), ("depth_factor", C.c_float),
+                ("width", C.c_int), ("height", C.c_int), ("device", C.c_int), ("batch", C.c_int),
+                ("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("orb_gray_order", C.c_int), ("kp_capacity", C.c_int),
+                ("staged_slots", C.c_int)]
+
+
+def build_library() -> None:
+    subprocess.run(["make", "-s", "-j8", "-C", os.path.join(_HERE, "csrc")], check=True)
+
+
+_lib = None
+vp = C.c_void_p
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int)
+
+# every symbol include/gdslam_cuda.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "gd_last_error": (C.c_char_p, []),
+    "gd_abi_version": (C.c_int, []),
+    "gd_device_count": (C.c_int, [ip]),
+    "gd_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, ip, C.POINTER(C.c_size_t)]),
+    "gd_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+    "gd_host_free": (C.c_int, [vp]),
+    "gd_geomask_create": (C.c_int, [C.POINTER(vp), fp, fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gd_geomask_destroy": (None, [vp]),
+    "gd_geomask_push": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
+    "gd_geomask_mask": (C.c_int, [vp, fp, fp, ip, C.POINTER(vp), C.c_size_t]),
+    "gd_geomask_frames": (C.c_int, [vp]),
+    "gd_geomask_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
+    "gd_orb_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int]),
+    "gd_orb_destroy": (None, [vp]),
+    "gd_orb_extract": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                 C.c_int, ip]),
+    "gd_orb_fetch_level": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t, ip, ip]),
+    "gd_orb_level_size": (C.c_int, [vp, C.c_int, ip, ip]),
+    "gd_orb_features_per_level": (C.c_int, [vp, ip]),
+    "gd_frontend_create": (C.c_int, [C.POINTER(vp), C.POINTER(FrontendConfig)]),
+    "gd_frontend_destroy": (None, [vp]),
+    "gd_frontend_step": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t, fp, fp, ip,
+                                   C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_frontend_stage": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
+    "gd_frontend_step_staged": (C.c_int, [vp, C.c_int, fp, fp, ip]),
+    "gd_frontend_fetch": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_frontend_sync": (C.c_int, [vp]),
+    "gd_frontend_timer_begin": (C.c_int, [vp]),
+    "gd_frontend_timer_end": (C.c_int, [vp, fp]),
+    "gd_frontend_launch_count": (C.c_int, [vp, C.POINTER(C.c_longlong)]),
+    "gd_frontend_profile": (C.c_int, [vp, C.c_int]),
+    "gd_frontend_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), fp, C.POINTER(C.c_longlong), ip]),
+    "gd_frontend_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
+    "gd_frontend_flush_l2": (C.c_int, [vp]),
+    "gd_stage_gray": (C.c_int, [C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]),
+    "gd_stage_depth_edge": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, fp, vp]),
+    "gd_stage_mahalanobis": (C.c_int, [C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, fp, fp, fp, vp, vp, vp]),
+    "gd_stage_farneback": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, vp]),
+    "gd_stage_polyexp": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, ip, ip]),
+    "gd_stage_orb_pyramid": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, ip]),
+    "gd_stage_fast_cells": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]),
+    "gd_stage_gaussian7": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libgdslam_cuda.so; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GdError(GD_ENODEVICE, f"{LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                                        "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name, None)
+            if fn is None:  # reported by missing_symbols(); tests/test_capi_symbols.py fails on any
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def missing_symbols():
+    L = lib()
+    return [n for n in SYMBOLS if not hasattr(L, n)]
+
+
+def check(code: int) -> None:
+    if code != GD_OK:
+        raise GdError(code, lib().gd_last_error().decode(errors="replace"))
+
+
+def _fptr(a):
+    return None if a is None else a.ctypes.data_as(fp)
+
+
+def _vptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def _ptr_array(arrs):
+    return (vp * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    code = lib().gd_device_count(C.byref(n))
+    return n.value if code == GD_OK else 0
+
+
+def device_info(device=0):
+    name = C.create_string_buffer(256)
+    sm = C.c_int(0)
+    mem = C.c_size_t(0)
+    check(lib().gd_device_info(device, name, 256, C.byref(sm), C.byref(mem)))
+    return name.value.decode(), sm.value, mem.value
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from gd_host_alloc (kept alive by the returned array)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = vp()
+    check(lib().gd_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}
+
+
+# ---------------------------------------------------------------------------------------------- stages
+def stage_gray(bgr, order=0, device=0):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w = bgr.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    check(lib().gd_stage_gray(device, _vptr(bgr), w * 3, w, h, order, _vptr(out)))
+    return out
+
+
+def stage_depth_edge(depth, K, device=0):
+    depth = np.ascontiguousarray(depth, np.float32)
+    K = np.ascontiguousarray(K, np.float32)
+    h, w = depth.shape
+    out = np.empty((h, w), np.uint8)
+    check(lib().gd_stage_depth_edge(device, _vptr(depth), w, h, _fptr(K), _vptr(out)))
+    return out
+
+
+def stage_mahalanobis(flow, d_ref, d_cur, e_ref, e_cur, K, R, T, lut=None, device=0):
+    flow = np.ascontiguousarray(flow, np.float32)
+    h, w = flow.shape[:2]
+    d_ref = np.ascontiguousarray(d_ref, np.float32)
+    d_cur = np.ascontiguousarray(d_cur, np.float32)
+    e_ref = np.ascontiguousarray(e_ref, np.uint8)
+    e_cur = np.ascontiguousarray(e_cur, np.uint8)
+    K = np.ascontiguousarray(K, np.float32)
+    R = np.ascontiguousarray(R, np.float32)
+    T = np.ascontiguousarray(T, np.float32)
+    if lut is not None:
+        lut = np.ascontiguousarray(lut, np.float32)
+    dist = np.empty((h, w), np.float32)
+    mask = np.empty((h, w), np.uint8)
+    mm = np.empty(2, np.float32)
+    check(lib().gd_stage_mahalanobis(device, _vptr(flow), _vptr(d_ref), _vptr(d_cur), _vptr(e_ref), _vptr(e_cur),
+                                     _vptr(lut), w, h, _fptr(K), _fptr(R), _fptr(T), _vptr(dist), _vptr(mask),
+                                     _vptr(mm)))
+    return dist, mask, mm
+
+
+def stage_farneback(prev, nxt, device=0):
+    prev = np.ascontiguousarray(prev, np.uint8)
+    nxt = np.ascontiguousarray(nxt, np.uint8)
+    h, w = prev.shape
+    flow = np.empty((h, w, 2), np.float32)
+    check(lib().gd_stage_farneback(device, _vptr(prev), _vptr(nxt), w, h, _vptr(flow)))
+    return flow
+
+
+def stage_polyexp(gray, k, device=0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.empty(5 * h * w, np.float32)
+    lw, lh = C.c_int(0), C.c_int(0)
+    check(lib().gd_stage_polyexp(device, _vptr(gray), w, h, k, _vptr(out), C.byref(lw), C.byref(lh)))
+    n = lw.value * lh.value
+    planes = out[: 5 * n].reshape(5, lh.value, lw.value)
+    return np.ascontiguousarray(np.moveaxis(planes, 0, 2))  # (lh, lw, 5) like OpenCV's CV_32FC5
+
+
+# ---------------------------------------------------------------------------------------------- GeoMaskMaker
+class GeoMask:
+    """Mirror of the reference's GeoMaskMaker for `batch` lockstep streams (include/GeoMaskMaker.h:52-116)."""
+
+    def __init__(self, K, dist=None, depth_factor=5000.0, width=640, height=480, device=0, batch=1):
+        self.w, self.h, self.batch = width, height, batch
+        K = np.ascontiguousarray(K, np.float32)
+        d = None if dist is None else np.ascontiguousarray(dist, np.float32)
+        self._h = vp()
+        check(lib().gd_geomask_create(C.byref(self._h), _fptr(K), _fptr(d), 0 if d is None else d.size, depth_factor,
+                                      width, height, device, batch))
+
+    def close(self):
+        if self._h:
+            lib().gd_geomask_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_new_image(self, bgrs, depths):
+        """AddNewImage (GeoMaskMaker.cc:409-429): one (bgr, depth_m) per stream."""
+        bgrs = [np.ascontiguousarray(b, np.uint8) for b in bgrs]
+        depths = [np.ascontiguousarray(d, np.float32) for d in depths]
+        assert len(bgrs) == self.batch and len(depths) == self.batch
+        check(lib().gd_geomask_push(self._h, _ptr_array(bgrs), self.w * 3, _ptr_array(depths), self.w * 4))
+
+    def get_no_gmm_mask(self, R=None, T=None, pose_valid=None):
+        """GetNoGMMmask (GeoMaskMaker.cc:167-408) with the pose as input; returns one {0,1} mask per stream."""
+        B = self.batch
+        R = np.ascontiguousarray(np.tile(np.eye(3, dtype=np.float32), (B, 1, 1)) if R is None else R, np.float32)
+        T = np.ascontiguousarray(np.zeros((B, 3), np.float32) if T is None else T, np.float32)
+        pv = np.ascontiguousarray(np.ones(B, np.int32) if pose_valid is None else pose_valid, np.int32)
+        masks = [np.empty((self.h, self.w), np.uint8) for _ in range(B)]
+        check(lib().gd_geomask_mask(self._h, _fptr(R), _fptr(T), pv.ctypes.data_as(ip), _ptr_array(masks), self.w))
+        return masks
+
+    def frames(self):
+        return lib().gd_geomask_frames(self._h)
+
+    def debug(self, what, stream=0):
+        shapes = {DBG_FLOW: ((self.h, self.w, 2), np.float32), DBG_DIST: ((self.h, self.w), np.float32),
+                  DBG_EDGE_REF: ((self.h, self.w), np.uint8), DBG_EDGE_CUR: ((self.h, self.w), np.uint8),
+                  DBG_GRAY_CUR: ((self.h, self.w), np.uint8), DBG_MINMAX: ((2,), np.float32)}
+        shp, dt = shapes[what]
+        out = np.empty(shp, dt)
+        check(lib().gd_geomask_debug_fetch(self._h, what, stream, _vptr(out), out.nbytes))
+        return out

@@ -1,0 +1,512 @@
+// farneback.cu — Farnebäck dense optical flow for sm_100a, batched over independent RGB-D streams.
+//
+// Replaces cv::calcOpticalFlowFarneback(prvs, next, flow, 0.5, 3, 15, 3, 5, 1.2, 0) called by
+// GeoMaskMaker::GetFlow (GD-SLAM src/GeoMaskMaker.cc:158-166).  OpenCV-4.13 semantics:
+//   per image  : GaussianBlur(f32, ksize/sigma of the level, on the FULL-RES image) -> resize(INTER_LINEAR)
+//                -> FarnebackPolyExp(n=5, sigma=1.2)  ==> R: 5 f32 planes per level           [k_fb_pyr, k_fb_polyexp]
+//   per pair   : per level, coarse to fine: flow = 2*resize(prev level flow) (or 0), then 3 x
+//                { M = UpdateMatrices(R0, R1, flow); flow = solve(box15x15(M)) }              [k_fb_upsample, k_fb_flow_iter]
+// The per-image half is computed ONCE per frame and kept in the stream's device ring (the reference recomputes
+// both pyramids on every call); M never touches HBM: each CTA recomputes it for its tile + 7-px halo in shared
+// memory, runs the 15x15 box sums in FP64 (like OpenCV's double vsum) and solves the 2x2 system.
+#include "farneback.cuh"
+
+#include <cfloat>
+#include <cmath>
+
+namespace gd {
+
+// ------------------------------------------------------------------------------------------------ plan
+static int cv_round_d(double v) { return (int)lrint(v); }
+
+static void gaussian_taps(int n, double sigma, float* k)
+{
+    if (sigma <= 0 && n == 3) {
+        k[0] = 0.25f; k[1] = 0.5f; k[2] = 0.25f;
+        return;
+    }
+    const double sx = sigma > 0 ? sigma : ((n - 1) * 0.5 - 1) * 0.3 + 0.8;
+    const double scale2x = -0.5 / (sx * sx);
+    double t[FB_MAX_KSIZE], sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const double x = i - (n - 1) * 0.5;
+        t[i] = std::exp(scale2x * x * x);
+        sum += t[i];
+    }
+    sum = 1.0 / sum;
+    for (int i = 0; i < n; ++i) k[i] = (float)(t[i] * sum);
+}
+
+// FarnebackPrepareGaussian: taps g, x*g, x*x*g and the four entries of inv(G) that are used
+static void poly_constants(int n, double sigma, FbPlan* p)
+{
+    if (sigma < FLT_EPSILON) sigma = n * 0.3;
+    float* g = p->g + n;
+    float* xg = p->xg + n;
+    float* xxg = p->xxg + n;
+    double s = 0.;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)std::exp(-x * x / (2 * sigma * sigma));
+        s += g[x];
+    }
+    s = 1. / s;
+    for (int x = -n; x <= n; x++) {
+        g[x] = (float)(g[x] * s);
+        xg[x] = (float)(x * g[x]);
+        xxg[x] = (float)(x * x * g[x]);
+    }
+    double G[6][6] = {};
+    for (int y = -n; y <= n; y++)
+        for (int x = -n; x <= n; x++) {
+            G[0][0] += g[y] * g[x];
+            G[1][1] += g[y] * g[x] * x * x;
+            G[3][3] += g[y] * g[x] * x * x * x * x;
+            G[5][5] += g[y] * g[x] * x * x * y * y;
+        }
+    G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+    G[4][4] = G[3][3];
+    G[3][4] = G[4][3] = G[5][5];
+    // G is block structured: {1, x^2, y^2} couple, x, y, xy are diagonal.  Invert the 3x3 block in closed form.
+    const double a = G[0][0], b = G[0][3], c = G[3][3], d = G[3][4];
+    // block [[a,b,b],[b,c,d],[b,d,c]]
+    const double det = a * (c * c - d * d) - 2.0 * b * b * (c - d);
+    p->ig03 = -b * (c - d) / det;            // inv(0,3)
+    p->ig33 = (a * c - b * b) / det;         // inv(3,3)
+    p->ig11 = 1.0 / G[1][1];
+    p->ig55 = 1.0 / G[5][5];
+}
+
+int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int poly_n, double poly_sigma, int winsize,
+                 FbPlan* plan)
+{
+    GD_REQUIRE(poly_n == FB_POLY_N && winsize == FB_WIN, "only poly_n=5 / winsize=15 (the reference's parameters) are built");
+    GD_REQUIRE(w >= 16 && h >= 16, "image too small");
+    *plan = FbPlan();
+    plan->w = w;
+    plan->h = h;
+    plan->iterations = iterations;
+    const int min_size = 32;
+    int k;
+    double scale = 1;
+    for (k = 0; k < levels; k++) {
+        scale *= pyr_scale;
+        if (w * scale < min_size || h * scale < min_size) break;
+    }
+    levels = k;
+    GD_REQUIRE(levels + 1 <= FB_MAX_LEVELS, "too many pyramid levels");
+    plan->nlevels = levels + 1;
+    size_t r_off = 0, i_off = 0, f_off = 0;
+    for (k = 0; k <= levels; ++k) {
+        FbLevel& L = plan->lv[k];
+        double sc = 1;
+        for (int i = 0; i < k; i++) sc *= pyr_scale;
+        const double sigma = (1. / sc - 1) * 0.5;
+        int sz = cv_round_d(sigma * 5) | 1;
+        L.ksize = sz > 3 ? sz : 3;
+        GD_REQUIRE(L.ksize <= FB_MAX_KSIZE, "pyramid blur kernel too large");
+        L.w = cv_round_d(w * sc);
+        L.h = cv_round_d(h * sc);
+        gaussian_taps(L.ksize, sigma, L.taps);
+        L.scale_x = (double)w / L.w;
+        L.scale_y = (double)h / L.h;
+        L.r_off = r_off;
+        L.i_off = i_off;
+        L.f_off = f_off;
+        const size_t n = align_up((size_t)L.w * L.h, 64);
+        r_off += 5 * n;
+        i_off += n;
+        f_off += n;
+    }
+    plan->r_floats = r_off;
+    plan->i_floats = i_off;
+    plan->f_float2 = f_off;
+    poly_constants(poly_n, poly_sigma, plan);
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K1a-1
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+struct PyrArgs {
+    int W, H, lw, lh, ksize;
+    double scale_x, scale_y;
+    float taps[FB_MAX_KSIZE];
+};
+
+// one thread = one level pixel: blur (rows then columns, f32) of the four full-res neighbours, then bilinear
+template <int KS>
+__global__ void __launch_bounds__(128) k_fb_pyr(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
+                                                float* __restrict__ I, size_t istride_b)
+{
+    constexpr int MAXK = KS ? KS : FB_MAX_KSIZE;
+    const int ks = KS ? KS : a.ksize;
+    const int r = ks >> 1;
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy = blockIdx.y;
+    const int b = blockIdx.z;
+    if (dx >= a.lw) return;
+    const uint8_t* g = gray + (size_t)b * gstride_b;
+    // cv::resize coordinate mapping
+    float fx = (float)((dx + 0.5) * a.scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= a.W - 1) { fx = 0; sx = a.W - 1; }
+    float fy = (float)((dy + 0.5) * a.scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    int sy1 = sy + 1;
+    sy = max(0, min(a.H - 1, sy));
+    sy1 = max(0, min(a.H - 1, sy1));
+    // row-blurred values at columns sx, sx+1 for rows sy-r .. sy-r+ks  (ks+1 rows cover both sy and sy+1)
+    float h0[MAXK + 1], h1[MAXK + 1];
+    const int ybase = sy - r;
+    const int nrows = ks + 1;
+#pragma unroll(KS ? KS + 1 : 1)
+    for (int j = 0; j < MAXK + 1; ++j) {
+        if (j < nrows) {
+            const uint8_t* row = g + (size_t)reflect101(ybase + j, a.H) * a.W;
+            float prev = (float)__ldg(row + reflect101(sx - r, a.W));
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll(KS ? KS : 1)
+            for (int i = 0; i < MAXK; ++i) {
+                if (i < ks) {
+                    const float nxt = (float)__ldg(row + reflect101(sx - r + i + 1, a.W));
+                    acc0 = i == 0 ? a.taps[0] * prev : acc0 + a.taps[i] * prev;
+                    acc1 = i == 0 ? a.taps[0] * nxt : acc1 + a.taps[i] * nxt;
+                    prev = nxt;
+                }
+            }
+            h0[j] = acc0;
+            h1[j] = acc1;
+        }
+    }
+    // column pass (symmetric form) centred on sy (index r) and sy1 (index r + (sy1 - sy))
+    const int c0 = r, c1 = r + (sy1 - sy);
+    float B00 = a.taps[r] * h0[c0], B01 = a.taps[r] * h1[c0];
+    float B10 = a.taps[r] * h0[c1], B11 = a.taps[r] * h1[c1];
+    // rows outside the image were fetched through reflect101(ybase + j), which equals the column-pass border rule
+    // only when the row index maps identically; handle it by re-deriving indices relative to the centre row
+#pragma unroll(KS ? KS / 2 : 1)
+    for (int i = 1; i <= MAXK / 2; ++i) {
+        if (i <= r) {
+            const float t = a.taps[r + i];
+            B00 += t * (h0[c0 + i] + h0[c0 - i]);
+            B01 += t * (h1[c0 + i] + h1[c0 - i]);
+            // for the sy1 centre the window is rows c1-r .. c1+r; c1 + r = ks when sy1 = sy + 1
+            const int up = c1 + i, dn = c1 - i;
+            B10 += t * (h0[up] + h0[dn]);
+            B11 += t * (h1[up] + h1[dn]);
+        }
+    }
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const float r0 = B00 * a0 + B01 * a1;
+    const float r1 = B10 * a0 + B11 * a1;
+    I[(size_t)b * istride_b + (size_t)dy * a.lw + dx] = r0 * b0 + r1 * b1;
+}
+
+// ------------------------------------------------------------------------------------------------ K1a-2
+struct PolyArgs {
+    int w, h;
+    float g[2 * FB_POLY_N + 1], xg[2 * FB_POLY_N + 1], xxg[2 * FB_POLY_N + 1];
+    double ig11, ig03, ig33, ig55;
+};
+
+constexpr int PT_W = 32, PT_H = 8, PN = FB_POLY_N;
+
+__global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs a,
+                                                            float* __restrict__ R, size_t rstride_b)
+{
+    __shared__ float sI[PT_H + 2 * PN][PT_W + 2 * PN];
+    __shared__ float sR[3][PT_H][PT_W + 2 * PN];
+    const int b = blockIdx.z;
+    const float* Ip = I + (size_t)b * istride_b;
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+    const int tid = threadIdx.y * PT_W + threadIdx.x;
+    for (int i = tid; i < (PT_H + 2 * PN) * (PT_W + 2 * PN); i += PT_W * PT_H) {
+        const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
+        const int x = min(max(x0 + lx - PN, 0), a.w - 1), y = min(max(y0 + ly - PN, 0), a.h - 1);
+        sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
+    }
+    __syncthreads();
+    // vertical pass for PT_H rows x (PT_W + 10) columns
+    const float* g = a.g + PN;
+    const float* xg = a.xg + PN;
+    const float* xxg = a.xxg + PN;
+    for (int i = tid; i < PT_H * (PT_W + 2 * PN); i += PT_W * PT_H) {
+        const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
+        const int cy = ly + PN;
+        float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 1; k <= PN; ++k) {
+            const float s0 = sI[cy - k][lx], s1 = sI[cy + k][lx];
+            const float p = s0 + s1;
+            t0 = t0 + g[k] * p;
+            t1 = t1 + xg[k] * (s1 - s0);
+            t2 = t2 + xxg[k] * p;
+        }
+        sR[0][ly][lx] = t0;
+        sR[1][ly][lx] = t1;
+        sR[2][ly][lx] = t2;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= a.w || y >= a.h) return;
+    const int lx = threadIdx.x + PN, ly = threadIdx.y;
+    const float* r0 = sR[0][ly];
+    const float* r1 = sR[1][ly];
+    const float* r2 = sR[2][ly];
+    double b1 = r0[lx] * g[0], b2 = 0, b3 = r1[lx] * g[0], b4 = 0, b5 = r2[lx] * g[0], b6 = 0;
+#pragma unroll
+    for (int k = 1; k <= PN; ++k) {
+        const double tg = r0[lx + k] + r0[lx - k];
+        b1 += tg * g[k];
+        b4 += tg * xxg[k];
+        b2 += (r0[lx + k] - r0[lx - k]) * xg[k];
+        b3 += (r1[lx + k] + r1[lx - k]) * g[k];
+        b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
+        b5 += (r2[lx + k] + r2[lx - k]) * g[k];
+    }
+    const size_t plane = (size_t)a.w * a.h;
+    float* Rp = R + (size_t)b * rstride_b + (size_t)y * a.w + x;
+    Rp[0] = (float)(b3 * a.ig11);
+    Rp[plane] = (float)(b2 * a.ig11);
+    Rp[2 * plane] = (float)(b1 * a.ig03 + b5 * a.ig33);
+    Rp[3 * plane] = (float)(b1 * a.ig03 + b4 * a.ig33);
+    Rp[4 * plane] = (float)(b6 * a.ig55);
+}
+
+int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gray_stride_b, int batch, float* scratch_I,
+                              size_t i_stride_b, float* R, size_t r_stride_b, cudaStream_t s, LaunchStats* st)
+{
+    for (int k = 0; k < plan.nlevels; ++k) {
+        const FbLevel& L = plan.lv[k];
+        PyrArgs pa;
+        pa.W = plan.w; pa.H = plan.h; pa.lw = L.w; pa.lh = L.h; pa.ksize = L.ksize;
+        pa.scale_x = L.scale_x; pa.scale_y = L.scale_y;
+        std::memcpy(pa.taps, L.taps, sizeof(pa.taps));
+        {
+            LaunchScope ls(st, s, "K1a_blur_resample", 1);
+            dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
+            float* Ik = scratch_I + L.i_off;
+            switch (L.ksize) {
+                case 3: k_fb_pyr<3><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
+                case 9: k_fb_pyr<9><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
+                case 19: k_fb_pyr<19><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
+                default: k_fb_pyr<0><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
+            }
+            GD_CUDA(cudaGetLastError());
+        }
+        {
+            LaunchScope ls(st, s, "K1a_polyexp", 1);
+            PolyArgs po;
+            po.w = L.w; po.h = L.h;
+            std::memcpy(po.g, plan.g, sizeof(po.g));
+            std::memcpy(po.xg, plan.xg, sizeof(po.xg));
+            std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
+            po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
+            dim3 block(PT_W, PT_H), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
+            k_fb_polyexp<<<grid, block, 0, s>>>(scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b);
+            GD_CUDA(cudaGetLastError());
+        }
+    }
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K1b
+// flow upsample: cv::resize(prevFlow, flow, INTER_LINEAR) then flow *= 1/pyr_scale
+__global__ void __launch_bounds__(128) k_fb_upsample(const float2* __restrict__ src, int sw, int sh, float2* __restrict__ dst,
+                                                     int dw, int dh, size_t fstride_b, float mul)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
+    if (dx >= dw) return;
+    const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    const int sx1 = min(sx + 1, sw - 1);
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    int sy1 = sy + 1;
+    sy = max(0, min(sh - 1, sy));
+    sy1 = max(0, min(sh - 1, sy1));
+    const float2* sp = src + (size_t)b * fstride_b;
+    const float2 p00 = __ldg(sp + (size_t)sy * sw + sx), p01 = __ldg(sp + (size_t)sy * sw + sx1);
+    const float2 p10 = __ldg(sp + (size_t)sy1 * sw + sx), p11 = __ldg(sp + (size_t)sy1 * sw + sx1);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    float2 o;
+    o.x = ((p00.x * a0 + p01.x * a1) * b0 + (p10.x * a0 + p11.x * a1) * b1) * mul;
+    o.y = ((p00.y * a0 + p01.y * a1) * b0 + (p10.y * a0 + p11.y * a1) * b1) * mul;
+    dst[(size_t)b * fstride_b + (size_t)dy * dw + dx] = o;
+}
+
+constexpr int FT_W = 32, FT_H = 16, FHALO = FB_WIN / 2;          // 7
+constexpr int FH_W = FT_W + 2 * FHALO, FH_H = FT_H + 2 * FHALO;  // 46 x 30
+constexpr int FT_THREADS = 256;
+constexpr size_t FT_SMEM = sizeof(float) * 5 * FH_H * FH_W + sizeof(double) * 5 * FH_H * FT_W;
+
+// FarnebackUpdateMatrices for one pixel
+__device__ __forceinline__ void fb_update_matrix(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
+                                                 int w, int h, int x, int y, float2 fl, float M[5])
+{
+    const size_t o = (size_t)y * w + x;
+    const float dx = fl.x, dy = fl.y;
+    float fx = x + dx, fy = y + dy;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= x1;
+    fy -= y1;
+    float r2, r3, r4, r5, r6;
+    const float R00 = __ldg(R0 + o), R01 = __ldg(R0 + plane + o), R02 = __ldg(R0 + 2 * plane + o),
+                R03 = __ldg(R0 + 3 * plane + o), R04 = __ldg(R0 + 4 * plane + o);
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const float* p = R1 + (size_t)y1 * w + x1;
+        r2 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
+        p += plane;
+        r3 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
+        p += plane;
+        r4 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
+        p += plane;
+        r5 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
+        p += plane;
+        r6 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
+        r4 = (R02 + r4) * 0.5f;
+        r5 = (R03 + r5) * 0.5f;
+        r6 = (R04 + r6) * 0.25f;
+    } else {
+        r2 = r3 = 0.f;
+        r4 = R02;
+        r5 = R03;
+        r6 = R04 * 0.5f;
+    }
+    r2 = (R00 - r2) * 0.5f;
+    r3 = (R01 - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    constexpr int BORDER = 5;
+    if ((unsigned)(x - BORDER) >= (unsigned)(w - BORDER * 2) || (unsigned)(y - BORDER) >= (unsigned)(h - BORDER * 2)) {
+        const float border[BORDER] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+        const float scale = (x < BORDER ? border[x] : 1.f) * (x >= w - BORDER ? border[w - x - 1] : 1.f) *
+                            (y < BORDER ? border[y] : 1.f) * (y >= h - BORDER ? border[h - y - 1] : 1.f);
+        r2 *= scale; r3 *= scale; r4 *= scale; r5 *= scale; r6 *= scale;
+    }
+    M[0] = r4 * r4 + r6 * r6;
+    M[1] = (r4 + r5) * r6;
+    M[2] = r5 * r5 + r6 * r6;
+    M[3] = r4 * r2 + r6 * r3;
+    M[4] = r6 * r2 + r5 * r3;
+}
+
+// one iteration of FarnebackUpdateFlow_Blur with the UpdateMatrices that precedes it fused in
+__global__ void __launch_bounds__(FT_THREADS) k_fb_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                             size_t rstride_b, const float2* __restrict__ fin,
+                                                             float2* __restrict__ fout, size_t fstride_b, int w, int h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sM = reinterpret_cast<float*>(smem_raw);                                   // [5][FH_H][FH_W]
+    double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 5 * FH_H * FH_W);  // [5][FH_H][FT_W]
+    const int b = blockIdx.z;
+    const size_t plane = (size_t)w * h;
+    const float* r0 = R0 + (size_t)b * rstride_b;
+    const float* r1 = R1 + (size_t)b * rstride_b;
+    const float2* fi = fin + (size_t)b * fstride_b;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < FH_H * FH_W; i += FT_THREADS) {
+        const int ly = i / FH_W, lx = i - ly * FH_W;
+        const int x = min(max(x0 + lx - FHALO, 0), w - 1), y = min(max(y0 + ly - FHALO, 0), h - 1);
+        float M[5];
+        fb_update_matrix(r0, r1, plane, w, h, x, y, __ldg(fi + (size_t)y * w + x), M);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sM[(c * FH_H + ly) * FH_W + lx] = M[c];
+    }
+    __syncthreads();
+    // horizontal 15-tap sums (f64) for every halo row
+    for (int i = tid; i < FH_H * FT_W; i += FT_THREADS) {
+        const int ly = i / FT_W, lx = i - ly * FT_W;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const float* m = sM + (c * FH_H + ly) * FH_W + lx;
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < FB_WIN; ++d) s += (double)m[d];
+            sH[(c * FH_H + ly) * FT_W + lx] = s;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < FT_H * FT_W; i += FT_THREADS) {
+        const int ly = i / FT_W, lx = i - ly * FT_W;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x >= w || y >= h) continue;
+        double v[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const double* hp = sH + (c * FH_H + ly) * FT_W + lx;
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < FB_WIN; ++d) s += hp[d * FT_W];
+            v[c] = s;
+        }
+        const double scale = 1. / (FB_WIN * FB_WIN);
+        const double g11 = v[0] * scale, g12 = v[1] * scale, g22 = v[2] * scale, h1 = v[3] * scale, h2 = v[4] * scale;
+        const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+        float2 o;
+        o.x = (float)((g11 * h2 - g12 * h1) * idet);
+        o.y = (float)((g22 * h1 - g12 * h2) * idet);
+        fout[(size_t)b * fstride_b + (size_t)y * w + x] = o;
+    }
+}
+
+int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
+                   float2* flowB, size_t f_stride_b, const float2** final_flow, cudaStream_t s, LaunchStats* st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        attr_set = true;
+    }
+    const float2* prev = nullptr;
+    int pw = 0, ph = 0;
+    for (int k = plan.nlevels - 1; k >= 0; --k) {
+        const FbLevel& L = plan.lv[k];
+        float2* A = flowA + L.f_off;
+        float2* B = flowB + L.f_off;
+        if (!prev) {
+            if (batch == 1)
+                GD_CUDA(cudaMemsetAsync(A, 0, (size_t)L.w * L.h * sizeof(float2), s));
+            else
+                GD_CUDA(cudaMemset2DAsync(A, f_stride_b * sizeof(float2), 0, (size_t)L.w * L.h * sizeof(float2), batch, s));
+        } else {
+            LaunchScope ls(st, s, "K1b_flow_upsample", 1);
+            dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
+            k_fb_upsample<<<grid, block, 0, s>>>(prev, pw, ph, A, L.w, L.h, f_stride_b, 2.0f);
+            GD_CUDA(cudaGetLastError());
+        }
+        float2* in = A;
+        float2* out = B;
+        for (int it = 0; it < plan.iterations; ++it) {
+            LaunchScope ls(st, s, "K1b_flow_iter", 1);
+            dim3 grid(cdiv(L.w, FT_W), cdiv(L.h, FT_H), batch);
+            k_fb_flow_iter<<<grid, FT_THREADS, FT_SMEM, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, out, f_stride_b, L.w, L.h);
+            GD_CUDA(cudaGetLastError());
+            float2* t = in;
+            in = out;
+            out = t;
+        }
+        prev = in;  // result of the last iteration
+        pw = L.w;
+        ph = L.h;
+    }
+    *final_flow = prev;
+    return GD_OK;
+}
+
+}  // namespace gd

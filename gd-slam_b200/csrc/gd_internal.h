@@ -1,0 +1,162 @@
+// gd_internal.h — shared host-side plumbing of libgdslam_cuda (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gdslam_cuda.h"
+
+namespace gd {
+
+void set_error(const char* fmt, ...);
+
+#define GD_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            gd::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return GD_ECUDA;                                                                       \
+        }                                                                                          \
+    } while (0)
+
+#define GD_TRY(expr)                 \
+    do {                             \
+        int r__ = (expr);            \
+        if (r__ != GD_OK) return r__; \
+    } while (0)
+
+#define GD_REQUIRE(cond, msg)                               \
+    do {                                                    \
+        if (!(cond)) {                                      \
+            gd::set_error("%s: %s", __func__, msg);         \
+            return GD_EINVAL;                               \
+        }                                                   \
+    } while (0)
+
+int select_device(int device);  // validates + cudaSetDevice; GD_ENODEVICE when there is none
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// RAII device allocation
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t n)
+    {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+            return GD_ENOMEM;
+        }
+        bytes = n;
+        return GD_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
+    int alloc(size_t n)
+    {
+        release();
+        if (n == 0) n = 16;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMallocHost(%zu) failed: %s", n, cudaGetErrorString(e));
+            return GD_ENOMEM;
+        }
+        bytes = n;
+        return GD_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// launch accounting / optional per-family event profile (gd_frontend_profile*)
+struct LaunchStats {
+    long long launches = 0;
+    bool profiling = false;
+    struct Family {
+        const char* name;
+        long long launches = 0;
+        float ms = 0.f;
+    };
+    std::vector<Family> fam;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int family_index(const char* name)
+    {
+        for (size_t i = 0; i < fam.size(); ++i)
+            if (fam[i].name == name || std::strcmp(fam[i].name, name) == 0) return (int)i;
+        Family f;
+        f.name = name;
+        fam.push_back(f);
+        return (int)fam.size() - 1;
+    }
+};
+
+// Brackets kernel launches of one family: counts them and, when profiling, times them with events
+// (profiling serialises the stream; it is only enabled by the bench's profile pass).
+struct LaunchScope {
+    LaunchStats* st;
+    cudaStream_t s;
+    int idx;
+    LaunchScope(LaunchStats* st_, cudaStream_t s_, const char* name, int n_launches) : st(st_), s(s_), idx(-1)
+    {
+        if (!st) return;
+        st->launches += n_launches;
+        if (st->profiling) {
+            idx = st->family_index(name);
+            st->fam[idx].launches += n_launches;
+            if (!st->e0) {
+                cudaEventCreate(&st->e0);
+                cudaEventCreate(&st->e1);
+            }
+            cudaEventRecord(st->e0, s);
+        }
+    }
+    ~LaunchScope()
+    {
+        if (st && idx >= 0) {
+            cudaEventRecord(st->e1, s);
+            cudaEventSynchronize(st->e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, st->e0, st->e1);
+            st->fam[idx].ms += ms;
+        }
+    }
+};
+
+}  // namespace gd

@@ -1,0 +1,533 @@
+// geomask.cu — GeoMaskMaker kernels for sm_100a (compiled with --fmad=false: every f32/f64 operation below
+// is the individually rounded operation the CPU oracle performs; the two fused operations OpenCV itself
+// performs are explicit fmaf()).
+//
+// Reference being replaced (GD-SLAM tree):
+//   K0  gray             src/GeoMaskMaker.cc:163-164 (BGR2GRAY), src/Tracking.cc:219-225 (RGB2GRAY on BGR bytes)
+//   K2a depth edge       src/GeoMaskMaker.cc:854-964 (GetEdge)
+//   K2b Mahalanobis      src/GeoMaskMaker.cc:208-272
+//   K3  normalise/mask   src/GeoMaskMaker.cc:276-277, 405-407
+//
+// All of these are HBM-bound streaming kernels: one pass over the inputs, coalesced vector loads/stores,
+// no tensor-core work (largest matrix on the path is 6x6).
+#include "geomask.cuh"
+
+namespace gd {
+
+// ------------------------------------------------------------------------------------------------
+// host helpers: OpenCV-semantics 3x3 inverse (f64 determinant/cofactors) and f32 3x3 gemm
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__host__ __device__ inline bool inv3_cv(const T* m_, T* out)
+{
+    double m[9];
+    for (int i = 0; i < 9; ++i) m[i] = (double)m_[i];
+    double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (d == 0.0) {
+        for (int i = 0; i < 9; ++i) out[i] = (T)0;
+        return false;
+    }
+    d = 1.0 / d;
+    out[0] = (T)((m[4] * m[8] - m[5] * m[7]) * d);
+    out[1] = (T)((m[2] * m[7] - m[1] * m[8]) * d);
+    out[2] = (T)((m[1] * m[5] - m[2] * m[4]) * d);
+    out[3] = (T)((m[5] * m[6] - m[3] * m[8]) * d);
+    out[4] = (T)((m[0] * m[8] - m[2] * m[6]) * d);
+    out[5] = (T)((m[2] * m[3] - m[0] * m[5]) * d);
+    out[6] = (T)((m[3] * m[7] - m[4] * m[6]) * d);
+    out[7] = (T)((m[1] * m[6] - m[0] * m[7]) * d);
+    out[8] = (T)((m[0] * m[4] - m[1] * m[3]) * d);
+    return true;
+}
+
+// host-side strict f32 helpers (this TU is built with -ffp-contract=off on the host side as well)
+static inline float h_dot3(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    volatile float t = a0 * b0;
+    volatile float u = a1 * b1;
+    t = t + u;
+    u = a2 * b2;
+    t = t + u;
+    return t;
+}
+
+void make_cam_const(const float K[9], CamConst* c)
+{
+    c->fu = K[0];
+    c->fv = K[4];
+    c->cu = K[2];
+    c->cv = K[5];
+    inv3_cv<float>(K, c->Ki);
+    double Kd[9];
+    for (int i = 0; i < 9; ++i) Kd[i] = (double)K[i];
+    inv3_cv<double>(Kd, c->Kid);
+}
+
+void make_pose(const float K[9], const float R[9], const float T[3], int valid, PoseDev* p)
+{
+    float Ki[9];
+    inv3_cv<float>(K, Ki);
+    for (int i = 0; i < 9; ++i) p->R[i] = R[i];
+    for (int i = 0; i < 3; ++i) p->T[i] = T[i];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            p->RK[3 * i + j] = h_dot3(R[3 * i], Ki[j], R[3 * i + 1], Ki[3 + j], R[3 * i + 2], Ki[6 + j]);
+    p->valid = valid;
+    p->pad[0] = p->pad[1] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0 gray: g = (c0*k0 + c1*19235 + c2*k2 + 16384) >> 15
+// one thread = 4 pixels = 12 input bytes (3 x u32 when aligned) -> one u32 store per output plane
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned gray_px(unsigned c0, unsigned c1, unsigned c2, unsigned k0, unsigned k2)
+{
+    return (c0 * k0 + c1 * 19235u + c2 * k2 + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ bgr, size_t step, size_t stride_b, int w, int h,
+                                              uint8_t* __restrict__ g_flow, uint8_t* __restrict__ g_orb, int orb_order,
+                                              size_t gstride_b, int aligned)
+{
+    const int b = blockIdx.z;
+    const int groups = (w + 3) >> 2;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (gx >= groups) return;
+    const uint8_t* row = bgr + (size_t)b * stride_b + (size_t)y * step;
+    const int x0 = gx * 4;
+    unsigned c[12];
+    const int npx = min(4, w - x0);
+    if (aligned && npx == 4) {
+        const uint3 v = *reinterpret_cast<const uint3*>(row + (size_t)x0 * 3);
+        const unsigned ww[3] = {v.x, v.y, v.z};
+#pragma unroll
+        for (int i = 0; i < 12; ++i) c[i] = (ww[i >> 2] >> (8 * (i & 3))) & 0xffu;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) c[i] = (i < npx * 3) ? row[(size_t)x0 * 3 + i] : 0u;
+    }
+    unsigned of = 0, oo = 0;
+    const unsigned ok0 = orb_order == 0 ? 3735u : 9798u, ok2 = orb_order == 0 ? 9798u : 3735u;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        of |= gray_px(c[3 * p], c[3 * p + 1], c[3 * p + 2], 3735u, 9798u) << (8 * p);
+        oo |= gray_px(c[3 * p], c[3 * p + 1], c[3 * p + 2], ok0, ok2) << (8 * p);
+    }
+    const size_t o = (size_t)b * gstride_b + (size_t)y * w + x0;
+    if (npx == 4 && (w & 3) == 0 && (gstride_b & 3) == 0) {
+        if (g_flow) *reinterpret_cast<unsigned*>(g_flow + o) = of;
+        if (g_orb) *reinterpret_cast<unsigned*>(g_orb + o) = oo;
+    } else {
+        for (int p = 0; p < npx; ++p) {
+            if (g_flow) g_flow[o + p] = (uint8_t)(of >> (8 * p));
+            if (g_orb) g_orb[o + p] = (uint8_t)(oo >> (8 * p));
+        }
+    }
+}
+
+int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w, int h, int batch, uint8_t* g_flow,
+                uint8_t* g_orb, int orb_order, size_t gray_stride_b, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "K0_gray", 1);
+    const int aligned = ((reinterpret_cast<uintptr_t>(bgr) & 3) == 0 && (bgr_step & 3) == 0 && (bgr_stride_b & 3) == 0) ? 1 : 0;
+    dim3 block(128), grid(cdiv((w + 3) / 4, 128), h, batch);
+    k_gray<<<grid, block, 0, s>>>(bgr, bgr_step, bgr_stride_b, w, h, g_flow, g_orb, orb_order, gray_stride_b, aligned);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a depth edge (FP64, bit-exact vs oracle).  Tile 32x8, depth halo 2, normal/vertex halo 1 in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int ET_W = 32, ET_H = 8;
+
+__global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
+                                                            CamConst cam, uint8_t* __restrict__ edge, size_t estride_b)
+{
+    __shared__ double sd[ET_H + 4][ET_W + 4];        // clamped depth, halo 2
+    __shared__ double sn[ET_H + 2][ET_W + 2][3];     // normals, halo 1
+    __shared__ double sv[ET_H + 2][ET_W + 2][3];     // vertices, halo 1
+    const int b = blockIdx.z;
+    const float* dp = depth + (size_t)b * dstride_b;
+    const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
+    const int tid = threadIdx.y * ET_W + threadIdx.x;
+    for (int i = tid; i < (ET_H + 4) * (ET_W + 4); i += ET_W * ET_H) {
+        const int ly = i / (ET_W + 4), lx = i - ly * (ET_W + 4);
+        const int x = x0 + lx - 2, y = y0 + ly - 2;
+        double v = 0.0;
+        if (x >= 0 && y >= 0 && x < w && y < h) {
+            v = (double)__ldg(dp + (size_t)y * w + x);
+            const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
+            if (interior && v > 3.5) v = 0.0;  // :870-874
+        }
+        sd[ly][lx] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
+        const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
+        const int x = x0 + lx - 1, y = y0 + ly - 1;
+        double n0 = 0, n1 = 0, n2 = 0, v0 = 0, v1 = 0, v2 = 0;
+        if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
+            const double dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
+            if (dc != 0.0 && dt != 0.0 && dl != 0.0) {
+                const double a0 = -1.0, a1 = 0.0, a2 = dl - dc;
+                const double b0 = 0.0, b1 = -1.0, b2 = dt - dc;
+                const double c0 = a1 * b2 - a2 * b1;
+                const double c1 = a2 * b0 - a0 * b2;
+                const double c2 = a0 * b1 - a1 * b0;
+                double ss = 0.0;
+                ss += c0 * c0;
+                ss += c1 * c1;
+                ss += c2 * c2;
+                const double nv = sqrt(ss);
+                const double inv = nv != 0.0 ? 1.0 / nv : 0.0;
+                n0 = c0 * inv;
+                n1 = c1 * inv;
+                n2 = c2 * inv;
+                const double px = (double)x, py = (double)y;
+                const double h0 = cam.Kid[0] * px + cam.Kid[1] * py + cam.Kid[2] * 1.0;
+                const double h1 = cam.Kid[3] * px + cam.Kid[4] * py + cam.Kid[5] * 1.0;
+                const double h2 = cam.Kid[6] * px + cam.Kid[7] * py + cam.Kid[8] * 1.0;
+                v0 = h0 * dc;
+                v1 = h1 * dc;
+                v2 = h2 * dc;
+            }
+        }
+        sn[ly][lx][0] = n0; sn[ly][lx][1] = n1; sn[ly][lx][2] = n2;
+        sv[ly][lx][0] = v0; sv[ly][lx][1] = v1; sv[ly][lx][2] = v2;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint8_t e = 0;
+    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
+    if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.0) {
+        const int nx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+        const int ny[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+        bool zero_nb = false;
+        double max_phi_d = -1.0, max_phi_c = -1.0;
+        const double cn0 = sn[ly][lx][0], cn1 = sn[ly][lx][1], cn2 = sn[ly][lx][2];
+        const double cv0 = sv[ly][lx][0], cv1 = sv[ly][lx][1], cv2 = sv[ly][lx][2];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int jx = lx + nx[k], jy = ly + ny[k];
+            const double z = sv[jy][jx][2];
+            if (z == 0.0) {
+                zero_nb = true;
+                continue;
+            }
+            double phi_d = 0.0;
+            phi_d += (sv[jy][jx][0] - cv0) * cn0;
+            phi_d += (sv[jy][jx][1] - cv1) * cn1;
+            phi_d += (z - cv2) * cn2;
+            const double ad = fabs(phi_d);
+            if (max_phi_d < ad) max_phi_d = ad;
+            if (phi_d < 0.0) {
+                if (max_phi_c < 0.0) max_phi_c = 0.0;
+            } else {
+                double dot = 0.0;
+                dot += sn[jy][jx][0] * cn0;
+                dot += sn[jy][jx][1] * cn1;
+                dot += sn[jy][jx][2] * cn2;
+                const double phi_c = 1.0 - dot;
+                if (phi_c > max_phi_c) max_phi_c = phi_c;
+            }
+        }
+        if (zero_nb)
+            e = 255;
+        else if (!(max_phi_c == -1.0 || max_phi_d == -1.0)) {
+            const double thres_edge = max_phi_d + 0.05 * max_phi_c;
+            if (thres_edge > 0.04) e = 255;
+        }
+    }
+    edge[(size_t)b * estride_b + (size_t)y * w + x] = e;
+}
+
+int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, int batch, const CamConst& cam,
+                      uint8_t* edge, size_t edge_stride_b, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "K2a_depth_edge", 1);
+    dim3 block(ET_W, ET_H), grid(cdiv(w, ET_W), cdiv(h, ET_H), batch);
+    k_depth_edge<<<grid, block, 0, s>>>(depth, depth_stride_b, w, h, cam, edge, edge_stride_b);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b Mahalanobis + scatter.  One thread per source pixel.  Scatter = 64-bit atomicMax on
+// ((src_index+1) << 32 | float_bits(value)): the high word orders writers by raster index, so the
+// last raster-order writer wins exactly like the sequential loop (GeoMaskMaker.cc:269).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot3f(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    float t = a0 * b0;
+    t = t + a1 * b1;
+    t = t + a2 * b2;
+    return t;
+}
+
+__device__ __forceinline__ float depth2std(float depth, float fu)
+{
+    const float inv = 1.0f / fu;
+    float r = inv * inv;
+    r = r * 0.5f;
+    r = r * 0.5f;
+    r = r * depth;
+    r = r * depth;
+    r = r * depth;
+    r = r * depth;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
+                                                     const float* __restrict__ depth_ref, const float* __restrict__ depth_cur,
+                                                     size_t dstride_b, const uint8_t* __restrict__ edge_ref,
+                                                     const uint8_t* __restrict__ edge_cur, size_t estride_b,
+                                                     const float2* __restrict__ lut, int w, int h, CamConst cam,
+                                                     const PoseDev* __restrict__ poses, unsigned long long* __restrict__ keys,
+                                                     size_t kstride_b)
+{
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const PoseDev* __restrict__ P = poses + b;
+    if (!P->valid) return;
+    const size_t i = (size_t)y * w + x;
+    const float2 f = __ldg(flow + (size_t)b * fstride_b + i);
+    const float cur_x = (float)x + f.x;
+    const float cur_y = (float)y + f.y;
+    if (!(cur_x == cur_x) || !(cur_y == cur_y)) return;
+    if (cur_x < 0 || cur_y < 0 || cur_x > (float)(w - 1) || cur_y > (float)(h - 1)) return;
+    const int icx = (int)cur_x, icy = (int)cur_y;
+    float rx, ry, cx, cy;
+    if (lut) {
+        const float2 a = __ldg(lut + i), c = __ldg(lut + (size_t)icy * w + icx);
+        rx = a.x; ry = a.y; cx = c.x; cy = c.y;
+    } else {
+        rx = (float)x; ry = (float)y; cx = (float)icx; cy = (float)icy;
+    }
+    const int rix = (int)rx, riy = (int)ry, cix = (int)cx, ciy = (int)cy;
+    if (rix < 0 || riy < 0 || rix >= w || riy >= h || cix < 0 || ciy < 0 || cix >= w || ciy >= h) return;
+    const size_t ri = (size_t)riy * w + rix, ci = (size_t)ciy * w + cix;
+    const float ref_depth = __ldg(depth_ref + (size_t)b * dstride_b + ri);
+    const float cur_depth = __ldg(depth_cur + (size_t)b * dstride_b + ci);
+    if (__ldg(edge_ref + (size_t)b * estride_b + ri) == 255 || __ldg(edge_cur + (size_t)b * estride_b + ci) == 255) return;
+    if (cur_depth == 0.f || (double)cur_depth > 3.5 || ref_depth == 0.f || (double)ref_depth > 3.5) return;
+
+    const float fu = cam.fu, fv = cam.fv, cu = cam.cu;
+    const float U0 = dot3f(P->RK[0], rx, P->RK[1], ry, P->RK[2], 1.0f);
+    const float U1 = dot3f(P->RK[3], rx, P->RK[4], ry, P->RK[5], 1.0f);
+    const float U2 = dot3f(P->RK[6], rx, P->RK[7], ry, P->RK[8], 1.0f);
+    const float C0 = dot3f(cam.Ki[0], cx, cam.Ki[1], cy, cam.Ki[2], 1.0f) * cur_depth;
+    const float C1 = dot3f(cam.Ki[3], cx, cam.Ki[4], cy, cam.Ki[5], 1.0f) * cur_depth;
+    const float C2 = dot3f(cam.Ki[6], cx, cam.Ki[7], cy, cam.Ki[8], 1.0f) * cur_depth;
+    const float P0 = fmaf(U0, ref_depth, P->T[0]);  // cv::scaleAdd is fused in OpenCV 4.13
+    const float P1 = fmaf(U1, ref_depth, P->T[1]);
+    const float P2 = fmaf(U2, ref_depth, P->T[2]);
+    const float e0 = C0 - P0, e1 = C1 - P1, e2 = C2 - P2;
+
+    const float s2 = depth2std(ref_depth, fu);
+    const float s5 = depth2std(cur_depth, fu);
+    // J rows (index slips of the reference kept: J(1,1) uses ref_depth, J(1,2) uses x)
+    float J[3][6];
+    J[0][0] = cur_depth / fu;      J[0][1] = 0.f;               J[0][2] = (cx - cu) / fu;
+    J[0][3] = -P->R[0] * ref_depth / fu; J[0][4] = -P->R[1] * ref_depth / fv; J[0][5] = -U0;
+    J[1][0] = 0.f;                 J[1][1] = ref_depth / fv;    J[1][2] = (cx - cu) / fv;
+    J[1][3] = -P->R[3] * ref_depth / fu; J[1][4] = -P->R[4] * ref_depth / fv; J[1][5] = -U1;
+    J[2][0] = 0.f;                 J[2][1] = 0.f;               J[2][2] = 1.0f;
+    J[2][3] = -P->R[6] * ref_depth / fu; J[2][4] = -P->R[7] * ref_depth / fv; J[2][5] = -U2;
+    float Cm[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float JS[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) JS[c] = J[r][c];
+        JS[2] = J[r][2] * s2;
+        JS[5] = J[r][5] * s5;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s += (double)JS[k] * (double)J[c][k];
+            Cm[3 * r + c] = (float)s;
+        }
+    }
+    float Ci[9];
+    inv3_cv<float>(Cm, Ci);
+    float q[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        s += (double)e0 * (double)Ci[c];
+        s += (double)e1 * (double)Ci[3 + c];
+        s += (double)e2 * (double)Ci[6 + c];
+        q[c] = (float)s;
+    }
+    double l = 0.0;
+    l += (double)q[0] * (double)e0;
+    l += (double)q[1] * (double)e1;
+    l += (double)q[2] * (double)e2;
+    float value = sqrtf((float)l);
+    value = value + 0.0f;  // -0 -> +0 so that the bit pattern orders like the value
+    const unsigned long long key = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned long long)__float_as_uint(value);
+    atomicMax(keys + (size_t)b * kstride_b + (size_t)icy * w + icx, key);
+}
+
+int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* depth_ref, const float* depth_cur,
+                       size_t depth_stride_b, const uint8_t* edge_ref, const uint8_t* edge_cur, size_t edge_stride_b,
+                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses,
+                       unsigned long long* keys, size_t keys_stride_b, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "K2b_mahalanobis", 1);
+    dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), batch);
+    k_mahalanobis<<<grid, block, 0, s>>>(flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
+                                          edge_stride_b, lut, w, h, cam, poses, keys, keys_stride_b);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 pass 1: min / max over the resolved low words (unwritten pixels contribute 0.0f)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_minmax(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
+                                                unsigned int* __restrict__ minmax_bits)
+{
+    const int b = blockIdx.y;
+    const unsigned long long* kp = keys + (size_t)b * kstride_b;
+    unsigned mn = 0xFFFFFFFFu, mx = 0u;
+    const int n2 = n_px >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(kp) + i);
+        const unsigned a = (unsigned)v.x, c = (unsigned)v.y;
+        mn = min(mn, min(a, c));
+        mx = max(mx, max(a, c));
+    }
+    if ((n_px & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned a = (unsigned)kp[n_px - 1];
+        mn = min(mn, a);
+        mx = max(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ unsigned smn[8], smx[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        smn[warp] = mn;
+        smx[warp] = mx;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        mn = lane < (blockDim.x >> 5) ? smn[lane] : 0xFFFFFFFFu;
+        mx = lane < (blockDim.x >> 5) ? smx[lane] : 0u;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) {
+            atomicMin(minmax_bits + 2 * b, mn);
+            atomicMin(minmax_bits + 2 * b + 1, ~mx);
+        }
+    }
+}
+
+int launch_minmax_reset(unsigned int* minmax_bits, int batch, cudaStream_t s)
+{
+    GD_CUDA(cudaMemsetAsync(minmax_bits, 0xFF, sizeof(unsigned) * 2 * batch, s));
+    return GD_OK;
+}
+
+int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, unsigned int* minmax_bits,
+                  cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "K3a_minmax", 1);
+    int blocks = cdiv(n_px / 2, 256 * 4);
+    if (blocks < 1) blocks = 1;
+    dim3 grid(blocks, batch);
+    k_minmax<<<grid, 256, 0, s>>>(keys, keys_stride_b, n_px, minmax_bits);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 pass 2: v*a+b (fused, like cv convertTo), round half even, saturate, (<20) -> {1,0}; clear keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned mask_of(float d, float a, float bsh)
+{
+    const float v = fmaf(d, a, bsh);
+    int r = (v == v) ? __float2int_rn(v) : 0;
+    r = max(0, min(255, r));
+    return r < 20 ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_normalize_mask(unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
+                                                        const unsigned int* __restrict__ minmax_bits,
+                                                        const PoseDev* __restrict__ poses, uint8_t* __restrict__ mask,
+                                                        size_t mstride_b, float* __restrict__ dist_out, size_t dstride_b)
+{
+    const int b = blockIdx.y;
+    unsigned long long* kp = keys + (size_t)b * kstride_b;
+    uint8_t* mp = mask + (size_t)b * mstride_b;
+    const bool valid = poses[b].valid != 0;
+    const float smin_f = __uint_as_float(minmax_bits[2 * b]);
+    const float smax_f = __uint_as_float(~minmax_bits[2 * b + 1]);
+    const double smin = (double)smin_f, smax = (double)smax_f;
+    const double scale = 255.0 * ((smax - smin) > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+    const double shift = 0.0 - smin * scale;
+    const float a = (float)scale, bsh = (float)shift;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
+    const int i0 = g * 4;
+    if (i0 >= n_px) return;
+    if (i0 + 4 <= n_px && (mstride_b & 3) == 0 && (kstride_b & 1) == 0) {
+        ulonglong2* k2 = reinterpret_cast<ulonglong2*>(kp + i0);
+        const ulonglong2 v0 = k2[0], v1 = k2[1];
+        const float d0 = __uint_as_float((unsigned)v0.x), d1 = __uint_as_float((unsigned)v0.y);
+        const float d2 = __uint_as_float((unsigned)v1.x), d3 = __uint_as_float((unsigned)v1.y);
+        unsigned m = 0x01010101u;
+        if (valid) m = mask_of(d0, a, bsh) | (mask_of(d1, a, bsh) << 8) | (mask_of(d2, a, bsh) << 16) | (mask_of(d3, a, bsh) << 24);
+        *reinterpret_cast<unsigned*>(mp + i0) = m;
+        if (dist_out) *reinterpret_cast<float4*>(dist_out + (size_t)b * dstride_b + i0) = make_float4(d0, d1, d2, d3);
+        k2[0] = make_ulonglong2(0ull, 0ull);
+        k2[1] = make_ulonglong2(0ull, 0ull);
+    } else {
+        for (int i = i0; i < min(i0 + 4, n_px); ++i) {
+            const float d = __uint_as_float((unsigned)kp[i]);
+            mp[i] = valid ? (uint8_t)mask_of(d, a, bsh) : (uint8_t)1;
+            if (dist_out) dist_out[(size_t)b * dstride_b + i] = d;
+            kp[i] = 0ull;
+        }
+    }
+}
+
+int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
+                          const unsigned int* minmax_bits, const PoseDev* poses, uint8_t* mask, size_t mask_stride_b,
+                          float* dist_out, size_t dist_stride_b, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "K3b_normalize_mask", 1);
+    dim3 grid(cdiv(cdiv(n_px, 4), 256), batch);
+    k_normalize_mask<<<grid, 256, 0, s>>>(keys, keys_stride_b, n_px, minmax_bits, poses, mask, mask_stride_b, dist_out,
+                                          dist_stride_b);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+__global__ void k_fill_u8(uint8_t* dst, size_t n, uint8_t v)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "fill_u8", 1);
+    k_fill_u8<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, n, v);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+}  // namespace gd

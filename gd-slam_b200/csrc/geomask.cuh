@@ -1,0 +1,55 @@
+// geomask.cuh — launchers of the GeoMaskMaker kernels (K0 gray, K2a depth edge, K2b Mahalanobis scatter,
+// K3 min-max + normalise + threshold).  All launchers are batched over `batch` independent streams
+// (blockIdx.z / blockIdx.y = stream) and asynchronous on `s`.
+#pragma once
+#include "gd_internal.h"
+
+namespace gd {
+
+// per-stream pose block read by K2b / K3 (uploaded once per step)
+struct PoseDev {
+    float R[9];
+    float T[3];
+    float RK[9];  // R * inv(K), f32 gemm semantics of OpenCV (GeoMaskMaker.cc:241)
+    int valid;    // 0 -> all-ones mask (GetRt failure path / warm-up)
+    int pad[2];
+};
+
+// camera constants shared by all streams of a handle (kernel argument by value)
+struct CamConst {
+    float fu, fv, cu, cv;
+    float Ki[9];    // inv(K) in f32  (GeoMaskMaker.cc:200)
+    double Kid[9];  // inv((double)K)  (GeoMaskMaker.cc:888)
+};
+
+void make_cam_const(const float K[9], CamConst* c);
+void make_pose(const float K[9], const float R[9], const float T[3], int valid, PoseDev* p);
+
+// K0: 8UC3 -> 8UC1 (cv::cvtColor 8-bit, 15-bit fixed point).  Either output may be null.
+int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w, int h, int batch, uint8_t* gray_bgr2gray,
+                uint8_t* gray_orb, int orb_order, size_t gray_stride_b, cudaStream_t s, LaunchStats* st);
+
+// K2a: GetEdge.  depth f32 [b][h][w] -> edge u8 {0,255}
+int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, int batch, const CamConst& cam,
+                      uint8_t* edge, size_t edge_stride_b, cudaStream_t s, LaunchStats* st);
+
+// K2b: fused back-projection + J S J^T + 3x3 inverse + Mahalanobis + scatter (64-bit atomicMax keys)
+int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* depth_ref, const float* depth_cur,
+                       size_t depth_stride_b, const uint8_t* edge_ref, const uint8_t* edge_cur, size_t edge_stride_b,
+                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses,
+                       unsigned long long* keys, size_t keys_stride_b, cudaStream_t s, LaunchStats* st);
+
+// K3 pass 1: per-stream min / max of the resolved dist image.  minmax_bits: [batch][2] u32, must hold 0xFFFFFFFF
+// on entry (launch_minmax_reset).  Encoding: [0] = min(bits(v)), [1] = min(~bits(v)).
+int launch_minmax_reset(unsigned int* minmax_bits, int batch, cudaStream_t s);
+int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, unsigned int* minmax_bits,
+                  cudaStream_t s, LaunchStats* st);
+// K3 pass 2: normalise (0..255), round half even, < 20 -> mask {1,0}; clears the keys for the next frame.
+// dist_out (optional) receives the resolved f32 dist image.
+int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
+                          const unsigned int* minmax_bits, const PoseDev* poses, uint8_t* mask, size_t mask_stride_b,
+                          float* dist_out, size_t dist_stride_b, cudaStream_t s, LaunchStats* st);
+// all-ones mask (warm-up path)
+int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st);
+
+}  // namespace gd

@@ -1,0 +1,56 @@
+// geomask_core.cuh — device-resident state of `batch` GeoMaskMaker streams (ring buffer of per-image products)
+// and the per-frame sequence AddNewImage / GetNoGMMmask (GD-SLAM src/GeoMaskMaker.cc:167-277, 405-429).
+#pragma once
+#include "farneback.cuh"
+#include "geomask.cuh"
+
+namespace gd {
+
+constexpr int GD_RING = 6;  // inter_frame_size (5) + 1, include/GeoMaskMaker.h:55
+
+struct GeoMaskCore {
+    int device = 0, batch = 0, w = 0, h = 0;
+    size_t n = 0;  // pixels per image (padded strides below)
+    float K[9];
+    CamConst cam;
+    FbPlan plan;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    LaunchStats* stats = nullptr;
+    int frames = 0;  // frames pushed so far
+    bool has_lut = false;
+
+    // device memory (HBM layout: stream-major, ring-slot-minor)
+    DevBuf bgr;        // [B][h][w][3]   newest frame (input staging)
+    DevBuf gray;       // [B][n]         BGR2GRAY of the newest frame
+    DevBuf depth;      // [B][RING][n]   f32 metres
+    DevBuf edge;       // [B][RING][n]   u8 {0,255}
+    DevBuf R;          // [B][RING][r_floats]  Farnebäck polynomial expansion pyramid
+    DevBuf scratchI;   // [B][i_floats]
+    DevBuf flowA, flowB;  // [B][f_float2]
+    DevBuf keys;       // [B][n] u64 scatter keys (zero between frames)
+    DevBuf minmax;     // [B][2] u32
+    DevBuf poses;      // [B] PoseDev
+    DevBuf mask;       // [B][n] u8
+    DevBuf dist;       // [B][n] f32 (resolved dist image, kept for debug fetch)
+    DevBuf lut;        // [n] float2 or empty
+    PinnedBuf h_poses;
+    const float2* last_flow = nullptr;
+    int last_ref_slot = -1, last_cur_slot = -1;
+
+    size_t n_pad = 0;  // n rounded up to 64 elements
+
+    int init(const float K_[9], const float* dist_coef, int ndist, int width, int height, int device_, int batch_,
+             cudaStream_t s, LaunchStats* st);
+    // new frame already resident in this->bgr and in depth slot (frames % RING): computes the per-image products
+    int push_resident();
+    float* depth_slot_ptr(int slot) { return depth.as<float>() + (size_t)slot * n_pad; }
+    size_t depth_stride_b() const { return (size_t)GD_RING * n_pad; }
+    int cur_slot() const { return frames % GD_RING; }  // slot the NEXT push writes
+    // GetNoGMMmask for all streams; result stays in this->mask.  R: [B][9], T: [B][3], valid: [B] (host)
+    int compute_mask(const float* R, const float* T, const int* pose_valid);
+    int debug_fetch(int what, int stream_idx, void* dst, size_t dst_bytes);
+    ~GeoMaskCore();
+};
+
+}  // namespace gd

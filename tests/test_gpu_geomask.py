@@ -1,0 +1,167 @@
+"""GPU parity (-m gpu): GeoMaskMaker kernels through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import flow_tol_violations, load_pkg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    c = load_pkg("capi")
+    c.lib()
+    assert c.device_count() >= 1, "no CUDA device: the GPU tests must run on the B200 box"
+    return c
+
+
+@pytest.fixture(scope="module")
+def pair(synth):
+    s = synth.SyntheticStream(0)
+    return s, s.frame(0), s.frame(5)
+
+
+def test_gray_both_orders_bit_exact(capi, oracle, pair):
+    _, f0, _ = pair
+    for order in (0, 1):
+        assert np.array_equal(capi.stage_gray(f0.bgr, order), oracle.gray(f0.bgr, order))
+    # ragged width (not a multiple of 4) and an unaligned start
+    sub = np.ascontiguousarray(f0.bgr[3:100, 5:142])
+    assert np.array_equal(capi.stage_gray(sub, 0), oracle.gray(sub, 0))
+
+
+def test_depth_edge_bit_exact(capi, oracle, synth, pair, golden):
+    _, f0, f5 = pair
+    K = synth.intrinsics()
+    for d in (f0.depth_m, f5.depth_m):
+        assert np.array_equal(capi.stage_depth_edge(d, K), oracle.depth_edge(d, K))
+    g = golden("geomask_small.npz")  # literal-transcription golden incl. >3.5 m border pixels
+    assert np.array_equal(capi.stage_depth_edge(g["depth_ref"], g["K"]), g["edge_ref"])
+    # ragged size
+    sub = np.ascontiguousarray(f0.depth_m[:101, :203])
+    assert np.array_equal(capi.stage_depth_edge(sub, K), oracle.depth_edge(sub, K))
+
+
+def test_mahalanobis_scatter_vs_oracle(capi, oracle, synth, pair):
+    s, f0, f5 = pair
+    K = synth.intrinsics()
+    R, T = s.pair_pose(0, 5)
+    flow = oracle.farneback(oracle.gray(f0.bgr), oracle.gray(f5.bgr))
+    e0, e5 = oracle.depth_edge(f0.depth_m, K), oracle.depth_edge(f5.depth_m, K)
+    dist_o, written, src = oracle.mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T)
+    mask_o, d8, mm_o = oracle.normalize_threshold(dist_o)
+    dist_g, mask_g, mm_g = capi.stage_mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T)
+    nviol, dmax = flow_tol_violations(dist_g, dist_o)
+    assert nviol == 0, (nviol, dmax)
+    assert np.array_equal(dist_g, dist_o), "same arithmetic sequence -> expected bit-exact"
+    assert np.array_equal(mm_g, mm_o)
+    assert np.array_equal(mask_g, mask_o)
+    # the scene exercises collisions (last-writer-wins) and unwritten pixels
+    assert (written == 0).mean() > 0.05 and 0.01 < (mask_o == 0).mean() < 0.5
+
+
+def test_mahalanobis_literal_cv2_golden(capi, golden):
+    g = golden("geomask_small.npz")
+    dist, mask, _ = capi.stage_mahalanobis(g["flow"], g["depth_ref"], g["depth_cur"], g["edge_ref"], g["edge_cur"],
+                                           g["K"], g["R"], g["T"])
+    nviol, dmax = flow_tol_violations(dist, g["dist"])
+    assert nviol == 0, (nviol, dmax)
+    assert (mask == g["mask"]).mean() >= 0.999
+
+
+def test_mahalanobis_roll_pose_and_lut(capi, oracle, synth):
+    s = synth.SyntheticStream(2, roll_deg_per_frame=0.04)
+    f0, f5 = s.frame(1), s.frame(6)
+    K = synth.intrinsics()
+    R, T = s.pair_pose(1, 6)
+    flow = oracle.farneback(oracle.gray(f0.bgr), oracle.gray(f5.bgr))
+    e0, e5 = oracle.depth_edge(f0.depth_m, K), oracle.depth_edge(f5.depth_m, K)
+    # an explicit (slightly shifted) LUT exercises the undistortedPoint path of GeoMaskMaker.cc:219-223
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float32)
+    lut = np.stack([xx + 0.3, yy + 0.6], -1).astype(np.float32)
+    for l in (None, lut):
+        do, _, _ = oracle.mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T, lut=l)
+        dg, mg, _ = capi.stage_mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T, lut=l)
+        assert np.array_equal(dg, do)
+        assert np.array_equal(mg, oracle.normalize_threshold(do)[0])
+
+
+def test_scatter_collision_last_writer(capi, oracle):
+    w, h = 64, 32
+    K = np.array([[50, 0, 32], [0, 50, 16], [0, 0, 1]], np.float32)
+    rs = np.random.RandomState(0)
+    flow = (rs.rand(h, w, 2).astype(np.float32) - 0.5) * 6  # heavy collisions
+    d0 = (1 + rs.rand(h, w)).astype(np.float32)
+    d1 = (1 + rs.rand(h, w)).astype(np.float32)
+    e = np.zeros((h, w), np.uint8)
+    R = np.eye(3, dtype=np.float32)
+    T = np.array([0.01, -0.02, 0.005], np.float32)
+    do, wr, src = oracle.mahalanobis(flow, d0, d1, e, e, K, R, T)
+    dg, mg, _ = capi.stage_mahalanobis(flow, d0, d1, e, e, K, R, T)
+    assert np.array_equal(dg, do)
+    assert np.array_equal(mg, oracle.normalize_threshold(do)[0])
+
+
+def test_polyexp_levels_vs_oracle(capi, oracle, pair):
+    _, f0, _ = pair
+    g = oracle.gray(f0.bgr)
+    for k in range(4):
+        a = capi.stage_polyexp(g, k)
+        b = oracle.polyexp_level(g, k)
+        assert a.shape == b.shape
+        d = np.abs(a - b)
+        assert d.max() <= 2e-4 * max(1.0, np.abs(b).max()), (k, d.max(), np.abs(b).max())
+
+
+def test_farneback_vs_oracle_and_cv2_golden(capi, oracle, pair, golden):
+    _, f0, f5 = pair
+    g0, g5 = oracle.gray(f0.bgr), oracle.gray(f5.bgr)
+    flow = capi.stage_farneback(g0, g5)
+    ref = oracle.farneback(g0, g5)
+    nviol, dmax = flow_tol_violations(flow, ref)
+    assert nviol == 0, (nviol, dmax)
+    gold = golden("farneback.npz")
+    nviol, dmax = flow_tol_violations(flow[::8], gold["flow_640_rows8"])
+    assert nviol == 0, (nviol, dmax)
+
+
+def test_farneback_small_and_ragged_vs_cv2_golden(capi, golden):
+    gold = golden("farneback.npz")
+    for a, b, f in (("gray_320_a", "gray_320_b", "flow_320"), ("gray_150_a", "gray_150_b", "flow_150")):
+        flow = capi.stage_farneback(gold[a], gold[b])
+        nviol, dmax = flow_tol_violations(flow, gold[f])
+        assert nviol == 0, (f, nviol, dmax)
+
+
+def test_geomask_handle_warmup_pair_and_batch(capi, oracle, synth):
+    """AddNewImage x6 -> GetNoGMMmask: warm-up all-ones, then the (t-5, t) pair; two streams in one handle."""
+    K = synth.intrinsics()
+    streams = [synth.SyntheticStream(0), synth.SyntheticStream(1, roll_deg_per_frame=0.04)]
+    gm = capi.GeoMask(K, None, 5000.0, 640, 480, 0, batch=2)
+    frames = [[s.frame(f) for f in range(7)] for s in streams]
+    R = T = None
+    for f in range(7):
+        gm.add_new_image([frames[b][f].bgr for b in range(2)], [frames[b][f].depth_m for b in range(2)])
+        if f < 5:
+            masks = gm.get_no_gmm_mask()
+            assert all(m.min() == 1 and m.max() == 1 for m in masks)  # GeoMaskMaker.cc:171-175
+            continue
+        poses = [streams[b].pair_pose(f - 5, f) for b in range(2)]
+        R = np.stack([p[0] for p in poses])
+        T = np.stack([p[1] for p in poses])
+        masks = gm.get_no_gmm_mask(R, T)
+        for b in range(2):
+            mo, flow_o, dist_o = oracle.geomask_pair(frames[b][f - 5].bgr, frames[b][f].bgr, frames[b][f - 5].depth_m,
+                                                     frames[b][f].depth_m, K, R[b], T[b], want_debug=True)
+            flow_g = gm.debug(capi.DBG_FLOW, b)
+            nviol, dmax = flow_tol_violations(flow_g, flow_o)
+            assert nviol == 0, (f, b, nviol, dmax)
+            assert np.array_equal(gm.debug(capi.DBG_EDGE_CUR, b), oracle.depth_edge(frames[b][f].depth_m, K))
+            assert np.array_equal(gm.debug(capi.DBG_EDGE_REF, b), oracle.depth_edge(frames[b][f - 5].depth_m, K))
+            agree = (masks[b] == mo).mean()
+            assert agree >= 0.999, (f, b, agree)
+            assert 0.01 < (mo == 0).mean() < 0.5
+    # GetRt failure path: all-ones for that stream only (GeoMaskMaker.cc:179-185)
+    masks = gm.get_no_gmm_mask(R, T, pose_valid=[0, 1])
+    assert masks[0].min() == 1 and (masks[1] == 0).any()
+    gm.close()
