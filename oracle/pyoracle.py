@@ -142,3 +142,128 @@ def geomask_pair(bgr_ref, bgr_cur, depth_ref, depth_cur, K, R, T, want_debug=Fal
                            flow.ctypes.data_as(C.c_void_p) if want_debug else None,
                            dist.ctypes.data_as(C.c_void_p) if want_debug else None)
     return (mask, flow, dist) if want_debug else mask
+
+
+# ---------------------------------------------------------------------------------------------- ORB
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+_ORB_BOUND = False
+_REF = None
+
+
+def _orb():
+    global _ORB_BOUND
+    L = lib()
+    if not _ORB_BOUND:
+        ip = C.POINTER(C.c_int)
+        L.gdo_orb_config.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
+        L.gdo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.gdo_fast_atan2.restype = C.c_float
+        L.gdo_resize_u8.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+        L.gdo_gaussian7_u8.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.gdo_fast_detect.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
+        L.gdo_orb_candidates.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int]
+        L.gdo_orb_distribute.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
+        L.gdo_ic_angle.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+        L.gdo_ic_angle.restype = C.c_float
+        L.gdo_orb_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _ORB_BOUND = True
+    return L
+
+
+def orb_config(w=640, h=480, nfeatures=1500, scale=1.2, nlevels=8):
+    n = np.zeros(nlevels, np.int32)
+    sz = np.zeros((nlevels, 2), np.int32)
+    sc = np.zeros(nlevels, np.float32)
+    um = np.zeros(16, np.int32)
+    _orb().gdo_orb_config(nfeatures, scale, nlevels, w, h, n.ctypes.data, sz.ctypes.data, sc.ctypes.data, um.ctypes.data)
+    return dict(n_per_level=n, level_sizes=sz, scales=sc, umax=um)
+
+
+def fast_atan2(y, x):
+    return _orb().gdo_fast_atan2(float(y), float(x))
+
+
+def resize_u8(src, dw, dh):
+    src = _c(src, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    _orb().gdo_resize_u8(src.reshape(-1), src.shape[1], src.shape[0], out.reshape(-1), dw, dh)
+    return out
+
+
+def gaussian7(src):
+    src = _c(src, np.uint8)
+    out = np.empty_like(src)
+    _orb().gdo_gaussian7_u8(src.reshape(-1), src.shape[1], src.shape[0], out.reshape(-1))
+    return out
+
+
+def fast_detect(img, threshold):
+    img = _c(img, np.uint8)
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = _orb().gdo_fast_detect(img.reshape(-1), img.shape[1], img.shape[0], threshold, out.reshape(-1), cap)
+    return out[:n].copy()
+
+
+def orb_candidates(img, ini_th=20, min_th=7):
+    img = _c(img, np.uint8)
+    cap = img.size // 4
+    out = np.empty((cap, 3), np.float32)
+    n = _orb().gdo_orb_candidates(img.reshape(-1), img.shape[1], img.shape[0], ini_th, min_th, out.reshape(-1), cap)
+    return out[:n].copy()
+
+
+def orb_distribute(cand, minX, maxX, minY, maxY, N):
+    cand = _c(cand, np.float32)
+    kept = np.empty(N + 64, np.int32)
+    n = _orb().gdo_orb_distribute(cand.reshape(-1), cand.shape[0], minX, maxX, minY, maxY, N, kept, kept.size)
+    return kept[:n].copy()
+
+
+def ic_angle(img, x, y):
+    img = _c(img, np.uint8)
+    return _orb().gdo_ic_angle(img.reshape(-1), img.shape[1], int(x), int(y))
+
+
+def _extract(fn, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, has_nlevel):
+    gray = _c(gray, np.uint8)
+    h, w = gray.shape
+    cap = nfeatures + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    cfg = orb_config(w, h, nfeatures, scale, nlevels)
+    tot = int(sum(int(a) * int(b) for a, b in cfg["level_sizes"]))
+    pyr = np.zeros(tot, np.uint8) if want_pyramid else None
+    aux = np.zeros(nlevels * 2, np.int32)
+    n = fn(gray.reshape(-1), w, h, w, nfeatures, scale, nlevels, ini_th, min_th, kps.ctypes.data, desc.ctypes.data, cap,
+           pyr.ctypes.data if want_pyramid else None, aux.ctypes.data)
+    assert n <= cap
+    levels = None
+    if want_pyramid:
+        levels, off = [], 0
+        for lw, lh in cfg["level_sizes"]:
+            levels.append(pyr[off: off + lw * lh].reshape(lh, lw))
+            off += lw * lh
+    return kps[:n].copy(), desc[:n].copy(), levels
+
+
+def orb_extract(gray, nfeatures=1500, scale=1.2, nlevels=8, ini_th=20, min_th=7, want_pyramid=False):
+    """Restated ORBextractor::operator() (oracle/orb_oracle.cpp)."""
+    return _extract(_orb().gdo_orb_extract, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, True)
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "liborbref.so"))
+
+
+def orbref_extract(gray, nfeatures=1500, scale=1.2, nlevels=8, ini_th=20, min_th=7, want_pyramid=False):
+    """The reference's own src/ORBextractor.cc (compiled verbatim, oracle/_ref/liborbref.so)."""
+    global _REF
+    if _REF is None:
+        _REF = C.CDLL(os.path.join(_HERE, "_ref", "liborbref.so"))
+        _REF.orbref_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return _extract(_REF.orbref_extract, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, False)
