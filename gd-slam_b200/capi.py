@@ -277,3 +277,97 @@ class GeoMask:
         out = np.empty(shp, dt)
         check(lib().gd_geomask_debug_fetch(self._h, what, stream, _vptr(out), out.nbytes))
         return out
+
+
+# ---------------------------------------------------------------------------------------------- ORB stages
+def stage_orb_pyramid(gray, nlevels=8, scale=1.2, device=0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    out = np.empty(w * h * 4, np.uint8)
+    sizes = np.zeros((nlevels, 2), np.int32)
+    check(lib().gd_stage_orb_pyramid(device, _vptr(gray), w, h, nlevels, scale, _vptr(out), sizes.ctypes.data_as(ip)))
+    levels, off = [], 0
+    for lw, lh in sizes:
+        levels.append(out[off: off + lw * lh].reshape(lh, lw).copy())
+        off += lw * lh
+    return levels
+
+
+def stage_fast_cells(gray, ini_th=20, min_th=7, device=0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    h, w = gray.shape
+    cap = w * h // 4
+    out = np.empty((cap, 3), np.float32)
+    n = C.c_int(0)
+    check(lib().gd_stage_fast_cells(device, _vptr(gray), w, h, ini_th, min_th, _vptr(out), cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
+def stage_gaussian7(gray, device=0):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty_like(gray)
+    check(lib().gd_stage_gaussian7(device, _vptr(gray), gray.shape[1], gray.shape[0], _vptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- ORBextractor
+class Orb:
+    """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111) for `batch` images per call."""
+
+    def __init__(self, nfeatures=1500, scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7, max_width=640,
+                 max_height=480, device=0, batch=1):
+        self.batch, self.nlevels, self.nfeatures = batch, nlevels, nfeatures
+        self._h = vp()
+        check(lib().gd_orb_create(C.byref(self._h), nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast, max_width,
+                                  max_height, device, batch))
+
+    def close(self):
+        if self._h:
+            lib().gd_orb_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, grays):
+        """operator(): list of 8UC1 images (same size) -> list of (keypoints[KP_DTYPE], descriptors[n,32])."""
+        grays = [np.ascontiguousarray(g, np.uint8) for g in grays]
+        assert len(grays) == self.batch
+        h, w = grays[0].shape
+        cap = self.nfeatures + 3 * self.nlevels + 8
+        kps = [np.zeros(cap, KP_DTYPE) for _ in grays]
+        desc = [np.zeros((cap, 32), np.uint8) for _ in grays]
+        n = (C.c_int * self.batch)()
+        check(lib().gd_orb_extract(self._h, _ptr_array(grays), w, w, h, _ptr_array(kps), _ptr_array(desc), cap, n))
+        return [(kps[b][: n[b]].copy(), desc[b][: n[b]].copy()) for b in range(self.batch)]
+
+    def level(self, level, stream=0):
+        w, h = C.c_int(0), C.c_int(0)
+        check(lib().gd_orb_level_size(self._h, level, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        check(lib().gd_orb_fetch_level(self._h, stream, level, _vptr(out), w.value, None, None))
+        return out
+
+    def features_per_level(self):
+        n = (C.c_int * self.nlevels)()
+        check(lib().gd_orb_features_per_level(self._h, n))
+        return list(n)
+
+
+def smoke_orb(po):
+    """Tiny ORB extraction on cuda:0 checked bit-exactly against the oracle (used by __graft_entry__.smoke)."""
+    import importlib
+
+    synth = importlib.import_module("gd-slam_b200.synth")
+    s = synth.SyntheticStream(0, 320, 240)
+    gray = po.gray(s.frame(0).bgr, 1)
+    orb = Orb(500, 1.2, 6, 20, 7, 320, 240, 0, 1)
+    kp, desc = orb([gray])[0]
+    rkp, rdesc, _ = po.orb_extract(gray, nfeatures=500, nlevels=6)
+    ok = len(kp) == len(rkp) and all(np.array_equal(kp[f], rkp[f]) for f in kp.dtype.names) and np.array_equal(desc, rdesc)
+    print(f"smoke: ORB 320x240 {len(kp)} keypoints, bit-exact vs oracle = {ok}")
+    assert ok
+    orb.close()

@@ -1,0 +1,962 @@
+// orb.cu — ORBextractor for sm_100a (built with --fmad=false: integer stages and individually rounded f32).
+//
+// Replaces ORB_SLAM2::ORBextractor::operator() (GD-SLAM src/ORBextractor.cc:1043-1105), bit-exact:
+//   K4a k_orb_resize     ComputePyramid               :1107-1132  (cv::resize 8U INTER_LINEAR, 11-bit fixed point)
+//   K4b k_orb_fast       cell loop + cv::FAST          :789-829    (FAST-9/16 score, cell-local NMS, threshold fallback,
+//                                                                   raster-ordered compaction per cell)
+//   K4c k_orb_quadtree   DistributeOctTree/DivideNode  :539-763, :481-537  (one CTA per level and stream; the std::list
+//                                                                   algorithm restated with level-synchronous passes,
+//                                                                   prefix sums and ranking — see the kernel comment)
+//   K4e k_orb_blur       GaussianBlur 7x7 sigma 2      :1085-1086  (integer taps, single rounding)
+//   K4d/e k_orb_describe IC_Angle + computeOrbDescriptor :77-147, fix-up :837-847, scaling :1095-1101
+#include "orb.cuh"
+
+#include <cmath>
+
+namespace gd {
+
+__constant__ signed char c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// ------------------------------------------------------------------------------------------------ plan (host)
+static int cv_round_f(float v) { return (int)lrintf(v); }
+static int cv_round_dd(double v) { return (int)lrint(v); }
+static int cv_floor_d(double v)
+{
+    int i = (int)v;
+    return i - (i > v);
+}
+static int cv_ceil_d(double v)
+{
+    int i = (int)v;
+    return i + (i < v);
+}
+
+int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int w, int h, OrbPlan* p)
+{
+    GD_REQUIRE(nlevels >= 1 && nlevels <= ORB_MAX_LEVELS, "nlevels out of range");
+    GD_REQUIRE(nfeatures >= 1 && scale_factor > 1.0f, "bad nfeatures / scale factor");
+    *p = OrbPlan();
+    p->nlevels = nlevels;
+    p->nfeatures = nfeatures;
+    p->iniTh = ini_th;
+    p->minTh = min_th;
+    p->w = w;
+    p->h = h;
+    // ORBextractor::ORBextractor, :410-446 (scaleFactor is a double member initialised from the float argument)
+    const double scaleFactor = (double)scale_factor;
+    float sc[ORB_MAX_LEVELS], inv[ORB_MAX_LEVELS];
+    sc[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) sc[i] = (float)(sc[i - 1] * scaleFactor);
+    for (int i = 0; i < nlevels; i++) inv[i] = 1.0f / sc[i];
+    int nper[ORB_MAX_LEVELS];
+    const float factor = (float)(1.0f / scaleFactor);
+    float nDesired = (float)(nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels)));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        nper[l] = cv_round_f(nDesired);
+        sum += nper[l];
+        nDesired *= factor;
+    }
+    nper[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // umax, :452-469
+    {
+        int v, v0, vmax = cv_floor_d(ORB_HALF * std::sqrt(2.f) / 2 + 1);
+        int vmin = cv_ceil_d(ORB_HALF * std::sqrt(2.f) / 2);
+        const double hp2 = ORB_HALF * ORB_HALF;
+        for (v = 0; v <= vmax; ++v) p->umax[v] = cv_round_dd(std::sqrt(hp2 - v * v));
+        for (v = ORB_HALF, v0 = 0; v >= vmin; --v) {
+            while (p->umax[v0] == p->umax[v0 + 1]) ++v0;
+            p->umax[v] = v0;
+            ++v0;
+        }
+    }
+    size_t off = 0;
+    int cells = 0, cand = 0, kept = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        OrbLevel& L = p->lv[l];
+        L.w = cv_round_f((float)w * inv[l]);
+        L.h = cv_round_f((float)h * inv[l]);
+        GD_REQUIRE(L.w >= 2 * ORB_BORDER + 30 && L.h >= 2 * ORB_BORDER + 30, "image too small for this pyramid depth");
+        L.pitch = (int)align_up((size_t)L.w, 64);
+        L.off = off;
+        off += align_up((size_t)L.pitch * L.h, 256);
+        L.scale = sc[l];
+        L.kp_size = (float)(int)(31 * sc[l]);
+        L.N = nper[l];
+        if (l > 0) {
+            L.scale_x = (double)p->lv[l - 1].w / L.w;
+            L.scale_y = (double)p->lv[l - 1].h / L.h;
+        } else {
+            L.scale_x = L.scale_y = 1.0;
+        }
+        // cell grid, :773-787
+        const int minB = ORB_BORDER, maxBX = L.w - ORB_EDGE + 3, maxBY = L.h - ORB_EDGE + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        L.nCols = (int)(width / 30.f);
+        L.nRows = (int)(height / 30.f);
+        GD_REQUIRE(L.nCols >= 1 && L.nRows >= 1, "level too small for one FAST cell");
+        L.wCell = (int)std::ceil(width / L.nCols);
+        L.hCell = (int)std::ceil(height / L.nRows);
+        L.cell_start = cells;
+        cells += L.nCols * L.nRows;
+        p->max_cells_level = std::max(p->max_cells_level, L.nCols * L.nRows);
+        p->tile_w = std::max(p->tile_w, L.wCell + 6);
+        p->tile_h = std::max(p->tile_h, L.hCell + 6);
+        // DistributeOctTree initial nodes, :543-545
+        L.nIni = (int)std::round((float)(maxBX - minB) / (maxBY - minB));
+        GD_REQUIRE(L.nIni >= 1, "aspect ratio not supported by DistributeOctTree (nIni = 0)");
+        L.hX = (float)(maxBX - minB) / L.nIni;
+        L.cand_off = cand;
+        L.cand_cap = ((maxBX - minB + 1) / 2 + 1) * ((maxBY - minB + 1) / 2 + 1);  // NMS: no two 8-adjacent survivors
+        cand += (int)align_up((size_t)L.cand_cap, 64);
+        L.kept_off = kept;
+        kept += L.N + 8;
+        p->max_N = std::max(p->max_N, L.N);
+        p->kp_capacity += L.N + 3;
+    }
+    p->pyr_bytes = off;
+    p->total_cells = cells;
+    p->cell_cap = ((p->tile_w - 6 + 1) / 2) * ((p->tile_h - 6 + 1) / 2);
+    p->cand_total = cand;
+    p->kept_total = kept;
+    GD_REQUIRE(p->max_N + 8 < 30000 && p->tile_w * p->tile_h * 2 < 200 * 1024, "plan exceeds kernel limits");
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K4a resize
+__global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                    uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t stride_b,
+                                                    double scale_x, double scale_y)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * stride_b;
+    uint8_t* d = dst + (size_t)blockIdx.z * stride_b;
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0; sx = 0; }
+    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+    const int a0 = __float2int_rn((1.f - fx) * 2048), a1 = __float2int_rn(fx * 2048);
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    const int b0 = __float2int_rn((1.f - fy) * 2048), b1 = __float2int_rn(fy * 2048);
+    const int sy0 = max(0, min(sh - 1, sy)), sy1 = max(0, min(sh - 1, sy + 1));
+    const int sx1 = sx < sw - 1 ? sx + 1 : sx;
+    const uint8_t* r0 = s + (size_t)sy0 * spitch;
+    const uint8_t* r1 = s + (size_t)sy1 * spitch;
+    const int h0 = r0[sx] * a0 + r0[sx1] * a1;
+    const int h1 = r1[sx] * a0 + r1[sx1] * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    d[(size_t)dy * dpitch + dx] = (uint8_t)max(0, min(255, v));
+}
+
+// ------------------------------------------------------------------------------------------------ K4b FAST
+struct FastLevelDev {
+    int w, h, pitch;
+    unsigned long long off;
+    int nCols, nRows, wCell, hCell, cell_start;
+};
+struct FastArgs {
+    int nlevels, total_cells, cell_cap, tile_w, tile_h, iniTh, minTh;
+    FastLevelDev lv[ORB_MAX_LEVELS];
+};
+
+// NOTE (toolchain hazard, CUDA 12.9 / sm_100a): `max(best, max(mn, -mx))` is folded by ptxas into VIMNMX3 with the
+// negation DROPPED (verified on B200 with a 20-line repro: device returns max|d| where the host returns the FAST score).
+// The dark-arc score is therefore computed as a min over the negated differences (ring - v) — no negated min/max operand.
+__device__ __forceinline__ int fast_sprime_smem(const uint8_t* p, int tp, int min_th)
+{
+    const int v = p[0];
+    int r[16];  // ring pixels, clockwise from (0,+3)
+    r[0] = p[3 * tp];
+    r[4] = p[3];
+    r[8] = p[-3 * tp];
+    r[12] = p[-3];
+    // a 9-arc contains at least two of the four compass points
+    const int nb = (v - r[0] > min_th) + (v - r[4] > min_th) + (v - r[8] > min_th) + (v - r[12] > min_th);
+    const int nd = (r[0] - v > min_th) + (r[4] - v > min_th) + (r[8] - v > min_th) + (r[12] - v > min_th);
+    if (nb < 2 && nd < 2) return 0;
+    r[1] = p[3 * tp + 1];
+    r[2] = p[2 * tp + 2];
+    r[3] = p[tp + 3];
+    r[5] = p[-tp + 3];
+    r[6] = p[-2 * tp + 2];
+    r[7] = p[-3 * tp + 1];
+    r[9] = p[-3 * tp - 1];
+    r[10] = p[-2 * tp - 2];
+    r[11] = p[-tp - 3];
+    r[13] = p[tp - 3];
+    r[14] = p[2 * tp - 2];
+    r[15] = p[3 * tp - 1];
+    int d[16], e[16];  // d = v - ring (centre brighter), e = ring - v (centre darker)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d[k] = v - r[k];
+        e[k] = r[k] - v;
+    }
+    int d2[16], e2[16], d4[16], e4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d2[k] = min(d[k], d[(k + 1) & 15]);
+        e2[k] = min(e[k], e[(k + 1) & 15]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d4[k] = min(d2[k], d2[(k + 2) & 15]);
+        e4[k] = min(e2[k], e2[(k + 2) & 15]);
+    }
+    int best = -256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
+        best = max(best, max(d9, e9));
+    }
+    return best;  // S'
+}
+
+constexpr int FAST_THREADS = 256;
+
+__global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __restrict__ pyr, size_t pyr_stride_b, FastArgs a,
+                                                          int* __restrict__ cell_cnt, ushort4* __restrict__ slabs)
+{
+    extern __shared__ unsigned char sm[];
+    const int tp = a.tile_w;                       // tile pitch
+    uint8_t* tile = sm;                            // [tile_h][tile_w]
+    uint8_t* sc = sm + a.tile_w * a.tile_h;        // S' (0 when <= minTh)
+    __shared__ int s_warp[FAST_THREADS / 32];
+    __shared__ int s_base, s_cnt20;
+    const int b = blockIdx.y;
+    int cell = blockIdx.x, l = 0;
+    while (l + 1 < a.nlevels && cell >= a.lv[l + 1].cell_start) ++l;
+    const FastLevelDev& L = a.lv[l];
+    const int ci = cell - L.cell_start;
+    const int i = ci / L.nCols, j = ci - i * L.nCols;
+    const int maxBX = L.w - ORB_EDGE + 3, maxBY = L.h - ORB_EDGE + 3;
+    const int x0 = ORB_BORDER + j * L.wCell, y0 = ORB_BORDER + i * L.hCell;
+    int x1 = x0 + L.wCell + 6, y1 = y0 + L.hCell + 6;
+    int* cnt_out = cell_cnt + (size_t)b * a.total_cells + cell;
+    if (y0 >= maxBY - 3 || x0 >= maxBX - 6) {  // :794, :803
+        if (threadIdx.x == 0) *cnt_out = 0;
+        return;
+    }
+    x1 = min(x1, maxBX);
+    y1 = min(y1, maxBY);
+    const int cw = x1 - x0, ch = y1 - y0;
+    const int iw = cw - 6, ih = ch - 6;
+    if (iw <= 0 || ih <= 0) {
+        if (threadIdx.x == 0) *cnt_out = 0;
+        return;
+    }
+    const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off;
+    for (int t = threadIdx.x; t < cw * ch; t += FAST_THREADS) {
+        const int y = t / cw, x = t - y * cw;
+        tile[y * tp + x] = __ldg(img + (size_t)(y0 + y) * L.pitch + x0 + x);
+        sc[y * tp + x] = 0;
+    }
+    if (threadIdx.x == 0) {
+        s_base = 0;
+        s_cnt20 = 0;
+    }
+    __syncthreads();
+    const int npix = iw * ih;
+    for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
+        const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+        const int s = fast_sprime_smem(tile + y * tp + x, tp, a.minTh);
+        sc[y * tp + x] = (uint8_t)(s > a.minTh ? s : 0);
+    }
+    __syncthreads();
+    // NMS at iniTh: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th
+    auto keep_at = [&](int t, int th) -> bool {
+        const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+        const uint8_t* q = sc + y * tp + x;
+        const int s = q[0];
+        if (s <= th) return false;
+        bool k = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dx == 0 && dy == 0) continue;
+                const int n = q[dy * tp + dx];
+                k = k && !(n > th && n >= s);
+            }
+        return k;
+    };
+    int local20 = 0;
+    for (int t = threadIdx.x; t < npix; t += FAST_THREADS) local20 += keep_at(t, a.iniTh) ? 1 : 0;
+    if (local20) atomicAdd(&s_cnt20, local20);
+    __syncthreads();
+    const int th = s_cnt20 > 0 ? a.iniTh : a.minTh;  // :812-816
+    ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < npix; base += FAST_THREADS) {
+        const int t = base + threadIdx.x;
+        const bool k = t < npix && keep_at(t, th);
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < FAST_THREADS / 32; ++w2) {
+            if (w2 < warp) woff += s_warp[w2];
+            tot += s_warp[w2];
+        }
+        const int pos = s_base + woff + __popc(bal & ((1u << lane) - 1));
+        if (k && pos < a.cell_cap) {
+            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+            slab[pos] = make_ushort4((unsigned short)(x + j * L.wCell), (unsigned short)(y + i * L.hCell),
+                                     (unsigned short)(sc[y * tp + x] - 1), 0);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *cnt_out = min(s_base, a.cell_cap);
+}
+
+// ------------------------------------------------------------------------------------------------ K4c quadtree
+// DistributeOctTree restated for one CTA.  The reference keeps a std::list of nodes: every pass of its first loop
+// splits ALL nodes holding more than one key (children are push_front'ed, the parent erased); once another full pass
+// would overshoot N it switches to splitting one node at a time in order of (key count desc, newest first) until the
+// list holds >= N nodes.  Observations that make it data parallel:
+//   * list order after a pass = children of the last processed parent first (n4,n3,n2,n1), ..., then the untouched
+//     single-key nodes in their old order  -> positions by prefix sums over the old list;
+//   * "newest first" among nodes created in the same pass = smaller list position (SURVEY B-3 canonical rule);
+//   * which child a key lands in depends only on the parent's bounds -> keys carry a node index, no key lists;
+//   * the best key of a node = max response, ties to the earliest candidate (stable partitions keep candidate order).
+struct QtLevelDev {
+    int nCols, nRows, cell_start, N, nIni, cand_off, cand_cap, kept_off, maxX, maxY;
+    float hX;
+};
+struct QtArgs {
+    int nlevels, total_cells, cell_cap, cand_total, kept_total, LN, max_cells;
+    QtLevelDev lv[ORB_MAX_LEVELS];
+};
+
+constexpr int QT_THREADS = 512;
+
+// exclusive scan of data[0..n) by warp 0; all threads must call; result in place, returns the total
+__device__ int block_excl_scan(int* data, int n, int* s_total)
+{
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + threadIdx.x;
+            const int v = idx < n ? data[idx] : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if ((int)threadIdx.x >= o) x += y;
+            }
+            if (idx < n) data[idx] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (threadIdx.x == 0) *s_total = carry;
+    }
+    __syncthreads();
+    return *s_total;
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_orb_quadtree(QtArgs a, const int* __restrict__ cell_cnt,
+                                                             const ushort4* __restrict__ slabs, ushort4* __restrict__ cand,
+                                                             uint8_t* __restrict__ cand_q, int* __restrict__ kept,
+                                                             int* __restrict__ kept_cnt, int* __restrict__ cand_cnt,
+                                                             int* __restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const int LN = a.LN;
+    // shared arrays (ints unless noted)
+    short4* ndA = reinterpret_cast<short4*>(qsm);             // node bounds (ulx, uly, brx, bry), ping
+    short4* ndB = ndA + LN;                                     // pong
+    int* szA = reinterpret_cast<int*>(ndB + LN);
+    int* szB = szA + LN;
+    int* cc = szB + LN;          // child key counts [LN*4]
+    int* cpos = cc + 4 * LN;     // child new positions [LN*4]
+    int* kpos = cpos + 4 * LN;   // new position of a kept node [LN]
+    int* sA = kpos + LN;         // scan scratch A [max(LN, max_cells)]
+    int* sB = sA + max(LN, a.max_cells);  // scan scratch B [LN]
+    int* rk = sB + LN;           // rank of a candidate [LN]
+    int* byrank = rk + LN;       // node index by rank [LN]
+    unsigned char* candA = reinterpret_cast<unsigned char*>(byrank + LN);  // candidate flag ping [LN]
+    unsigned char* candB = candA + LN;
+    unsigned char* dv = candB + LN;  // divide flag [LN]
+    unsigned long long* best = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(dv + LN) + 7) & ~(uintptr_t)7);  // [LN]
+    __shared__ int s_total, s_flag, s_rstar;
+
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const QtLevelDev& L = a.lv[l];
+    ushort4* cd = cand + (size_t)b * a.cand_total + L.cand_off;
+    uint8_t* cq = cand_q + (size_t)b * a.cand_total + L.cand_off;
+    int* kp = kept + (size_t)b * a.kept_total + L.kept_off;
+    const int N = L.N;
+
+    // ---- compact the per-cell lists (cells row-major, raster inside a cell = vToDistributeKeys order)
+    const int ncell = L.nCols * L.nRows;
+    const int* cc_in = cell_cnt + (size_t)b * a.total_cells + L.cell_start;
+    for (int c = tid; c < ncell; c += QT_THREADS) sA[c] = cc_in[c];
+    int n = block_excl_scan(sA, ncell, &s_total);
+    if (n > L.cand_cap) {  // cannot happen (NMS density bound); flag instead of corrupting memory
+        if (tid == 0) atomicOr(err, 1);
+        n = L.cand_cap;
+    }
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int c = warp; c < ncell; c += QT_THREADS / 32) {
+            const int cnt = cc_in[c], o = sA[c];
+            const ushort4* src = slabs + ((size_t)b * a.total_cells + L.cell_start + c) * a.cell_cap;
+            for (int e = lane; e < cnt; e += 32)
+                if (o + e < n) cd[o + e] = src[e];
+        }
+    }
+    if (tid == 0) cand_cnt[b * a.nlevels + l] = n;
+    __syncthreads();
+    if (n == 0) {
+        if (tid == 0) kept_cnt[b * a.nlevels + l] = 0;
+        return;
+    }
+    // ---- initial nodes (:543-585)
+    int cnt = L.nIni;
+    for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) {
+        ndA[i2] = make_short4((short)(int)(L.hX * (float)i2), 0, (short)(int)(L.hX * (float)(i2 + 1)), (short)L.maxY);
+        szA[i2] = 0;
+        candA[i2] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += QT_THREADS) {
+        ushort4 c = cd[k];
+        const int ni = (int)((float)c.x / L.hX);
+        c.w = (unsigned short)ni;
+        cd[k] = c;
+        atomicAdd(&szA[ni], 1);
+    }
+    __syncthreads();
+    {  // erase empty initial nodes, keep order
+        for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) sB[i2] = szA[i2] > 0 ? 1 : 0;
+        const int newcnt = block_excl_scan(sB, cnt, &s_total);
+        if (newcnt != cnt) {
+            for (int i2 = tid; i2 < cnt; i2 += QT_THREADS)
+                if (szA[i2] > 0) {
+                    ndB[sB[i2]] = ndA[i2];
+                    szB[sB[i2]] = szA[i2];
+                    candB[sB[i2]] = 0;
+                }
+            __syncthreads();
+            for (int k = tid; k < n; k += QT_THREADS) {
+                ushort4 c = cd[k];
+                c.w = (unsigned short)sB[c.w];
+                cd[k] = c;
+            }
+            __syncthreads();
+            for (int i2 = tid; i2 < newcnt; i2 += QT_THREADS) {
+                ndA[i2] = ndB[i2];
+                szA[i2] = szB[i2];
+                candA[i2] = 0;
+            }
+            cnt = newcnt;
+            __syncthreads();
+        }
+    }
+    short4* nd = ndA;
+    short4* nd2 = ndB;
+    int* sz = szA;
+    int* sz2 = szB;
+    unsigned char* cf = candA;
+    unsigned char* cf2 = candB;
+
+    // one splitting step: nodes with dv[i] set are divided; `order` gives the processing order of divided nodes:
+    //   order == nullptr : list order (phase 1);  otherwise rank order (phase 2), byrank[r] = node, nproc = #processed
+    auto split_step = [&](bool by_rank, int nproc) -> int {
+        for (int i2 = tid; i2 < 4 * cnt; i2 += QT_THREADS) cc[i2] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += QT_THREADS) {
+            const ushort4 c = cd[k];
+            const int ni = c.w;
+            if (by_rank ? cf[ni] : dv[ni]) {  // phase 2 counts children of every candidate (needed to find the stop)
+                const short4 bnd = nd[ni];
+                const int mx = bnd.x + ((bnd.z - bnd.x + 1) >> 1), my = bnd.y + ((bnd.w - bnd.y + 1) >> 1);
+                const int q = ((int)c.x < mx) ? (((int)c.y < my) ? 0 : 2) : (((int)c.y < my) ? 1 : 3);
+                cq[k] = (uint8_t)q;
+                atomicAdd(&cc[4 * ni + q], 1);
+            }
+        }
+        __syncthreads();
+        return 0;
+    };
+    auto build_lists = [&](bool by_rank, int nproc) -> int {
+        // sA: per processing slot number of non-empty children (exclusive scanned); sB: keep flags (scanned)
+        const int nslots = by_rank ? nproc : cnt;
+        for (int s2 = tid; s2 < nslots; s2 += QT_THREADS) {
+            const int ni = by_rank ? byrank[s2] : s2;
+            int c = 0;
+            if (dv[ni]) c = (cc[4 * ni] > 0) + (cc[4 * ni + 1] > 0) + (cc[4 * ni + 2] > 0) + (cc[4 * ni + 3] > 0);
+            sA[s2] = c;
+        }
+        const int totalC = block_excl_scan(sA, nslots, &s_total);
+        for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) sB[i2] = dv[i2] ? 0 : 1;
+        const int totalK = block_excl_scan(sB, cnt, &s_total);
+        const int newcnt = totalC + totalK;
+        if (newcnt > LN) {  // cannot happen: the list never exceeds N + 3
+            if (tid == 0) atomicOr(err, 2);
+            return -1;
+        }
+        for (int s2 = tid; s2 < nslots; s2 += QT_THREADS) {
+            const int ni = by_rank ? byrank[s2] : s2;
+            if (!dv[ni]) continue;
+            const short4 bnd = nd[ni];
+            const int mx = bnd.x + ((bnd.z - bnd.x + 1) >> 1), my = bnd.y + ((bnd.w - bnd.y + 1) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = cc[4 * ni + q];
+                if (k > 0) {
+                    const int pos = totalC - 1 - (sA[s2] + c);
+                    short4 cb;
+                    cb.x = (q & 1) ? (short)mx : bnd.x;
+                    cb.z = (q & 1) ? bnd.z : (short)mx;
+                    cb.y = (q & 2) ? (short)my : bnd.y;
+                    cb.w = (q & 2) ? bnd.w : (short)my;
+                    nd2[pos] = cb;
+                    sz2[pos] = k;
+                    cf2[pos] = k > 1 ? 1 : 0;
+                    cpos[4 * ni + q] = pos;
+                    ++c;
+                }
+            }
+        }
+        for (int i2 = tid; i2 < cnt; i2 += QT_THREADS)
+            if (!dv[i2]) {
+                const int pos = totalC + sB[i2];
+                kpos[i2] = pos;
+                nd2[pos] = nd[i2];
+                sz2[pos] = sz[i2];
+                cf2[pos] = 0;
+            }
+        __syncthreads();
+        for (int k = tid; k < n; k += QT_THREADS) {
+            ushort4 c = cd[k];
+            const int ni = c.w;
+            c.w = (unsigned short)(dv[ni] ? cpos[4 * ni + cq[k]] : kpos[ni]);
+            cd[k] = c;
+        }
+        __syncthreads();
+        short4* t1 = nd; nd = nd2; nd2 = t1;
+        int* t2 = sz; sz = sz2; sz2 = t2;
+        unsigned char* t3 = cf; cf = cf2; cf2 = t3;
+        return newcnt;
+    };
+    auto count_flag = [&](const unsigned char* f, int m) -> int {
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        int c = 0;
+        for (int i2 = tid; i2 < m; i2 += QT_THREADS) c += f[i2] ? 1 : 0;
+        if (c) atomicAdd(&s_flag, c);
+        __syncthreads();
+        const int r = s_flag;
+        __syncthreads();
+        return r;
+    };
+
+    bool finish = false;
+    while (!finish) {
+        const int prev = cnt;
+        for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) dv[i2] = sz[i2] > 1 ? 1 : 0;
+        __syncthreads();
+        split_step(false, 0);
+        const int newcnt = build_lists(false, 0);
+        if (newcnt < 0) break;
+        cnt = newcnt;
+        const int nToExpand = count_flag(cf, cnt);
+        if (cnt >= N || cnt == prev)
+            finish = true;
+        else if (cnt + nToExpand * 3 > N) {
+            while (!finish) {
+                const int prev2 = cnt;
+                // rank the candidates: key count descending, then list position ascending (newest first)
+                for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) {
+                    int r = -1;
+                    if (cf[i2]) {
+                        r = 0;
+                        const int si = sz[i2];
+                        for (int j2 = 0; j2 < cnt; ++j2)
+                            if (cf[j2] && (sz[j2] > si || (sz[j2] == si && j2 < i2))) ++r;
+                    }
+                    rk[i2] = r;
+                }
+                __syncthreads();
+                const int C = count_flag(cf, cnt);
+                for (int i2 = tid; i2 < cnt; i2 += QT_THREADS)
+                    if (rk[i2] >= 0) byrank[rk[i2]] = i2;
+                __syncthreads();
+                split_step(true, C);  // child counts of every candidate
+                // gain in rank order -> first rank where the list reaches N
+                for (int r = tid; r < C; r += QT_THREADS) {
+                    const int ni = byrank[r];
+                    sA[r] = (cc[4 * ni] > 0) + (cc[4 * ni + 1] > 0) + (cc[4 * ni + 2] > 0) + (cc[4 * ni + 3] > 0) - 1;
+                }
+                block_excl_scan(sA, C, &s_total);
+                if (tid == 0) s_rstar = C - 1;
+                __syncthreads();
+                for (int r = tid; r < C; r += QT_THREADS) {
+                    const int ni = byrank[r];
+                    const int gain = (cc[4 * ni] > 0) + (cc[4 * ni + 1] > 0) + (cc[4 * ni + 2] > 0) + (cc[4 * ni + 3] > 0) - 1;
+                    if (cnt + sA[r] + gain >= N) atomicMin(&s_rstar, r);
+                }
+                __syncthreads();
+                const int nproc = s_rstar + 1;
+                for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) dv[i2] = (rk[i2] >= 0 && rk[i2] < nproc) ? 1 : 0;
+                __syncthreads();
+                const int nc2 = build_lists(true, nproc);
+                if (nc2 < 0) {
+                    finish = true;
+                    break;
+                }
+                cnt = nc2;
+                if (cnt >= N || cnt == prev2) finish = true;
+            }
+        }
+    }
+    // ---- best key per node (:741-760): max response, first in candidate order
+    for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) best[i2] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < n; k += QT_THREADS) {
+        const ushort4 c = cd[k];
+        const unsigned long long key = ((unsigned long long)c.z << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+        atomicMax(&best[c.w], key);
+    }
+    __syncthreads();
+    for (int i2 = tid; i2 < cnt; i2 += QT_THREADS) kp[i2] = (int)(0xFFFFFFFFu - (unsigned)(best[i2] & 0xFFFFFFFFull));
+    if (tid == 0) kept_cnt[b * a.nlevels + l] = cnt;
+}
+
+static size_t qt_smem_bytes(int LN, int max_cells)
+{
+    size_t s = 0;
+    s += sizeof(short4) * 2 * LN;
+    s += sizeof(int) * (2 * LN + 4 * LN + 4 * LN + LN + std::max(LN, max_cells) + LN + LN + LN);
+    s += 3 * (size_t)LN + 8;
+    s += sizeof(unsigned long long) * LN;
+    return align_up(s, 16);
+}
+
+// ------------------------------------------------------------------------------------------------ K4e blur
+struct BlurLevelDev {
+    int w, h, pitch, tiles_x, tile_start;
+    unsigned long long off;
+};
+struct BlurArgs {
+    int nlevels, total_tiles;
+    BlurLevelDev lv[ORB_MAX_LEVELS];
+};
+constexpr int BT_W = 64, BT_H = 16;
+
+__device__ __forceinline__ int reflect101i(int p, int len)
+{
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ out, size_t stride_b,
+                                                  BlurArgs a)
+{
+    __shared__ uint8_t s_in[BT_H + 6][BT_W + 8];
+    __shared__ unsigned short s_h[BT_H + 6][BT_W];
+    int t = blockIdx.x, l = 0;
+    while (l + 1 < a.nlevels && t >= a.lv[l + 1].tile_start) ++l;
+    const BlurLevelDev& L = a.lv[l];
+    t -= L.tile_start;
+    const int ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+    const int x0 = tx * BT_W, y0 = ty * BT_H;
+    const uint8_t* img = pyr + (size_t)blockIdx.y * stride_b + L.off;
+    uint8_t* dst = out + (size_t)blockIdx.y * stride_b + L.off;
+    for (int i = threadIdx.x; i < (BT_H + 6) * (BT_W + 6); i += 256) {
+        const int ly = i / (BT_W + 6), lx = i - ly * (BT_W + 6);
+        const int x = reflect101i(x0 + lx - 3, L.w), y = reflect101i(y0 + ly - 3, L.h);
+        s_in[ly][lx] = __ldg(img + (size_t)y * L.pitch + x);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (BT_H + 6) * BT_W; i += 256) {
+        const int ly = i / BT_W, lx = i - ly * BT_W;
+        const uint8_t* r = &s_in[ly][lx];
+        s_h[ly][lx] = (unsigned short)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BT_H * BT_W; i += 256) {
+        const int ly = i / BT_W, lx = i - ly * BT_W;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x >= L.w || y >= L.h) continue;
+        const int acc = 18 * (s_h[ly][lx] + s_h[ly + 6][lx]) + 34 * (s_h[ly + 1][lx] + s_h[ly + 5][lx]) +
+                        48 * (s_h[ly + 2][lx] + s_h[ly + 4][lx]) + 56 * s_h[ly + 3][lx];
+        dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768) >> 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4d/e describe
+struct DescLevelDev {
+    int pitch, cand_off, kept_off;
+    unsigned long long off;
+    float scale, kp_size;
+};
+struct DescArgs {
+    int nlevels, cand_total, kept_total, kp_capacity;
+    int umax[ORB_HALF + 1];
+    DescLevelDev lv[ORB_MAX_LEVELS];
+};
+
+__device__ __forceinline__ float fast_atan2_dev(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
+                p7 = -0.04432655554792128f * scale;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + 2.2204460492503131e-16f);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + 2.2204460492503131e-16f);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// one warp per output keypoint
+__global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                                                      size_t stride_b, DescArgs a, const ushort4* __restrict__ cand,
+                                                      const int* __restrict__ kept, const int* __restrict__ kept_cnt,
+                                                      gd_keypoint* __restrict__ out_kp, uint8_t* __restrict__ out_desc,
+                                                      int* __restrict__ out_n)
+{
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int l = -1, within = 0, total = 0;
+    for (int q = 0; q < a.nlevels; ++q) {
+        const int c = kept_cnt[b * a.nlevels + q];
+        if (l < 0 && g < total + c) {
+            l = q;
+            within = g - total;
+        }
+        total += c;
+    }
+    if (g == 0 && lane == 0) out_n[b] = total;
+    if (l < 0 || g >= a.kp_capacity) return;
+    const DescLevelDev& L = a.lv[l];
+    const int ci = kept[(size_t)b * a.kept_total + L.kept_off + within];
+    const ushort4 c = cand[(size_t)b * a.cand_total + L.cand_off + ci];
+    const int x = c.x + ORB_BORDER, y = c.y + ORB_BORDER;  // :843-844
+    const uint8_t* center = pyr + (size_t)b * stride_b + L.off + (size_t)y * L.pitch + x;
+    // IC_Angle: lane <-> u = lane - 15
+    int m01 = 0, m10 = 0;
+    const int u = lane - ORB_HALF;
+    if (lane < 2 * ORB_HALF + 1) {
+        m10 = u * center[u];
+        const int au = abs(u);
+#pragma unroll
+        for (int v = 1; v <= ORB_HALF; ++v) {
+            if (au <= a.umax[v]) {
+                const int vp = center[u + v * L.pitch], vm = center[u - v * L.pitch];
+                m01 += v * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    const float angle = fast_atan2_dev((float)m01, (float)m10);
+    // steered BRIEF on the blurred level: lane -> descriptor byte
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ar = angle * factorPI;
+    const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+    const uint8_t* bc = blur + (size_t)b * stride_b + L.off + (size_t)y * L.pitch + x;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const signed char* pp = c_pattern + (lane * 16 + 2 * k) * 2;
+        const float x0 = (float)pp[0], y0 = (float)pp[1], x1 = (float)pp[2], y1 = (float)pp[3];
+        const int t0 = bc[__float2int_rn(x0 * sa + y0 * ca) * L.pitch + __float2int_rn(x0 * ca - y0 * sa)];
+        const int t1 = bc[__float2int_rn(x1 * sa + y1 * ca) * L.pitch + __float2int_rn(x1 * ca - y1 * sa)];
+        val |= (t0 < t1) << k;
+    }
+    out_desc[((size_t)b * a.kp_capacity + g) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        gd_keypoint k;
+        k.x = (float)x;
+        k.y = (float)y;
+        if (l != 0) {  // :1095-1101
+            k.x = k.x * L.scale;
+            k.y = k.y * L.scale;
+        }
+        k.size = L.kp_size;
+        k.angle = angle;
+        k.response = (float)c.z;
+        k.octave = l;
+        k.class_id = -1;
+        out_kp[(size_t)b * a.kp_capacity + g] = k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ core
+int OrbCore::init(int nfeatures_, float scale_factor_, int nlevels_, int ini_th, int min_th, int max_width, int max_height,
+                  int device_, int batch_, cudaStream_t s, LaunchStats* st)
+{
+    GD_REQUIRE(batch_ >= 1, "bad batch");
+    GD_TRY(select_device(device_));
+    device = device_;
+    batch = batch_;
+    stats = st;
+    nfeatures = nfeatures_;
+    scale_factor = scale_factor_;
+    nlevels = nlevels_;
+    iniTh = ini_th;
+    minTh = min_th;
+    max_w = max_width;
+    max_h = max_height;
+    GD_TRY(orb_make_plan(nfeatures, scale_factor, nlevels, iniTh, minTh, max_w, max_h, &plan));
+    if (s) {
+        stream = s;
+    } else {
+        GD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    const size_t B = (size_t)batch;
+    GD_TRY(gray_in.alloc(B * (size_t)max_w * max_h));
+    GD_TRY(pyr.alloc(B * plan.pyr_bytes));
+    GD_TRY(blur.alloc(B * plan.pyr_bytes));
+    GD_TRY(cell_cnt.alloc(B * plan.total_cells * sizeof(int)));
+    GD_TRY(slabs.alloc(B * (size_t)plan.total_cells * plan.cell_cap * sizeof(ushort4)));
+    GD_TRY(cand.alloc(B * (size_t)plan.cand_total * sizeof(ushort4)));
+    GD_TRY(cand_q.alloc(B * (size_t)plan.cand_total));
+    GD_TRY(kept.alloc(B * (size_t)plan.kept_total * sizeof(int)));
+    GD_TRY(kept_cnt.alloc(B * nlevels * sizeof(int)));
+    GD_TRY(cand_cnt.alloc(B * nlevels * sizeof(int)));
+    GD_TRY(out_kp.alloc(B * (size_t)plan.kp_capacity * sizeof(gd_keypoint)));
+    GD_TRY(out_desc.alloc(B * (size_t)plan.kp_capacity * 32));
+    GD_TRY(out_n.alloc(B * sizeof(int)));
+    GD_TRY(err.alloc(sizeof(int)));
+    GD_TRY(h_n.alloc((B + 1) * sizeof(int)));
+    GD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
+    GD_CUDA(cudaMemsetAsync(pyr.p, 0, pyr.bytes, stream));
+    const size_t fast_smem = (size_t)plan.tile_w * plan.tile_h * 2;
+    if (fast_smem > 48 * 1024) GD_CUDA(cudaFuncSetAttribute(k_orb_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    const size_t qs = qt_smem_bytes(plan.max_N + 8, plan.max_cells_level);
+    GD_REQUIRE(qs <= 220 * 1024, "nfeatures too large for the quadtree kernel's shared memory");
+    if (qs > 48 * 1024) GD_CUDA(cudaFuncSetAttribute(k_orb_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs));
+    GD_CUDA(cudaStreamSynchronize(stream));
+    return GD_OK;
+}
+
+int OrbCore::set_size(int w, int h)
+{
+    if (w == plan.w && h == plan.h) return GD_OK;
+    GD_REQUIRE(w <= max_w && h <= max_h, "image larger than the size given at creation");
+    OrbPlan p;
+    GD_TRY(orb_make_plan(nfeatures, scale_factor, nlevels, iniTh, minTh, w, h, &p));
+    // a smaller image needs no more memory than the plan the buffers were sized for
+    OrbPlan big;
+    GD_TRY(orb_make_plan(nfeatures, scale_factor, nlevels, iniTh, minTh, max_w, max_h, &big));
+    GD_REQUIRE(p.pyr_bytes <= big.pyr_bytes && (size_t)p.total_cells * p.cell_cap <= (size_t)big.total_cells * big.cell_cap &&
+                   p.cand_total <= big.cand_total && p.kept_total <= big.kept_total && p.kp_capacity <= big.kp_capacity &&
+                   p.total_cells <= big.total_cells,
+               "image size needs more memory than the maximum size given at creation");
+    plan = p;
+    return GD_OK;
+}
+
+OrbCore::~OrbCore()
+{
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+int OrbCore::extract_resident()
+{
+    const OrbPlan& P = plan;
+    uint8_t* py = pyr.as<uint8_t>();
+    // K4a: pyramid chain
+    for (int l = 1; l < P.nlevels; ++l) {
+        LaunchScope ls(stats, stream, "K4a_pyramid_resize", 1);
+        const OrbLevel &S = P.lv[l - 1], &D = P.lv[l];
+        dim3 block(32, 8), grid(cdiv(D.w, 32), cdiv(D.h, 8), batch);
+        k_orb_resize<<<grid, block, 0, stream>>>(py + S.off, S.w, S.h, S.pitch, py + D.off, D.w, D.h, D.pitch, P.pyr_bytes,
+                                                 D.scale_x, D.scale_y);
+        GD_CUDA(cudaGetLastError());
+    }
+    {  // K4b: FAST over every cell of every level
+        LaunchScope ls(stats, stream, "K4b_fast_cells", 1);
+        FastArgs fa;
+        fa.nlevels = P.nlevels; fa.total_cells = P.total_cells; fa.cell_cap = P.cell_cap;
+        fa.tile_w = P.tile_w; fa.tile_h = P.tile_h; fa.iniTh = P.iniTh; fa.minTh = P.minTh;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start};
+        }
+        dim3 grid(P.total_cells, batch);
+        k_orb_fast<<<grid, FAST_THREADS, (size_t)P.tile_w * P.tile_h * 2, stream>>>(py, P.pyr_bytes, fa, cell_cnt.as<int>(),
+                                                                                      slabs.as<ushort4>());
+        GD_CUDA(cudaGetLastError());
+    }
+    {  // K4c: quadtree, one CTA per (level, stream)
+        LaunchScope ls(stats, stream, "K4c_quadtree", 1);
+        QtArgs qa;
+        qa.nlevels = P.nlevels; qa.total_cells = P.total_cells; qa.cell_cap = P.cell_cap; qa.cand_total = P.cand_total;
+        qa.kept_total = P.kept_total; qa.LN = P.max_N + 8; qa.max_cells = P.max_cells_level;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            qa.lv[l] = {L.nCols, L.nRows, L.cell_start, L.N, L.nIni, L.cand_off, L.cand_cap, L.kept_off,
+                        L.w - ORB_EDGE + 3 - ORB_BORDER, L.h - ORB_EDGE + 3 - ORB_BORDER, L.hX};
+        }
+        dim3 grid(P.nlevels, batch);
+        k_orb_quadtree<<<grid, QT_THREADS, qt_smem_bytes(qa.LN, qa.max_cells), stream>>>(
+            qa, cell_cnt.as<int>(), slabs.as<ushort4>(), cand.as<ushort4>(), cand_q.as<uint8_t>(), kept.as<int>(),
+            kept_cnt.as<int>(), cand_cnt.as<int>(), err.as<int>());
+        GD_CUDA(cudaGetLastError());
+    }
+    {  // K4e: 7x7 Gaussian of every level
+        LaunchScope ls(stats, stream, "K4e_blur7", 1);
+        BlurArgs ba;
+        ba.nlevels = P.nlevels;
+        int tiles = 0;
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            ba.lv[l] = {L.w, L.h, L.pitch, cdiv(L.w, BT_W), tiles, (unsigned long long)L.off};
+            tiles += cdiv(L.w, BT_W) * cdiv(L.h, BT_H);
+        }
+        ba.total_tiles = tiles;
+        dim3 grid(tiles, batch);
+        k_orb_blur<<<grid, 256, 0, stream>>>(py, blur.as<uint8_t>(), P.pyr_bytes, ba);
+        GD_CUDA(cudaGetLastError());
+    }
+    {  // K4d/e: orientation + descriptors + output records
+        LaunchScope ls(stats, stream, "K4de_orient_describe", 1);
+        DescArgs da;
+        da.nlevels = P.nlevels; da.cand_total = P.cand_total; da.kept_total = P.kept_total; da.kp_capacity = P.kp_capacity;
+        for (int i = 0; i <= ORB_HALF; ++i) da.umax[i] = P.umax[i];
+        for (int l = 0; l < P.nlevels; ++l) {
+            const OrbLevel& L = P.lv[l];
+            da.lv[l] = {L.pitch, L.cand_off, L.kept_off, (unsigned long long)L.off, L.scale, L.kp_size};
+        }
+        dim3 grid(cdiv(P.kp_capacity, 8), batch);
+        k_orb_describe<<<grid, 256, 0, stream>>>(py, blur.as<uint8_t>(), P.pyr_bytes, da, cand.as<ushort4>(), kept.as<int>(),
+                                                 kept_cnt.as<int>(), out_kp.as<gd_keypoint>(), out_desc.as<uint8_t>(),
+                                                 out_n.as<int>());
+        GD_CUDA(cudaGetLastError());
+    }
+    return GD_OK;
+}
+
+}  // namespace gd

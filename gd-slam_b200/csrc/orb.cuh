@@ -1,0 +1,81 @@
+// orb.cuh — ORBextractor (ORB-SLAM2 / GD-SLAM src/ORBextractor.cc) as a batched CUDA pipeline.
+#pragma once
+#include "gd_internal.h"
+
+namespace gd {
+
+constexpr int ORB_MAX_LEVELS = 16;
+constexpr int ORB_EDGE = 19;   // EDGE_THRESHOLD
+constexpr int ORB_HALF = 15;   // HALF_PATCH_SIZE
+constexpr int ORB_BORDER = 16; // minBorder = EDGE_THRESHOLD - 3
+
+struct OrbLevel {
+    int w, h, pitch;      // level size, row pitch in bytes
+    size_t off;           // byte offset of the level inside one stream's pyramid buffer
+    int nCols, nRows, wCell, hCell;  // FAST cell grid (ComputeKeyPointsOctTree, :781-787)
+    int cell_start;       // index of the level's first cell in the per-stream cell arrays
+    int N;                // mnFeaturesPerLevel
+    int nIni;             // initial quadtree nodes
+    float hX;
+    int cand_off, cand_cap;  // slice of the compact candidate arrays
+    int kept_off;            // slice of the kept-index arrays (capacity N + 4)
+    float scale;             // mvScaleFactor[level]
+    float kp_size;           // (float)(int)(31 * scale)
+    double scale_x, scale_y; // resize ratios from the previous level
+};
+
+struct OrbPlan {
+    int nlevels = 0, nfeatures = 0, iniTh = 20, minTh = 7;
+    int w = 0, h = 0;
+    OrbLevel lv[ORB_MAX_LEVELS];
+    size_t pyr_bytes = 0;   // one stream's pyramid
+    int total_cells = 0;
+    int max_cells_level = 0;
+    int cell_cap = 0;       // slab capacity per cell (NMS density bound)
+    int tile_w = 0, tile_h = 0;  // largest cell (incl. the 6-px overlap)
+    int cand_total = 0;     // compact candidate capacity per stream
+    int kept_total = 0;
+    int max_N = 0;
+    int kp_capacity = 0;    // sum(N + 3)
+    int umax[ORB_HALF + 1];
+};
+
+int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int w, int h, OrbPlan* plan);
+
+struct OrbCore {
+    int device = 0, batch = 0;
+    OrbPlan plan;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    LaunchStats* stats = nullptr;
+    int max_w = 0, max_h = 0;
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    float scale_factor = 0;
+    size_t alloc_px = 0;
+
+    DevBuf gray_in;   // [B][max_h][max_w] staging when the caller passes host gray
+    DevBuf pyr;       // [B][pyr_bytes]   level 0 is filled by the caller (copy or K0)
+    DevBuf blur;      // [B][pyr_bytes]
+    DevBuf cell_cnt;  // [B][total_cells] int
+    DevBuf slabs;     // [B][total_cells][cell_cap] ushort4 (x, y, response, -)
+    DevBuf cand;      // [B][cand_total] ushort4 (x, y, response, node)
+    DevBuf cand_q;    // [B][cand_total] u8
+    DevBuf kept;      // [B][kept_total] int (candidate index)
+    DevBuf kept_cnt;  // [B][nlevels] int
+    DevBuf cand_cnt;  // [B][nlevels] int
+    DevBuf out_kp;    // [B][kp_capacity] gd_keypoint
+    DevBuf out_desc;  // [B][kp_capacity][32]
+    DevBuf out_n;     // [B] int
+    DevBuf err;       // [1] int  (capacity overflow flags)
+    PinnedBuf h_n;
+
+    int init(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int max_width, int max_height,
+             int device_, int batch_, cudaStream_t s, LaunchStats* st);
+    int set_size(int w, int h);  // (re)plans for an image size <= max
+    uint8_t* level0(int b = 0) { return pyr.as<uint8_t>() + (size_t)b * plan.pyr_bytes; }
+    // level 0 of every stream already resident in `pyr` (pitch = plan.lv[0].pitch): run the whole extraction
+    int extract_resident();
+    ~OrbCore();
+};
+
+}  // namespace gd

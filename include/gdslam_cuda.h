@@ -187,6 +187,17 @@ GD_API int gd_stage_farneback(int device, const uint8_t* prev, const uint8_t* ne
 /* polynomial expansion of pyramid level k: out = 5 planes (lh*lw each) in OpenCV channel order */
 GD_API int gd_stage_polyexp(int device, const uint8_t* gray, int w, int h, int k, float* out, int* lw, int* lh);
 
+/* ORB pyramid (ComputePyramid, ORBextractor.cc:1107-1132): `out` receives the levels tightly packed one after another,
+ * level_sizes = nlevels x (w, h) */
+GD_API int gd_stage_orb_pyramid(int device, const uint8_t* gray, int w, int h, int nlevels, float scale, uint8_t* out,
+                                int* level_sizes);
+/* cell loop of ComputeKeyPointsOctTree (ORBextractor.cc:789-829) on `gray` taken as ONE pyramid level:
+ * out = (x, y, response) float triples relative to the 16-px border, in vToDistributeKeys order */
+GD_API int gd_stage_fast_cells(int device, const uint8_t* gray, int w, int h, int ini_th, int min_th, float* out, int capacity,
+                               int* n);
+/* GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image (ORBextractor.cc:1086) */
+GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif
