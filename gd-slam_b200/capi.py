@@ -371,3 +371,124 @@ def smoke_orb(po):
     print(f"smoke: ORB 320x240 {len(kp)} keypoints, bit-exact vs oracle = {ok}")
     assert ok
     orb.close()
+
+
+# ---------------------------------------------------------------------------------------------- batched front-end
+class Frontend:
+    """gd_frontend_*: GrabImageRGBD_GD's per-frame sequence (gray, ORB, AddNewImage, GetNoGMMmask) for `batch` streams."""
+
+    def __init__(self, K, width=640, height=480, batch=1, device=0, dist=None, depth_factor=5000.0, nfeatures=1500,
+                 scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7, orb_gray_order=1, staged_slots=0):
+        cfg = FrontendConfig()
+        K = np.ascontiguousarray(K, np.float32).reshape(-1)
+        for i in range(9):
+            cfg.K[i] = float(K[i])
+        d = np.zeros(5, np.float32) if dist is None else np.ascontiguousarray(dist, np.float32).reshape(-1)
+        for i in range(min(5, d.size)):
+            cfg.dist[i] = float(d[i])
+        cfg.ndist = 0 if dist is None else int(d.size)
+        cfg.depth_factor = depth_factor
+        cfg.width, cfg.height, cfg.device, cfg.batch = width, height, device, batch
+        cfg.nfeatures, cfg.scale_factor, cfg.nlevels = nfeatures, scale_factor, nlevels
+        cfg.ini_th_fast, cfg.min_th_fast, cfg.orb_gray_order = ini_th_fast, min_th_fast, orb_gray_order
+        cfg.kp_capacity = nfeatures + 3 * nlevels
+        cfg.staged_slots = staged_slots
+        self.cfg = cfg
+        self.w, self.h, self.batch, self.cap = width, height, batch, cfg.kp_capacity
+        self._h = vp()
+        check(lib().gd_frontend_create(C.byref(self._h), C.byref(cfg)))
+        B = batch
+        # result buffers: page-locked, densely packed per batch (one D2H copy for the masks)
+        self.masks = pinned_empty((B, height, width), np.uint8)
+        self.kps = pinned_empty((B, self.cap), KP_DTYPE)
+        self.desc = pinned_empty((B, self.cap, 32), np.uint8)
+        self.n_kp = np.zeros(B, np.int32)
+        self._mask_ptrs = _ptr_array([self.masks[b] for b in range(B)])
+        self._kp_ptrs = _ptr_array([self.kps[b] for b in range(B)])
+        self._desc_ptrs = _ptr_array([self.desc[b] for b in range(B)])
+
+    def close(self):
+        if self._h:
+            lib().gd_frontend_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _pose(R, T, pv, B):
+        R = np.ascontiguousarray(np.tile(np.eye(3, dtype=np.float32), (B, 1, 1)) if R is None else R, np.float32)
+        T = np.ascontiguousarray(np.zeros((B, 3), np.float32) if T is None else T, np.float32)
+        pv = np.ascontiguousarray(np.ones(B, np.int32) if pv is None else pv, np.int32)
+        return R, T, pv
+
+    def step(self, bgr, depth, R=None, T=None, pose_valid=None, fetch=True):
+        """bgr: (B,H,W,3) u8 array or list of (H,W,3); depth: (B,H,W) f32 or list.  Host buffers in, results out."""
+        B = self.batch
+        R, T, pv = self._pose(R, T, pose_valid, B)
+        bp = _ptr_array([bgr[b] for b in range(B)])
+        dp = _ptr_array([depth[b] for b in range(B)])
+        check(lib().gd_frontend_step(self._h, bp, self.w * 3, dp, self.w * 4, _fptr(R), _fptr(T), pv.ctypes.data_as(ip),
+                                     self._mask_ptrs if fetch else None, self.w, self._kp_ptrs if fetch else None,
+                                     self._desc_ptrs if fetch else None, self.n_kp.ctypes.data_as(ip)))
+        return self.results() if fetch else None
+
+    def stage(self, slot, bgr, depth):
+        B = self.batch
+        bp = _ptr_array([bgr[b] for b in range(B)])
+        dp = _ptr_array([depth[b] for b in range(B)])
+        check(lib().gd_frontend_stage(self._h, slot, bp, self.w * 3, dp, self.w * 4))
+
+    def step_staged(self, slot, R=None, T=None, pose_valid=None):
+        R, T, pv = self._pose(R, T, pose_valid, self.batch)
+        check(lib().gd_frontend_step_staged(self._h, slot, _fptr(R), _fptr(T), pv.ctypes.data_as(ip)))
+
+    def fetch(self):
+        check(lib().gd_frontend_fetch(self._h, self._mask_ptrs, self.w, self._kp_ptrs, self._desc_ptrs,
+                                      self.n_kp.ctypes.data_as(ip)))
+        return self.results()
+
+    def results(self):
+        return [(self.masks[b], self.kps[b][: self.n_kp[b]], self.desc[b][: self.n_kp[b]]) for b in range(self.batch)]
+
+    def sync(self):
+        check(lib().gd_frontend_sync(self._h))
+
+    def timer_begin(self):
+        check(lib().gd_frontend_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        check(lib().gd_frontend_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        check(lib().gd_frontend_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def profile(self, enable):
+        check(lib().gd_frontend_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        ln = (C.c_longlong * 64)()
+        n = C.c_int(0)
+        check(lib().gd_frontend_profile_read(self._h, 64, names, ms, ln, C.byref(n)))
+        return [(names[i].decode(), ms[i], ln[i]) for i in range(min(n.value, 64))]
+
+    def flush_l2(self):
+        check(lib().gd_frontend_flush_l2(self._h))
+
+    def debug(self, what, stream=0):
+        shapes = {DBG_FLOW: ((self.h, self.w, 2), np.float32), DBG_DIST: ((self.h, self.w), np.float32),
+                  DBG_EDGE_REF: ((self.h, self.w), np.uint8), DBG_EDGE_CUR: ((self.h, self.w), np.uint8),
+                  DBG_GRAY_CUR: ((self.h, self.w), np.uint8), DBG_MINMAX: ((2,), np.float32)}
+        shp, dt = shapes[what]
+        out = np.empty(shp, dt)
+        check(lib().gd_frontend_debug_fetch(self._h, what, stream, _vptr(out), out.nbytes))
+        return out

@@ -1,0 +1,297 @@
+// api_frontend.cu — C ABI: gd_frontend_* — the per-frame sequence of Tracking::GrabImageRGBD_GD
+// (GD-SLAM src/Tracking.cc:212-252: cvtColor, Frame() -> ORBextractor, AddNewImage, GetNoGMMmask) for `batch`
+// independent RGB-D streams stepped together on one GPU, one CUDA stream, BGR uploaded once per frame.
+#include "geomask_core.cuh"
+#include "orb.cuh"
+
+namespace gd {
+int orb_fetch_results(OrbCore& c, gd_keypoint* const* kps, uint8_t* const* desc, int capacity, int* n_out);
+}
+
+struct gd_frontend {
+    gd_frontend_config cfg;
+    gd::LaunchStats stats;
+    cudaStream_t stream = nullptr;
+    gd::GeoMaskCore geo;
+    gd::OrbCore orb;
+    gd::DevBuf staged_bgr;    // [slots][B][n_pad*3]
+    gd::DevBuf staged_depth;  // [slots][B][n_pad] f32
+    gd::DevBuf l2_scratch;
+    gd::PinnedBuf h_n;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool results_ready = false;
+    ~gd_frontend()
+    {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        // cores do not own the shared stream
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+using namespace gd;
+
+// per-frame device work once the new frame sits in geo.bgr and in the depth ring slot
+static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b, const float* R, const float* T,
+                            const int* pose_valid)
+{
+    GeoMaskCore& g = h->geo;
+    OrbCore& o = h->orb;
+    // K0: both grays in one pass over the BGR bytes (BGR2GRAY for the flow, cfg.orb_gray_order for ORB level 0)
+    GD_TRY(launch_gray(bgr_dev, (size_t)g.w * 3, bgr_stride_b, g.w, g.h, g.batch, g.gray.as<uint8_t>(), g.n_pad, o.level0(0),
+                       h->cfg.orb_gray_order, (size_t)o.plan.lv[0].pitch, o.plan.pyr_bytes, h->stream, &h->stats));
+    GD_TRY(o.extract_resident());           // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
+    GD_TRY(g.push_resident(true));          // AddNewImage                          (Tracking.cc:242)
+    GD_TRY(g.compute_mask(R, T, pose_valid));  // GetNoGMMmask                       (Tracking.cc:245)
+    h->results_ready = true;
+    return GD_OK;
+}
+
+extern "C" {
+
+int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
+{
+    GD_REQUIRE(out && cfg, "null argument");
+    *out = nullptr;
+    GD_TRY(select_device(cfg->device));
+    gd_frontend* h = new (std::nothrow) gd_frontend();
+    if (!h) return GD_ENOMEM;
+    h->cfg = *cfg;
+    int r = GD_OK;
+    do {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("cudaStreamCreate failed");
+            r = GD_ECUDA;
+            break;
+        }
+        if ((r = h->geo.init(cfg->K, cfg->dist, cfg->ndist, cfg->width, cfg->height, cfg->device, cfg->batch, h->stream, &h->stats)) != GD_OK) break;
+        if ((r = h->orb.init(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast, cfg->width,
+                             cfg->height, cfg->device, cfg->batch, h->stream, &h->stats)) != GD_OK)
+            break;
+        if (cfg->staged_slots > 0) {
+            const size_t B = (size_t)cfg->batch, S = (size_t)cfg->staged_slots;
+            if ((r = h->staged_bgr.alloc(S * B * h->geo.n_pad * 3)) != GD_OK) break;
+            if ((r = h->staged_depth.alloc(S * B * h->geo.n_pad * sizeof(float))) != GD_OK) break;
+        }
+        if ((r = h->h_n.alloc(sizeof(int) * (size_t)(cfg->batch + 1))) != GD_OK) break;
+        if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            r = GD_ECUDA;
+            break;
+        }
+    } while (0);
+    if (r != GD_OK) {
+        delete h;
+        return r;
+    }
+    *out = h;
+    return GD_OK;
+}
+
+void gd_frontend_destroy(gd_frontend_t* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    delete h;
+}
+
+static int upload_frames(gd_frontend* h, uint8_t* bgr_dst, float* depth_dst, size_t depth_stride_b, const uint8_t* const* bgr,
+                         size_t bgr_step, const float* const* depth_m, size_t depth_step)
+{
+    GeoMaskCore& g = h->geo;
+    GD_REQUIRE(bgr_step >= (size_t)g.w * 3 && depth_step >= (size_t)g.w * sizeof(float), "step smaller than a row");
+    // one copy for the whole batch when the caller's frames are densely packed back to back (pinned batch buffers)
+    bool packed_bgr = bgr_step == (size_t)g.w * 3 && g.n_pad == g.n, packed_d = depth_step == (size_t)g.w * 4 && g.n_pad == g.n;
+    for (int b = 0; b < g.batch; ++b) {
+        GD_REQUIRE(bgr[b] && depth_m[b], "null image pointer");
+        if (b > 0) {
+            packed_bgr = packed_bgr && bgr[b] == bgr[b - 1] + g.n * 3;
+            packed_d = packed_d && depth_m[b] == depth_m[b - 1] + g.n;
+        }
+    }
+    if (packed_bgr) {
+        GD_CUDA(cudaMemcpyAsync(bgr_dst, bgr[0], (size_t)g.batch * g.n * 3, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int b = 0; b < g.batch; ++b)
+            GD_CUDA(cudaMemcpy2DAsync(bgr_dst + (size_t)b * g.n_pad * 3, (size_t)g.w * 3, bgr[b], bgr_step, (size_t)g.w * 3, g.h,
+                                      cudaMemcpyHostToDevice, h->stream));
+    }
+    if (packed_d && depth_stride_b == g.n) {
+        GD_CUDA(cudaMemcpyAsync(depth_dst, depth_m[0], (size_t)g.batch * g.n * 4, cudaMemcpyHostToDevice, h->stream));
+    } else if (packed_d) {
+        GD_CUDA(cudaMemcpy2DAsync(depth_dst, depth_stride_b * 4, depth_m[0], g.n * 4, g.n * 4, g.batch, cudaMemcpyHostToDevice,
+                                  h->stream));
+    } else {
+        for (int b = 0; b < g.batch; ++b)
+            GD_CUDA(cudaMemcpy2DAsync(depth_dst + (size_t)b * depth_stride_b, (size_t)g.w * 4, depth_m[b], depth_step,
+                                      (size_t)g.w * 4, g.h, cudaMemcpyHostToDevice, h->stream));
+    }
+    return GD_OK;
+}
+
+int gd_frontend_fetch(gd_frontend_t* h, uint8_t* const* mask_out, size_t mask_step, gd_keypoint* const* kps, uint8_t* const* desc,
+                      int* n_kp)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_REQUIRE(h->results_ready, "no step has run yet");
+    GeoMaskCore& g = h->geo;
+    OrbCore& o = h->orb;
+    const int cap = h->cfg.kp_capacity > 0 ? std::min(h->cfg.kp_capacity, o.plan.kp_capacity) : o.plan.kp_capacity;
+    int* hn = h->h_n.as<int>();
+    if (mask_out) {
+        GD_REQUIRE(mask_step >= (size_t)g.w, "mask_step smaller than a row");
+        bool packed = mask_step == (size_t)g.w && g.n_pad == g.n;
+        for (int b = 1; b < g.batch && packed; ++b) packed = mask_out[b] == mask_out[b - 1] + g.n;
+        if (packed && mask_out[0]) {
+            GD_CUDA(cudaMemcpyAsync(mask_out[0], g.mask.p, (size_t)g.batch * g.n, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            for (int b = 0; b < g.batch; ++b)
+                if (mask_out[b])
+                    GD_CUDA(cudaMemcpy2DAsync(mask_out[b], mask_step, g.mask.as<uint8_t>() + (size_t)b * g.n_pad, (size_t)g.w,
+                                              (size_t)g.w, g.h, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    // keypoints: copy the fixed capacity (count is data dependent; one synchronisation instead of two)
+    for (int b = 0; b < g.batch; ++b) {
+        if (kps && kps[b])
+            GD_CUDA(cudaMemcpyAsync(kps[b], o.out_kp.as<gd_keypoint>() + (size_t)b * o.plan.kp_capacity, sizeof(gd_keypoint) * cap,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        if (desc && desc[b])
+            GD_CUDA(cudaMemcpyAsync(desc[b], o.out_desc.as<uint8_t>() + (size_t)b * o.plan.kp_capacity * 32, (size_t)32 * cap,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    }
+    GD_CUDA(cudaMemcpyAsync(hn, o.out_n.p, sizeof(int) * g.batch, cudaMemcpyDeviceToHost, h->stream));
+    GD_CUDA(cudaMemcpyAsync(hn + g.batch, o.err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GD_CUDA(cudaStreamSynchronize(h->stream));
+    if (hn[g.batch] != 0) {
+        set_error("ORB kernel reported an internal capacity overflow (flags %d)", hn[g.batch]);
+        return GD_ECAPACITY;
+    }
+    int rc = GD_OK;
+    for (int b = 0; b < g.batch; ++b) {
+        if (n_kp) n_kp[b] = hn[b];
+        if (hn[b] > cap && ((kps && kps[b]) || (desc && desc[b]))) {
+            set_error("keypoint capacity %d too small for %d keypoints", cap, hn[b]);
+            rc = GD_ECAPACITY;
+        }
+    }
+    return rc;
+}
+
+int gd_frontend_step(gd_frontend_t* h, const uint8_t* const* bgr, size_t bgr_step, const float* const* depth_m, size_t depth_step,
+                     const float* R, const float* T, const int* pose_valid, uint8_t* const* mask_out, size_t mask_step,
+                     gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp)
+{
+    GD_REQUIRE(h && bgr && depth_m, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GeoMaskCore& g = h->geo;
+    const int slot = g.cur_slot();
+    GD_TRY(upload_frames(h, g.bgr.as<uint8_t>(), g.depth_slot_ptr(slot), g.depth_stride_b(), bgr, bgr_step, depth_m, depth_step));
+    GD_TRY(frontend_compute(h, g.bgr.as<uint8_t>(), g.n_pad * 3, R, T, pose_valid));
+    return gd_frontend_fetch(h, mask_out, mask_step, kps, desc, n_kp);
+}
+
+int gd_frontend_stage(gd_frontend_t* h, int slot, const uint8_t* const* bgr, size_t bgr_step, const float* const* depth_m,
+                      size_t depth_step)
+{
+    GD_REQUIRE(h && bgr && depth_m, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GD_REQUIRE(slot >= 0 && slot < h->cfg.staged_slots, "slot out of range");
+    GeoMaskCore& g = h->geo;
+    const size_t B = (size_t)g.batch;
+    GD_TRY(upload_frames(h, h->staged_bgr.as<uint8_t>() + (size_t)slot * B * g.n_pad * 3,
+                         h->staged_depth.as<float>() + (size_t)slot * B * g.n_pad, g.n_pad, bgr, bgr_step, depth_m, depth_step));
+    GD_CUDA(cudaStreamSynchronize(h->stream));
+    return GD_OK;
+}
+
+int gd_frontend_step_staged(gd_frontend_t* h, int slot, const float* R, const float* T, const int* pose_valid)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_REQUIRE(slot >= 0 && slot < h->cfg.staged_slots, "slot out of range");
+    GeoMaskCore& g = h->geo;
+    const size_t B = (size_t)g.batch;
+    const int ring = g.cur_slot();
+    // the depth image joins the stream's ring (it is read again five frames later); BGR is consumed in place
+    GD_CUDA(cudaMemcpy2DAsync(g.depth_slot_ptr(ring), g.depth_stride_b() * 4, h->staged_depth.as<float>() + (size_t)slot * B * g.n_pad,
+                              g.n_pad * 4, g.n * 4, g.batch, cudaMemcpyDeviceToDevice, h->stream));
+    return frontend_compute(h, h->staged_bgr.as<uint8_t>() + (size_t)slot * B * g.n_pad * 3, g.n_pad * 3, R, T, pose_valid);
+}
+
+int gd_frontend_sync(gd_frontend_t* h)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_CUDA(cudaStreamSynchronize(h->stream));
+    return GD_OK;
+}
+
+int gd_frontend_timer_begin(gd_frontend_t* h)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    return GD_OK;
+}
+
+int gd_frontend_timer_end(gd_frontend_t* h, float* ms)
+{
+    GD_REQUIRE(h && ms, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    GD_CUDA(cudaEventSynchronize(h->ev1));
+    GD_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return GD_OK;
+}
+
+int gd_frontend_launch_count(gd_frontend_t* h, long long* launches)
+{
+    GD_REQUIRE(h && launches, "null argument");
+    *launches = h->stats.launches;
+    return GD_OK;
+}
+
+int gd_frontend_profile(gd_frontend_t* h, int enable)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_CUDA(cudaStreamSynchronize(h->stream));
+    h->stats.profiling = enable != 0;
+    if (enable) h->stats.fam.clear();
+    return GD_OK;
+}
+
+int gd_frontend_profile_read(gd_frontend_t* h, int max_entries, const char** names, float* ms, long long* launches, int* n_entries)
+{
+    GD_REQUIRE(h && n_entries, "null argument");
+    const int n = (int)h->stats.fam.size();
+    *n_entries = n;
+    for (int i = 0; i < n && i < max_entries; ++i) {
+        if (names) names[i] = h->stats.fam[i].name;
+        if (ms) ms[i] = h->stats.fam[i].ms;
+        if (launches) launches[i] = h->stats.fam[i].launches;
+    }
+    return GD_OK;
+}
+
+int gd_frontend_debug_fetch(gd_frontend_t* h, int what, int stream, void* dst, size_t dst_bytes)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    return h->geo.debug_fetch(what, stream, dst, dst_bytes);
+}
+
+int gd_frontend_flush_l2(gd_frontend_t* h)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
+    if (!h->l2_scratch.p) GD_TRY(h->l2_scratch.alloc(bytes));
+    GD_CUDA(cudaMemsetAsync(h->l2_scratch.p, 0x5a, bytes, h->stream));
+    return GD_OK;
+}
+
+}  // extern "C"

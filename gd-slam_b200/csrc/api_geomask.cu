@@ -92,9 +92,9 @@ int gd_stage_gray(int device, const uint8_t* bgr, size_t bgr_step, int w, int h,
     GD_TRY(out.alloc((size_t)w * h));
     GD_CUDA(cudaMemcpy(in.p, bgr, bgr_step * h, cudaMemcpyHostToDevice));
     if (order == 0)
-        GD_TRY(launch_gray(in.as<uint8_t>(), bgr_step, 0, w, h, 1, out.as<uint8_t>(), nullptr, 0, 0, 0, nullptr));
+        GD_TRY(launch_gray(in.as<uint8_t>(), bgr_step, 0, w, h, 1, out.as<uint8_t>(), 0, nullptr, 0, 0, 0, 0, nullptr));
     else
-        GD_TRY(launch_gray(in.as<uint8_t>(), bgr_step, 0, w, h, 1, nullptr, out.as<uint8_t>(), order, 0, 0, nullptr));
+        GD_TRY(launch_gray(in.as<uint8_t>(), bgr_step, 0, w, h, 1, nullptr, 0, out.as<uint8_t>(), order, (size_t)w, 0, 0, nullptr));
     GD_CUDA(cudaDeviceSynchronize());
     GD_CUDA(cudaMemcpy(gray, out.p, (size_t)w * h, cudaMemcpyDeviceToHost));
     return GD_OK;

@@ -86,8 +86,8 @@ __device__ __forceinline__ unsigned gray_px(unsigned c0, unsigned c1, unsigned c
 }
 
 __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ bgr, size_t step, size_t stride_b, int w, int h,
-                                              uint8_t* __restrict__ g_flow, uint8_t* __restrict__ g_orb, int orb_order,
-                                              size_t gstride_b, int aligned)
+                                              uint8_t* __restrict__ g_flow, size_t gstride_b, uint8_t* __restrict__ g_orb,
+                                              int orb_order, size_t opitch, size_t ostride_b, int aligned)
 {
     const int b = blockIdx.z;
     const int groups = (w + 3) >> 2;
@@ -115,24 +115,29 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ bgr, s
         oo |= gray_px(c[3 * p], c[3 * p + 1], c[3 * p + 2], ok0, ok2) << (8 * p);
     }
     const size_t o = (size_t)b * gstride_b + (size_t)y * w + x0;
-    if (npx == 4 && (w & 3) == 0 && (gstride_b & 3) == 0) {
-        if (g_flow) *reinterpret_cast<unsigned*>(g_flow + o) = of;
-        if (g_orb) *reinterpret_cast<unsigned*>(g_orb + o) = oo;
-    } else {
-        for (int p = 0; p < npx; ++p) {
-            if (g_flow) g_flow[o + p] = (uint8_t)(of >> (8 * p));
-            if (g_orb) g_orb[o + p] = (uint8_t)(oo >> (8 * p));
-        }
+    const size_t oo_off = (size_t)b * ostride_b + (size_t)y * opitch + x0;
+    if (g_flow) {
+        if (npx == 4 && (w & 3) == 0 && (gstride_b & 3) == 0)
+            *reinterpret_cast<unsigned*>(g_flow + o) = of;
+        else
+            for (int p = 0; p < npx; ++p) g_flow[o + p] = (uint8_t)(of >> (8 * p));
+    }
+    if (g_orb) {
+        if (npx == 4 && (opitch & 3) == 0 && (ostride_b & 3) == 0)
+            *reinterpret_cast<unsigned*>(g_orb + oo_off) = oo;
+        else
+            for (int p = 0; p < npx; ++p) g_orb[oo_off + p] = (uint8_t)(oo >> (8 * p));
     }
 }
 
 int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w, int h, int batch, uint8_t* g_flow,
-                uint8_t* g_orb, int orb_order, size_t gray_stride_b, cudaStream_t s, LaunchStats* st)
+                size_t gray_stride_b, uint8_t* g_orb, int orb_order, size_t orb_pitch, size_t orb_stride_b, cudaStream_t s,
+                LaunchStats* st)
 {
     LaunchScope ls(st, s, "K0_gray", 1);
     const int aligned = ((reinterpret_cast<uintptr_t>(bgr) & 3) == 0 && (bgr_step & 3) == 0 && (bgr_stride_b & 3) == 0) ? 1 : 0;
     dim3 block(128), grid(cdiv((w + 3) / 4, 128), h, batch);
-    k_gray<<<grid, block, 0, s>>>(bgr, bgr_step, bgr_stride_b, w, h, g_flow, g_orb, orb_order, gray_stride_b, aligned);
+    k_gray<<<grid, block, 0, s>>>(bgr, bgr_step, bgr_stride_b, w, h, g_flow, gray_stride_b, g_orb, orb_order, orb_pitch, orb_stride_b, aligned);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

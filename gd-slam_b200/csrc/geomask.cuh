@@ -26,8 +26,10 @@ void make_cam_const(const float K[9], CamConst* c);
 void make_pose(const float K[9], const float R[9], const float T[3], int valid, PoseDev* p);
 
 // K0: 8UC3 -> 8UC1 (cv::cvtColor 8-bit, 15-bit fixed point).  Either output may be null.
+// gray_bgr2gray: rows of w bytes, stream stride gray_stride_b.  gray_orb: row pitch orb_pitch, stream stride orb_stride_b.
 int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w, int h, int batch, uint8_t* gray_bgr2gray,
-                uint8_t* gray_orb, int orb_order, size_t gray_stride_b, cudaStream_t s, LaunchStats* st);
+                size_t gray_stride_b, uint8_t* gray_orb, int orb_order, size_t orb_pitch, size_t orb_stride_b, cudaStream_t s,
+                LaunchStats* st);
 
 // K2a: GetEdge.  depth f32 [b][h][w] -> edge u8 {0,255}
 int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, int batch, const CamConst& cam,

@@ -94,11 +94,13 @@ GeoMaskCore::~GeoMaskCore()
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
-int GeoMaskCore::push_resident()
+int GeoMaskCore::push_resident(bool gray_done)
 {
     const int slot = frames % GD_RING;
-    // K0: gray for the flow
-    GD_TRY(launch_gray(bgr.as<uint8_t>(), (size_t)w * 3, n_pad * 3, w, h, batch, gray.as<uint8_t>(), nullptr, 0, n_pad, stream, stats));
+    // K0: gray for the flow (the batched front-end computes it together with the ORB gray)
+    if (!gray_done)
+        GD_TRY(launch_gray(bgr.as<uint8_t>(), (size_t)w * 3, n_pad * 3, w, h, batch, gray.as<uint8_t>(), n_pad, nullptr, 0, 0, 0,
+                           stream, stats));
     // K1a: blur + resample + polynomial expansion, all levels, into the ring slot
     GD_TRY(fb_launch_pyramid_polyexp(plan, gray.as<uint8_t>(), n_pad, batch, scratchI.as<float>(), plan.i_floats,
                                      R.as<float>() + (size_t)slot * plan.r_floats, (size_t)GD_RING * plan.r_floats, stream, stats));

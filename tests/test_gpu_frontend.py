@@ -1,0 +1,89 @@
+"""GPU parity (-m gpu): the batched front-end (gd_frontend_*) = GrabImageRGBD_GD's per-frame sequence, vs the oracle."""
+import numpy as np
+import pytest
+
+from conftest import flow_tol_violations, load_pkg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    c = load_pkg("capi")
+    c.lib()
+    assert c.device_count() >= 1
+    return c
+
+
+def _same_kp(kp, desc, rkp, rdesc):
+    assert len(kp) == len(rkp)
+    for f in kp.dtype.names:
+        assert np.array_equal(kp[f], rkp[f]), f
+    assert np.array_equal(desc, rdesc)
+
+
+def test_frontend_stream_of_frames_host_and_staged(capi, oracle, synth):
+    B, NF = 3, 8
+    K = synth.intrinsics()
+    streams = [synth.SyntheticStream(s, roll_deg_per_frame=0.04 if s == 1 else 0.0) for s in range(B)]
+    frames = [[s.frame(f) for f in range(NF)] for s in streams]
+    fe = capi.Frontend(K, 640, 480, batch=B, staged_slots=NF)
+    fe2 = capi.Frontend(K, 640, 480, batch=B, staged_slots=NF)
+    for f in range(NF):
+        fe2.stage(f, [frames[b][f].bgr for b in range(B)], [frames[b][f].depth_m for b in range(B)])
+    launches0 = fe.launch_count()
+    for f in range(NF):
+        bgr = [frames[b][f].bgr for b in range(B)]
+        dep = [frames[b][f].depth_m for b in range(B)]
+        if f >= 5:
+            poses = [streams[b].pair_pose(f - 5, f) for b in range(B)]
+            R, T = np.stack([p[0] for p in poses]), np.stack([p[1] for p in poses])
+        else:
+            R = T = None
+        res = fe.step(bgr, dep, R, T)
+        fe2.step_staged(f, R, T)
+        res2 = fe2.fetch()
+        for b in range(B):
+            mask, kp, desc = res[b]
+            # ORB: bit-exact vs the oracle on the RGB2GRAY image (Tracking.cc:219-225)
+            rkp, rdesc, _ = oracle.orb_extract(oracle.gray(bgr[b], 1))
+            _same_kp(kp, desc, rkp, rdesc)
+            # device-resident path gives identical results
+            assert np.array_equal(res2[b][0], mask)
+            _same_kp(res2[b][1], res2[b][2], rkp, rdesc)
+            if f < 5:
+                assert mask.min() == 1 and mask.max() == 1
+            else:
+                mo, flow_o, dist_o = oracle.geomask_pair(frames[b][f - 5].bgr, bgr[b], frames[b][f - 5].depth_m, dep[b], K,
+                                                         R[b], T[b], want_debug=True)
+                nviol, dmax = flow_tol_violations(fe.debug(capi.DBG_FLOW, b), flow_o)
+                assert nviol == 0, (f, b, nviol, dmax)
+                agree = (mask == mo).mean()
+                assert agree >= 0.999, (f, b, agree)
+                # Mahalanobis values within tolerance wherever both wrote the same target
+                dg = fe.debug(capi.DBG_DIST, b)
+                both = (dg > 0) & (dist_o > 0)
+                rel = np.abs(dg[both] - dist_o[both]) / np.maximum(1.0, np.abs(dist_o[both]))
+                assert np.quantile(rel, 0.999) <= 1e-4 * 50, float(rel.max())  # flow differences move a few targets
+    assert fe.launch_count() > launches0
+    fe.close()
+    fe2.close()
+
+
+def test_frontend_profile_families(capi, synth):
+    K = synth.intrinsics(320, 240)
+    s = synth.SyntheticStream(0, 320, 240)
+    fe = capi.Frontend(K, 320, 240, batch=1, nfeatures=500, nlevels=6)
+    fr = [s.frame(f) for f in range(7)]
+    for f in range(6):
+        fe.step([fr[f].bgr], [fr[f].depth_m])
+    fe.profile(True)
+    R, T = s.pair_pose(1, 6)
+    fe.step([fr[6].bgr], [fr[6].depth_m], R[None], T[None])
+    fe.profile(False)
+    fam = {n: (ms, ln) for n, ms, ln in fe.profile_read()}
+    for name in ("K0_gray", "K1a_polyexp", "K1b_flow_iter", "K2a_depth_edge", "K2b_mahalanobis", "K3a_minmax",
+                 "K3b_normalize_mask", "K4a_pyramid_resize", "K4b_fast_cells", "K4c_quadtree", "K4e_blur7",
+                 "K4de_orient_describe"):
+        assert name in fam and fam[name][0] > 0, name
+    fe.close()
