@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — GeoMaskMaker + ORB frames/s at 640x480 on N B200s (BASELINE.json metric), with roofline and CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch: every one of the `batch` independent RGB-D streams of a rank
+advances by one frame (gray x2, ORB extraction, AddNewImage products, Farneback flow (t-5,t), Mahalanobis scatter,
+min-max/threshold mask).  Streams are sharded across ranks with no collective on the data path: weak scaling.
+
+  value : frames/s, inputs already resident in HBM (gd_frontend_step_staged), CUDA events on the handle's stream,
+          max over ranks.
+  e2e   : the same through the reference-facing C ABI with pinned HOST buffers (gd_frontend_step): H2D of BGR+depth and
+          D2H of mask + keypoints + descriptors inside the timed region.
+torch is used only for the multi-rank barrier / max-reduce (torch.distributed, NCCL); the product path is the C ABI.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+N_PX = W * H
+METRIC = "GeoMaskMaker+ORB frames/sec at 640x480"
+# algorithmic (compulsory) bytes per frame of the whole pipeline, steady state = 318.5 B/px
+ALGO_BYTES_PER_FRAME = 318.5 * N_PX
+FB_LEVEL_SUM = 1.328125  # (1 + 1/4 + 1/16 + 1/64) pixels over the 4 Farneback levels
+# algorithmic bytes per frame of each kernel family (DESIGN.md "kernels" table)
+FAMILY_BYTES = {
+    "K0_gray": (3 + 1 + 1) * N_PX,
+    "K1a_blur_resample": (4 * 1 + 4 * FB_LEVEL_SUM) * N_PX,
+    "K1a_polyexp": (4 + 20) * FB_LEVEL_SUM * N_PX,
+    "K1b_flow_iter": 3 * 56 * FB_LEVEL_SUM * N_PX,
+    "K1b_flow_upsample": (8 * 0.328125 / 4 + 8 * 0.328125) * N_PX,
+    "K2a_depth_edge": 5 * N_PX,
+    "K2b_mahalanobis": 22 * N_PX,
+    "K3a_minmax": 4 * N_PX,
+    "K3b_normalize_mask": 5 * N_PX,
+    "K4a_pyramid_resize": 2 * 2.094 * N_PX,
+    "K4b_fast_cells": 3.094 * N_PX,
+    "K4c_quadtree": 8 * 8000 * 4,
+    "K4e_blur7": 2 * 3.094 * N_PX,
+    "K4de_orient_describe": 1500 * (749 + 512 + 60),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _gen_frame(args):
+    stream, f = args
+    synth = importlib.import_module("gd-slam_b200.synth")
+    s = synth.SyntheticStream(stream)
+    fr = s.frame(f)
+    return stream, f, fr.bgr, fr.depth_m
+
+
+def make_data(n_distinct, n_frames, seed0):
+    """n_distinct synthetic streams x n_frames frames (seeded, SURVEY 8d generator), generated on all host cores."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    synth = importlib.import_module("gd-slam_b200.synth")
+    jobs = [(seed0 + s, f) for s in range(n_distinct) for f in range(n_frames)]
+    bgr = np.empty((n_distinct, n_frames, H, W, 3), np.uint8)
+    dep = np.empty((n_distinct, n_frames, H, W), np.float32)
+    with ProcessPoolExecutor(max_workers=min(os.cpu_count() or 1, 16)) as ex:
+        for s, f, b, d in ex.map(_gen_frame, jobs, chunksize=2):
+            bgr[s - seed0, f] = b
+            dep[s - seed0, f] = d
+    poses = {}
+    for s in range(n_distinct):
+        st = synth.SyntheticStream.__new__(synth.SyntheticStream)
+        st.roll, st.t = 0.0, np.asarray((0.002, -0.0012, 0.0))
+        for f in range(n_frames):
+            poses[(s, f)] = st.pair_pose((f - 5) % n_frames if f >= 5 else 0, f) if f >= 5 else st.pair_pose(0, 0)
+    return bgr, dep, poses
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One host process = one stream, structured like the reference: every frame recomputes both gray images, both
+    Farneback pyramids, both depth-edge maps (GeoMaskMaker.cc:158-199), then ORB on the new frame (Tracking.cc:238)."""
+    stream, n_frames = args
+    from oracle import pyoracle as po
+
+    synth = importlib.import_module("gd-slam_b200.synth")
+    s = synth.SyntheticStream(stream)
+    K = synth.intrinsics()
+    fr = [s.frame(f) for f in range(6)]
+    R, T = s.pair_pose(0, 5)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        a, b = fr[i % 1], fr[5]
+        po.orb_extract(po.gray(b.bgr, 1))
+        po.geomask_pair(a.bgr, b.bgr, a.depth_m, b.depth_m, K, R, T)
+    return n_frames, time.perf_counter() - t0
+
+
+def cpu_reference_rate(frames_per_proc, procs):
+    from concurrent.futures import ProcessPoolExecutor
+
+    from oracle import pyoracle as po
+
+    po.lib()
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=procs) as ex:
+        res = list(ex.map(_cpu_worker, [(p, frames_per_proc) for p in range(procs)]))
+    wall = time.perf_counter() - t0
+    busy = max(r[1] for r in res)
+    return sum(r[0] for r in res) / busy, wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    per_step = max(1, args.ref_frames_per_proc)
+    rates = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_rate(1, procs)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, _w = cpu_reference_rate(per_step, procs)
+        rates.append(r)
+    ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
+    v = float(statistics.median(rates))
+    sample = f"{procs} host processes x {per_step} frames per step (640x480 pair (t-5,t) + ORB on the new frame), oracle port"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "synthetic 640x480 RGB-D streams, full GeoMaskMaker + ORB (TUM3, ORB 1500/1.2/8/20/7)",
+                      "note": "reference's CPU path restated (oracle/): OpenCV-4.13 semantics, one process per host core"},
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GD_BENCH_BATCH", "32")), help="streams per GPU")
+    ap.add_argument("--slots", type=int, default=12, help="distinct frames kept resident per stream")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic streams generated per rank")
+    ap.add_argument("--ref-frames-per-proc", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    capi = importlib.import_module("gd-slam_b200.capi")
+    synth = importlib.import_module("gd-slam_b200.synth")
+    capi.lib()
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (libgdslam_cuda has no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    B, S, K_, Wm = args.batch, args.slots, args.steps, max(3, args.warmup)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- data: `distinct` seeded streams per rank, replicated over the batch with a frame offset
+    D = min(args.distinct, B)
+    bgr, dep, poses = make_data(D, S, seed0=1000 * rank)
+    K = synth.intrinsics(W, H)
+    fe = capi.Frontend(K, W, H, batch=B, device=device, staged_slots=S)
+    hb = capi.pinned_empty((S, B, H, W, 3), np.uint8)
+    hd = capi.pinned_empty((S, B, H, W), np.float32)
+    Rs = np.zeros((S, B, 3, 3), np.float32)
+    Ts = np.zeros((S, B, 3), np.float32)
+    for s in range(S):
+        for b in range(B):
+            src, off = b % D, (b // D) % S
+            f = (s + off) % S
+            hb[s, b] = bgr[src, f]
+            hd[s, b] = dep[src, f]
+            Rs[s, b], Ts[s, b] = poses[(src, f)]
+        fe.stage(s, hb[s], hd[s])
+    del bgr, dep
+
+    step_i = [0]
+
+    def step_staged():
+        s = step_i[0] % S
+        fe.step_staged(s, Rs[s], Ts[s])
+        step_i[0] += 1
+
+    def step_host():
+        s = step_i[0] % S
+        fe.step(hb[s], hd[s], Rs[s], Ts[s])
+        step_i[0] += 1
+
+    # ---- device-resident throughput (value)
+    for _ in range(6 + Wm):  # fill the 6-frame ring, then W warm-up steps
+        step_staged()
+    fe.sync()
+    barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    l0 = fe.launch_count()
+    fe.sync()
+    fe.timer_begin()
+    for _ in range(K_):
+        step_staged()
+    ms_total = fe.timer_end()
+    fe.sync()
+    launches = fe.launch_count() - l0
+    barrier()
+    ms_total = max_over_ranks(ms_total)
+    value = world * B * K_ / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers (e2e)
+    for _ in range(3):
+        step_host()
+    fe.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K_):
+        step_host()
+    fe.sync()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * B * K_ / e2e_s
+    h2d = B * (N_PX * 3 + N_PX * 4)
+    d2h = B * (N_PX + fe.cap * (28 + 32) + 4)
+
+    # ---- per-kernel-family device time (events on the handle's stream, serialised) -> dominant kernel + roofline
+    fe.profile(True)
+    PSTEPS = 3
+    for _ in range(PSTEPS):
+        step_staged()
+    fe.profile(False)
+    fam = fe.profile_read()
+    peak, peak_src = load_peaks()
+    tot_ms = sum(ms for _, ms, _ in fam) or 1.0
+    families = {}
+    for name, ms, ln in fam:
+        by = FAMILY_BYTES.get(name, 0.0) * B * PSTEPS
+        families[name] = {"ms_per_step": ms / PSTEPS, "launches_per_step": ln / PSTEPS, "share": ms / tot_ms,
+                          "achieved_gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else None}
+    dom = max(fam, key=lambda x: x[1])
+    dom_name, dom_ms, dom_ln = dom
+    dom_bytes_per_launch = FAMILY_BYTES.get(dom_name, 0.0) * B * PSTEPS / max(1, dom_ln)
+    achieved = dom_bytes_per_launch / (dom_ms / max(1, dom_ln) * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom_name)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch,
+                "avg_launch_ms": dom_ms / max(1, dom_ln),
+                "pipeline": {"algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
+                             "achieved": value / world * ALGO_BYTES_PER_FRAME / 1e9, "frac": value / world * ALGO_BYTES_PER_FRAME / 1e9 / peak},
+                "families": families}
+
+    out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K_, "warmup": Wm,
+           "ms_per_step": ms_total / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "synthetic 640x480 RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7), "
+                                  "steady state (per-image products cached in the 6-deep device ring)",
+                      "streams_per_gpu": B, "frames_per_step": B * world, "resident_frames_per_stream": S,
+                      "l2_hygiene": "inputs larger than L2: per-step working set %.0f MB per GPU (ring of polynomial-expansion "
+                                    "pyramids + staged frames), 126 MB L2" % (B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3)),
+                      "sharding": "independent streams per GPU, no collective"},
+           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": e2e_s * 1e3 / K_},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = os.cpu_count() or 1
+        per = 2
+        v, wall = cpu_reference_rate(per, procs)
+        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": procs, "kind": "port",
+                               "sample": f"{procs} host processes x {per} frames of the same workload through the oracle "
+                                         f"(reference-structured: both pyramids/edge maps per call), {wall:.1f} s wall"}
+    fe.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
