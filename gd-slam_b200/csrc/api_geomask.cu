@@ -187,7 +187,14 @@ int gd_stage_polyexp(int device, const uint8_t* gray, int w, int h, int k, float
     const FbLevel& L = plan.lv[k];
     *lw = L.w;
     *lh = L.h;
-    GD_CUDA(cudaMemcpy(out, R.as<float>() + L.r_off, (size_t)L.w * L.h * 5 * 4, cudaMemcpyDeviceToHost));
+    // device layout: float4 plane (channels 0..3) + float plane (channel 4); hand back 5 planes
+    const size_t npx = (size_t)L.w * L.h, npad = align_up(npx, 64);
+    std::vector<float> tmp(5 * npad);
+    GD_CUDA(cudaMemcpy(tmp.data(), R.as<float>() + L.r_off, 5 * npad * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < npx; ++i) {
+        for (int c = 0; c < 4; ++c) out[c * npx + i] = tmp[4 * i + c];
+        out[4 * npx + i] = tmp[4 * npad + i];
+    }
     return GD_OK;
 }
 

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(128) k_fb_pyr(const uint8_t* __restrict__ gray
 }
 
 // ------------------------------------------------------------------------------------------------ K1a-2
+__device__ __forceinline__ size_t align_up_dev(size_t v, size_t a);
 struct PolyArgs {
     int w, h;
     float g[2 * FB_POLY_N + 1], xg[2 * FB_POLY_N + 1], xxg[2 * FB_POLY_N + 1];
@@ -272,13 +273,14 @@ __global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restri
         b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
         b5 += (r2[lx + k] + r2[lx - k]) * g[k];
     }
-    const size_t plane = (size_t)a.w * a.h;
-    float* Rp = R + (size_t)b * rstride_b + (size_t)y * a.w + x;
-    Rp[0] = (float)(b3 * a.ig11);
-    Rp[plane] = (float)(b2 * a.ig11);
-    Rp[2 * plane] = (float)(b1 * a.ig03 + b5 * a.ig33);
-    Rp[3 * plane] = (float)(b1 * a.ig03 + b4 * a.ig33);
-    Rp[4 * plane] = (float)(b6 * a.ig55);
+    // R layout per level: float4 plane (channels 0..3) followed by a float plane (channel 4) -> the flow kernel's
+    // bilinear gather needs 2 loads per tap instead of 5
+    const size_t npad = align_up_dev((size_t)a.w * a.h, 64);
+    float* Rb = R + (size_t)b * rstride_b;
+    const size_t o = (size_t)y * a.w + x;
+    reinterpret_cast<float4*>(Rb)[o] = make_float4((float)(b3 * a.ig11), (float)(b2 * a.ig11), (float)(b1 * a.ig03 + b5 * a.ig33),
+                                                   (float)(b1 * a.ig03 + b4 * a.ig33));
+    Rb[4 * npad + o] = (float)(b6 * a.ig55);
 }
 
 int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gray_stride_b, int batch, float* scratch_I,
@@ -348,14 +350,21 @@ __global__ void __launch_bounds__(128) k_fb_upsample(const float2* __restrict__ 
     dst[(size_t)b * fstride_b + (size_t)dy * dw + dx] = o;
 }
 
-constexpr int FT_W = 32, FT_H = 16, FHALO = FB_WIN / 2;          // 7
-constexpr int FH_W = FT_W + 2 * FHALO, FH_H = FT_H + 2 * FHALO;  // 46 x 30
+constexpr int FT_W = 64, FT_H = 32, FHALO = FB_WIN / 2;            // output tile, 7-px halo
+constexpr int FH_W = FT_W + 2 * FHALO, FH_H = FT_H + 2 * FHALO;    // 78 x 46 cells of M per tile
+constexpr int FM_P = FH_W + 1;                                     // odd pitch: row-strided reads are conflict free
+constexpr int FHS_P = FT_W + 1;                                    // pitch (doubles) of the horizontal-sum buffer
 constexpr int FT_THREADS = 256;
-constexpr size_t FT_SMEM = sizeof(float) * 5 * FH_H * FH_W + sizeof(double) * 5 * FH_H * FT_W;
+constexpr int FT_SEG = 16;                                         // columns per horizontal running-sum task
+constexpr int FT_ROWS_PER_THREAD = FT_H / (FT_THREADS / FT_W);     // 8 output rows per thread in the vertical pass
+constexpr size_t FT_SMEM = sizeof(float) * 5 * FH_H * FM_P + sizeof(double) * FH_H * FHS_P;
 
-// FarnebackUpdateMatrices for one pixel
-__device__ __forceinline__ void fb_update_matrix(const float* __restrict__ R0, const float* __restrict__ R1, size_t plane,
-                                                 int w, int h, int x, int y, float2 fl, float M[5])
+__device__ __forceinline__ size_t align_up_dev(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// FarnebackUpdateMatrices for one pixel.  RA = float4 plane (channels 0..3), RB = float plane (channel 4).
+__device__ __forceinline__ void fb_update_matrix(const float4* __restrict__ R0A, const float* __restrict__ R0B,
+                                                 const float4* __restrict__ R1A, const float* __restrict__ R1B, int w, int h,
+                                                 int x, int y, float2 fl, float M[5])
 {
     const size_t o = (size_t)y * w + x;
     const float dx = fl.x, dy = fl.y;
@@ -364,31 +373,29 @@ __device__ __forceinline__ void fb_update_matrix(const float* __restrict__ R0, c
     fx -= x1;
     fy -= y1;
     float r2, r3, r4, r5, r6;
-    const float R00 = __ldg(R0 + o), R01 = __ldg(R0 + plane + o), R02 = __ldg(R0 + 2 * plane + o),
-                R03 = __ldg(R0 + 3 * plane + o), R04 = __ldg(R0 + 4 * plane + o);
+    const float4 a0 = __ldg(R0A + o);
+    const float a04 = __ldg(R0B + o);
     if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const float* p = R1 + (size_t)y1 * w + x1;
-        r2 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
-        p += plane;
-        r3 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
-        p += plane;
-        r4 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
-        p += plane;
-        r5 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
-        p += plane;
-        r6 = a00 * __ldg(p) + a01 * __ldg(p + 1) + a10 * __ldg(p + w) + a11 * __ldg(p + w + 1);
-        r4 = (R02 + r4) * 0.5f;
-        r5 = (R03 + r5) * 0.5f;
-        r6 = (R04 + r6) * 0.25f;
+        const size_t q = (size_t)y1 * w + x1;
+        const float4 p00 = __ldg(R1A + q), p01 = __ldg(R1A + q + 1), p10 = __ldg(R1A + q + w), p11 = __ldg(R1A + q + w + 1);
+        const float e00 = __ldg(R1B + q), e01 = __ldg(R1B + q + 1), e10 = __ldg(R1B + q + w), e11 = __ldg(R1B + q + w + 1);
+        r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
+        r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
+        r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
+        r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
+        r6 = a00 * e00 + a01 * e01 + a10 * e10 + a11 * e11;
+        r4 = (a0.z + r4) * 0.5f;
+        r5 = (a0.w + r5) * 0.5f;
+        r6 = (a04 + r6) * 0.25f;
     } else {
         r2 = r3 = 0.f;
-        r4 = R02;
-        r5 = R03;
-        r6 = R04 * 0.5f;
+        r4 = a0.z;
+        r5 = a0.w;
+        r6 = a04 * 0.5f;
     }
-    r2 = (R00 - r2) * 0.5f;
-    r3 = (R01 - r3) * 0.5f;
+    r2 = (a0.x - r2) * 0.5f;
+    r3 = (a0.y - r3) * 0.5f;
     r2 += r4 * dy + r6 * dx;
     r3 += r6 * dy + r5 * dx;
     constexpr int BORDER = 5;
@@ -405,18 +412,26 @@ __device__ __forceinline__ void fb_update_matrix(const float* __restrict__ R0, c
     M[4] = r6 * r2 + r5 * r3;
 }
 
-// one iteration of FarnebackUpdateFlow_Blur with the UpdateMatrices that precedes it fused in
-__global__ void __launch_bounds__(FT_THREADS) k_fb_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1,
-                                                             size_t rstride_b, const float2* __restrict__ fin,
-                                                             float2* __restrict__ fout, size_t fstride_b, int w, int h)
+// One iteration of FarnebackUpdateFlow_Blur with the UpdateMatrices that precedes it fused in.
+//   phase 1: M for the 64x32 tile + 7-px halo (clamped = replicate border) -> shared memory (f32, never in HBM)
+//   phase 2: per channel, 15-wide horizontal window sums as FP64 RUNNING sums (one task = one halo row x 16 columns),
+//            then 15-tall vertical running sums (one thread = one column x 8 rows) accumulated in registers
+//   phase 3: 2x2 solve in FP64, coalesced float2 store
+__global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1,
+                                                                size_t rstride_b, const float2* __restrict__ fin,
+                                                                float2* __restrict__ fout, size_t fstride_b, int w, int h)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sM = reinterpret_cast<float*>(smem_raw);                                   // [5][FH_H][FH_W]
-    double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 5 * FH_H * FH_W);  // [5][FH_H][FT_W]
+    float* sM = reinterpret_cast<float*>(smem_raw);                                     // [5][FH_H][FM_P]
+    double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 5 * FH_H * FM_P);  // [FH_H][FHS_P]
     const int b = blockIdx.z;
-    const size_t plane = (size_t)w * h;
+    const size_t npad = align_up_dev((size_t)w * h, 64);
     const float* r0 = R0 + (size_t)b * rstride_b;
     const float* r1 = R1 + (size_t)b * rstride_b;
+    const float4* R0A = reinterpret_cast<const float4*>(r0);
+    const float4* R1A = reinterpret_cast<const float4*>(r1);
+    const float* R0B = r0 + 4 * npad;
+    const float* R1B = r1 + 4 * npad;
     const float2* fi = fin + (size_t)b * fstride_b;
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const int tid = threadIdx.x;
@@ -424,44 +439,63 @@ __global__ void __launch_bounds__(FT_THREADS) k_fb_flow_iter(const float* __rest
         const int ly = i / FH_W, lx = i - ly * FH_W;
         const int x = min(max(x0 + lx - FHALO, 0), w - 1), y = min(max(y0 + ly - FHALO, 0), h - 1);
         float M[5];
-        fb_update_matrix(r0, r1, plane, w, h, x, y, __ldg(fi + (size_t)y * w + x), M);
+        fb_update_matrix(R0A, R0B, R1A, R1B, w, h, x, y, __ldg(fi + (size_t)y * w + x), M);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) sM[(c * FH_H + ly) * FH_W + lx] = M[c];
+        for (int c = 0; c < 5; ++c) sM[(c * FH_H + ly) * FM_P + lx] = M[c];
     }
     __syncthreads();
-    // horizontal 15-tap sums (f64) for every halo row
-    for (int i = tid; i < FH_H * FT_W; i += FT_THREADS) {
-        const int ly = i / FT_W, lx = i - ly * FT_W;
+    // horizontal task: seg-major so that the lanes of a warp walk different rows (odd pitch -> no bank conflicts)
+    constexpr int NSEG = FT_W / FT_SEG;          // 4
+    constexpr int NTASK = NSEG * FH_H;           // 184
+    const int hseg = tid / FH_H, hrow = tid - hseg * FH_H;
+    // vertical task: column cx, rows vr0 .. vr0+7
+    const int cx = tid & (FT_W - 1), vr0 = (tid / FT_W) * FT_ROWS_PER_THREAD;
+    double acc[5][FT_ROWS_PER_THREAD];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const float* m = sM + (c * FH_H + ly) * FH_W + lx;
+    for (int c = 0; c < 5; ++c) {
+        if (tid < NTASK) {
+            const float* m = sM + (c * FH_H + hrow) * FM_P + hseg * FT_SEG;
+            double* ho = sH + hrow * FHS_P + hseg * FT_SEG;
             double s = 0.0;
 #pragma unroll
-            for (int d = 0; d < FB_WIN; ++d) s += (double)m[d];
-            sH[(c * FH_H + ly) * FT_W + lx] = s;
+            for (int i = 0; i < FB_WIN; ++i) s += (double)m[i];
+            ho[0] = s;
+#pragma unroll
+            for (int j = 1; j < FT_SEG; ++j) {
+                s += (double)m[j + FB_WIN - 1] - (double)m[j - 1];
+                ho[j] = s;
+            }
         }
+        __syncthreads();
+        {
+            const double* hp = sH + vr0 * FHS_P + cx;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < FB_WIN; ++i) s += hp[i * FHS_P];
+            acc[c][0] = s;
+#pragma unroll
+            for (int j = 1; j < FT_ROWS_PER_THREAD; ++j) {
+                s += hp[(j + FB_WIN - 1) * FHS_P] - hp[(j - 1) * FHS_P];
+                acc[c][j] = s;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < FT_H * FT_W; i += FT_THREADS) {
-        const int ly = i / FT_W, lx = i - ly * FT_W;
-        const int x = x0 + lx, y = y0 + ly;
-        if (x >= w || y >= h) continue;
-        double v[5];
+    const int x = x0 + cx;
+    if (x >= w) return;
+    float2* fo = fout + (size_t)b * fstride_b;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const double* hp = sH + (c * FH_H + ly) * FT_W + lx;
-            double s = 0.0;
-#pragma unroll
-            for (int d = 0; d < FB_WIN; ++d) s += hp[d * FT_W];
-            v[c] = s;
-        }
+    for (int j = 0; j < FT_ROWS_PER_THREAD; ++j) {
+        const int y = y0 + vr0 + j;
+        if (y >= h) break;
         const double scale = 1. / (FB_WIN * FB_WIN);
-        const double g11 = v[0] * scale, g12 = v[1] * scale, g22 = v[2] * scale, h1 = v[3] * scale, h2 = v[4] * scale;
+        const double g11 = acc[0][j] * scale, g12 = acc[1][j] * scale, g22 = acc[2][j] * scale, h1 = acc[3][j] * scale,
+                     h2 = acc[4][j] * scale;
         const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
         float2 o;
         o.x = (float)((g11 * h2 - g12 * h1) * idet);
         o.y = (float)((g22 * h1 - g12 * h2) * idet);
-        fout[(size_t)b * fstride_b + (size_t)y * w + x] = o;
+        fo[(size_t)y * w + x] = o;
     }
 }
 
