@@ -362,24 +362,15 @@ constexpr size_t FT_SMEM = sizeof(float) * 5 * FH_H * FM_P + sizeof(double) * FH
 __device__ __forceinline__ size_t align_up_dev(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // FarnebackUpdateMatrices for one pixel.  RA = float4 plane (channels 0..3), RB = float plane (channel 4).
-__device__ __forceinline__ void fb_update_matrix(const float4* __restrict__ R0A, const float* __restrict__ R0B,
-                                                 const float4* __restrict__ R1A, const float* __restrict__ R1B, int w, int h,
-                                                 int x, int y, float2 fl, float M[5])
+__device__ __forceinline__ void fb_um_compute(const float4 a0, const float a04, const float4 p00, const float4 p01,
+                                              const float4 p10, const float4 p11, const float e00, const float e01,
+                                              const float e10, const float e11, const bool inside, const float fx, const float fy,
+                                              const float2 fl, const int x, const int y, const int w, const int h, float M[5])
 {
-    const size_t o = (size_t)y * w + x;
     const float dx = fl.x, dy = fl.y;
-    float fx = x + dx, fy = y + dy;
-    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= x1;
-    fy -= y1;
     float r2, r3, r4, r5, r6;
-    const float4 a0 = __ldg(R0A + o);
-    const float a04 = __ldg(R0B + o);
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+    if (inside) {
         const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t q = (size_t)y1 * w + x1;
-        const float4 p00 = __ldg(R1A + q), p01 = __ldg(R1A + q + 1), p10 = __ldg(R1A + q + w), p11 = __ldg(R1A + q + w + 1);
-        const float e00 = __ldg(R1B + q), e01 = __ldg(R1B + q + 1), e10 = __ldg(R1B + q + w), e11 = __ldg(R1B + q + w + 1);
         r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
         r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
         r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
@@ -435,13 +426,57 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __r
     const float2* fi = fin + (size_t)b * fstride_b;
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const int tid = threadIdx.x;
-    for (int i = tid; i < FH_H * FH_W; i += FT_THREADS) {
-        const int ly = i / FH_W, lx = i - ly * FH_W;
-        const int x = min(max(x0 + lx - FHALO, 0), w - 1), y = min(max(y0 + ly - FHALO, 0), h - 1);
-        float M[5];
-        fb_update_matrix(R0A, R0B, R1A, R1B, w, h, x, y, __ldg(fi + (size_t)y * w + x), M);
+    // phase 1, software pipelined: U cells per thread in flight (flow loads, then all gathers, then the arithmetic) so
+    // that the dependent global loads of several cells overlap (the kernel was long-scoreboard bound at 16 warps/SM)
+    constexpr int U = 3;
+    for (int i0 = tid; i0 < FH_H * FH_W; i0 += FT_THREADS * U) {
+        int lxs[U], lys[U], xs[U], ys[U];
+        float2 fl[U];
+        bool live[U];
 #pragma unroll
-        for (int c = 0; c < 5; ++c) sM[(c * FH_H + ly) * FM_P + lx] = M[c];
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * FT_THREADS;
+            live[u] = i < FH_H * FH_W;
+            const int ii = live[u] ? i : 0;
+            lys[u] = ii / FH_W;
+            lxs[u] = ii - lys[u] * FH_W;
+            xs[u] = min(max(x0 + lxs[u] - FHALO, 0), w - 1);
+            ys[u] = min(max(y0 + lys[u] - FHALO, 0), h - 1);
+            fl[u] = __ldg(fi + (size_t)ys[u] * w + xs[u]);
+        }
+        float4 a0[U], p00[U], p01[U], p10[U], p11[U];
+        float a04[U], e00[U], e01[U], e10[U], e11[U], fxs[U], fys[U];
+        bool inside[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t o = (size_t)ys[u] * w + xs[u];
+            a0[u] = __ldg(R0A + o);
+            a04[u] = __ldg(R0B + o);
+            float fx = xs[u] + fl[u].x, fy = ys[u] + fl[u].y;
+            const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+            fxs[u] = fx - x1;
+            fys[u] = fy - y1;
+            inside[u] = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+            const size_t q = inside[u] ? (size_t)y1 * w + x1 : 0;
+            p00[u] = __ldg(R1A + q);
+            p01[u] = __ldg(R1A + q + 1);
+            p10[u] = __ldg(R1A + q + w);
+            p11[u] = __ldg(R1A + q + w + 1);
+            e00[u] = __ldg(R1B + q);
+            e01[u] = __ldg(R1B + q + 1);
+            e10[u] = __ldg(R1B + q + w);
+            e11[u] = __ldg(R1B + q + w + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float M[5];
+            fb_um_compute(a0[u], a04[u], p00[u], p01[u], p10[u], p11[u], e00[u], e01[u], e10[u], e11[u], inside[u], fxs[u], fys[u],
+                          fl[u], xs[u], ys[u], w, h, M);
+            if (live[u]) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) sM[(c * FH_H + lys[u]) * FM_P + lxs[u]] = M[c];
+            }
+        }
     }
     __syncthreads();
     // horizontal task: seg-major so that the lanes of a warp walk different rows (odd pitch -> no bank conflicts)

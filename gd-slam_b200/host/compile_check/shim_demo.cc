@@ -1,0 +1,61 @@
+// shim_demo.cc — drives the drop-in C++ classes exactly like Tracking::GrabImageRGBD_GD does (src/Tracking.cc:238-252):
+// ORB on the new gray image (twice, second call memoised), AddNewImage, GetNoGMMmask.  Reads a raw sequence file written by
+// tests/test_gpu_shim.py, writes masks / keypoints / descriptors for the test to compare with the oracle.
+//   file: int32 w, h, nframes; per frame: bgr (w*h*3 u8), gray (w*h u8), depth (w*h f32), R (9 f32), T (3 f32)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../GeoMaskMaker.h"
+#include "../ORBextractor.h"
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) return 2;
+    FILE* f = std::fopen(argv[1], "rb");
+    FILE* o = std::fopen(argv[2], "wb");
+    if (!f || !o) return 3;
+    int hdr[3];
+    if (std::fread(hdr, 4, 3, f) != 3) return 4;
+    const int w = hdr[0], h = hdr[1], nf = hdr[2];
+    float Kv[9] = {535.4f * w / 640, 0, 320.1f * w / 640, 0, 539.2f * w / 640, 247.6f * w / 640, 0, 0, 1};
+    cv::Mat K(3, 3, CV_32FC1, Kv), D(4, 1, CV_32FC1);
+    for (int i = 0; i < 4; ++i) D.at<float>(i) = 0.f;
+    float Rv[9], Tv[3];
+    GeoMaskMaker gm(K, D, 5000.f, w, h, 0);
+    gm.SetPoseProvider([&](cv::Mat& R, cv::Mat& T) {
+        R.create(3, 3, CV_32FC1);
+        T.create(3, 1, CV_32FC1);
+        for (int i = 0; i < 9; ++i) R.at<float>(i / 3, i % 3) = Rv[i];
+        for (int i = 0; i < 3; ++i) T.at<float>(i, 0) = Tv[i];
+        return true;
+    });
+    ORB_SLAM2::ORBextractor orb(1500, 1.2f, 8, 20, 7);
+    std::vector<unsigned char> bgr((size_t)w * h * 3), gray((size_t)w * h);
+    std::vector<float> depth((size_t)w * h);
+    for (int i = 0; i < nf; ++i) {
+        if (std::fread(bgr.data(), 1, bgr.size(), f) != bgr.size() || std::fread(gray.data(), 1, gray.size(), f) != gray.size() ||
+            std::fread(depth.data(), 4, depth.size(), f) != depth.size() || std::fread(Rv, 4, 9, f) != 9 || std::fread(Tv, 4, 3, f) != 3)
+            return 5;
+        cv::Mat im(h, w, CV_8UC3, bgr.data()), g(h, w, CV_8UC1, gray.data()), d(h, w, CV_32FC1, depth.data()), label, mask;
+        std::vector<cv::KeyPoint> kps, kps2;
+        cv::Mat desc, desc2;
+        orb(cv::_InputArray(g), cv::_InputArray(label), kps, cv::_OutputArray(desc));    // Frame(), Tracking.cc:238
+        gm.AddNewImage(im, d, label, label);                                              // Tracking.cc:242
+        gm.GetNoGMMmask(mask);                                                            // Tracking.cc:245
+        orb(cv::_InputArray(g), cv::_InputArray(label), kps2, cv::_OutputArray(desc2));  // Frame(), Tracking.cc:252
+        if (kps2.size() != kps.size()) return 6;
+        int n = (int)kps.size();
+        std::fwrite(&n, 4, 1, o);
+        for (int k = 0; k < n; ++k) {
+            float rec[5] = {kps[k].pt.x, kps[k].pt.y, kps[k].size, kps[k].angle, kps[k].response};
+            std::fwrite(rec, 4, 5, o);
+            std::fwrite(&kps[k].octave, 4, 1, o);
+            std::fwrite(desc.ptr<unsigned char>(k), 1, 32, o);
+        }
+        for (int y = 0; y < h; ++y) std::fwrite(mask.ptr<unsigned char>(y), 1, (size_t)w, o);
+    }
+    std::fclose(f);
+    std::fclose(o);
+    return 0;
+}
