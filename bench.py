@@ -246,18 +246,15 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    sharding = importlib.import_module("gd-slam_b200.sharding")
+
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
+        return sharding.max_over_ranks(x, dist, f"cuda:{local_rank}" if dist is not None else None)
 
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- data: `distinct` seeded streams per rank, replicated over the batch with a frame offset
+    # ---- data: every rank owns its own `B` streams (weak scaling); `distinct` seeded streams are generated per rank and
+    #      replicated over the batch with a frame offset
     D = min(args.distinct, B)
-    bgr, dep, poses = make_data(D, S, seed0=1000 * rank)
+    bgr, dep, poses = make_data(D, S, seed0=sharding.stream_seed(rank, 0, B))
     K = synth.intrinsics(W, H)
     fe = capi.Frontend(K, W, H, batch=B, device=device, staged_slots=S)
     hb = capi.pinned_empty((S, B, H, W, 3), np.uint8)
