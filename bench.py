@@ -234,6 +234,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (libgdslam_cuda has no CPU fallback)")
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version at VERSION/INFO)
         import torch
         import torch.distributed as dist
 

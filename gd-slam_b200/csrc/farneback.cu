@@ -210,6 +210,26 @@ __global__ void __launch_bounds__(128) k_fb_pyr(const uint8_t* __restrict__ gray
     I[(size_t)b * istride_b + (size_t)dy * a.lw + dx] = r0 * b0 + r1 * b1;
 }
 
+// level 0: the level has the size of the image, cv::resize is a copy -> one 3x3 separable blur per pixel
+__global__ void __launch_bounds__(128) k_fb_blur3_same(const uint8_t* __restrict__ gray, size_t gstride_b, int W, int H, float t0,
+                                                       float t1, float t2, float* __restrict__ I, size_t istride_b)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* g = gray + (size_t)b * gstride_b;
+    const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    float h[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint8_t* row = g + (size_t)reflect101(y - 1 + j, H) * W;
+        float acc = t0 * (float)__ldg(row + xm);
+        acc = acc + t1 * (float)__ldg(row + x);
+        acc = acc + t2 * (float)__ldg(row + xp);
+        h[j] = acc;
+    }
+    I[(size_t)b * istride_b + (size_t)y * W + x] = t1 * h[1] + t2 * (h[2] + h[0]);
+}
+
 // ------------------------------------------------------------------------------------------------ K1a-2
 __device__ __forceinline__ size_t align_up_dev(size_t v, size_t a);
 struct PolyArgs {
@@ -296,7 +316,9 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
             LaunchScope ls(st, s, "K1a_blur_resample", 1);
             dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
             float* Ik = scratch_I + L.i_off;
-            switch (L.ksize) {
+            if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
+                k_fb_blur3_same<<<grid, block, 0, s>>>(gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b);
+            } else switch (L.ksize) {
                 case 3: k_fb_pyr<3><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
                 case 9: k_fb_pyr<9><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
                 case 19: k_fb_pyr<19><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;

@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     uint8_t* tile = sm;                            // [tile_h][tile_w]
     uint8_t* sc = sm + a.tile_w * a.tile_h;        // S' (0 when <= minTh)
     __shared__ int s_warp[FAST_THREADS / 32];
-    __shared__ int s_base, s_cnt20;
     const int b = blockIdx.y;
     int cell = blockIdx.x, l = 0;
     while (l + 1 < a.nlevels && cell >= a.lv[l + 1].cell_start) ++l;
@@ -259,10 +258,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         tile[y * tp + x] = __ldg(img + (size_t)(y0 + y) * L.pitch + x0 + x);
         sc[y * tp + x] = 0;
     }
-    if (threadIdx.x == 0) {
-        s_base = 0;
-        s_cnt20 = 0;
-    }
     __syncthreads();
     const int npix = iw * ih;
     for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
@@ -288,36 +283,65 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
             }
         return k;
     };
-    int local20 = 0;
-    for (int t = threadIdx.x; t < npix; t += FAST_THREADS) local20 += keep_at(t, a.iniTh) ? 1 : 0;
-    if (local20) atomicAdd(&s_cnt20, local20);
-    __syncthreads();
-    const int th = s_cnt20 > 0 ? a.iniTh : a.minTh;  // :812-816
-    ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
+    // raster-ordered compaction with 3 barriers: warp w owns the contiguous pixel range [w*R, (w+1)*R); a lane keeps one
+    // keep-bit per 32-pixel chunk of its warp's range, so the NMS test is evaluated once per threshold
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < npix; base += FAST_THREADS) {
-        const int t = base + threadIdx.x;
-        const bool k = t < npix && keep_at(t, th);
+    constexpr int NW = FAST_THREADS / 32;
+    const int R = ((npix + NW - 1) / NW + 31) & ~31;  // pixels per warp, multiple of 32 (<= 32 chunks: cells are tiny)
+    const int nchunk = R >> 5;
+    unsigned bits = 0;
+    int wcount = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int t = warp * R + c * 32 + lane;
+        const bool k = t < npix && keep_at(t, a.iniTh);
         const unsigned bal = __ballot_sync(0xffffffffu, k);
-        if (lane == 0) s_warp[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
+        bits |= (k ? 1u : 0u) << c;
+        wcount += __popc(bal);
+    }
+    if (lane == 0) s_warp[warp] = wcount;
+    __syncthreads();
+    int tot = 0, woff = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < FAST_THREADS / 32; ++w2) {
+    for (int w2 = 0; w2 < NW; ++w2) {
+        if (w2 < warp) woff += s_warp[w2];
+        tot += s_warp[w2];
+    }
+    if (tot == 0) {  // no corner survived NMS at iniThFAST -> redo the cell at minThFAST (:812-816)
+        __syncthreads();
+        bits = 0;
+        wcount = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            const int t = warp * R + c * 32 + lane;
+            const bool k = t < npix && keep_at(t, a.minTh);
+            const unsigned bal = __ballot_sync(0xffffffffu, k);
+            bits |= (k ? 1u : 0u) << c;
+            wcount += __popc(bal);
+        }
+        if (lane == 0) s_warp[warp] = wcount;
+        __syncthreads();
+        tot = 0;
+        woff = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) {
             if (w2 < warp) woff += s_warp[w2];
             tot += s_warp[w2];
         }
-        const int pos = s_base + woff + __popc(bal & ((1u << lane) - 1));
-        if (k && pos < a.cell_cap) {
-            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
-            slab[pos] = make_ushort4((unsigned short)(x + j * L.wCell), (unsigned short)(y + i * L.hCell),
-                                     (unsigned short)(sc[y * tp + x] - 1), 0);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += tot;
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *cnt_out = min(s_base, a.cell_cap);
+    ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
+    int pos = woff;
+    for (int c = 0; c < nchunk; ++c) {
+        const bool k = (bits >> c) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        const int my = pos + __popc(bal & ((1u << lane) - 1));
+        if (k && my < a.cell_cap) {
+            const int t = warp * R + c * 32 + lane;
+            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+            slab[my] = make_ushort4((unsigned short)(x + j * L.wCell), (unsigned short)(y + i * L.hCell),
+                                    (unsigned short)(sc[y * tp + x] - 1), 0);
+        }
+        pos += __popc(bal);
+    }
+    if (threadIdx.x == 0) *cnt_out = min(tot, a.cell_cap);
 }
 
 // ------------------------------------------------------------------------------------------------ K4c quadtree
