@@ -15,7 +15,8 @@
 
 namespace gd {
 
-__constant__ signed char c_pattern[1024] = {
+// global (not __constant__): every lane reads a different 32-byte slice, which the constant cache would serialise
+__device__ __align__(16) signed char d_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
@@ -262,8 +263,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     const int npix = iw * ih;
     for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
         const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
-        const int s = fast_sprime_smem(tile + y * tp + x, tp, a.minTh);
-        sc[y * tp + x] = (uint8_t)(s > a.minTh ? s : 0);
+        // first pass at iniThFAST only (like the reference's first cv::FAST call): the early-out then rejects most pixels
+        const int s = fast_sprime_smem(tile + y * tp + x, tp, a.iniTh);
+        sc[y * tp + x] = (uint8_t)(s > a.iniTh ? s : 0);
     }
     __syncthreads();
     // NMS at iniTh: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th
@@ -307,6 +309,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         tot += s_warp[w2];
     }
     if (tot == 0) {  // no corner survived NMS at iniThFAST -> redo the cell at minThFAST (:812-816)
+        __syncthreads();
+        for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
+            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+            const int s2 = fast_sprime_smem(tile + y * tp + x, tp, a.minTh);
+            sc[y * tp + x] = (uint8_t)(s2 > a.minTh ? s2 : 0);
+        }
         __syncthreads();
         bits = 0;
         wcount = 0;
@@ -809,10 +817,14 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
     const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
     const uint8_t* bc = blur + (size_t)b * stride_b + L.off + (size_t)y * L.pitch + x;
     int val = 0;
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2);
+    const int4 q1 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2 + 1);
+    const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};  // one test = 4 signed bytes (x0,y0,x1,y1)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const signed char* pp = c_pattern + (lane * 16 + 2 * k) * 2;
-        const float x0 = (float)pp[0], y0 = (float)pp[1], x1 = (float)pp[2], y1 = (float)pp[3];
+        const int wd = words[k];
+        const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff),
+                    x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
         const int t0 = bc[__float2int_rn(x0 * sa + y0 * ca) * L.pitch + __float2int_rn(x0 * ca - y0 * sa)];
         const int t1 = bc[__float2int_rn(x1 * sa + y1 * ca) * L.pitch + __float2int_rn(x1 * ca - y1 * sa)];
         val |= (t0 < t1) << k;
