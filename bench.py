@@ -43,7 +43,9 @@ FAMILY_BYTES = {
     "K0_gray": (3 + 1 + 1) * N_PX,
     "K1a_blur_resample": (4 * 1 + 4 * FB_LEVEL_SUM) * N_PX,
     "K1a_polyexp": (4 + 20) * FB_LEVEL_SUM * N_PX,
-    "K1b_flow_iter": 3 * 56 * FB_LEVEL_SUM * N_PX,
+    "K1b_flow_iter": 3 * 56 * FB_LEVEL_SUM * N_PX,      # fused form (GD_FLOW_FUSED=1)
+    "K1b_matrices": 3 * 68 * FB_LEVEL_SUM * N_PX,       # split form: R0 20 + R1 20 + flow 8 in, M 20 out
+    "K1b_box_solve": 3 * 28 * FB_LEVEL_SUM * N_PX,      # split form: M 20 in, flow 8 out
     "K1b_flow_upsample": (8 * 0.328125 / 4 + 8 * 0.328125) * N_PX,
     "K2a_depth_edge": 5 * N_PX,
     "K2b_mahalanobis": 22 * N_PX,

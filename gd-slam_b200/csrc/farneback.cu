@@ -120,6 +120,7 @@ int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int
     plan->r_floats = r_off;
     plan->i_floats = i_off;
     plan->f_float2 = f_off;
+    plan->m_floats = 5 * align_up((size_t)plan->lv[0].w * plan->lv[0].h, 64);
     poly_constants(poly_n, poly_sigma, plan);
     return GD_OK;
 }
@@ -556,12 +557,178 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K1b, split form
+// (a) k_fb_matrices: FarnebackUpdateMatrices for every pixel exactly once -> M (5 f32 planes) in HBM.  Embarrassingly
+//     parallel, no shared memory, full occupancy: the dependent bilinear gathers are hidden by ~40 resident warps.
+//     Algorithmic bytes: R0 20 + R1 20 + flow 8 + M 20 = 68 B/px.
+// (b) k_fb_box_solve: 15x15 box sums of M (FP64 running sums) + 2x2 solve -> flow.  28 B/px (M 20 + flow 8).
+__global__ void __launch_bounds__(256) k_fb_matrices(const float* __restrict__ R0, const float* __restrict__ R1, size_t rstride_b,
+                                                     const float2* __restrict__ fin, size_t fstride_b, float* __restrict__ Mout,
+                                                     size_t mstride_b, int w, int h)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= w || y >= h) return;
+    const size_t npad = align_up_dev((size_t)w * h, 64);
+    const float* r0 = R0 + (size_t)b * rstride_b;
+    const float* r1 = R1 + (size_t)b * rstride_b;
+    const float4* R0A = reinterpret_cast<const float4*>(r0);
+    const float4* R1A = reinterpret_cast<const float4*>(r1);
+    const float* R0B = r0 + 4 * npad;
+    const float* R1B = r1 + 4 * npad;
+    const int o = y * w + x;
+    const float2 fl = __ldg(fin + (size_t)b * fstride_b + o);
+    const float4 a0 = __ldg(R0A + o);
+    const float a04 = __ldg(R0B + o);
+    float fx = x + fl.x, fy = y + fl.y;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= x1;
+    fy -= y1;
+    const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int q = inside ? y1 * w + x1 : 0;
+    const float4 p00 = __ldg(R1A + q), p01 = __ldg(R1A + q + 1), p10 = __ldg(R1A + q + w), p11 = __ldg(R1A + q + w + 1);
+    const float e00 = __ldg(R1B + q), e01 = __ldg(R1B + q + 1), e10 = __ldg(R1B + q + w), e11 = __ldg(R1B + q + w + 1);
+    float M[5];
+    fb_um_compute(a0, a04, p00, p01, p10, p11, e00, e01, e10, e11, inside, fx, fy, fl, x, y, w, h, M);
+    float* mo = Mout + (size_t)b * mstride_b + o;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) mo[(size_t)c * npad] = M[c];
+}
+
+constexpr int BX_W = 64, BX_H = 32;
+constexpr int BXH_H = BX_H + 2 * FHALO;      // 46 tile rows
+constexpr int BX_LEFT = 8;                   // tile starts at x0 - 8 (16-byte aligned), of which 7 columns are halo
+constexpr int BXT_W = BX_W + 2 * BX_LEFT;    // 80 floats = 20 x 16-byte chunks per row
+constexpr int BXM_P = 84;                    // smem row pitch (floats): 16-byte aligned rows, LDS.128 by row is conflict free
+constexpr int BXS_P = BX_W + 1;              // 65 doubles
+constexpr int BX_THREADS = 256;
+constexpr int BX_ROWS = BX_H / (BX_THREADS / BX_W);  // 8 rows per thread in the vertical pass
+constexpr size_t BX_SMEM = sizeof(float) * 2 * BXH_H * BXM_P + sizeof(double) * BXH_H * BXS_P;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __restrict__ Min, size_t mstride_b,
+                                                                float2* __restrict__ fout, size_t fstride_b, int w, int h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sT = reinterpret_cast<float*>(smem_raw);                                        // [2][BXH_H][BXM_P] channel tile
+    double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 2 * BXH_H * BXM_P);  // [BXH_H][BXS_P]
+    const int b = blockIdx.z;
+    const size_t npad = align_up_dev((size_t)w * h, 64);
+    const float* Mb = Min + (size_t)b * mstride_b;
+    const int x0 = blockIdx.x * BX_W, y0 = blockIdx.y * BX_H;
+    const int tid = threadIdx.x;
+    const bool vec_ok = (w & 3) == 0;
+    // replicate-border tile of one channel plane: 16-byte async copies for chunks inside the image, clamped 4-byte
+    // copies for the few chunks that straddle the left / right image border (or when the row stride is not 16-byte aligned)
+    auto load_tile = [&](int c, int buf) {
+        const float* plane = Mb + (size_t)c * npad;
+        float* dst = sT + buf * BXH_H * BXM_P;
+        constexpr int CH = BXT_W / 4;  // 20 chunks per row
+        for (int i = tid; i < BXH_H * CH; i += BX_THREADS) {
+            const int ly = i / CH, ch = i - ly * CH;
+            const int y = min(max(y0 + ly - FHALO, 0), h - 1);
+            const int xs = x0 - BX_LEFT + 4 * ch;
+            const float* row = plane + (size_t)y * w;
+            float* d = dst + ly * BXM_P + 4 * ch;
+            if (vec_ok && xs >= 0 && xs + 3 < w) {
+                cp_async16(d, row + xs);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cp_async4(d + e, row + min(max(xs + e, 0), w - 1));
+            }
+        }
+        cp_async_commit();
+    };
+    constexpr int NTASK = (BX_W / FT_SEG) * BXH_H;  // 184 horizontal tasks: (segment of 16 columns) x (tile row)
+    const int hseg = tid / BXH_H, hrow = tid - hseg * BXH_H;
+    const int cx = tid & (BX_W - 1), vr0 = (tid / BX_W) * BX_ROWS;
+    double acc[5][BX_ROWS];
+    load_tile(0, 0);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        if (c + 1 < 5) {
+            load_tile(c + 1, (c + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (tid < NTASK) {
+            // window of output column j (tile-local) = tile floats [j + 1, j + 15]; the segment reads floats [16 seg, 16 seg + 32)
+            const float4* m4 = reinterpret_cast<const float4*>(sT + (c & 1) * BXH_H * BXM_P + hrow * BXM_P + hseg * FT_SEG);
+            float m[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = m4[q];
+                m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+            }
+            double* ho = sH + hrow * BXS_P + hseg * FT_SEG;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 1; i <= FB_WIN; ++i) s += (double)m[i];
+            ho[0] = s;
+#pragma unroll
+            for (int j = 1; j < FT_SEG; ++j) {
+                s += (double)m[j + FB_WIN] - (double)m[j];
+                ho[j] = s;
+            }
+        }
+        __syncthreads();
+        {
+            const double* hp = sH + vr0 * BXS_P + cx;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < FB_WIN; ++i) s += hp[i * BXS_P];
+            acc[c][0] = s;
+#pragma unroll
+            for (int j = 1; j < BX_ROWS; ++j) {
+                s += hp[(j + FB_WIN - 1) * BXS_P] - hp[(j - 1) * BXS_P];
+                acc[c][j] = s;
+            }
+        }
+        // the next iteration's first __syncthreads orders these sH reads before the next H-pass writes; the tile buffer
+        // (c & 1) is only overwritten by load_tile(c + 2), issued after that barrier as well
+    }
+    const int x = x0 + cx;
+    if (x >= w) return;
+    float2* fo = fout + (size_t)b * fstride_b;
+#pragma unroll
+    for (int j = 0; j < BX_ROWS; ++j) {
+        const int y = y0 + vr0 + j;
+        if (y >= h) break;
+        const double scale = 1. / (FB_WIN * FB_WIN);
+        const double g11 = acc[0][j] * scale, g12 = acc[1][j] * scale, g22 = acc[2][j] * scale, h1 = acc[3][j] * scale,
+                     h2 = acc[4][j] * scale;
+        const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+        float2 o;
+        o.x = (float)((g11 * h2 - g12 * h1) * idet);
+        o.y = (float)((g22 * h1 - g12 * h2) * idet);
+        fo[(size_t)y * w + x] = o;
+    }
+}
+
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, const float2** final_flow, cudaStream_t s, LaunchStats* st)
+                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_stride_b, const float2** final_flow, cudaStream_t s,
+                   LaunchStats* st)
 {
     static bool attr_set = false;
     if (!attr_set) {
         GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
         attr_set = true;
     }
     const float2* prev = nullptr;
@@ -584,10 +751,23 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
         float2* in = A;
         float2* out = B;
         for (int it = 0; it < plan.iterations; ++it) {
-            LaunchScope ls(st, s, "K1b_flow_iter", 1);
-            dim3 grid(cdiv(L.w, FT_W), cdiv(L.h, FT_H), batch);
-            k_fb_flow_iter<<<grid, FT_THREADS, FT_SMEM, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, out, f_stride_b, L.w, L.h);
-            GD_CUDA(cudaGetLastError());
+            if (Mbuf) {  // split form: matrices to HBM once per pixel, then box filter + solve
+                {
+                    LaunchScope ls(st, s, "K1b_matrices", 1);
+                    dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), batch);
+                    k_fb_matrices<<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, f_stride_b, Mbuf, m_stride_b, L.w, L.h);
+                    GD_CUDA(cudaGetLastError());
+                }
+                LaunchScope ls(st, s, "K1b_box_solve", 1);
+                dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), batch);
+                k_fb_box_solve<<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
+                GD_CUDA(cudaGetLastError());
+            } else {
+                LaunchScope ls(st, s, "K1b_flow_iter", 1);
+                dim3 grid(cdiv(L.w, FT_W), cdiv(L.h, FT_H), batch);
+                k_fb_flow_iter<<<grid, FT_THREADS, FT_SMEM, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, out, f_stride_b, L.w, L.h);
+                GD_CUDA(cudaGetLastError());
+            }
             float2* t = in;
             in = out;
             out = t;

@@ -28,6 +28,7 @@ struct FbPlan {
     size_t r_floats = 0;   // floats of one image's whole R pyramid (5 planes per level)
     size_t i_floats = 0;   // floats of one image's I scratch (all levels)
     size_t f_float2 = 0;   // float2 of one flow scratch (all levels)
+    size_t m_floats = 0;   // floats of the M scratch (5 planes of the largest level)
     // FarnebackPolyExp constants
     float g[2 * FB_POLY_N + 1], xg[2 * FB_POLY_N + 1], xxg[2 * FB_POLY_N + 1];
     double ig11, ig03, ig33, ig55;
@@ -43,7 +44,9 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
 
 // per-pair half: R0, R1 -> flow (level 0, float2 [b][h][w]).  flow scratch: two buffers [b][f_float2].
 // On return *final points at the level-0 flow (inside flowA or flowB).
+// Mbuf: [b][m_floats] scratch for the split form (matrices kernel + box/solve kernel); nullptr selects the fused kernel.
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, const float2** final_flow, cudaStream_t s, LaunchStats* st);
+                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_stride_b, const float2** final_flow, cudaStream_t s,
+                   LaunchStats* st);
 
 }  // namespace gd

@@ -2,6 +2,7 @@
 #include "geomask_core.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace gd {
 
@@ -66,6 +67,8 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
     GD_TRY(scratchI.alloc(B * plan.i_floats * sizeof(float)));
     GD_TRY(flowA.alloc(B * plan.f_float2 * sizeof(float2)));
     GD_TRY(flowB.alloc(B * plan.f_float2 * sizeof(float2)));
+    split_flow = std::getenv("GD_FLOW_FUSED") == nullptr;  // default: split form (matrices + box/solve)
+    if (split_flow) GD_TRY(Mbuf.alloc(B * plan.m_floats * sizeof(float)));
     GD_TRY(keys.alloc(B * n_pad * sizeof(unsigned long long)));
     GD_TRY(minmax.alloc(B * 2 * sizeof(unsigned)));
     GD_TRY(poses.alloc(B * sizeof(PoseDev)));
@@ -132,7 +135,8 @@ int GeoMaskCore::compute_mask(const float* Rm, const float* Tm, const int* pose_
     last_cur_slot = cur;
     const size_t rs = (size_t)GD_RING * plan.r_floats;
     GD_TRY(fb_launch_flow(plan, R.as<float>() + (size_t)ref * plan.r_floats, R.as<float>() + (size_t)cur * plan.r_floats, rs,
-                          batch, flowA.as<float2>(), flowB.as<float2>(), plan.f_float2, &last_flow, stream, stats));
+                          batch, flowA.as<float2>(), flowB.as<float2>(), plan.f_float2, split_flow ? Mbuf.as<float>() : nullptr, plan.m_floats,
+                          &last_flow, stream, stats));
     GD_TRY(launch_mahalanobis(last_flow, plan.f_float2, depth_slot_ptr(ref), depth_slot_ptr(cur), depth_stride_b(),
                               edge.as<uint8_t>() + (size_t)ref * n_pad, edge.as<uint8_t>() + (size_t)cur * n_pad,
                               (size_t)GD_RING * n_pad, has_lut ? lut.as<float2>() : nullptr, w, h, batch, cam,

@@ -28,6 +28,8 @@ struct GeoMaskCore {
     DevBuf R;          // [B][RING][r_floats]  Farnebäck polynomial expansion pyramid
     DevBuf scratchI;   // [B][i_floats]
     DevBuf flowA, flowB;  // [B][f_float2]
+    DevBuf Mbuf;          // [B][m_floats] UpdateMatrices output of the current level (split flow form)
+    bool split_flow = true;
     DevBuf keys;       // [B][n] u64 scatter keys (zero between frames)
     DevBuf minmax;     // [B][2] u32
     DevBuf poses;      // [B] PoseDev
