@@ -194,30 +194,27 @@ __device__ __forceinline__ int fast_sprime_smem(const uint8_t* p, int tp, int mi
     r[13] = p[tp - 3];
     r[14] = p[2 * tp - 2];
     r[15] = p[3 * tp - 1];
-    int d[16], e[16];  // d = v - ring (centre brighter), e = ring - v (centre darker)
+    // Both polarities at once with packed 16-bit SIMD min/max (VIMNMX.S16x2): low half = v - ring (centre brighter),
+    // high half = ring - v (centre darker); |values| <= 255 fit int16.
+    unsigned q[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        d[k] = v - r[k];
-        e[k] = r[k] - v;
+        const int d = v - r[k];
+        q[k] = __byte_perm((unsigned)d, (unsigned)(-d), 0x5410);
     }
-    int d2[16], e2[16], d4[16], e4[16];
+    unsigned q2[16], q4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q2[k] = __vmins2(q[k], q[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q4[k] = __vmins2(q2[k], q2[(k + 2) & 15]);
+    unsigned bestp = 0x80008000u;  // (-32768, -32768)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        d2[k] = min(d[k], d[(k + 1) & 15]);
-        e2[k] = min(e[k], e[(k + 1) & 15]);
+        const unsigned q9 = __vmins2(__vmins2(q4[k], q4[(k + 4) & 15]), q[(k + 8) & 15]);
+        bestp = __vmaxs2(bestp, q9);
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        d4[k] = min(d2[k], d2[(k + 2) & 15]);
-        e4[k] = min(e2[k], e2[(k + 2) & 15]);
-    }
-    int best = -256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
-        best = max(best, max(d9, e9));
-    }
+    const int blo = (int)(short)(bestp & 0xffffu), bhi = (int)(short)(bestp >> 16);
+    const int best = blo > bhi ? blo : bhi;
     return best;  // S'
 }
 

@@ -82,7 +82,8 @@ def test_frontend_profile_families(capi, synth):
     fe.step([fr[6].bgr], [fr[6].depth_m], R[None], T[None])
     fe.profile(False)
     fam = {n: (ms, ln) for n, ms, ln in fe.profile_read()}
-    for name in ("K0_gray", "K1a_polyexp", "K1b_flow_iter", "K2a_depth_edge", "K2b_mahalanobis", "K3a_minmax",
+    assert ("K1b_flow_iter" in fam) or ("K1b_matrices" in fam and "K1b_box_solve" in fam)  # fused or split flow form
+    for name in ("K0_gray", "K1a_polyexp", "K2a_depth_edge", "K2b_mahalanobis", "K3a_minmax",
                  "K3b_normalize_mask", "K4a_pyramid_resize", "K4b_fast_cells", "K4c_quadtree", "K4e_blur7",
                  "K4de_orient_describe"):
         assert name in fam and fam[name][0] > 0, name
