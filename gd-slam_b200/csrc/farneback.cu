@@ -239,9 +239,10 @@ struct PolyArgs {
     double ig11, ig03, ig33, ig55;
 };
 
-constexpr int PT_W = 32, PT_H = 8, PN = FB_POLY_N;
+constexpr int PT_W = 32, PT_H = 16, PT_TY = 8, PN = FB_POLY_N;  // 32x16 tile, 32x8 threads (2 rows per thread)
+constexpr int PT_NT = PT_W * PT_TY;
 
-__global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs a,
+__global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs a,
                                                             float* __restrict__ R, size_t rstride_b)
 {
     __shared__ float sI[PT_H + 2 * PN][PT_W + 2 * PN];
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restri
     const float* Ip = I + (size_t)b * istride_b;
     const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
     const int tid = threadIdx.y * PT_W + threadIdx.x;
-    for (int i = tid; i < (PT_H + 2 * PN) * (PT_W + 2 * PN); i += PT_W * PT_H) {
+    for (int i = tid; i < (PT_H + 2 * PN) * (PT_W + 2 * PN); i += PT_NT) {
         const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
         const int x = min(max(x0 + lx - PN, 0), a.w - 1), y = min(max(y0 + ly - PN, 0), a.h - 1);
         sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restri
     const float* g = a.g + PN;
     const float* xg = a.xg + PN;
     const float* xxg = a.xxg + PN;
-    for (int i = tid; i < PT_H * (PT_W + 2 * PN); i += PT_W * PT_H) {
+    for (int i = tid; i < PT_H * (PT_W + 2 * PN); i += PT_NT) {
         const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
         const int cy = ly + PN;
         float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
@@ -277,31 +278,36 @@ __global__ void __launch_bounds__(PT_W* PT_H) k_fb_polyexp(const float* __restri
         sR[2][ly][lx] = t2;
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= a.w || y >= a.h) return;
-    const int lx = threadIdx.x + PN, ly = threadIdx.y;
-    const float* r0 = sR[0][ly];
-    const float* r1 = sR[1][ly];
-    const float* r2 = sR[2][ly];
-    double b1 = r0[lx] * g[0], b2 = 0, b3 = r1[lx] * g[0], b4 = 0, b5 = r2[lx] * g[0], b6 = 0;
-#pragma unroll
-    for (int k = 1; k <= PN; ++k) {
-        const double tg = r0[lx + k] + r0[lx - k];
-        b1 += tg * g[k];
-        b4 += tg * xxg[k];
-        b2 += (r0[lx + k] - r0[lx - k]) * xg[k];
-        b3 += (r1[lx + k] + r1[lx - k]) * g[k];
-        b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
-        b5 += (r2[lx + k] + r2[lx - k]) * g[k];
-    }
-    // R layout per level: float4 plane (channels 0..3) followed by a float plane (channel 4) -> the flow kernel's
-    // bilinear gather needs 2 loads per tap instead of 5
+    const int x = x0 + threadIdx.x;
+    if (x >= a.w) return;
+    const int lx = threadIdx.x + PN;
     const size_t npad = align_up_dev((size_t)a.w * a.h, 64);
     float* Rb = R + (size_t)b * rstride_b;
-    const size_t o = (size_t)y * a.w + x;
-    reinterpret_cast<float4*>(Rb)[o] = make_float4((float)(b3 * a.ig11), (float)(b2 * a.ig11), (float)(b1 * a.ig03 + b5 * a.ig33),
-                                                   (float)(b1 * a.ig03 + b4 * a.ig33));
-    Rb[4 * npad + o] = (float)(b6 * a.ig55);
+#pragma unroll
+    for (int rr = 0; rr < PT_H / PT_TY; ++rr) {
+        const int ly = threadIdx.y + PT_TY * rr, y = y0 + ly;
+        if (y >= a.h) break;
+        const float* r0 = sR[0][ly];
+        const float* r1 = sR[1][ly];
+        const float* r2 = sR[2][ly];
+        double b1 = r0[lx] * g[0], b2 = 0, b3 = r1[lx] * g[0], b4 = 0, b5 = r2[lx] * g[0], b6 = 0;
+#pragma unroll
+        for (int k = 1; k <= PN; ++k) {
+            const double tg = r0[lx + k] + r0[lx - k];
+            b1 += tg * g[k];
+            b4 += tg * xxg[k];
+            b2 += (r0[lx + k] - r0[lx - k]) * xg[k];
+            b3 += (r1[lx + k] + r1[lx - k]) * g[k];
+            b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
+            b5 += (r2[lx + k] + r2[lx - k]) * g[k];
+        }
+        // R layout per level: float4 plane (channels 0..3) followed by a float plane (channel 4) -> the flow kernels'
+        // bilinear gather needs 2 loads per tap instead of 5
+        const size_t o = (size_t)y * a.w + x;
+        reinterpret_cast<float4*>(Rb)[o] = make_float4((float)(b3 * a.ig11), (float)(b2 * a.ig11), (float)(b1 * a.ig03 + b5 * a.ig33),
+                                                       (float)(b1 * a.ig03 + b4 * a.ig33));
+        Rb[4 * npad + o] = (float)(b6 * a.ig55);
+    }
 }
 
 int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gray_stride_b, int batch, float* scratch_I,
@@ -335,7 +341,7 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
             std::memcpy(po.xg, plan.xg, sizeof(po.xg));
             std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
             po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
-            dim3 block(PT_W, PT_H), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
+            dim3 block(PT_W, PT_TY), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
             k_fb_polyexp<<<grid, block, 0, s>>>(scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b);
             GD_CUDA(cudaGetLastError());
         }
@@ -562,9 +568,12 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __r
 //     parallel, no shared memory, full occupancy: the dependent bilinear gathers are hidden by ~40 resident warps.
 //     Algorithmic bytes: R0 20 + R1 20 + flow 8 + M 20 = 68 B/px.
 // (b) k_fb_box_solve: 15x15 box sums of M (FP64 running sums) + 2x2 solve -> flow.  28 B/px (M 20 + flow 8).
+// MODE 0: flow of this level read from `fin`; MODE 1: first iteration of a level, flow = 2 * cv::resize(coarser flow)
+// evaluated on the fly from `fin` (pw x ph), same arithmetic as k_fb_upsample; MODE 2: coarsest level, flow = 0.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_fb_matrices(const float* __restrict__ R0, const float* __restrict__ R1, size_t rstride_b,
-                                                     const float2* __restrict__ fin, size_t fstride_b, float* __restrict__ Mout,
-                                                     size_t mstride_b, int w, int h)
+                                                     const float2* __restrict__ fin, size_t fstride_b, int pw, int ph,
+                                                     float* __restrict__ Mout, size_t mstride_b, int w, int h)
 {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -578,7 +587,32 @@ __global__ void __launch_bounds__(256) k_fb_matrices(const float* __restrict__ R
     const float* R0B = r0 + 4 * npad;
     const float* R1B = r1 + 4 * npad;
     const int o = y * w + x;
-    const float2 fl = __ldg(fin + (size_t)b * fstride_b + o);
+    float2 fl;
+    if (MODE == 0) {
+        fl = __ldg(fin + (size_t)b * fstride_b + o);
+    } else if (MODE == 1) {
+        const double scale_x = (double)pw / w, scale_y = (double)ph / h;
+        float ux = (float)((x + 0.5) * scale_x - 0.5);
+        int sx = (int)floorf(ux);
+        ux -= sx;
+        if (sx < 0) { ux = 0; sx = 0; }
+        if (sx >= pw - 1) { ux = 0; sx = pw - 1; }
+        const int sx1 = min(sx + 1, pw - 1);
+        float uy = (float)((y + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(uy);
+        uy -= sy;
+        int sy1 = sy + 1;
+        sy = max(0, min(ph - 1, sy));
+        sy1 = max(0, min(ph - 1, sy1));
+        const float2* sp = fin + (size_t)b * fstride_b;
+        const float2 q00 = __ldg(sp + sy * pw + sx), q01 = __ldg(sp + sy * pw + sx1);
+        const float2 q10 = __ldg(sp + sy1 * pw + sx), q11 = __ldg(sp + sy1 * pw + sx1);
+        const float c0 = 1.f - ux, c1 = ux, d0 = 1.f - uy, d1 = uy;
+        fl.x = ((q00.x * c0 + q01.x * c1) * d0 + (q10.x * c0 + q11.x * c1) * d1) * 2.0f;
+        fl.y = ((q00.y * c0 + q01.y * c1) * d0 + (q10.y * c0 + q11.y * c1) * d1) * 2.0f;
+    } else {
+        fl = make_float2(0.f, 0.f);
+    }
     const float4 a0 = __ldg(R0A + o);
     const float a04 = __ldg(R0B + o);
     float fx = x + fl.x, fy = y + fl.y;
@@ -620,6 +654,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// VEC: the row stride is a multiple of 4 floats -> every 16-byte chunk is either fully inside or fully outside the image;
+//      outside chunks are skipped and the replicated border columns are filled in shared memory afterwards (edge tiles only).
+template <bool VEC>
 __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __restrict__ Min, size_t mstride_b,
                                                                 float2* __restrict__ fout, size_t fstride_b, int w, int h)
 {
@@ -631,27 +668,51 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
     const float* Mb = Min + (size_t)b * mstride_b;
     const int x0 = blockIdx.x * BX_W, y0 = blockIdx.y * BX_H;
     const int tid = threadIdx.x;
-    const bool vec_ok = (w & 3) == 0;
-    // replicate-border tile of one channel plane: 16-byte async copies for chunks inside the image, clamped 4-byte
-    // copies for the few chunks that straddle the left / right image border (or when the row stride is not 16-byte aligned)
+    // the chunk geometry is the same for the five channel planes: compute it once per thread (920 chunks / 256 threads)
+    constexpr int CH = BXT_W / 4;                                       // 20 chunks per row
+    constexpr int NCHUNK = (BXH_H * CH + BX_THREADS - 1) / BX_THREADS;  // 4 per thread
+    int c_src[NCHUNK], c_dst[NCHUNK];  // element offsets in the plane / in the smem tile; c_src < 0: nothing to copy
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k) {
+        const int i = tid + k * BX_THREADS;
+        const int ly = i / CH, ch = i - ly * CH;
+        const int y = min(max(y0 + ly - FHALO, 0), h - 1);
+        const int xs = x0 - BX_LEFT + 4 * ch;
+        c_dst[k] = ly * BXM_P + 4 * ch;
+        c_src[k] = (i < BXH_H * CH && xs >= 0 && xs + 3 < w) ? y * w + xs : -1;
+    }
+    const bool edge_l = x0 == 0, edge_r = x0 + BX_W + BX_LEFT > w;  // tile reaches beyond the left / right image border
     auto load_tile = [&](int c, int buf) {
         const float* plane = Mb + (size_t)c * npad;
         float* dst = sT + buf * BXH_H * BXM_P;
-        constexpr int CH = BXT_W / 4;  // 20 chunks per row
-        for (int i = tid; i < BXH_H * CH; i += BX_THREADS) {
-            const int ly = i / CH, ch = i - ly * CH;
-            const int y = min(max(y0 + ly - FHALO, 0), h - 1);
-            const int xs = x0 - BX_LEFT + 4 * ch;
-            const float* row = plane + (size_t)y * w;
-            float* d = dst + ly * BXM_P + 4 * ch;
-            if (vec_ok && xs >= 0 && xs + 3 < w) {
-                cp_async16(d, row + xs);
-            } else {
+        if (VEC) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) cp_async4(d + e, row + min(max(xs + e, 0), w - 1));
+            for (int k = 0; k < NCHUNK; ++k)
+                if (c_src[k] >= 0) cp_async16(dst + c_dst[k], plane + c_src[k]);
+        } else {  // unaligned row stride (odd level widths): clamped scalar copies
+            for (int i = tid; i < BXH_H * BXT_W; i += BX_THREADS) {
+                const int ly = i / BXT_W, lx = i - ly * BXT_W;
+                const int x = min(max(x0 - BX_LEFT + lx, 0), w - 1), y = min(max(y0 + ly - FHALO, 0), h - 1);
+                cp_async4(dst + ly * BXM_P + lx, plane + (size_t)y * w + x);
             }
         }
         cp_async_commit();
+    };
+    // replicate the border pixel into the tile columns that lie outside the image (VEC path, edge tiles only)
+    auto fix_border = [&](int buf) {
+        float* t = sT + buf * BXH_H * BXM_P;
+        if (edge_l)
+            for (int i = tid; i < BXH_H * BX_LEFT; i += BX_THREADS) {
+                const int ly = i / BX_LEFT, lx = i - ly * BX_LEFT;
+                t[ly * BXM_P + lx] = t[ly * BXM_P + BX_LEFT];
+            }
+        if (edge_r) {
+            const int last = w - 1 - (x0 - BX_LEFT);  // tile column of the last image pixel
+            for (int i = tid; i < BXH_H * BXT_W; i += BX_THREADS) {
+                const int ly = i / BXT_W, lx = i - ly * BXT_W;
+                if (lx > last) t[ly * BXM_P + lx] = t[ly * BXM_P + last];
+            }
+        }
     };
     constexpr int NTASK = (BX_W / FT_SEG) * BXH_H;  // 184 horizontal tasks: (segment of 16 columns) x (tile row)
     const int hseg = tid / BXH_H, hrow = tid - hseg * BXH_H;
@@ -667,6 +728,10 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
             cp_async_wait<0>();
         }
         __syncthreads();
+        if (VEC && (edge_l || edge_r)) {  // block-uniform
+            fix_border(c & 1);
+            __syncthreads();
+        }
         if (tid < NTASK) {
             // window of output column j (tile-local) = tile floats [j + 1, j + 15]; the segment reads floats [16 seg, 16 seg + 32)
             const float4* m4 = reinterpret_cast<const float4*>(sT + (c & 1) * BXH_H * BXM_P + hrow * BXM_P + hseg * FT_SEG);
@@ -728,7 +793,8 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
     static bool attr_set = false;
     if (!attr_set) {
         GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
         attr_set = true;
     }
     const float2* prev = nullptr;
@@ -737,7 +803,9 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
         const FbLevel& L = plan.lv[k];
         float2* A = flowA + L.f_off;
         float2* B = flowB + L.f_off;
-        if (!prev) {
+        if (Mbuf) {
+            // split form: the first matrices launch of a level takes its flow from the coarser level (or zero) on the fly
+        } else if (!prev) {
             if (batch == 1)
                 GD_CUDA(cudaMemsetAsync(A, 0, (size_t)L.w * L.h * sizeof(float2), s));
             else
@@ -755,12 +823,20 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
                 {
                     LaunchScope ls(st, s, "K1b_matrices", 1);
                     dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), batch);
-                    k_fb_matrices<<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, f_stride_b, Mbuf, m_stride_b, L.w, L.h);
+                    if (it > 0)
+                        k_fb_matrices<0><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, f_stride_b, 0, 0, Mbuf, m_stride_b, L.w, L.h);
+                    else if (prev)
+                        k_fb_matrices<1><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, prev, f_stride_b, pw, ph, Mbuf, m_stride_b, L.w, L.h);
+                    else
+                        k_fb_matrices<2><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, nullptr, f_stride_b, 0, 0, Mbuf, m_stride_b, L.w, L.h);
                     GD_CUDA(cudaGetLastError());
                 }
                 LaunchScope ls(st, s, "K1b_box_solve", 1);
                 dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), batch);
-                k_fb_box_solve<<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
+                if ((L.w & 3) == 0)
+                    k_fb_box_solve<true><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
+                else
+                    k_fb_box_solve<false><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
                 GD_CUDA(cudaGetLastError());
             } else {
                 LaunchScope ls(st, s, "K1b_flow_iter", 1);
