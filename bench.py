@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-W, H = 640, 480
+W, H = 640, 480  # BASELINE.json headline resolution; --res WxH runs the resolution sweep of configs[4]
 N_PX = W * H
 METRIC = "GeoMaskMaker+ORB frames/sec at 640x480"
 # algorithmic (compulsory) bytes per frame of the whole pipeline, steady state = 318.5 B/px
@@ -122,7 +122,7 @@ class ClockSampler:
 def _gen_frame(args):
     stream, f = args
     synth = importlib.import_module("gd-slam_b200.synth")
-    s = synth.SyntheticStream(stream)
+    s = synth.SyntheticStream(stream, W, H)
     fr = s.frame(f)
     return stream, f, fr.bgr, fr.depth_m
 
@@ -149,59 +149,74 @@ def make_data(n_distinct, n_frames, seed0):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def _cpu_worker(args):
-    """One host process = one stream, structured like the reference: every frame recomputes both gray images, both
-    Farneback pyramids, both depth-edge maps (GeoMaskMaker.cc:158-199), then ORB on the new frame (Tracking.cc:238)."""
-    stream, n_frames = args
+_CPU = {}
+
+
+def _cpu_init(res):
+    """Worker initialiser: one host process = one stream; frames of the pair (t-5, t) are generated once."""
+    global W, H
+    W, H = res
     from oracle import pyoracle as po
 
     synth = importlib.import_module("gd-slam_b200.synth")
-    s = synth.SyntheticStream(stream)
-    K = synth.intrinsics()
-    fr = [s.frame(f) for f in range(6)]
-    R, T = s.pair_pose(0, 5)
+    po.lib()
+    s = synth.SyntheticStream(os.getpid() % 97, W, H)
+    _CPU.update(po=po, K=synth.intrinsics(W, H), a=s.frame(0), b=s.frame(5), pose=s.pair_pose(0, 5))
+
+
+def _cpu_step(n_frames):
+    """Structured like the reference: every frame recomputes both gray images, both Farneback pyramids and both depth-edge
+    maps (GeoMaskMaker.cc:158-199), then ORB on the new frame (Tracking.cc:238)."""
+    po, K, a, b, (R, T) = _CPU["po"], _CPU["K"], _CPU["a"], _CPU["b"], _CPU["pose"]
     t0 = time.perf_counter()
-    for i in range(n_frames):
-        a, b = fr[i % 1], fr[5]
+    for _ in range(n_frames):
         po.orb_extract(po.gray(b.bgr, 1))
         po.geomask_pair(a.bgr, b.bgr, a.depth_m, b.depth_m, K, R, T)
     return n_frames, time.perf_counter() - t0
 
 
-def cpu_reference_rate(frames_per_proc, procs):
-    from concurrent.futures import ProcessPoolExecutor
+class CpuReference:
+    """The reference's CPU path (oracle port) on all host cores: one worker process per core, kept alive across steps."""
 
-    from oracle import pyoracle as po
+    def __init__(self, procs=None):
+        from concurrent.futures import ProcessPoolExecutor
 
-    po.lib()
-    t0 = time.perf_counter()
-    with ProcessPoolExecutor(max_workers=procs) as ex:
-        res = list(ex.map(_cpu_worker, [(p, frames_per_proc) for p in range(procs)]))
-    wall = time.perf_counter() - t0
-    busy = max(r[1] for r in res)
-    return sum(r[0] for r in res) / busy, wall
+        self.procs = procs or (os.cpu_count() or 1)
+        self.ex = ProcessPoolExecutor(max_workers=self.procs, initializer=_cpu_init, initargs=((W, H),))
+        list(self.ex.map(_cpu_step, [0] * self.procs))  # start the workers, build their frames
+
+    def step(self, frames_per_proc):
+        res = list(self.ex.map(_cpu_step, [frames_per_proc] * self.procs))
+        return sum(r[0] for r in res) / max(r[1] for r in res)
+
+    def close(self):
+        self.ex.shutdown()
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    per_step = max(1, args.ref_frames_per_proc)
+    ref = CpuReference()
+    procs = ref.procs
+    # bounded sample: keep the whole run within ~2 minutes whatever K the driver passes (one frame takes ~0.25 s per core)
+    per_step = max(1, min(args.ref_frames_per_proc, int(120.0 / (0.3 * max(1, args.steps + args.warmup)))))
+    for _ in range(max(0, args.warmup)):
+        ref.step(per_step)
     rates = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_rate(1, procs)
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        r, _w = cpu_reference_rate(per_step, procs)
-        rates.append(r)
+        rates.append(ref.step(per_step))
     ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
+    ref.close()
     v = float(statistics.median(rates))
-    sample = f"{procs} host processes x {per_step} frames per step (640x480 pair (t-5,t) + ORB on the new frame), oracle port"
+    sample = (f"{procs} host processes x {per_step} frame(s) per step ({W}x{H} pair (t-5,t) + ORB on the new frame), oracle port "
+              "(ORB part = the reference's algorithm restated; equal to its verbatim compile on the fixtures)")
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "synthetic 640x480 RGB-D streams, full GeoMaskMaker + ORB (TUM3, ORB 1500/1.2/8/20/7)",
-                      "note": "reference's CPU path restated (oracle/): OpenCV-4.13 semantics, one process per host core"},
+           "config": {"workload": f"synthetic {W}x{H} RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7)",
+                      "note": "reference's CPU path restated (oracle/): OpenCV-4.13 semantics, one process per host core, "
+                              "reference-structured (both pyramids / edge maps recomputed per call)"},
            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -211,7 +226,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("GD_BENCH_BATCH", "32")), help="streams per GPU")
@@ -220,7 +235,18 @@ def main():
     ap.add_argument("--ref-frames-per-proc", type=int, default=3)
     ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles (host threads) the e2e leg drives per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--res", default="640x480", help="WxH of the synthetic streams (configs[4]: 1280x720, 1920x1080)")
     args = ap.parse_args()
+    global W, H, N_PX, ALGO_BYTES_PER_FRAME, METRIC
+    W, H = (int(v) for v in args.res.lower().split("x"))
+    scale_px = (W * H) / N_PX
+    N_PX = W * H
+    ALGO_BYTES_PER_FRAME = 318.5 * N_PX
+    for k in list(FAMILY_BYTES):
+        if k not in ("K4c_quadtree", "K4de_orient_describe"):
+            FAMILY_BYTES[k] *= scale_px
+    if (W, H) != (640, 480):
+        METRIC = f"GeoMaskMaker+ORB frames/sec at {W}x{H}"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -386,23 +412,25 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K_, "warmup": Wm,
            "ms_per_step": ms_total / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": "synthetic 640x480 RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7), "
+           "config": {"workload": f"synthetic {W}x{H} RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7), "
                                   "steady state (per-image products cached in the 6-deep device ring)",
                       "streams_per_gpu": B, "frames_per_step": B * world, "resident_frames_per_stream": S,
                       "l2_hygiene": "inputs larger than L2: per-step working set %.0f MB per GPU (ring of polynomial-expansion "
-                                    "pyramids + staged frames), 126 MB L2" % (B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3)),
+                                    "pyramids + staged frames), 126 MB L2" % (B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3) * N_PX / 307200),
                       "sharding": "independent streams per GPU, no collective"},
            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s * 1e3 / K_, "handles_per_gpu": NH, "streams_per_handle": Bh},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        procs = os.cpu_count() or 1
-        per = 2
-        v, wall = cpu_reference_rate(per, procs)
-        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": procs, "kind": "port",
-                               "sample": f"{procs} host processes x {per} frames of the same workload through the oracle "
-                                         f"(reference-structured: both pyramids/edge maps per call), {wall:.1f} s wall"}
+        t0 = time.perf_counter()
+        ref = CpuReference()
+        per = 3
+        v = ref.step(per)
+        ref.close()
+        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": ref.procs, "kind": "port",
+                               "sample": f"{ref.procs} host processes x {per} frames of the same workload through the oracle "
+                                         f"(reference-structured: both pyramids/edge maps per call), {time.perf_counter() - t0:.1f} s wall"}
     fe.close()
     if dist is not None:
         dist.barrier()
