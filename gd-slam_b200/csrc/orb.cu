@@ -170,7 +170,17 @@ struct FastArgs {
 // NOTE (toolchain hazard, CUDA 12.9 / sm_100a): `max(best, max(mn, -mx))` is folded by ptxas into VIMNMX3 with the
 // negation DROPPED (verified on B200 with a 20-line repro: device returns max|d| where the host returns the FAST score).
 // The dark-arc score is therefore computed as a min over the negated differences (ring - v) — no negated min/max operand.
-__device__ __forceinline__ int fast_sprime_smem(const uint8_t* p, int tp, int min_th)
+// necessary condition for S' > th: a 9-arc contains at least two of the four compass points
+__device__ __forceinline__ bool fast_quick(const uint8_t* p, int tp, int th)
+{
+    const int v = p[0];
+    const int r0 = p[3 * tp], r4 = p[3], r8 = p[-3 * tp], r12 = p[-3];
+    const int nb = (v - r0 > th) + (v - r4 > th) + (v - r8 > th) + (v - r12 > th);
+    const int nd = (r0 - v > th) + (r4 - v > th) + (r8 - v > th) + (r12 - v > th);
+    return nb >= 2 || nd >= 2;
+}
+
+__device__ __forceinline__ int fast_full(const uint8_t* p, int tp)
 {
     const int v = p[0];
     int r[16];  // ring pixels, clockwise from (0,+3)
@@ -178,10 +188,6 @@ __device__ __forceinline__ int fast_sprime_smem(const uint8_t* p, int tp, int mi
     r[4] = p[3];
     r[8] = p[-3 * tp];
     r[12] = p[-3];
-    // a 9-arc contains at least two of the four compass points
-    const int nb = (v - r[0] > min_th) + (v - r[4] > min_th) + (v - r[8] > min_th) + (v - r[12] > min_th);
-    const int nd = (r[0] - v > min_th) + (r[4] - v > min_th) + (r[8] - v > min_th) + (r[12] - v > min_th);
-    if (nb < 2 && nd < 2) return 0;
     r[1] = p[3 * tp + 1];
     r[2] = p[2 * tp + 2];
     r[3] = p[tp + 3];
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     uint8_t* tile = sm;                            // [tile_h][tile_w]
     uint8_t* sc = sm + a.tile_w * a.tile_h;        // S' (0 when <= minTh)
     __shared__ int s_warp[FAST_THREADS / 32];
+    __shared__ int s_nlist;
     const int b = blockIdx.y;
     int cell = blockIdx.x, l = 0;
     while (l + 1 < a.nlevels && cell >= a.lv[l + 1].cell_start) ++l;
@@ -258,13 +265,41 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     }
     __syncthreads();
     const int npix = iw * ih;
-    for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
-        const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
-        // first pass at iniThFAST only (like the reference's first cv::FAST call): the early-out then rejects most pixels
-        const int s = fast_sprime_smem(tile + y * tp + x, tp, a.iniTh);
-        sc[y * tp + x] = (uint8_t)(s > a.iniTh ? s : 0);
-    }
-    __syncthreads();
+    // S' pass in two phases so that the 16-point network only runs on pixels that can be corners, densely packed:
+    //   phase 1: 4-point necessary test for every pixel, survivors appended to a shared list (warp-aggregated atomics)
+    //   phase 2: the full network over the list (a warp-divergent early-out would not save anything: in textured images
+    //            nearly every warp holds a survivor)
+    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * a.tile_w * a.tile_h);
+    auto score_pass = [&](int th) {
+        if (threadIdx.x == 0) s_nlist = 0;
+        __syncthreads();
+        for (int base = 0; base < npix; base += FAST_THREADS) {
+            const int t = base + threadIdx.x;
+            int pp = 0;
+            bool qk = false;
+            if (t < npix) {
+                const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+                pp = y * tp + x;
+                qk = fast_quick(tile + pp, tp, th);
+                if (!qk) sc[pp] = 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, qk);
+            int wbase = 0;
+            if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (qk) plist[wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1))] = (unsigned short)pp;
+        }
+        __syncthreads();
+        const int nl = s_nlist;
+        for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
+            const int pp = plist[q];
+            const int sv = fast_full(tile + pp, tp);
+            sc[pp] = (uint8_t)(sv > th ? sv : 0);
+        }
+        __syncthreads();
+    };
+    // first pass at iniThFAST only, like the reference's first cv::FAST call
+    score_pass(a.iniTh);
     // NMS at iniTh: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th
     auto keep_at = [&](int t, int th) -> bool {
         const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
@@ -307,12 +342,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     }
     if (tot == 0) {  // no corner survived NMS at iniThFAST -> redo the cell at minThFAST (:812-816)
         __syncthreads();
-        for (int t = threadIdx.x; t < npix; t += FAST_THREADS) {
-            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
-            const int s2 = fast_sprime_smem(tile + y * tp + x, tp, a.minTh);
-            sc[y * tp + x] = (uint8_t)(s2 > a.minTh ? s2 : 0);
-        }
-        __syncthreads();
+        score_pass(a.minTh);
         bits = 0;
         wcount = 0;
         for (int c = 0; c < nchunk; ++c) {
@@ -885,7 +915,7 @@ int OrbCore::init(int nfeatures_, float scale_factor_, int nlevels_, int ini_th,
     GD_TRY(h_n.alloc((B + 1) * sizeof(int)));
     GD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
     GD_CUDA(cudaMemsetAsync(pyr.p, 0, pyr.bytes, stream));
-    const size_t fast_smem = (size_t)plan.tile_w * plan.tile_h * 2;
+    const size_t fast_smem = (size_t)plan.tile_w * plan.tile_h * 4;
     if (fast_smem > 48 * 1024) GD_CUDA(cudaFuncSetAttribute(k_orb_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     const size_t qs = qt_smem_bytes(plan.max_N + 8, plan.max_cells_level);
     GD_REQUIRE(qs <= 220 * 1024, "nfeatures too large for the quadtree kernel's shared memory");
@@ -939,7 +969,7 @@ int OrbCore::extract_resident()
             fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start};
         }
         dim3 grid(P.total_cells, batch);
-        k_orb_fast<<<grid, FAST_THREADS, (size_t)P.tile_w * P.tile_h * 2, stream>>>(py, P.pyr_bytes, fa, cell_cnt.as<int>(),
+        k_orb_fast<<<grid, FAST_THREADS, (size_t)P.tile_w * P.tile_h * 4, stream>>>(py, P.pyr_bytes, fa, cell_cnt.as<int>(),
                                                                                       slabs.as<ushort4>());
         GD_CUDA(cudaGetLastError());
     }
