@@ -11,6 +11,7 @@
 // memory, runs the 15x15 box sums in FP64 (like OpenCV's double vsum) and solves the 2x2 system.
 #include "farneback.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -118,7 +119,12 @@ int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int
         f_off += n;
     }
     plan->r_floats = r_off;
-    plan->i_floats = i_off;
+    plan->hrow_off = align_up(i_off, 64);
+    {
+        size_t mx = 0;
+        for (int q = 0; q < plan->nlevels; ++q) mx = std::max(mx, (size_t)plan->lv[q].w);
+        plan->i_floats = align_up(plan->hrow_off + 2 * (size_t)h * mx, 64);  // + float2 row-pass scratch [h][max level width]
+    }
     plan->f_float2 = f_off;
     plan->m_floats = 5 * align_up((size_t)plan->lv[0].w * plan->lv[0].h, 64);
     poly_constants(poly_n, poly_sigma, plan);
@@ -139,70 +145,78 @@ struct PyrArgs {
     float taps[FB_MAX_KSIZE];
 };
 
-// one thread = one level pixel: blur (rows then columns, f32) of the four full-res neighbours, then bilinear
-template <int KS>
-__global__ void __launch_bounds__(128) k_fb_pyr(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
-                                                float* __restrict__ I, size_t istride_b)
+// cv::resize source column of level column dx (and its interpolation weight)
+__device__ __forceinline__ int fb_src_col(int dx, double scale_x, int W, float* frac)
 {
-    constexpr int MAXK = KS ? KS : FB_MAX_KSIZE;
-    const int ks = KS ? KS : a.ksize;
-    const int r = ks >> 1;
-    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dy = blockIdx.y;
-    const int b = blockIdx.z;
-    if (dx >= a.lw) return;
-    const uint8_t* g = gray + (size_t)b * gstride_b;
-    // cv::resize coordinate mapping
-    float fx = (float)((dx + 0.5) * a.scale_x - 0.5);
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
     int sx = (int)floorf(fx);
     fx -= sx;
     if (sx < 0) { fx = 0; sx = 0; }
-    if (sx >= a.W - 1) { fx = 0; sx = a.W - 1; }
+    if (sx >= W - 1) { fx = 0; sx = W - 1; }
+    *frac = fx;
+    return sx;
+}
+
+// Pass A of blur+resample: the row pass of the separable Gaussian on the FULL-RES rows, evaluated only at the two source
+// columns (sx, sx+1) every level column interpolates between.  One thread = one (full-res row, level column).
+__global__ void __launch_bounds__(128) k_fb_rowblur(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
+                                                    float2* __restrict__ Hrow, size_t hstride_b)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (dx >= a.lw) return;
+    float fx;
+    const int sx = fb_src_col(dx, a.scale_x, a.W, &fx);
+    const int r = a.ksize >> 1;
+    const uint8_t* row = gray + (size_t)b * gstride_b + (size_t)y * a.W;
+    float prev = (float)__ldg(row + reflect101(sx - r, a.W));
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < a.ksize; ++i) {
+        const float nxt = (float)__ldg(row + reflect101(sx - r + i + 1, a.W));
+        acc0 = i == 0 ? a.taps[0] * prev : acc0 + a.taps[i] * prev;
+        acc1 = i == 0 ? a.taps[0] * nxt : acc1 + a.taps[i] * nxt;
+        prev = nxt;
+    }
+    Hrow[(size_t)b * hstride_b + (size_t)y * a.lw + dx] = make_float2(acc0, acc1);
+}
+
+// Pass B: column pass (symmetric form, REFLECT_101) at the two source rows of every level pixel, then cv::resize's
+// bilinear combination (horizontal first, then vertical).  Reads of Hrow are coalesced across dx.
+__global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restrict__ Hrow, size_t hstride_b, PyrArgs a,
+                                                           float* __restrict__ I, size_t istride_b)
+{
+    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
+    if (dx >= a.lw) return;
+    float fx;
+    (void)fb_src_col(dx, a.scale_x, a.W, &fx);
     float fy = (float)((dy + 0.5) * a.scale_y - 0.5);
     int sy = (int)floorf(fy);
     fy -= sy;
     int sy1 = sy + 1;
     sy = max(0, min(a.H - 1, sy));
     sy1 = max(0, min(a.H - 1, sy1));
-    // row-blurred values at columns sx, sx+1 for rows sy-r .. sy-r+ks  (ks+1 rows cover both sy and sy+1)
-    float h0[MAXK + 1], h1[MAXK + 1];
-    const int ybase = sy - r;
-    const int nrows = ks + 1;
-#pragma unroll(KS ? KS + 1 : 1)
-    for (int j = 0; j < MAXK + 1; ++j) {
-        if (j < nrows) {
-            const uint8_t* row = g + (size_t)reflect101(ybase + j, a.H) * a.W;
-            float prev = (float)__ldg(row + reflect101(sx - r, a.W));
-            float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll(KS ? KS : 1)
-            for (int i = 0; i < MAXK; ++i) {
-                if (i < ks) {
-                    const float nxt = (float)__ldg(row + reflect101(sx - r + i + 1, a.W));
-                    acc0 = i == 0 ? a.taps[0] * prev : acc0 + a.taps[i] * prev;
-                    acc1 = i == 0 ? a.taps[0] * nxt : acc1 + a.taps[i] * nxt;
-                    prev = nxt;
-                }
-            }
-            h0[j] = acc0;
-            h1[j] = acc1;
-        }
+    const int r = a.ksize >> 1;
+    const float2* hp = Hrow + (size_t)b * hstride_b + dx;
+    const float2 c0 = __ldg(hp + (size_t)sy * a.lw);
+    float B00 = a.taps[r] * c0.x, B01 = a.taps[r] * c0.y;
+#pragma unroll 4
+    for (int i = 1; i <= r; ++i) {
+        const float t = a.taps[r + i];
+        const float2 u = __ldg(hp + (size_t)reflect101(sy + i, a.H) * a.lw), d = __ldg(hp + (size_t)reflect101(sy - i, a.H) * a.lw);
+        B00 += t * (u.x + d.x);
+        B01 += t * (u.y + d.y);
     }
-    // column pass (symmetric form) centred on sy (index r) and sy1 (index r + (sy1 - sy))
-    const int c0 = r, c1 = r + (sy1 - sy);
-    float B00 = a.taps[r] * h0[c0], B01 = a.taps[r] * h1[c0];
-    float B10 = a.taps[r] * h0[c1], B11 = a.taps[r] * h1[c1];
-    // rows outside the image were fetched through reflect101(ybase + j), which equals the column-pass border rule
-    // only when the row index maps identically; handle it by re-deriving indices relative to the centre row
-#pragma unroll(KS ? KS / 2 : 1)
-    for (int i = 1; i <= MAXK / 2; ++i) {
-        if (i <= r) {
+    float B10 = B00, B11 = B01;
+    if (sy1 != sy) {
+        const float2 c1 = __ldg(hp + (size_t)sy1 * a.lw);
+        B10 = a.taps[r] * c1.x;
+        B11 = a.taps[r] * c1.y;
+#pragma unroll 4
+        for (int i = 1; i <= r; ++i) {
             const float t = a.taps[r + i];
-            B00 += t * (h0[c0 + i] + h0[c0 - i]);
-            B01 += t * (h1[c0 + i] + h1[c0 - i]);
-            // for the sy1 centre the window is rows c1-r .. c1+r; c1 + r = ks when sy1 = sy + 1
-            const int up = c1 + i, dn = c1 - i;
-            B10 += t * (h0[up] + h0[dn]);
-            B11 += t * (h1[up] + h1[dn]);
+            const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, a.H) * a.lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, a.H) * a.lw);
+            B10 += t * (u.x + d.x);
+            B11 += t * (u.y + d.y);
         }
     }
     const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
@@ -320,16 +334,17 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
         pa.scale_x = L.scale_x; pa.scale_y = L.scale_y;
         std::memcpy(pa.taps, L.taps, sizeof(pa.taps));
         {
-            LaunchScope ls(st, s, "K1a_blur_resample", 1);
+            LaunchScope ls(st, s, "K1a_blur_resample", (L.w == plan.w && L.h == plan.h && L.ksize == 3) ? 1 : 2);
             dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
             float* Ik = scratch_I + L.i_off;
             if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
                 k_fb_blur3_same<<<grid, block, 0, s>>>(gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b);
-            } else switch (L.ksize) {
-                case 3: k_fb_pyr<3><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
-                case 9: k_fb_pyr<9><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
-                case 19: k_fb_pyr<19><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
-                default: k_fb_pyr<0><<<grid, block, 0, s>>>(gray, gray_stride_b, pa, Ik, i_stride_b); break;
+            } else {
+                float2* Hrow = reinterpret_cast<float2*>(scratch_I + plan.hrow_off);
+                dim3 gridA(cdiv(L.w, 128), plan.h, batch);
+                k_fb_rowblur<<<gridA, block, 0, s>>>(gray, gray_stride_b, pa, Hrow, i_stride_b / 2);
+                GD_CUDA(cudaGetLastError());
+                k_fb_colblur_resize<<<grid, block, 0, s>>>(Hrow, i_stride_b / 2, pa, Ik, i_stride_b);
             }
             GD_CUDA(cudaGetLastError());
         }

@@ -26,7 +26,8 @@ struct FbPlan {
     int iterations = 3;
     FbLevel lv[FB_MAX_LEVELS];
     size_t r_floats = 0;   // floats of one image's whole R pyramid (5 planes per level)
-    size_t i_floats = 0;   // floats of one image's I scratch (all levels)
+    size_t i_floats = 0;   // floats of one image's I scratch (all levels) + the row-pass scratch
+    size_t hrow_off = 0;   // offset (floats) of the float2 row-pass scratch inside the I scratch
     size_t f_float2 = 0;   // float2 of one flow scratch (all levels)
     size_t m_floats = 0;   // floats of the M scratch (5 planes of the largest level)
     // FarnebackPolyExp constants
