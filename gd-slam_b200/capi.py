@@ -79,6 +79,8 @@ SYMBOLS = {
     "gd_frontend_stage": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
     "gd_frontend_step_staged": (C.c_int, [vp, C.c_int, fp, fp, ip]),
     "gd_frontend_fetch": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_frontend_fetch_filtered": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_stage_erode_filter": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "gd_frontend_sync": (C.c_int, [vp]),
     "gd_frontend_timer_begin": (C.c_int, [vp]),
     "gd_frontend_timer_end": (C.c_int, [vp, fp]),
@@ -204,6 +206,14 @@ def stage_mahalanobis(flow, d_ref, d_cur, e_ref, e_cur, K, R, T, lut=None, devic
                                      _vptr(lut), w, h, _fptr(K), _fptr(R), _fptr(T), _vptr(dist), _vptr(mask),
                                      _vptr(mm)))
     return dist, mask, mm
+
+
+def stage_erode_filter(mask, kps, device=0):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    kps = np.ascontiguousarray(kps)
+    keep = np.zeros(len(kps), np.uint8)
+    check(lib().gd_stage_erode_filter(device, _vptr(mask), mask.shape[1], mask.shape[0], _vptr(kps), len(kps), _vptr(keep)))
+    return keep
 
 
 def stage_farneback(prev, nxt, device=0):
@@ -453,6 +463,15 @@ class Frontend:
 
     def results(self):
         return [(self.masks[b], self.kps[b][: self.n_kp[b]], self.desc[b][: self.n_kp[b]]) for b in range(self.batch)]
+
+    def fetch_filtered(self):
+        """Frame ctor filter (Frame.cc:258-282) with the new mask: list of (keypoints, descriptors) per stream."""
+        B = self.batch
+        kps = [np.zeros(self.cap, KP_DTYPE) for _ in range(B)]
+        desc = [np.zeros((self.cap, 32), np.uint8) for _ in range(B)]
+        n = np.zeros(B, np.int32)
+        check(lib().gd_frontend_fetch_filtered(self._h, _ptr_array(kps), _ptr_array(desc), n.ctypes.data_as(ip)))
+        return [(kps[b][: n[b]].copy(), desc[b][: n[b]].copy()) for b in range(B)]
 
     def sync(self):
         check(lib().gd_frontend_sync(self._h))

@@ -17,6 +17,7 @@ struct gd_frontend {
     gd::DevBuf staged_bgr;    // [slots][B][n_pad*3]
     gd::DevBuf staged_depth;  // [slots][B][n_pad] f32
     gd::DevBuf l2_scratch;
+    gd::DevBuf keep, filt_kp, filt_desc, filt_n;  // Frame-ctor filter (row f-2): [B][cap] flags / records, [B] counts
     gd::PinnedBuf h_n;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool results_ready = false;
@@ -219,6 +220,58 @@ int gd_frontend_step_staged(gd_frontend_t* h, int slot, const float* R, const fl
     GD_CUDA(cudaMemcpy2DAsync(g.depth_slot_ptr(ring), g.depth_stride_b() * 4, h->staged_depth.as<float>() + (size_t)slot * B * g.n_pad,
                               g.n_pad * 4, g.n * 4, g.batch, cudaMemcpyDeviceToDevice, h->stream));
     return frontend_compute(h, h->staged_bgr.as<uint8_t>() + (size_t)slot * B * g.n_pad * 3, g.n_pad * 3, R, T, pose_valid);
+}
+
+int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp)
+{
+    GD_REQUIRE(h && n_kp, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GD_REQUIRE(h->results_ready, "no step has run yet");
+    GeoMaskCore& g = h->geo;
+    OrbCore& o = h->orb;
+    const size_t cap = (size_t)o.plan.kp_capacity, B = (size_t)g.batch;
+    if (!h->keep.p) {
+        GD_TRY(h->keep.alloc(B * cap));
+        GD_TRY(h->filt_kp.alloc(B * cap * sizeof(gd_keypoint)));
+        GD_TRY(h->filt_desc.alloc(B * cap * 32));
+        GD_TRY(h->filt_n.alloc(B * sizeof(int)));
+    }
+    GD_TRY(launch_erode_filter(g.mask.as<uint8_t>(), g.n_pad, g.w, g.h, g.batch, o.out_kp.as<gd_keypoint>(), cap, o.out_n.as<int>(), 0,
+                               h->keep.as<uint8_t>(), h->stream, &h->stats));
+    GD_TRY(launch_compact_keypoints(o.out_kp.as<gd_keypoint>(), o.out_desc.as<uint8_t>(), h->keep.as<uint8_t>(), cap, g.batch,
+                                    o.out_n.as<int>(), h->filt_kp.as<gd_keypoint>(), h->filt_desc.as<uint8_t>(), h->filt_n.as<int>(),
+                                    h->stream, &h->stats));
+    const int ucap = h->cfg.kp_capacity > 0 ? std::min(h->cfg.kp_capacity, o.plan.kp_capacity) : o.plan.kp_capacity;
+    int* hn = h->h_n.as<int>();
+    for (int b = 0; b < g.batch; ++b) {
+        if (kps && kps[b])
+            GD_CUDA(cudaMemcpyAsync(kps[b], h->filt_kp.as<gd_keypoint>() + (size_t)b * cap, sizeof(gd_keypoint) * ucap,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        if (desc && desc[b])
+            GD_CUDA(cudaMemcpyAsync(desc[b], h->filt_desc.as<uint8_t>() + (size_t)b * cap * 32, (size_t)32 * ucap, cudaMemcpyDeviceToHost,
+                                    h->stream));
+    }
+    GD_CUDA(cudaMemcpyAsync(hn, h->filt_n.p, sizeof(int) * g.batch, cudaMemcpyDeviceToHost, h->stream));
+    GD_CUDA(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < g.batch; ++b) n_kp[b] = hn[b];
+    return GD_OK;
+}
+
+int gd_stage_erode_filter(int device, const uint8_t* mask, int w, int h, const gd_keypoint* kps, int n, uint8_t* keep)
+{
+    GD_REQUIRE(mask && kps && keep && w > 0 && h > 0 && n >= 0, "bad argument");
+    GD_TRY(select_device(device));
+    if (n == 0) return GD_OK;
+    DevBuf dm, dk, dkeep;
+    GD_TRY(dm.alloc((size_t)w * h));
+    GD_TRY(dk.alloc((size_t)n * sizeof(gd_keypoint)));
+    GD_TRY(dkeep.alloc((size_t)n));
+    GD_CUDA(cudaMemcpy(dm.p, mask, (size_t)w * h, cudaMemcpyHostToDevice));
+    GD_CUDA(cudaMemcpy(dk.p, kps, (size_t)n * sizeof(gd_keypoint), cudaMemcpyHostToDevice));
+    GD_TRY(launch_erode_filter(dm.as<uint8_t>(), 0, w, h, 1, dk.as<gd_keypoint>(), (size_t)n, nullptr, n, dkeep.as<uint8_t>(), 0, nullptr));
+    GD_CUDA(cudaDeviceSynchronize());
+    GD_CUDA(cudaMemcpy(keep, dkeep.p, (size_t)n, cudaMemcpyDeviceToHost));
+    return GD_OK;
 }
 
 int gd_frontend_sync(gd_frontend_t* h)

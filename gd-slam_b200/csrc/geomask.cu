@@ -12,6 +12,8 @@
 // no tensor-core work (largest matrix on the path is 6x6).
 #include "geomask.cuh"
 
+#include <cmath>
+
 namespace gd {
 
 // ------------------------------------------------------------------------------------------------
@@ -531,6 +533,113 @@ int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStat
 {
     LaunchScope ls(st, s, "fill_u8", 1);
     k_fill_u8<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, n, v);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+}  // namespace gd
+
+// ------------------------------------------------------------------------------------------------
+// "next" row (f)-2 of SURVEY section 8: the Frame constructor's mask erosion + keypoint filter
+// (GD-SLAM src/Frame.cc:258-282): erode(mask, 31x31 MORPH_ELLIPSE) and keep keypoint i iff
+// eroded((int)pt.y, (int)pt.x) == 1.  The eroded image is only ever sampled at the keypoints, so it is evaluated there:
+// one warp per keypoint (lane = structuring-element row), then an order-preserving compaction per stream.
+// ------------------------------------------------------------------------------------------------
+namespace gd {
+
+void make_ellipse31(EllipseSE* se)
+{
+    const int r = 15, c = 15;
+    const double inv_r2 = 1.0 / ((double)r * r);
+    for (int i = 0; i < 31; ++i) {  // cv::getStructuringElement(MORPH_ELLIPSE)
+        const int dy = i - r;
+        const int dx = (int)lrint(c * sqrt((r * r - dy * dy) * inv_r2));
+        se->j1[i] = c - dx > 0 ? c - dx : 0;
+        se->j2[i] = c + dx + 1 < 31 ? c + dx + 1 : 31;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_erode_filter(const uint8_t* __restrict__ mask, size_t mstride_b, int w, int h,
+                                                      const gd_keypoint* __restrict__ kps, size_t kstride_b,
+                                                      const int* __restrict__ n_kp, int n_fixed, EllipseSE se,
+                                                      uint8_t* __restrict__ keep, size_t keep_stride_b)
+{
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n = n_kp ? n_kp[b] : n_fixed;
+    if (g >= n) return;
+    const gd_keypoint kp = kps[(size_t)b * kstride_b + g];
+    const int x = (int)kp.x, y = (int)kp.y;  // Mask_dil.at<uchar>(pt.y, pt.x): float -> int truncation
+    const uint8_t* m = mask + (size_t)b * mstride_b;
+    int mn = 255;
+    if (lane < 31) {
+        const int yy = y + lane - 15;
+        if (yy >= 0 && yy < h) {
+            const int xa = max(x + se.j1[lane] - 15, 0), xb = min(x + se.j2[lane] - 15, w);  // border: outside pixels ignored
+            for (int xx = xa; xx < xb; ++xx) mn = min(mn, (int)__ldg(m + (size_t)yy * w + xx));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) keep[(size_t)b * keep_stride_b + g] = (uint8_t)(mn == 1);
+}
+
+__global__ void __launch_bounds__(256) k_compact_keypoints(const gd_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+                                                           const uint8_t* __restrict__ keep, size_t cap, const int* __restrict__ n_kp,
+                                                           gd_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
+                                                           int* __restrict__ out_n)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.x, n = n_kp[b];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 256) {
+        const int i = base + threadIdx.x;
+        const bool k = i < n && keep[b * cap + i];
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) {
+            if (w2 < warp) woff += s_warp[w2];
+            tot += s_warp[w2];
+        }
+        if (k) {
+            const size_t o = b * cap + s_base + woff + __popc(bal & ((1u << lane) - 1));
+            out_kps[o] = kps[b * cap + i];
+            const uint4* s4 = reinterpret_cast<const uint4*>(desc + (b * cap + i) * 32);
+            uint4* d4 = reinterpret_cast<uint4*>(out_desc + o * 32);
+            d4[0] = s4[0];
+            d4[1] = s4[1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_n[b] = s_base;
+}
+
+int launch_erode_filter(const uint8_t* mask, size_t mask_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
+                        const int* n_kp, int n_fixed, uint8_t* keep, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "F2_erode_filter", 1);
+    EllipseSE se;
+    make_ellipse31(&se);
+    dim3 grid(cdiv((int)cap, 8), batch);
+    k_erode_filter<<<grid, 256, 0, s>>>(mask, mask_stride_b, w, h, kps, cap, n_kp, n_fixed, se, keep, cap);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+int launch_compact_keypoints(const gd_keypoint* kps, const uint8_t* desc, const uint8_t* keep, size_t cap, int batch,
+                             const int* n_kp, gd_keypoint* out_kps, uint8_t* out_desc, int* out_n, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "F2_compact_keypoints", 1);
+    k_compact_keypoints<<<batch, 256, 0, s>>>(kps, desc, keep, cap, n_kp, out_kps, out_desc, out_n);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

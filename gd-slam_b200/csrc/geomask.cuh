@@ -51,6 +51,17 @@ int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px
 int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
                           const unsigned int* minmax_bits, const PoseDev* poses, uint8_t* mask, size_t mask_stride_b,
                           float* dist_out, size_t dist_stride_b, cudaStream_t s, LaunchStats* st);
+// "next" row (f)-2: Frame ctor erosion + keypoint filter (src/Frame.cc:258-282)
+struct EllipseSE {
+    int j1[31], j2[31];  // [j1, j2) columns of each row of cv::getStructuringElement(MORPH_ELLIPSE, 31x31)
+};
+void make_ellipse31(EllipseSE* se);
+// keep[b][i] = eroded(mask_b)((int)kp.y, (int)kp.x) == 1 for the first n_kp[b] (or n_fixed) keypoints of every stream
+int launch_erode_filter(const uint8_t* mask, size_t mask_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
+                        const int* n_kp, int n_fixed, uint8_t* keep, cudaStream_t s, LaunchStats* st);
+// order-preserving compaction of the kept keypoints + descriptors
+int launch_compact_keypoints(const gd_keypoint* kps, const uint8_t* desc, const uint8_t* keep, size_t cap, int batch,
+                             const int* n_kp, gd_keypoint* out_kps, uint8_t* out_desc, int* out_n, cudaStream_t s, LaunchStats* st);
 // all-ones mask (warm-up path)
 int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st);
 

@@ -161,6 +161,10 @@ GD_API int gd_frontend_stage(gd_frontend_t* h, int slot, const uint8_t* const* b
 GD_API int gd_frontend_step_staged(gd_frontend_t* h, int slot, const float* R, const float* T, const int* pose_valid);
 GD_API int gd_frontend_fetch(gd_frontend_t* h, uint8_t* const* mask_out, size_t mask_step, gd_keypoint* const* kps,
                       uint8_t* const* desc, int* n_kp);
+/* SURVEY section 8 row (f)-2, the step right after both kernels — Frame::Frame's mask erosion + keypoint filter
+ * (src/Frame.cc:258-282) for the second Frame() of GrabImageRGBD_GD (src/Tracking.cc:252): erode(new mask, 31x31 ellipse),
+ * keep keypoint i iff eroded((int)pt.y,(int)pt.x) == 1, order preserved.  Uses the mask and keypoints of the last step. */
+GD_API int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp);
 GD_API int gd_frontend_sync(gd_frontend_t* h);
 /* CUDA-event timing on the handle's own stream: begin records an event, end records + synchronises and returns ms */
 GD_API int gd_frontend_timer_begin(gd_frontend_t* h);
@@ -187,6 +191,8 @@ GD_API int gd_stage_farneback(int device, const uint8_t* prev, const uint8_t* ne
 /* polynomial expansion of pyramid level k: out = 5 planes (lh*lw each) in OpenCV channel order */
 GD_API int gd_stage_polyexp(int device, const uint8_t* gray, int w, int h, int k, float* out, int* lw, int* lh);
 
+/* keep flags of the Frame-ctor filter (src/Frame.cc:258-282) for n keypoints against an 8UC1 mask (w x h, dense rows) */
+GD_API int gd_stage_erode_filter(int device, const uint8_t* mask, int w, int h, const gd_keypoint* kps, int n, uint8_t* keep);
 /* ORB pyramid (ComputePyramid, ORBextractor.cc:1107-1132): `out` receives the levels tightly packed one after another,
  * level_sizes = nlevels x (w, h) */
 GD_API int gd_stage_orb_pyramid(int device, const uint8_t* gray, int w, int h, int nlevels, float scale, uint8_t* out,

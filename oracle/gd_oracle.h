@@ -58,6 +58,11 @@ void gdo_mahalanobis(const float* flow /*w*h*2*/, const float* depth_ref, const 
  * d8 (optional) receives the 8-bit normalised image; minmax (optional) receives {min,max}. */
 void gdo_normalize_threshold(const float* dist, int w, int h, uint8_t* mask, uint8_t* d8, float* minmax);
 
+/* "next" row (f)-2, Frame ctor (src/Frame.cc:258-282): erode(mask, 31x31 ellipse) and the keypoint filter */
+void gdo_ellipse31(int* j1, int* j2);
+void gdo_erode31(const uint8_t* mask, int w, int h, uint8_t* out);
+int gdo_erode_filter(const uint8_t* mask, int w, int h, const float* kps, int n, uint8_t* keep);
+
 /* depth2std (GeoMaskMaker.cc:1386-1391) */
 float gdo_depth2std(float depth, float fu);
 

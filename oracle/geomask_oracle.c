@@ -335,3 +335,63 @@ void gdo_normalize_threshold(const float* dist, int w, int h, uint8_t* mask, uin
         mask[i] = (uint8_t)(r < 20 ? 1 : 0); /* (dist<20)/255  :405-406 */
     }
 }
+
+/* ---- "next" row (f)-2: Frame ctor mask erosion + keypoint filter (src/Frame.cc:258-282) ----------------
+ * cv::getStructuringElement(MORPH_ELLIPSE, 31x31, anchor (15,15)) + cv::erode with the default border (pixels outside
+ * the image do not take part in the minimum), then keep keypoint i iff eroded((int)pt.y, (int)pt.x) == 1. */
+void gdo_ellipse31(int* j1, int* j2)
+{
+    const int r = 15, c = 15;
+    const double inv_r2 = 1.0 / ((double)r * r);
+    for (int i = 0; i < 31; ++i) {
+        const int dy = i - r;
+        const int dx = (int)lrint(c * sqrt((r * r - dy * dy) * inv_r2));
+        j1[i] = c - dx > 0 ? c - dx : 0;
+        j2[i] = c + dx + 1 < 31 ? c + dx + 1 : 31; /* exclusive */
+    }
+}
+
+void gdo_erode31(const uint8_t* mask, int w, int h, uint8_t* out)
+{
+    int j1[31], j2[31];
+    gdo_ellipse31(j1, j2);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int mn = 255;
+            for (int i = 0; i < 31; ++i) {
+                const int yy = y + i - 15;
+                if (yy < 0 || yy >= h) continue;
+                for (int j = j1[i]; j < j2[i]; ++j) {
+                    const int xx = x + j - 15;
+                    if (xx < 0 || xx >= w) continue;
+                    const int v = mask[(size_t)yy * w + xx];
+                    if (v < mn) mn = v;
+                }
+            }
+            out[(size_t)y * w + x] = (uint8_t)mn;
+        }
+}
+
+/* kps: n records of 7 x 4 bytes (x, y, size, angle, response, octave, class_id); keep: n flags */
+int gdo_erode_filter(const uint8_t* mask, int w, int h, const float* kps, int n, uint8_t* keep)
+{
+    int j1[31], j2[31], kept = 0;
+    gdo_ellipse31(j1, j2);
+    for (int k = 0; k < n; ++k) {
+        const int x = (int)kps[7 * k], y = (int)kps[7 * k + 1];
+        int mn = 255;
+        for (int i = 0; i < 31; ++i) {
+            const int yy = y + i - 15;
+            if (yy < 0 || yy >= h) continue;
+            for (int j = j1[i]; j < j2[i]; ++j) {
+                const int xx = x + j - 15;
+                if (xx < 0 || xx >= w) continue;
+                const int v = mask[(size_t)yy * w + xx];
+                if (v < mn) mn = v;
+            }
+        }
+        keep[k] = (uint8_t)(mn == 1);
+        kept += keep[k];
+    }
+    return kept;
+}

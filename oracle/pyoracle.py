@@ -267,3 +267,26 @@ def orbref_extract(gray, nfeatures=1500, scale=1.2, nlevels=8, ini_th=20, min_th
         _REF.orbref_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return _extract(_REF.orbref_extract, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, False)
+
+
+# ---------------------------------------------------------------------------------------------- Frame ctor filter (8f-2)
+def erode31(mask):
+    mask = _c(mask, np.uint8)
+    out = np.empty_like(mask)
+    L = lib()
+    L.gdo_erode31.argtypes = [u8p, C.c_int, C.c_int, u8p]
+    L.gdo_erode31(mask.reshape(-1), mask.shape[1], mask.shape[0], out.reshape(-1))
+    return out
+
+
+def erode_filter(mask, kps):
+    """keep flags of Frame.cc:267-277 for keypoints given as KP_DTYPE records."""
+    mask = _c(mask, np.uint8)
+    kps = np.ascontiguousarray(kps)
+    keep = np.zeros(len(kps), np.uint8)
+    L = lib()
+    L.gdo_erode_filter.argtypes = [u8p, C.c_int, C.c_int, C.c_void_p, C.c_int, u8p]
+    L.gdo_erode_filter.restype = C.c_int
+    n = L.gdo_erode_filter(mask.reshape(-1), mask.shape[1], mask.shape[0], kps.ctypes.data, len(kps), keep)
+    assert n == int(keep.sum())
+    return keep

@@ -224,7 +224,41 @@ def make_farneback():
     print("farneback: absmax", out["flow_640_absmax"], "150x100 median", np.median(out["flow_150"][..., 0]))
 
 
+def make_erode():
+    """Frame ctor filter (src/Frame.cc:258-282): cv2.erode with the 31x31 ellipse on a real mask of the pipeline, and the
+    keep flags of the reference's loop on the reference ORB keypoints of the newest frame."""
+    from oracle import pyoracle as po
+
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = synth.intrinsics()
+    R, T = s.pair_pose(0, 5)
+    g0 = cv2.cvtColor(f0.bgr, cv2.COLOR_BGR2GRAY)
+    g5 = cv2.cvtColor(f5.bgr, cv2.COLOR_BGR2GRAY)
+    flow = cv2.calcOpticalFlowFarneback(g0, g5, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    e0, e5 = literal_get_edge_fast(f0.depth_m, K, po), literal_get_edge_fast(f5.depth_m, K, po)
+    dist, _, _ = po.mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T)
+    n = cv2.normalize(dist, None, 0.0, 255.0, cv2.NORM_MINMAX)
+    mask = (np.clip(np.rint(n), 0, 255).astype(np.uint8) < 20).astype(np.uint8)
+    kernel = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (31, 31), (15, 15))
+    er = cv2.erode(mask, kernel)
+    kp, _, _ = po.orbref_extract(cv2.cvtColor(f5.bgr, cv2.COLOR_RGB2GRAY)) if po.have_ref() else po.orb_extract(
+        cv2.cvtColor(f5.bgr, cv2.COLOR_RGB2GRAY))
+    keep = np.array([er[int(k["y"]), int(k["x"])] == 1 for k in kp], np.uint8)
+    np.savez_compressed(os.path.join(HERE, "erode.npz"), mask=np.packbits(mask), eroded=np.packbits(er), kp=kp, keep=keep,
+                        se_rows=np.array([(int(np.nonzero(r)[0].min()), int(np.nonzero(r)[0].max()) + 1) for r in kernel], np.int32))
+    print("erode: static", mask.mean(), "eroded", er.mean(), "kept", int(keep.sum()), "of", len(kp))
+
+
+def literal_get_edge_fast(depth, K, po):
+    return po.depth_edge(depth, K)  # pinned bit-exact against literal_get_edge by geomask_small.npz
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "erode":
+        make_erode()
+        sys.exit(0)
     make_geomask_small()
     make_farneback()
+    make_erode()
     print("cv2", cv2.__version__)

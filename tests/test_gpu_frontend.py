@@ -111,3 +111,33 @@ def test_frontend_1280x720_pair(capi, oracle, synth):
     rkp, rdesc, _ = oracle.orb_extract(oracle.gray(fr[5].bgr, 1))
     _same_kp(kp, desc, rkp, rdesc)
     fe.close()
+
+
+def test_erode_filter_stage_and_frontend(capi, oracle, synth, golden):
+    """Row (f)-2 (Frame.cc:258-282): keep flags bit-exact vs the cv2.erode golden; filtered keypoints of the front-end."""
+    g = golden("erode.npz")
+    mask = np.unpackbits(g["mask"])[: 480 * 640].reshape(480, 640)
+    assert np.array_equal(capi.stage_erode_filter(mask, g["kp"]), g["keep"])
+    # keypoints near the image border exercise the "outside pixels are ignored" rule
+    kp = np.zeros(6, capi.KP_DTYPE)
+    kp["x"] = [0.9, 639.2, 3.0, 320.5, 630.0, 19.99]
+    kp["y"] = [0.1, 479.9, 470.0, 2.0, 5.0, 19.99]
+    assert np.array_equal(capi.stage_erode_filter(mask, kp), oracle.erode_filter(mask, kp))
+    K = synth.intrinsics()
+    s = synth.SyntheticStream(0)
+    fr = [s.frame(f) for f in range(6)]
+    fe = capi.Frontend(K, 640, 480, batch=2)
+    for f in range(6):
+        R, T = s.pair_pose(max(f - 5, 0), f)
+        res = fe.step([fr[f].bgr, fr[f].bgr], [fr[f].depth_m, fr[f].depth_m], np.stack([R, R]), np.stack([T, T]))
+    filt = fe.fetch_filtered()
+    for b in range(2):
+        m, kps, desc = res[b]
+        keep = oracle.erode_filter(np.ascontiguousarray(m), kps).astype(bool)
+        assert 0 < keep.sum() < len(kps)
+        fk, fd = filt[b]
+        assert len(fk) == keep.sum()
+        for name in kps.dtype.names:
+            assert np.array_equal(fk[name], kps[name][keep]), name
+        assert np.array_equal(fd, desc[keep])
+    fe.close()

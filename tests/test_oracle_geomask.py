@@ -64,3 +64,14 @@ def test_scatter_last_raster_writer_wins(oracle):
     dist2, _, src2 = oracle.mahalanobis(f2, d0, d1, e, e, K, R, T)
     assert src2[5, 11] == 5 * w + 10
     assert dist2[5, 11] != dist[5, 11]
+
+
+def test_erode_filter_vs_cv2_golden(oracle, golden):
+    """Row (f)-2: erode(mask, 31x31 ellipse) + keypoint filter of Frame.cc:258-282 against cv2.erode."""
+    g = golden("erode.npz")
+    mask = np.unpackbits(g["mask"])[: 480 * 640].reshape(480, 640)
+    er = np.unpackbits(g["eroded"])[: 480 * 640].reshape(480, 640)
+    assert np.array_equal(oracle.erode31(mask), er)
+    keep = oracle.erode_filter(mask, g["kp"])
+    assert np.array_equal(keep, g["keep"])
+    assert 0 < keep.sum() < len(keep)
