@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgdslam_cuda.so")
 
 GD_OK, GD_EINVAL, GD_ENODEVICE, GD_ECUDA, GD_ENOMEM, GD_ECAPACITY = 0, -1, -2, -3, -4, -5
-DBG_FLOW, DBG_DIST, DBG_EDGE_REF, DBG_EDGE_CUR, DBG_GRAY_CUR, DBG_MINMAX = range(6)
+DBG_FLOW, DBG_DIST, DBG_EDGE_REF, DBG_EDGE_CUR, DBG_GRAY_CUR, DBG_MINMAX, DBG_LUT = range(7)
 
 
 class GdError(RuntimeError):
@@ -282,7 +282,8 @@ class GeoMask:
     def debug(self, what, stream=0):
         shapes = {DBG_FLOW: ((self.h, self.w, 2), np.float32), DBG_DIST: ((self.h, self.w), np.float32),
                   DBG_EDGE_REF: ((self.h, self.w), np.uint8), DBG_EDGE_CUR: ((self.h, self.w), np.uint8),
-                  DBG_GRAY_CUR: ((self.h, self.w), np.uint8), DBG_MINMAX: ((2,), np.float32)}
+                  DBG_GRAY_CUR: ((self.h, self.w), np.uint8), DBG_MINMAX: ((2,), np.float32),
+                  DBG_LUT: ((self.h, self.w, 2), np.float32)}
         shp, dt = shapes[what]
         out = np.empty(shp, dt)
         check(lib().gd_geomask_debug_fetch(self._h, what, stream, _vptr(out), out.nbytes))

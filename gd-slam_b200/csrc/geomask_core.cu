@@ -171,6 +171,11 @@ int GeoMaskCore::debug_fetch(int what, int b, void* dst, size_t dst_bytes)
             bytes = n;
             break;
         }
+        case GD_DBG_LUT:
+            GD_REQUIRE(has_lut, "no LUT: the distortion coefficients are zero (identity path)");
+            src = lut.p;
+            bytes = n * sizeof(float2);
+            break;
         case GD_DBG_GRAY_CUR:
             src = gray.as<uint8_t>() + (size_t)b * n_pad;
             bytes = n;

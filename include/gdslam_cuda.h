@@ -109,7 +109,8 @@ enum gd_debug_what {
     GD_DBG_EDGE_REF = 2, /* u8   H*W   GetEdge(_firstDepth)                   */
     GD_DBG_EDGE_CUR = 3, /* u8   H*W   GetEdge(_secondDepth)                  */
     GD_DBG_GRAY_CUR = 4, /* u8   H*W   BGR2GRAY of the newest frame           */
-    GD_DBG_MINMAX = 5    /* f32  2     min, max of dist_image                 */
+    GD_DBG_MINMAX = 5,   /* f32  2     min, max of dist_image                 */
+    GD_DBG_LUT = 6       /* f32  H*W*2 undistortedPoint LUT of the ctor (GeoMaskMaker.cc:56-69); error when D == 0 */
 };
 GD_API int gd_geomask_debug_fetch(gd_geomask_t* h, int what, int stream, void* dst, size_t dst_bytes);
 

@@ -250,6 +250,17 @@ def make_erode():
     print("erode: static", mask.mean(), "eroded", er.mean(), "kept", int(keep.sum()), "of", len(kp))
 
 
+def make_undistort():
+    """undistorted-pixel LUT of the GeoMaskMaker ctor (GeoMaskMaker.cc:56-69) for TUM1.yaml's distortion."""
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    D = np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)
+    w, h = 640, 480
+    pts = np.stack(np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32)), -1).reshape(-1, 1, 2)
+    u = cv2.undistortPoints(pts, K, D, None, K).reshape(h, w, 2)
+    np.savez_compressed(os.path.join(HERE, "undistort_tum1.npz"), K=K, D=D, lut_rows16=u[::16].copy(),
+                        lut_sum=np.float64(u.astype(np.float64).sum()))
+
+
 def literal_get_edge_fast(depth, K, po):
     return po.depth_edge(depth, K)  # pinned bit-exact against literal_get_edge by geomask_small.npz
 
@@ -261,4 +272,5 @@ if __name__ == "__main__":
     make_geomask_small()
     make_farneback()
     make_erode()
+    make_undistort()
     print("cv2", cv2.__version__)

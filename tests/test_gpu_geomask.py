@@ -165,3 +165,26 @@ def test_geomask_handle_warmup_pair_and_batch(capi, oracle, synth):
     masks = gm.get_no_gmm_mask(R, T, pose_valid=[0, 1])
     assert masks[0].min() == 1 and (masks[1] == 0).any()
     gm.close()
+
+
+def test_distorted_camera_lut_and_mask(capi, oracle, synth, golden):
+    """TUM1-style distortion: the ctor's undistorted-pixel LUT (GeoMaskMaker.cc:56-69) is bit-exact vs cv2.undistortPoints,
+    and the loop indexes depth / edges through it exactly like :219-228."""
+    g = golden("undistort_tum1.npz")
+    K, D = g["K"], g["D"]
+    gm = capi.GeoMask(K, D, 5000.0, 640, 480, 0, batch=1)
+    s = synth.SyntheticStream(0)
+    frames = [s.frame(f) for f in range(6)]
+    for fr in frames:
+        gm.add_new_image([fr.bgr], [fr.depth_m])
+    R, T = s.pair_pose(0, 5)
+    mask = gm.get_no_gmm_mask(R[None], T[None])[0]
+    lut = gm.debug(capi.DBG_LUT)
+    assert np.array_equal(lut[::16], g["lut_rows16"])
+    assert abs(float(lut.astype(np.float64).sum()) - float(g["lut_sum"])) < 1e-3
+    flow = gm.debug(capi.DBG_FLOW)
+    e0, e5 = oracle.depth_edge(frames[0].depth_m, K), oracle.depth_edge(frames[5].depth_m, K)
+    dist_o, _, _ = oracle.mahalanobis(flow, frames[0].depth_m, frames[5].depth_m, e0, e5, K, R, T, lut=lut)
+    assert np.array_equal(gm.debug(capi.DBG_DIST), dist_o)
+    assert np.array_equal(mask, oracle.normalize_threshold(dist_o)[0])
+    gm.close()
