@@ -76,6 +76,8 @@ SYMBOLS = {
     "gd_frontend_destroy": (None, [vp]),
     "gd_frontend_step": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t, fp, fp, ip,
                                    C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_frontend_step_u16": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t, fp, fp, ip,
+                                       C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
     "gd_frontend_stage": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
     "gd_frontend_step_staged": (C.c_int, [vp, C.c_int, fp, fp, ip]),
     "gd_frontend_fetch": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
@@ -446,6 +448,17 @@ class Frontend:
                                      self._mask_ptrs if fetch else None, self.w, self._kp_ptrs if fetch else None,
                                      self._desc_ptrs if fetch else None, self.n_kp.ctypes.data_as(ip)))
         return self.results() if fetch else None
+
+    def step_u16(self, bgr, depth_u16, R=None, T=None, pose_valid=None):
+        """Same as step() with the raw 16-bit TUM depth (row f-4: converted on the device like Tracking.cc:234-235)."""
+        B = self.batch
+        R, T, pv = self._pose(R, T, pose_valid, B)
+        bp = _ptr_array([np.ascontiguousarray(bgr[b], np.uint8) for b in range(B)])
+        dl = [np.ascontiguousarray(depth_u16[b], np.uint16) for b in range(B)]
+        check(lib().gd_frontend_step_u16(self._h, bp, self.w * 3, _ptr_array(dl), self.w * 2, _fptr(R), _fptr(T),
+                                         pv.ctypes.data_as(ip), self._mask_ptrs, self.w, self._kp_ptrs, self._desc_ptrs,
+                                         self.n_kp.ctypes.data_as(ip)))
+        return self.results()
 
     def stage(self, slot, bgr, depth):
         B = self.batch

@@ -17,6 +17,7 @@ struct gd_frontend {
     gd::DevBuf staged_bgr;    // [slots][B][n_pad*3]
     gd::DevBuf staged_depth;  // [slots][B][n_pad] f32
     gd::DevBuf l2_scratch;
+    gd::DevBuf raw_depth;  // [B][n_pad] u16 staging of gd_frontend_step_u16
     gd::DevBuf keep, filt_kp, filt_desc, filt_n;  // Frame-ctor filter (row f-2): [B][cap] flags / records, [B] counts
     gd::PinnedBuf h_n;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -190,6 +191,31 @@ int gd_frontend_step(gd_frontend_t* h, const uint8_t* const* bgr, size_t bgr_ste
     GeoMaskCore& g = h->geo;
     const int slot = g.cur_slot();
     GD_TRY(upload_frames(h, g.bgr.as<uint8_t>(), g.depth_slot_ptr(slot), g.depth_stride_b(), bgr, bgr_step, depth_m, depth_step));
+    GD_TRY(frontend_compute(h, g.bgr.as<uint8_t>(), g.n_pad * 3, R, T, pose_valid));
+    return gd_frontend_fetch(h, mask_out, mask_step, kps, desc, n_kp);
+}
+
+int gd_frontend_step_u16(gd_frontend_t* h, const uint8_t* const* bgr, size_t bgr_step, const uint16_t* const* depth_raw,
+                         size_t depth_step, const float* R, const float* T, const int* pose_valid, uint8_t* const* mask_out,
+                         size_t mask_step, gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp)
+{
+    GD_REQUIRE(h && bgr && depth_raw, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GeoMaskCore& g = h->geo;
+    GD_REQUIRE(bgr_step >= (size_t)g.w * 3 && depth_step >= (size_t)g.w * 2, "step smaller than a row");
+    GD_REQUIRE(h->cfg.depth_factor != 0.f, "depth_factor is zero");
+    if (!h->raw_depth.p) GD_TRY(h->raw_depth.alloc((size_t)g.batch * g.n_pad * sizeof(uint16_t)));
+    const int slot = g.cur_slot();
+    for (int b = 0; b < g.batch; ++b) {
+        GD_REQUIRE(bgr[b] && depth_raw[b], "null image pointer");
+        GD_CUDA(cudaMemcpy2DAsync(g.bgr.as<uint8_t>() + (size_t)b * g.n_pad * 3, (size_t)g.w * 3, bgr[b], bgr_step, (size_t)g.w * 3, g.h,
+                                  cudaMemcpyHostToDevice, h->stream));
+        GD_CUDA(cudaMemcpy2DAsync(h->raw_depth.as<uint16_t>() + (size_t)b * g.n_pad, (size_t)g.w * 2, depth_raw[b], depth_step,
+                                  (size_t)g.w * 2, g.h, cudaMemcpyHostToDevice, h->stream));
+    }
+    const float inv_factor = 1.0f / h->cfg.depth_factor;  // mDepthMapFactor = 1.0f/mDepthMapFactor, Tracking.cc:130-134
+    GD_TRY(launch_depth_u16_to_m(h->raw_depth.as<uint16_t>(), g.n_pad, g.depth_slot_ptr(slot), g.depth_stride_b(), g.n, g.batch,
+                                 inv_factor, h->stream, &h->stats));
     GD_TRY(frontend_compute(h, g.bgr.as<uint8_t>(), g.n_pad * 3, R, T, pose_valid));
     return gd_frontend_fetch(h, mask_out, mask_step, kps, desc, n_kp);
 }

@@ -623,6 +623,31 @@ __global__ void __launch_bounds__(256) k_compact_keypoints(const gd_keypoint* __
     if (threadIdx.x == 0) out_n[b] = s_base;
 }
 
+__global__ void __launch_bounds__(256) k_depth_u16_to_m(const uint16_t* __restrict__ raw, size_t rstride_b, float* __restrict__ depth,
+                                                        size_t dstride_b, size_t n, float inv_factor)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const uint16_t* r = raw + (size_t)blockIdx.y * rstride_b;
+    float* d = depth + (size_t)blockIdx.y * dstride_b;
+    if (i + 4 <= n && (rstride_b & 3) == 0 && (dstride_b & 3) == 0) {
+        const ushort4 v = *reinterpret_cast<const ushort4*>(r + i);
+        *reinterpret_cast<float4*>(d + i) = make_float4((float)v.x * inv_factor, (float)v.y * inv_factor, (float)v.z * inv_factor,
+                                                        (float)v.w * inv_factor);
+    } else {
+        for (size_t k = i; k < n && k < i + 4; ++k) d[k] = (float)r[k] * inv_factor;
+    }
+}
+
+int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth, size_t depth_stride_b, size_t n, int batch,
+                          float inv_factor, cudaStream_t s, LaunchStats* st)
+{
+    LaunchScope ls(st, s, "F4_depth_u16_to_m", 1);
+    dim3 grid((unsigned)((n / 4 + 255) / 256 + 1), batch);
+    k_depth_u16_to_m<<<grid, 256, 0, s>>>(raw, raw_stride_b, depth, depth_stride_b, n, inv_factor);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 int launch_erode_filter(const uint8_t* mask, size_t mask_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
                         const int* n_kp, int n_fixed, uint8_t* keep, cudaStream_t s, LaunchStats* st)
 {

@@ -62,6 +62,9 @@ int launch_erode_filter(const uint8_t* mask, size_t mask_stride_b, int w, int h,
 // order-preserving compaction of the kept keypoints + descriptors
 int launch_compact_keypoints(const gd_keypoint* kps, const uint8_t* desc, const uint8_t* keep, size_t cap, int batch,
                              const int* n_kp, gd_keypoint* out_kps, uint8_t* out_desc, int* out_n, cudaStream_t s, LaunchStats* st);
+// "next" row (f)-4: raw 16-bit depth -> metres, (float)v * inv_factor (Tracking.cc:234-235)
+int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth, size_t depth_stride_b, size_t n, int batch,
+                          float inv_factor, cudaStream_t s, LaunchStats* st);
 // all-ones mask (warm-up path)
 int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st);
 

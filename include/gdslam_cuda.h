@@ -155,6 +155,13 @@ GD_API int gd_frontend_step(gd_frontend_t* h, const uint8_t* const* bgr, size_t 
                      size_t depth_step, const float* R, const float* T, const int* pose_valid,
                      uint8_t* const* mask_out, size_t mask_step, gd_keypoint* const* kps, uint8_t* const* desc,
                      int* n_kp);
+/* SURVEY section 8 row (f)-4, depth ingest: same as gd_frontend_step but the depth arrives as the raw 16-bit TUM image
+ * and is converted on the device exactly like Tracking.cc:234-235 (imDepth.convertTo(CV_32F, 1/DepthMapFactor)):
+ * metres = (float)v * (1.0f / depth_factor).  Halves the depth H2D bytes. */
+GD_API int gd_frontend_step_u16(gd_frontend_t* h, const uint8_t* const* bgr, size_t bgr_step, const uint16_t* const* depth_raw,
+                                size_t depth_step, const float* R, const float* T, const int* pose_valid,
+                                uint8_t* const* mask_out, size_t mask_step, gd_keypoint* const* kps, uint8_t* const* desc,
+                                int* n_kp);
 /* device-resident variant: upload frames into slot `slot` once, then step from HBM (no PCIe in the step);
  * results stay on the device until gd_frontend_fetch. */
 GD_API int gd_frontend_stage(gd_frontend_t* h, int slot, const uint8_t* const* bgr, size_t bgr_step,

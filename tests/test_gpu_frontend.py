@@ -141,3 +141,20 @@ def test_erode_filter_stage_and_frontend(capi, oracle, synth, golden):
             assert np.array_equal(fk[name], kps[name][keep]), name
         assert np.array_equal(fd, desc[keep])
     fe.close()
+
+
+def test_step_u16_depth_ingest_equals_float_path(capi, synth):
+    """Row (f)-4: raw 16-bit depth converted on the device == (float)v * (1/5000.f) done by Tracking.cc:234-235."""
+    K = synth.intrinsics()
+    s = synth.SyntheticStream(2)
+    fr = [s.frame(f) for f in range(6)]
+    a = capi.Frontend(K, 640, 480, batch=1)
+    b = capi.Frontend(K, 640, 480, batch=1)
+    for f in range(6):
+        R, T = s.pair_pose(max(f - 5, 0), f)
+        ra = a.step([fr[f].bgr], [fr[f].depth_m], R[None], T[None])[0]
+        rb = b.step_u16([fr[f].bgr], [fr[f].depth_u16], R[None], T[None])[0]
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2])
+    assert np.array_equal(a.debug(capi.DBG_DIST), b.debug(capi.DBG_DIST)) and (ra[0] == 0).any()
+    a.close()
+    b.close()
