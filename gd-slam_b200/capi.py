@@ -83,6 +83,7 @@ SYMBOLS = {
     "gd_frontend_fetch": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.POINTER(vp), ip]),
     "gd_frontend_fetch_filtered": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), ip]),
     "gd_stage_erode_filter": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
+    "gd_frontend_fetch_stereo_grid": (C.c_int, [vp, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "gd_frontend_sync": (C.c_int, [vp]),
     "gd_frontend_timer_begin": (C.c_int, [vp]),
     "gd_frontend_timer_end": (C.c_int, [vp, fp]),
@@ -474,6 +475,16 @@ class Frontend:
         check(lib().gd_frontend_fetch(self._h, self._mask_ptrs, self.w, self._kp_ptrs, self._desc_ptrs,
                                       self.n_kp.ctypes.data_as(ip)))
         return self.results()
+
+    def fetch_stereo_grid(self, bf):
+        """Row f-3 for the filtered keypoints: list of (mvDepth, mvuRight, cell_start[3073], cell_items) per stream."""
+        B = self.batch
+        d = [np.zeros(self.cap, np.float32) for _ in range(B)]
+        ur = [np.zeros(self.cap, np.float32) for _ in range(B)]
+        cs = [np.zeros(64 * 48 + 1, np.int32) for _ in range(B)]
+        ci = [np.zeros(self.cap, np.int32) for _ in range(B)]
+        check(lib().gd_frontend_fetch_stereo_grid(self._h, bf, _ptr_array(d), _ptr_array(ur), _ptr_array(cs), _ptr_array(ci)))
+        return [(d[b], ur[b], cs[b], ci[b][: cs[b][-1]].copy()) for b in range(B)]
 
     def results(self):
         return [(self.masks[b], self.kps[b][: self.n_kp[b]], self.desc[b][: self.n_kp[b]]) for b in range(self.batch)]

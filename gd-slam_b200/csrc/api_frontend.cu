@@ -18,6 +18,8 @@ struct gd_frontend {
     gd::DevBuf staged_depth;  // [slots][B][n_pad] f32
     gd::DevBuf l2_scratch;
     gd::DevBuf raw_depth;  // [B][n_pad] u16 staging of gd_frontend_step_u16
+    gd::DevBuf sg_depth, sg_uright, sg_start, sg_items;  // row f-3 outputs
+    bool filtered_ready = false;
     gd::DevBuf keep, filt_kp, filt_desc, filt_n;  // Frame-ctor filter (row f-2): [B][cap] flags / records, [B] counts
     gd::PinnedBuf h_n;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -46,6 +48,7 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
     GD_TRY(g.push_resident(true));          // AddNewImage                          (Tracking.cc:242)
     GD_TRY(g.compute_mask(R, T, pose_valid));  // GetNoGMMmask                       (Tracking.cc:245)
     h->results_ready = true;
+    h->filtered_ready = false;
     return GD_OK;
 }
 
@@ -280,6 +283,42 @@ int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_
     GD_CUDA(cudaMemcpyAsync(hn, h->filt_n.p, sizeof(int) * g.batch, cudaMemcpyDeviceToHost, h->stream));
     GD_CUDA(cudaStreamSynchronize(h->stream));
     for (int b = 0; b < g.batch; ++b) n_kp[b] = hn[b];
+    h->filtered_ready = true;
+    return GD_OK;
+}
+
+int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* depth, float* const* uright, int* const* cell_start,
+                                  int* const* cell_items)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_TRY(select_device(h->cfg.device));
+    GD_REQUIRE(h->filtered_ready, "call gd_frontend_fetch_filtered first");
+    GeoMaskCore& g = h->geo;
+    OrbCore& o = h->orb;
+    const size_t cap = (size_t)o.plan.kp_capacity, B = (size_t)g.batch;
+    const int ncell = 64 * 48 + 1;
+    if (!h->sg_depth.p) {
+        GD_TRY(h->sg_depth.alloc(B * cap * sizeof(float)));
+        GD_TRY(h->sg_uright.alloc(B * cap * sizeof(float)));
+        GD_TRY(h->sg_start.alloc(B * ncell * sizeof(int)));
+        GD_TRY(h->sg_items.alloc(B * cap * sizeof(int)));
+    }
+    const int cur = (g.frames - 1) % GD_RING;  // depth image of the newest frame
+    GD_TRY(launch_stereo_grid(g.depth_slot_ptr(cur), g.depth_stride_b(), g.w, g.h, g.batch, h->filt_kp.as<gd_keypoint>(), cap,
+                              h->filt_n.as<int>(), bf, h->sg_depth.as<float>(), h->sg_uright.as<float>(), h->sg_start.as<int>(),
+                              h->sg_items.as<int>(), h->stream, &h->stats));
+    const int ucap = h->cfg.kp_capacity > 0 ? std::min(h->cfg.kp_capacity, o.plan.kp_capacity) : o.plan.kp_capacity;
+    for (int b = 0; b < g.batch; ++b) {
+        if (depth && depth[b])
+            GD_CUDA(cudaMemcpyAsync(depth[b], h->sg_depth.as<float>() + (size_t)b * cap, sizeof(float) * ucap, cudaMemcpyDeviceToHost, h->stream));
+        if (uright && uright[b])
+            GD_CUDA(cudaMemcpyAsync(uright[b], h->sg_uright.as<float>() + (size_t)b * cap, sizeof(float) * ucap, cudaMemcpyDeviceToHost, h->stream));
+        if (cell_start && cell_start[b])
+            GD_CUDA(cudaMemcpyAsync(cell_start[b], h->sg_start.as<int>() + (size_t)b * ncell, sizeof(int) * ncell, cudaMemcpyDeviceToHost, h->stream));
+        if (cell_items && cell_items[b])
+            GD_CUDA(cudaMemcpyAsync(cell_items[b], h->sg_items.as<int>() + (size_t)b * cap, sizeof(int) * ucap, cudaMemcpyDeviceToHost, h->stream));
+    }
+    GD_CUDA(cudaStreamSynchronize(h->stream));
     return GD_OK;
 }
 

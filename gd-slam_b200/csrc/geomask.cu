@@ -648,6 +648,82 @@ int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth
     return GD_OK;
 }
 
+constexpr int SG_MAX = 4096;     // keypoints per stream the grid kernel sorts in shared memory
+constexpr int SG_CELLS = 64 * 48;
+
+__global__ void __launch_bounds__(512) k_stereo_grid(const float* __restrict__ depth, size_t dstride_b, int w, int h,
+                                                     const gd_keypoint* __restrict__ kps, size_t cap, const int* __restrict__ n_kp,
+                                                     float bf, float* __restrict__ depth_out, float* __restrict__ uright,
+                                                     int* __restrict__ cell_start, int* __restrict__ cell_items)
+{
+    __shared__ unsigned keys[SG_MAX];  // (cell << 12 | index), 0xFFFFFFFF = not in the grid / padding
+    const int b = blockIdx.x, n = min(n_kp[b], SG_MAX);
+    const float inv_w = 64.f / (float)w, inv_h = 48.f / (float)h;  // mfGridElementWidthInv / HeightInv for bounds = image
+    const float* dp = depth + (size_t)b * dstride_b;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        unsigned key = 0xFFFFFFFFu;
+        if (i < n) {
+            const gd_keypoint kp = kps[(size_t)b * cap + i];
+            const float d = dp[(size_t)(int)kp.y * w + (int)kp.x];
+            float dv = -1.f, ur = -1.f;
+            if (d > 0.f) {
+                dv = d;
+                ur = kp.x - bf / d;
+            }
+            depth_out[(size_t)b * cap + i] = dv;
+            uright[(size_t)b * cap + i] = ur;
+            const int px = (int)roundf((kp.x - 0.f) * inv_w), py = (int)roundf((kp.y - 0.f) * inv_h);
+            if (px >= 0 && px < 64 && py >= 0 && py < 48) key = ((unsigned)(px * 48 + py) << 12) | (unsigned)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1)  // bitonic sort: (cell, index) ascending = mGrid push_back order
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned a = keys[i], c = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) {
+                        keys[i] = c;
+                        keys[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    int* cs = cell_start + (size_t)b * (SG_CELLS + 1);
+    int* ci = cell_items + (size_t)b * cap;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const unsigned key = keys[i];
+        if (key != 0xFFFFFFFFu) ci[i] = (int)(key & 0xFFFu);
+        // cell_start[c] = first sorted position whose cell >= c
+        const int cell = key == 0xFFFFFFFFu ? SG_CELLS : (int)(key >> 12);
+        const int prev = i == 0 ? -1 : (keys[i - 1] == 0xFFFFFFFFu ? SG_CELLS : (int)(keys[i - 1] >> 12));
+        for (int c = prev + 1; c <= cell; ++c) cs[c] = i;
+    }
+    if (threadIdx.x == 0) {
+        const int last = npad == 0 ? -1 : (keys[npad - 1] == 0xFFFFFFFFu ? SG_CELLS : (int)(keys[npad - 1] >> 12));
+        int total = 0;
+        for (int i = 0; i < npad; ++i) total += keys[i] != 0xFFFFFFFFu;  // n <= 4096: trivial
+        for (int c = last + 1; c <= SG_CELLS; ++c) cs[c] = total;
+    }
+}
+
+int launch_stereo_grid(const float* depth, size_t depth_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
+                       const int* n_kp, float bf, float* depth_out, float* uright, int* cell_start, int* cell_items,
+                       cudaStream_t s, LaunchStats* st)
+{
+    GD_REQUIRE(cap <= (size_t)SG_MAX, "keypoint capacity above 4096 is not supported by the grid kernel");
+    LaunchScope ls(st, s, "F3_stereo_grid", 1);
+    k_stereo_grid<<<batch, 512, 0, s>>>(depth, depth_stride_b, w, h, kps, cap, n_kp, bf, depth_out, uright, cell_start, cell_items);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 int launch_erode_filter(const uint8_t* mask, size_t mask_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
                         const int* n_kp, int n_fixed, uint8_t* keep, cudaStream_t s, LaunchStats* st)
 {

@@ -65,6 +65,10 @@ int launch_compact_keypoints(const gd_keypoint* kps, const uint8_t* desc, const 
 // "next" row (f)-4: raw 16-bit depth -> metres, (float)v * inv_factor (Tracking.cc:234-235)
 int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth, size_t depth_stride_b, size_t n, int batch,
                           float inv_factor, cudaStream_t s, LaunchStats* st);
+// "next" row (f)-3: ComputeStereoFromRGBD + AssignFeaturesToGrid (Frame.cc:815-837, 402-417, 553-565), one CTA per stream
+int launch_stereo_grid(const float* depth, size_t depth_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
+                       const int* n_kp, float bf, float* depth_out, float* uright, int* cell_start, int* cell_items,
+                       cudaStream_t s, LaunchStats* st);
 // all-ones mask (warm-up path)
 int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st);
 

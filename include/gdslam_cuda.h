@@ -173,6 +173,13 @@ GD_API int gd_frontend_fetch(gd_frontend_t* h, uint8_t* const* mask_out, size_t 
  * (src/Frame.cc:258-282) for the second Frame() of GrabImageRGBD_GD (src/Tracking.cc:252): erode(new mask, 31x31 ellipse),
  * keep keypoint i iff eroded((int)pt.y,(int)pt.x) == 1, order preserved.  Uses the mask and keypoints of the last step. */
 GD_API int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp);
+/* SURVEY section 8 row (f)-3 — Frame::ComputeStereoFromRGBD (src/Frame.cc:815-837) and AssignFeaturesToGrid / PosInGrid
+ * (:402-417, :553-565) for the FILTERED keypoints of the last gd_frontend_fetch_filtered call, undistorted camera
+ * (TUM3: mvKeysUn == mvKeys, image bounds = image).  depth[b][i] / uright[b][i]: mvDepth / mvuRight (-1 when d <= 0), bf =
+ * Camera.bf.  Grid: cell = col * 48 + row (mGrid[col][row]); cell_start[b] has 64*48+1 entries, cell_items[b] lists the
+ * keypoint indices of each cell in increasing order.  All output arrays must hold kp_capacity entries. */
+GD_API int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* depth, float* const* uright,
+                                         int* const* cell_start, int* const* cell_items);
 GD_API int gd_frontend_sync(gd_frontend_t* h);
 /* CUDA-event timing on the handle's own stream: begin records an event, end records + synchronises and returns ms */
 GD_API int gd_frontend_timer_begin(gd_frontend_t* h);

@@ -395,3 +395,34 @@ int gdo_erode_filter(const uint8_t* mask, int w, int h, const float* kps, int n,
     }
     return kept;
 }
+
+/* ---- "next" row (f)-3: Frame::ComputeStereoFromRGBD (src/Frame.cc:815-837) + AssignFeaturesToGrid / PosInGrid
+ * (:402-417, :553-565) for an undistorted camera (TUM3: mvKeysUn == mvKeys, bounds = image, ComputeImageBounds :603-634).
+ * cell = col * 48 + row (mGrid[col][row]); cell_start has 64*48+1 entries; items are keypoint indices in increasing order. */
+void gdo_stereo_grid(const float* depth_m, int w, int h, const float* kps, int n, float bf, float* depth_out, float* uright,
+                     int* cell_start, int* cell_items)
+{
+    enum { COLS = 64, ROWS = 48 };
+    const float inv_w = (float)COLS / (float)(w - 0), inv_h = (float)ROWS / (float)(h - 0);
+    int* cell = (int*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
+    for (int i = 0; i < n; ++i) {
+        const float u = kps[7 * i], v = kps[7 * i + 1];
+        const float d = depth_m[(size_t)(int)v * w + (int)u]; /* imDepth.at<float>(v,u): float -> int truncation */
+        depth_out[i] = -1.f;
+        uright[i] = -1.f;
+        if (d > 0) {
+            depth_out[i] = d;
+            uright[i] = u - bf / d;
+        }
+        const int px = (int)roundf((u - 0.f) * inv_w), py = (int)roundf((v - 0.f) * inv_h);
+        cell[i] = (px < 0 || px >= COLS || py < 0 || py >= ROWS) ? -1 : px * ROWS + py;
+    }
+    int pos = 0;
+    for (int c = 0; c < COLS * ROWS; ++c) {
+        cell_start[c] = pos;
+        for (int i = 0; i < n; ++i)
+            if (cell[i] == c) cell_items[pos++] = i;
+    }
+    cell_start[COLS * ROWS] = pos;
+    free(cell);
+}

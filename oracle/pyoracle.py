@@ -290,3 +290,18 @@ def erode_filter(mask, kps):
     n = L.gdo_erode_filter(mask.reshape(-1), mask.shape[1], mask.shape[0], kps.ctypes.data, len(kps), keep)
     assert n == int(keep.sum())
     return keep
+
+
+def stereo_grid(depth_m, kps, bf):
+    """Frame::ComputeStereoFromRGBD + AssignFeaturesToGrid for D = 0: (depth, uright, cell_start[3073], cell_items)."""
+    depth_m = _c(depth_m, np.float32)
+    kps = np.ascontiguousarray(kps)
+    n = len(kps)
+    d = np.empty(n, np.float32)
+    ur = np.empty(n, np.float32)
+    cs = np.empty(64 * 48 + 1, np.int32)
+    ci = np.empty(max(n, 1), np.int32)
+    L = lib()
+    L.gdo_stereo_grid.argtypes = [f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, f32p, f32p, i32p, i32p]
+    L.gdo_stereo_grid(depth_m.reshape(-1), depth_m.shape[1], depth_m.shape[0], kps.ctypes.data, n, bf, d, ur, cs, ci)
+    return d, ur, cs, ci[: cs[-1]].copy()

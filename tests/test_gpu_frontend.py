@@ -158,3 +158,26 @@ def test_step_u16_depth_ingest_equals_float_path(capi, synth):
     assert np.array_equal(a.debug(capi.DBG_DIST), b.debug(capi.DBG_DIST)) and (ra[0] == 0).any()
     a.close()
     b.close()
+
+
+def test_stereo_from_rgbd_and_grid(capi, oracle, synth):
+    """Row (f)-3: mvDepth / mvuRight (Frame.cc:815-837) and the 64x48 feature grid (:402-417, :553-565) of the filtered keypoints."""
+    K = synth.intrinsics()
+    s = synth.SyntheticStream(1)
+    fr = [s.frame(f) for f in range(6)]
+    fe = capi.Frontend(K, 640, 480, batch=2)
+    for f in range(6):
+        R, T = s.pair_pose(max(f - 5, 0), f)
+        fe.step([fr[f].bgr, fr[5 - f].bgr], [fr[f].depth_m, fr[5 - f].depth_m], np.stack([R, R]), np.stack([T, T]))
+    filt = fe.fetch_filtered()
+    bf = 40.0
+    sg = fe.fetch_stereo_grid(bf)
+    for b, depth in enumerate((fr[5].depth_m, fr[0].depth_m)):
+        kp = filt[b][0]
+        d, ur, cs, ci = oracle.stereo_grid(depth, kp, bf)
+        gd_, gur, gcs, gci = sg[b]
+        n = len(kp)
+        assert np.array_equal(gd_[:n], d) and np.array_equal(gur[:n], ur)
+        assert np.array_equal(gcs, cs) and np.array_equal(gci, ci)
+        assert cs[-1] == n and n > 0  # every keypoint of an undistorted camera falls inside the grid
+    fe.close()
