@@ -4,6 +4,10 @@
 #include "geomask_core.cuh"
 #include "orb.cuh"
 
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
 namespace gd {
 int orb_fetch_results(OrbCore& c, gd_keypoint* const* kps, uint8_t* const* desc, int capacity, int* n_out);
 }
@@ -24,11 +28,21 @@ struct gd_frontend {
     gd::PinnedBuf h_n;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool results_ready = false;
+    // CUDA graphs of the per-frame device work, one per (ring phase, input buffer): the launch sequence of a step is
+    // static, so small batches (launch bound: 51 launches per frame) replay a graph instead of re-issuing every launch
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+    };
+    std::map<std::tuple<int, const void*, size_t>, GraphEntry> graphs;
+    bool use_graphs = false;
     ~gd_frontend()
     {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         // cores do not own the shared stream
+        for (auto& kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -36,17 +50,68 @@ struct gd_frontend {
 using namespace gd;
 
 // per-frame device work once the new frame sits in geo.bgr and in the depth ring slot
-static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b, const float* R, const float* T,
-                            const int* pose_valid)
+static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b)
 {
     GeoMaskCore& g = h->geo;
     OrbCore& o = h->orb;
     // K0: both grays in one pass over the BGR bytes (BGR2GRAY for the flow, cfg.orb_gray_order for ORB level 0)
     GD_TRY(launch_gray(bgr_dev, (size_t)g.w * 3, bgr_stride_b, g.w, g.h, g.batch, g.gray.as<uint8_t>(), g.n_pad, o.level0(0),
                        h->cfg.orb_gray_order, (size_t)o.plan.lv[0].pitch, o.plan.pyr_bytes, h->stream, &h->stats));
+    // (launch_gray above and everything below is what a graph replays)
     GD_TRY(o.extract_resident());           // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
     GD_TRY(g.push_resident(true));          // AddNewImage                          (Tracking.cc:242)
-    GD_TRY(g.compute_mask(R, T, pose_valid));  // GetNoGMMmask                       (Tracking.cc:245)
+    GD_TRY(g.enqueue_mask());               // GetNoGMMmask                          (Tracking.cc:245)
+    h->results_ready = true;
+    h->filtered_ready = false;
+    return GD_OK;
+}
+
+static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b, const float* R, const float* T,
+                            const int* pose_valid)
+{
+    GeoMaskCore& g = h->geo;
+    g.prepare_poses(R, T, pose_valid, g.frames + 1);  // the frame of this step is pushed before the mask is evaluated
+    // graphs only in steady state (every code path has run un-captured at least once: lazy attribute setup, ring full)
+    // and never while the per-family event profile is on (events + synchronisation inside the launch scopes)
+    if (!h->use_graphs || h->stats.profiling || g.frames < 2 * GD_RING) return frontend_enqueue(h, bgr_dev, bgr_stride_b);
+    const auto key = std::make_tuple(g.frames % GD_RING, (const void*)bgr_dev, bgr_stride_b);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        const int frames0 = g.frames;
+        const long long l0 = h->stats.launches;
+        cudaGraph_t graph = nullptr;
+        GD_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = frontend_enqueue(h, bgr_dev, bgr_stride_b);
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != GD_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->use_graphs = false;  // fall back to plain launches for good
+            g.frames = frames0;
+            h->stats.launches = l0;
+            return frontend_enqueue(h, bgr_dev, bgr_stride_b);
+        }
+        gd_frontend::GraphEntry e;
+        e.launches = h->stats.launches - l0;
+        const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            h->use_graphs = false;
+            g.frames = frames0;
+            h->stats.launches = l0;
+            return frontend_enqueue(h, bgr_dev, bgr_stride_b);
+        }
+        h->stats.launches = l0;  // the capture issued nothing; the replay below is what runs
+        g.frames = frames0;
+        it = h->graphs.emplace(key, e).first;
+    }
+    GD_CUDA(cudaGraphLaunch(it->second.exec, h->stream));
+    h->stats.launches += it->second.launches;
+    // host-side state the enqueue path advances
+    g.frames += 1;
+    g.last_cur_slot = (g.frames - 1) % GD_RING;
+    g.last_ref_slot = (g.frames - GD_RING) % GD_RING;
     h->results_ready = true;
     h->filtered_ready = false;
     return GD_OK;
@@ -79,6 +144,10 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
             if ((r = h->staged_depth.alloc(S * B * h->geo.n_pad * sizeof(float))) != GD_OK) break;
         }
         if ((r = h->h_n.alloc(sizeof(int) * (size_t)(cfg->batch + 1))) != GD_OK) break;
+        {  // graphs pay off when a step is launch bound (small batches); GD_GRAPHS=0/1 overrides
+            const char* e = std::getenv("GD_GRAPHS");
+            h->use_graphs = e ? std::atoi(e) != 0 : cfg->batch <= 8;
+        }
         if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
             set_error("cudaEventCreate failed");
             r = GD_ECUDA;

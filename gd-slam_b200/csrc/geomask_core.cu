@@ -116,13 +116,27 @@ int GeoMaskCore::push_resident(bool gray_done)
 
 int GeoMaskCore::compute_mask(const float* Rm, const float* Tm, const int* pose_valid)
 {
-    const bool started = frames >= GD_RING;  // start_flag, GeoMaskMaker.cc:419-428
+    prepare_poses(Rm, Tm, pose_valid, frames);
+    return enqueue_mask();
+}
+
+// host half: pose blocks into the pinned staging buffer (read by the H2D copy enqueue_mask() issues, possibly from a graph)
+void GeoMaskCore::prepare_poses(const float* Rm, const float* Tm, const int* pose_valid, int frames_pushed)
+{
+    const bool started = frames_pushed >= GD_RING;  // start_flag, GeoMaskMaker.cc:419-428
     PoseDev* hp = h_poses.as<PoseDev>();
     for (int b = 0; b < batch; ++b) {
         const int valid = started && (!pose_valid || pose_valid[b]) ? 1 : 0;
         static const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
         make_pose(K, Rm ? Rm + 9 * b : I3, Tm ? Tm + 3 * b : Z3, valid, hp + b);
     }
+}
+
+// device half: everything GetNoGMMmask enqueues on the stream (capturable into a CUDA graph)
+int GeoMaskCore::enqueue_mask()
+{
+    const bool started = frames >= GD_RING;
+    PoseDev* hp = h_poses.as<PoseDev>();
     GD_CUDA(cudaMemcpyAsync(poses.p, hp, sizeof(PoseDev) * batch, cudaMemcpyHostToDevice, stream));
     if (!started) {  // warm-up: all-ones mask (:171-175)
         GD_TRY(launch_fill_u8(mask.as<uint8_t>(), (size_t)batch * n_pad, 1, stream, stats));

@@ -51,6 +51,9 @@ struct GeoMaskCore {
     int cur_slot() const { return frames % GD_RING; }  // slot the NEXT push writes
     // GetNoGMMmask for all streams; result stays in this->mask.  R: [B][9], T: [B][3], valid: [B] (host)
     int compute_mask(const float* R, const float* T, const int* pose_valid);
+    // host half; frames_pushed = number of frames pushed when the mask will be evaluated
+    void prepare_poses(const float* R, const float* T, const int* pose_valid, int frames_pushed);
+    int enqueue_mask();                                                         // device half (graph capturable)
     int debug_fetch(int what, int stream_idx, void* dst, size_t dst_bytes);
     ~GeoMaskCore();
 };

@@ -181,3 +181,27 @@ def test_stereo_from_rgbd_and_grid(capi, oracle, synth):
         assert np.array_equal(gcs, cs) and np.array_equal(gci, ci)
         assert cs[-1] == n and n > 0  # every keypoint of an undistorted camera falls inside the grid
     fe.close()
+
+
+def test_cuda_graph_replay_equals_plain_launches(capi, synth, monkeypatch):
+    """Small batches replay a CUDA graph of the per-frame launch sequence after two ring cycles: identical results."""
+    K = synth.intrinsics(320, 240)
+    s = synth.SyntheticStream(3, 320, 240)
+    fr = [s.frame(f) for f in range(8)]
+    monkeypatch.setenv("GD_GRAPHS", "0")
+    plain = capi.Frontend(K, 320, 240, batch=1, nfeatures=600, nlevels=6)
+    monkeypatch.setenv("GD_GRAPHS", "1")
+    graph = capi.Frontend(K, 320, 240, batch=1, nfeatures=600, nlevels=6)
+    for i in range(22):  # graphs start at frame 12; 6 ring phases are captured, then replayed
+        f = fr[i % 8]
+        R, T = s.pair_pose(0, 5)
+        a = plain.step([f.bgr], [f.depth_m], R[None], T[None])[0]
+        b = graph.step([f.bgr], [f.depth_m], R[None], T[None])[0]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), i
+        if i >= 5:
+            assert np.array_equal(plain.debug(capi.DBG_DIST), graph.debug(capi.DBG_DIST))
+    assert graph.launch_count() == plain.launch_count()
+    fa, fb = plain.fetch_filtered(), graph.fetch_filtered()
+    assert np.array_equal(fa[0][0], fb[0][0])
+    plain.close()
+    graph.close()
