@@ -302,25 +302,34 @@ __global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ 
     const PoseDev* __restrict__ P = poses + b;
     if (!P->valid) return;
     const size_t i = (size_t)y * w + x;
+    // everything that depends only on the source pixel is requested before the flow arrives (one dependent round less)
     const float2 f = __ldg(flow + (size_t)b * fstride_b + i);
+    float rx = (float)x, ry = (float)y;
+    if (lut) {
+        const float2 a = __ldg(lut + i);
+        rx = a.x; ry = a.y;
+    }
+    const int rix = (int)rx, riy = (int)ry;
+    const bool ref_in = rix >= 0 && riy >= 0 && rix < w && riy < h;
+    const size_t ri = ref_in ? (size_t)riy * w + rix : 0;
+    const float ref_depth = __ldg(depth_ref + (size_t)b * dstride_b + ri);
+    const uint8_t ref_edge = __ldg(edge_ref + (size_t)b * estride_b + ri);
     const float cur_x = (float)x + f.x;
     const float cur_y = (float)y + f.y;
     if (!(cur_x == cur_x) || !(cur_y == cur_y)) return;
     if (cur_x < 0 || cur_y < 0 || cur_x > (float)(w - 1) || cur_y > (float)(h - 1)) return;
     const int icx = (int)cur_x, icy = (int)cur_y;
-    float rx, ry, cx, cy;
+    float cx = (float)icx, cy = (float)icy;
     if (lut) {
-        const float2 a = __ldg(lut + i), c = __ldg(lut + (size_t)icy * w + icx);
-        rx = a.x; ry = a.y; cx = c.x; cy = c.y;
-    } else {
-        rx = (float)x; ry = (float)y; cx = (float)icx; cy = (float)icy;
+        const float2 c = __ldg(lut + (size_t)icy * w + icx);
+        cx = c.x; cy = c.y;
     }
-    const int rix = (int)rx, riy = (int)ry, cix = (int)cx, ciy = (int)cy;
-    if (rix < 0 || riy < 0 || rix >= w || riy >= h || cix < 0 || ciy < 0 || cix >= w || ciy >= h) return;
-    const size_t ri = (size_t)riy * w + rix, ci = (size_t)ciy * w + cix;
-    const float ref_depth = __ldg(depth_ref + (size_t)b * dstride_b + ri);
+    const int cix = (int)cx, ciy = (int)cy;
+    if (!ref_in || cix < 0 || ciy < 0 || cix >= w || ciy >= h) return;
+    const size_t ci = (size_t)ciy * w + cix;
     const float cur_depth = __ldg(depth_cur + (size_t)b * dstride_b + ci);
-    if (__ldg(edge_ref + (size_t)b * estride_b + ri) == 255 || __ldg(edge_cur + (size_t)b * estride_b + ci) == 255) return;
+    const uint8_t cur_edge = __ldg(edge_cur + (size_t)b * estride_b + ci);
+    if (ref_edge == 255 || cur_edge == 255) return;
     if (cur_depth == 0.f || (double)cur_depth > 3.5 || ref_depth == 0.f || (double)ref_depth > 3.5) return;
 
     const float fu = cam.fu, fv = cam.fv, cu = cam.cu;
@@ -345,19 +354,26 @@ __global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ 
     J[1][3] = -P->R[3] * ref_depth / fu; J[1][4] = -P->R[4] * ref_depth / fv; J[1][5] = -U1;
     J[2][0] = 0.f;                 J[2][1] = 0.f;               J[2][2] = 1.0f;
     J[2][3] = -P->R[6] * ref_depth / fu; J[2][4] = -P->R[7] * ref_depth / fv; J[2][5] = -U2;
+    // (J S) J^T like cv::gemm: f32 operands, f64 accumulator, k ascending.  The product of two f32 is exact in f64, so
+    // fma(a, b, s) rounds exactly like s + a * b; terms with a structural zero of J add +-0 to a sum that is never -0
+    // and are skipped (J(0,1) = J(1,0) = J(2,0) = J(2,1) = 0).  Bit-identical to the dense loop, 38 DFMA instead of 108 ops.
     float Cm[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        float JS[6];
+        double JS[6];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) JS[c] = J[r][c];
-        JS[2] = J[r][2] * s2;
-        JS[5] = J[r][5] * s5;
+        for (int c = 0; c < 6; ++c) JS[c] = (double)J[r][c];
+        JS[2] = (double)(J[r][2] * s2);
+        JS[5] = (double)(J[r][5] * s5);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s += (double)JS[k] * (double)J[c][k];
+            for (int k = 0; k < 6; ++k) {
+                const bool zr = (k == 1 && r != 1) || (k == 0 && r != 0);
+                const bool zc = (k == 1 && c != 1) || (k == 0 && c != 0);
+                if (!zr && !zc) s = fma(JS[k], (double)J[c][k], s);
+            }
             Cm[3 * r + c] = (float)s;
         }
     }
@@ -366,16 +382,14 @@ __global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ 
     float q[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        double s = 0.0;
-        s += (double)e0 * (double)Ci[c];
-        s += (double)e1 * (double)Ci[3 + c];
-        s += (double)e2 * (double)Ci[6 + c];
+        double s = fma((double)e0, (double)Ci[c], 0.0);  // exact products: fma == multiply then add
+        s = fma((double)e1, (double)Ci[3 + c], s);
+        s = fma((double)e2, (double)Ci[6 + c], s);
         q[c] = (float)s;
     }
-    double l = 0.0;
-    l += (double)q[0] * (double)e0;
-    l += (double)q[1] * (double)e1;
-    l += (double)q[2] * (double)e2;
+    double l = fma((double)q[0], (double)e0, 0.0);
+    l = fma((double)q[1], (double)e1, l);
+    l = fma((double)q[2], (double)e2, l);
     float value = sqrtf((float)l);
     value = value + 0.0f;  // -0 -> +0 so that the bit pattern orders like the value
     const unsigned long long key = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned long long)__float_as_uint(value);

@@ -123,6 +123,8 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
     p->cand_total = cand;
     p->kept_total = kept;
     GD_REQUIRE(p->max_N + 8 < 30000 && p->tile_w * p->tile_h * 2 < 200 * 1024, "plan exceeds kernel limits");
+    GD_REQUIRE((long long)(p->tile_w * p->tile_h + 8 * 64) * std::max(p->tile_w, p->tile_h) < (1ll << 20),
+               "FAST tile too large for the reciprocal-multiply index split");
     return GD_OK;
 }
 
@@ -257,9 +259,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         if (threadIdx.x == 0) *cnt_out = 0;
         return;
     }
+    // t / d for t * d < 2^20 (tiles are <= ~45 x 45): multiply by ceil-ish reciprocal, exact in that range
+    const unsigned inv_cw = (1u << 20) / (unsigned)cw + 1u, inv_iw = (1u << 20) / (unsigned)iw + 1u;
     const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off;
     for (int t = threadIdx.x; t < cw * ch; t += FAST_THREADS) {
-        const int y = t / cw, x = t - y * cw;
+        const int y = (int)(((unsigned)t * inv_cw) >> 20), x = t - y * cw;
         tile[y * tp + x] = __ldg(img + (size_t)(y0 + y) * L.pitch + x0 + x);
         sc[y * tp + x] = 0;
     }
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
             int pp = 0;
             bool qk = false;
             if (t < npix) {
-                const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+                const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
                 pp = y * tp + x;
                 qk = fast_quick(tile + pp, tp, th);
                 if (!qk) sc[pp] = 0;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     score_pass(a.iniTh);
     // NMS at iniTh: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th
     auto keep_at = [&](int t, int th) -> bool {
-        const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+        const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
         const uint8_t* q = sc + y * tp + x;
         const int s = q[0];
         if (s <= th) return false;
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         const int my = pos + __popc(bal & ((1u << lane) - 1));
         if (k && my < a.cell_cap) {
             const int t = warp * R + c * 32 + lane;
-            const int y = t / iw + 3, x = t - (y - 3) * iw + 3;
+            const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
             slab[my] = make_ushort4((unsigned short)(x + j * L.wCell), (unsigned short)(y + i * L.hCell),
                                     (unsigned short)(sc[y * tp + x] - 1), 0);
         }
@@ -715,7 +719,11 @@ struct BlurArgs {
     int nlevels, total_tiles;
     BlurLevelDev lv[ORB_MAX_LEVELS];
 };
-constexpr int BT_W = 64, BT_H = 16;
+// One warp blurs a 120 x 32 block: lane i owns the 4-pixel group at x0 - 4 + 4 i (lanes 0 and 31 only supply halo words),
+// marches down 32 + 6 rows with the 7-row window of horizontal sums in registers.  Horizontal pass on packed 16-bit
+// pairs (sums <= 255 * 256 fit a lane), vertical pass in 32 bit, one rounding at the end: the integer arithmetic is
+// order independent, so the result equals the row-then-column cv::GaussianBlur fixed-point path bit for bit.
+constexpr int BT_W = 120, BT_H = 32;
 
 __device__ __forceinline__ int reflect101i(int p, int len)
 {
@@ -726,35 +734,67 @@ __device__ __forceinline__ int reflect101i(int p, int len)
 __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ out, size_t stride_b,
                                                   BlurArgs a)
 {
-    __shared__ uint8_t s_in[BT_H + 6][BT_W + 8];
-    __shared__ unsigned short s_h[BT_H + 6][BT_W];
-    int t = blockIdx.x, l = 0;
+    const int lane = threadIdx.x & 31;
+    int t = blockIdx.x * 8 + (threadIdx.x >> 5), l = 0;
+    if (t >= a.total_tiles) return;  // warp-uniform
     while (l + 1 < a.nlevels && t >= a.lv[l + 1].tile_start) ++l;
     const BlurLevelDev& L = a.lv[l];
     t -= L.tile_start;
     const int ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
-    const int x0 = tx * BT_W, y0 = ty * BT_H;
+    const int w = L.w, h = L.h, pitch = L.pitch;
+    const int x = tx * BT_W - 4 + 4 * lane, y0 = ty * BT_H;
     const uint8_t* img = pyr + (size_t)blockIdx.y * stride_b + L.off;
     uint8_t* dst = out + (size_t)blockIdx.y * stride_b + L.off;
-    for (int i = threadIdx.x; i < (BT_H + 6) * (BT_W + 6); i += 256) {
-        const int ly = i / (BT_W + 6), lx = i - ly * (BT_W + 6);
-        const int x = reflect101i(x0 + lx - 3, L.w), y = reflect101i(y0 + ly - 3, L.h);
-        s_in[ly][lx] = __ldg(img + (size_t)y * L.pitch + x);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (BT_H + 6) * BT_W; i += 256) {
-        const int ly = i / BT_W, lx = i - ly * BT_W;
-        const uint8_t* r = &s_in[ly][lx];
-        s_h[ly][lx] = (unsigned short)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < BT_H * BT_W; i += 256) {
-        const int ly = i / BT_W, lx = i - ly * BT_W;
-        const int x = x0 + lx, y = y0 + ly;
-        if (x >= L.w || y >= L.h) continue;
-        const int acc = 18 * (s_h[ly][lx] + s_h[ly + 6][lx]) + 34 * (s_h[ly + 1][lx] + s_h[ly + 5][lx]) +
-                        48 * (s_h[ly + 2][lx] + s_h[ly + 4][lx]) + 56 * s_h[ly + 3][lx];
-        dst[(size_t)y * L.pitch + x] = (uint8_t)((acc + 32768) >> 16);
+    const bool fast = x >= 0 && x + 3 < w;   // aligned word fully inside the row
+    const bool need = x < w + 3;             // groups further right are never read
+    int xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xr[k] = need ? reflect101i(x + k, w) : 0;
+    const bool owner = lane >= 1 && lane <= 30 && x < w;
+    unsigned hw[7][4];
+#pragma unroll
+    for (int r = 0; r < BT_H + 6; ++r) {
+        const int yy = reflect101i(y0 + r - 3, h);
+        const uint8_t* row = img + (size_t)yy * pitch;
+        unsigned B;
+        if (fast)
+            B = __ldg(reinterpret_cast<const unsigned*>(row + x));
+        else
+            B = (unsigned)__ldg(row + xr[0]) | ((unsigned)__ldg(row + xr[1]) << 8) | ((unsigned)__ldg(row + xr[2]) << 16) |
+                ((unsigned)__ldg(row + xr[3]) << 24);
+        const unsigned A = __shfl_up_sync(0xffffffffu, B, 1), C = __shfl_down_sync(0xffffffffu, B, 1);
+        // byte windows starting k pixels from the group start, split into 16-bit pairs P_k = (b[k], b[k+1])
+        const unsigned wm3 = __funnelshift_r(A, B, 8), wm2 = __funnelshift_r(A, B, 16);
+        const unsigned wp1 = __funnelshift_r(B, C, 8), wp2 = __funnelshift_r(B, C, 16), wp3 = __funnelshift_r(B, C, 24);
+        const unsigned Pm3 = __byte_perm(wm3, 0u, 0x4140), Pm1 = __byte_perm(wm3, 0u, 0x4342);
+        const unsigned Pm2 = __byte_perm(wm2, 0u, 0x4140), P0 = __byte_perm(wm2, 0u, 0x4342);
+        const unsigned P1 = __byte_perm(wp1, 0u, 0x4140), P3 = __byte_perm(wp1, 0u, 0x4342);
+        const unsigned P2 = __byte_perm(wp2, 0u, 0x4140), P4 = __byte_perm(wp2, 0u, 0x4342);
+        const unsigned P5 = __byte_perm(wp3, 0u, 0x4342);
+        const unsigned h01 = 18u * (Pm3 + P3) + 34u * (Pm2 + P2) + 48u * (Pm1 + P1) + 56u * P0;
+        const unsigned h23 = 18u * (Pm1 + P5) + 34u * (P0 + P4) + 48u * (P1 + P3) + 56u * P2;
+        unsigned* hn = hw[r % 7];
+        hn[0] = h01 & 0xffffu; hn[1] = h01 >> 16; hn[2] = h23 & 0xffffu; hn[3] = h23 >> 16;
+        if (r >= 6) {
+            const int y = y0 + r - 6;
+            unsigned o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned acc = 18u * (hw[(r + 1) % 7][j] + hw[r % 7][j]) + 34u * (hw[(r + 2) % 7][j] + hw[(r + 6) % 7][j]) +
+                                     48u * (hw[(r + 3) % 7][j] + hw[(r + 5) % 7][j]) + 56u * hw[(r + 4) % 7][j];
+                o[j] = (acc + 32768u) >> 16;
+            }
+            if (owner && y < h) {
+                uint8_t* q = dst + (size_t)y * pitch + x;
+                if (x + 3 < w) {
+                    *reinterpret_cast<unsigned*>(q) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < w) q[j] = (uint8_t)o[j];
+                }
+            }
+        }
     }
 }
 
@@ -1000,7 +1040,7 @@ int OrbCore::extract_resident()
             tiles += cdiv(L.w, BT_W) * cdiv(L.h, BT_H);
         }
         ba.total_tiles = tiles;
-        dim3 grid(tiles, batch);
+        dim3 grid(cdiv(tiles, 8), batch);  // one warp per 120 x 32 block
         k_orb_blur<<<grid, 256, 0, stream>>>(py, blur.as<uint8_t>(), P.pyr_bytes, ba);
         GD_CUDA(cudaGetLastError());
     }
