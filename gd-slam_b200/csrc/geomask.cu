@@ -145,9 +145,9 @@ int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2a depth edge (FP64, bit-exact vs oracle).  Tile 32x8, depth halo 2, normal/vertex halo 1 in smem.
+// K2a depth edge (FP64, bit-exact vs oracle).  Tile 32x16, depth halo 2, normal/vertex halo 1 in smem.
 // ------------------------------------------------------------------------------------------------
-constexpr int ET_W = 32, ET_H = 8;
+constexpr int ET_W = 32, ET_H = 16;
 
 __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
                                                             CamConst cam, uint8_t* __restrict__ edge, size_t estride_b)
@@ -178,13 +178,10 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
         if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
             const double dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
             if (dc != 0.0 && dt != 0.0 && dl != 0.0) {
-                const double a0 = -1.0, a1 = 0.0, a2 = dl - dc;
-                const double b0 = 0.0, b1 = -1.0, b2 = dt - dc;
-                const double c0 = a1 * b2 - a2 * b1;
-                const double c1 = a2 * b0 - a0 * b2;
-                const double c2 = a0 * b1 - a1 * b0;
-                double ss = 0.0;
-                ss += c0 * c0;
+                // cross((-1, 0, dl - dc), (0, -1, dt - dc)) = (dl - dc, dt - dc, 1): the products with the constant
+                // components are exact and the differences are never -0, so the three components need no arithmetic
+                const double c0 = dl - dc, c1 = dt - dc, c2 = 1.0;
+                double ss = c0 * c0;  // cv::norm: 0 + c0^2 + c1^2 + c2^2 in this order (0 + x == x for x >= 0)
                 ss += c1 * c1;
                 ss += c2 * c2;
                 const double nv = sqrt(ss);
@@ -224,8 +221,9 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
                 zero_nb = true;
                 continue;
             }
-            double phi_d = 0.0;
-            phi_d += (sv[jy][jx][0] - cv0) * cn0;
+            // the leading "0 +" of the dot products is dropped: it can only turn a -0 sum into +0, which no later
+            // comparison distinguishes
+            double phi_d = (sv[jy][jx][0] - cv0) * cn0;
             phi_d += (sv[jy][jx][1] - cv1) * cn1;
             phi_d += (z - cv2) * cn2;
             const double ad = fabs(phi_d);
@@ -233,8 +231,7 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
             if (phi_d < 0.0) {
                 if (max_phi_c < 0.0) max_phi_c = 0.0;
             } else {
-                double dot = 0.0;
-                dot += sn[jy][jx][0] * cn0;
+                double dot = sn[jy][jx][0] * cn0;
                 dot += sn[jy][jx][1] * cn1;
                 dot += sn[jy][jx][2] * cn2;
                 const double phi_c = 1.0 - dot;
@@ -298,12 +295,19 @@ __global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ 
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const PoseDev* __restrict__ P = poses + b;
-    if (!P->valid) return;
-    const size_t i = (size_t)y * w + x;
+    // the stream's pose goes through shared memory: 24 words read once per CTA instead of 24 dependent global loads per thread
+    __shared__ PoseDev s_pose;
+    {
+        const int t = threadIdx.y * blockDim.x + threadIdx.x;
+        if (t < (int)(sizeof(PoseDev) / 4)) reinterpret_cast<int*>(&s_pose)[t] = reinterpret_cast<const int*>(poses + b)[t];
+    }
+    const bool in_img = x < w && y < h;
+    const size_t i = in_img ? (size_t)y * w + x : 0;
     // everything that depends only on the source pixel is requested before the flow arrives (one dependent round less)
     const float2 f = __ldg(flow + (size_t)b * fstride_b + i);
+    __syncthreads();
+    const PoseDev* __restrict__ P = &s_pose;
+    if (!in_img || !P->valid) return;
     float rx = (float)x, ry = (float)y;
     if (lut) {
         const float2 a = __ldg(lut + i);

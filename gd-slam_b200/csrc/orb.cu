@@ -129,33 +129,54 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
 }
 
 // ------------------------------------------------------------------------------------------------ K4a resize
-__global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
-                                                    uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t stride_b,
-                                                    double scale_x, double scale_y)
+// The source index and the two 11-bit weights of cv::resize depend on one coordinate only: they are tabulated per level
+// on the host (ushort4 = {i0, i1, w0, w1}; same f64 -> f32 -> round-half-even arithmetic as the per-pixel form) so the
+// kernel is four byte loads and the fixed-point blend per pixel.
+constexpr int RS_ROWS = 4;
+__global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ src, int spitch, uint8_t* __restrict__ dst, int dw,
+                                                    int dh, int dpitch, size_t stride_b, const ushort4* __restrict__ xt,
+                                                    const ushort4* __restrict__ yt)
 {
-    const int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (dx >= dw || dy >= dh) return;
+    const int dx = blockIdx.x * 32 + threadIdx.x;
+    if (dx >= dw) return;
     const uint8_t* s = src + (size_t)blockIdx.z * stride_b;
     uint8_t* d = dst + (size_t)blockIdx.z * stride_b;
-    float fx = (float)((dx + 0.5) * scale_x - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= sx;
-    if (sx < 0) { fx = 0; sx = 0; }
-    if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
-    const int a0 = __float2int_rn((1.f - fx) * 2048), a1 = __float2int_rn(fx * 2048);
-    float fy = (float)((dy + 0.5) * scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= sy;
-    const int b0 = __float2int_rn((1.f - fy) * 2048), b1 = __float2int_rn(fy * 2048);
-    const int sy0 = max(0, min(sh - 1, sy)), sy1 = max(0, min(sh - 1, sy + 1));
-    const int sx1 = sx < sw - 1 ? sx + 1 : sx;
-    const uint8_t* r0 = s + (size_t)sy0 * spitch;
-    const uint8_t* r1 = s + (size_t)sy1 * spitch;
-    const int h0 = r0[sx] * a0 + r0[sx1] * a1;
-    const int h1 = r1[sx] * a0 + r1[sx1] * a1;
-    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-    d[(size_t)dy * dpitch + dx] = (uint8_t)max(0, min(255, v));
+    const ushort4 X = __ldg(xt + dx);
+    const int a0 = X.z, a1 = X.w;
+#pragma unroll
+    for (int j = 0; j < RS_ROWS; ++j) {
+        const int dy = (blockIdx.y * RS_ROWS + j) * 8 + threadIdx.y;
+        if (dy >= dh) break;
+        const ushort4 Y = __ldg(yt + dy);
+        const uint8_t* r0 = s + (size_t)Y.x * spitch;
+        const uint8_t* r1 = s + (size_t)Y.y * spitch;
+        const int h0 = __ldg(r0 + X.x) * a0 + __ldg(r0 + X.y) * a1;
+        const int h1 = __ldg(r1 + X.x) * a0 + __ldg(r1 + X.y) * a1;
+        const int v = ((((int)Y.z * (h0 >> 4)) >> 16) + (((int)Y.w * (h1 >> 4)) >> 16) + 2) >> 2;
+        d[(size_t)dy * dpitch + dx] = (uint8_t)max(0, min(255, v));
+    }
+}
+
+// host side of the tables (cv::resize INTER_LINEAR 8U: coordinate in f64, cast to f32, weights rounded to 11 bits)
+static void orb_resize_axis_table(int dn, int sn, double scale, bool clamp_like_x, ushort4* t)
+{
+    for (int dpos = 0; dpos < dn; ++dpos) {
+        float f = (float)((dpos + 0.5) * scale - 0.5);
+        int si = (int)std::floor(f);
+        f -= si;
+        int i0, i1;
+        if (clamp_like_x) {
+            if (si < 0) { f = 0; si = 0; }
+            if (si >= sn - 1) { f = 0; si = sn - 1; }
+            i0 = si;
+            i1 = si < sn - 1 ? si + 1 : si;
+        } else {
+            i0 = std::max(0, std::min(sn - 1, si));
+            i1 = std::max(0, std::min(sn - 1, si + 1));
+        }
+        const int w0 = (int)std::nearbyintf((1.f - f) * 2048), w1 = (int)std::nearbyintf(f * 2048);
+        t[dpos] = make_ushort4((unsigned short)i0, (unsigned short)i1, (unsigned short)w0, (unsigned short)w1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K4b FAST
@@ -953,6 +974,8 @@ int OrbCore::init(int nfeatures_, float scale_factor_, int nlevels_, int ini_th,
     GD_TRY(out_n.alloc(B * sizeof(int)));
     GD_TRY(err.alloc(sizeof(int)));
     GD_TRY(h_n.alloc((B + 1) * sizeof(int)));
+    GD_TRY(rs_tab.alloc((size_t)(max_w + max_h) * nlevels * sizeof(ushort4)));
+    GD_TRY(upload_resize_tables());
     GD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
     GD_CUDA(cudaMemsetAsync(pyr.p, 0, pyr.bytes, stream));
     const size_t fast_smem = (size_t)plan.tile_w * plan.tile_h * 4;
@@ -978,6 +1001,27 @@ int OrbCore::set_size(int w, int h)
                    p.total_cells <= big.total_cells,
                "image size needs more memory than the maximum size given at creation");
     plan = p;
+    return upload_resize_tables();
+}
+
+int OrbCore::upload_resize_tables()
+{
+    std::vector<ushort4> tab;
+    for (int l = 1; l < plan.nlevels; ++l) {
+        const OrbLevel &S = plan.lv[l - 1], &D = plan.lv[l];
+        rs_x_off[l] = (int)tab.size();
+        tab.resize(tab.size() + D.w);
+        orb_resize_axis_table(D.w, S.w, D.scale_x, true, tab.data() + rs_x_off[l]);
+        rs_y_off[l] = (int)tab.size();
+        tab.resize(tab.size() + D.h);
+        orb_resize_axis_table(D.h, S.h, D.scale_y, false, tab.data() + rs_y_off[l]);
+    }
+    GD_REQUIRE(tab.size() * sizeof(ushort4) <= rs_tab.bytes, "resize tables exceed their buffer");
+    if (!tab.empty()) {
+        GD_CUDA(cudaStreamSynchronize(stream));  // a previous plan's tables may still be in use
+        GD_CUDA(cudaMemcpyAsync(rs_tab.p, tab.data(), tab.size() * sizeof(ushort4), cudaMemcpyHostToDevice, stream));
+        GD_CUDA(cudaStreamSynchronize(stream));
+    }
     return GD_OK;
 }
 
@@ -994,9 +1038,9 @@ int OrbCore::extract_resident()
     for (int l = 1; l < P.nlevels; ++l) {
         LaunchScope ls(stats, stream, "K4a_pyramid_resize", 1);
         const OrbLevel &S = P.lv[l - 1], &D = P.lv[l];
-        dim3 block(32, 8), grid(cdiv(D.w, 32), cdiv(D.h, 8), batch);
-        k_orb_resize<<<grid, block, 0, stream>>>(py + S.off, S.w, S.h, S.pitch, py + D.off, D.w, D.h, D.pitch, P.pyr_bytes,
-                                                 D.scale_x, D.scale_y);
+        dim3 block(32, 8), grid(cdiv(D.w, 32), cdiv(D.h, 8 * RS_ROWS), batch);
+        k_orb_resize<<<grid, block, 0, stream>>>(py + S.off, S.pitch, py + D.off, D.w, D.h, D.pitch, P.pyr_bytes,
+                                                 rs_tab.as<ushort4>() + rs_x_off[l], rs_tab.as<ushort4>() + rs_y_off[l]);
         GD_CUDA(cudaGetLastError());
     }
     {  // K4b: FAST over every cell of every level

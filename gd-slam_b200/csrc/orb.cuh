@@ -67,11 +67,14 @@ struct OrbCore {
     DevBuf out_desc;  // [B][kp_capacity][32]
     DevBuf out_n;     // [B] int
     DevBuf err;       // [1] int  (capacity overflow flags)
+    DevBuf rs_tab;    // cv::resize index/weight tables per level: x table then y table (ushort4)
+    int rs_x_off[ORB_MAX_LEVELS] = {0}, rs_y_off[ORB_MAX_LEVELS] = {0};
     PinnedBuf h_n;
 
     int init(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int max_width, int max_height,
              int device_, int batch_, cudaStream_t s, LaunchStats* st);
     int set_size(int w, int h);  // (re)plans for an image size <= max
+    int upload_resize_tables();
     uint8_t* level0(int b = 0) { return pyr.as<uint8_t>() + (size_t)b * plan.pyr_bytes; }
     // level 0 of every stream already resident in `pyr` (pitch = plan.lv[0].pitch): run the whole extraction
     int extract_resident();
