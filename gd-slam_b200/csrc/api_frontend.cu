@@ -28,6 +28,12 @@ struct gd_frontend {
     gd::PinnedBuf h_n;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool results_ready = false;
+    // The ORB chain (pyramid, FAST, quadtree, blur, describe) and the GeoMask chain (pyramids, flow, edges, Mahalanobis)
+    // only share the gray conversion: they run on two streams forked after K0 and joined at the end of the step, so the
+    // many small ORB launches fill the SMs the flow kernels leave idle.  GD_OVERLAP=0 serialises them on one stream.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap = true;
     // CUDA graphs of the per-frame device work, one per (ring phase, input buffer): the launch sequence of a step is
     // static, so small batches (launch bound: 51 launches per frame) replay a graph instead of re-issuing every launch
     struct GraphEntry {
@@ -40,6 +46,9 @@ struct gd_frontend {
     {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
         // cores do not own the shared stream
         for (auto& kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -58,9 +67,19 @@ static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
     GD_TRY(launch_gray(bgr_dev, (size_t)g.w * 3, bgr_stride_b, g.w, g.h, g.batch, g.gray.as<uint8_t>(), g.n_pad, o.level0(0),
                        h->cfg.orb_gray_order, (size_t)o.plan.lv[0].pitch, o.plan.pyr_bytes, h->stream, &h->stats));
     // (launch_gray above and everything below is what a graph replays)
-    GD_TRY(o.extract_resident());           // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
+    const bool fork = h->overlap && !h->stats.profiling;  // the per-family event profile wants serialised kernels
+    if (fork) {
+        GD_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        GD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        o.stream = h->aux_stream;
+    }
+    int rc = o.extract_resident();          // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
+    o.stream = h->stream;
+    if (fork && rc == GD_OK) GD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+    if (rc != GD_OK) return rc;
     GD_TRY(g.push_resident(true));          // AddNewImage                          (Tracking.cc:242)
     GD_TRY(g.enqueue_mask());               // GetNoGMMmask                          (Tracking.cc:245)
+    if (fork) GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->results_ready = true;
     h->filtered_ready = false;
     return GD_OK;
@@ -148,6 +167,17 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
             const char* e = std::getenv("GD_GRAPHS");
             h->use_graphs = e ? std::atoi(e) != 0 : cfg->batch <= 8;
         }
+        {
+            const char* e = std::getenv("GD_OVERLAP");
+            h->overlap = e ? std::atoi(e) != 0 : true;
+        }
+        if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cudaStreamCreate/cudaEventCreate failed");
+            r = GD_ECUDA;
+            break;
+        }
         if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
             set_error("cudaEventCreate failed");
             r = GD_ECUDA;
@@ -167,6 +197,7 @@ void gd_frontend_destroy(gd_frontend_t* h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     delete h;
 }
 
