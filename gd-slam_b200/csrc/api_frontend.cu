@@ -32,7 +32,7 @@ struct gd_frontend {
     // only share the gray conversion: they run on two streams forked after K0 and joined at the end of the step, so the
     // many small ORB launches fill the SMs the flow kernels leave idle.  GD_OVERLAP=0 serialises them on one stream.
     cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_edge = nullptr, ev_join = nullptr;
     bool overlap = true;
     // CUDA graphs of the per-frame device work, one per (ring phase, input buffer): the launch sequence of a step is
     // static, so small batches (launch bound: 51 launches per frame) replay a graph instead of re-issuing every launch
@@ -48,6 +48,7 @@ struct gd_frontend {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_edge) cudaEventDestroy(ev_edge);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         // cores do not own the shared stream
         for (auto& kv : graphs)
@@ -68,18 +69,29 @@ static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
                        h->cfg.orb_gray_order, (size_t)o.plan.lv[0].pitch, o.plan.pyr_bytes, h->stream, &h->stats));
     // (launch_gray above and everything below is what a graph replays)
     const bool fork = h->overlap && !h->stats.profiling;  // the per-family event profile wants serialised kernels
-    if (fork) {
+    if (!fork) {
+        GD_TRY(o.extract_resident());       // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
+        GD_TRY(g.push_resident(true));      // AddNewImage                          (Tracking.cc:242)
+        GD_TRY(g.enqueue_mask());           // GetNoGMMmask                          (Tracking.cc:245)
+    } else {
+        // aux stream: depth edges (FP64 bound, only needed by the Mahalanobis kernel at the end) then the ORB chain;
+        // main stream: flow pyramids, polynomial expansion, flow iterations, Mahalanobis, mask
         GD_CUDA(cudaEventRecord(h->ev_fork, h->stream));
         GD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+        g.edge_stream = h->aux_stream;
+        int rc = g.push_resident(true);
+        g.edge_stream = nullptr;
+        if (rc != GD_OK) return rc;
+        GD_CUDA(cudaEventRecord(h->ev_edge, h->aux_stream));
         o.stream = h->aux_stream;
+        rc = o.extract_resident();
+        o.stream = h->stream;
+        if (rc != GD_OK) return rc;
+        GD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+        GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
+        GD_TRY(g.enqueue_mask());
+        GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
-    int rc = o.extract_resident();          // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
-    o.stream = h->stream;
-    if (fork && rc == GD_OK) GD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
-    if (rc != GD_OK) return rc;
-    GD_TRY(g.push_resident(true));          // AddNewImage                          (Tracking.cc:242)
-    GD_TRY(g.enqueue_mask());               // GetNoGMMmask                          (Tracking.cc:245)
-    if (fork) GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->results_ready = true;
     h->filtered_ready = false;
     return GD_OK;
@@ -173,6 +185,7 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
         }
         if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
             set_error("cudaStreamCreate/cudaEventCreate failed");
             r = GD_ECUDA;

@@ -109,7 +109,8 @@ int GeoMaskCore::push_resident(bool gray_done)
                                      R.as<float>() + (size_t)slot * plan.r_floats, (size_t)GD_RING * plan.r_floats, stream, stats));
     // K2a: depth edges of the new depth image
     GD_TRY(launch_depth_edge(depth_slot_ptr(slot), depth_stride_b(), w, h, batch, cam,
-                             edge.as<uint8_t>() + (size_t)slot * n_pad, (size_t)GD_RING * n_pad, stream, stats));
+                             edge.as<uint8_t>() + (size_t)slot * n_pad, (size_t)GD_RING * n_pad,
+                             edge_stream ? edge_stream : stream, stats));
     frames += 1;
     return GD_OK;
 }

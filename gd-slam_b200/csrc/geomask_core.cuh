@@ -45,6 +45,9 @@ struct GeoMaskCore {
     int init(const float K_[9], const float* dist_coef, int ndist, int width, int height, int device_, int batch_,
              cudaStream_t s, LaunchStats* st);
     // new frame already resident in this->bgr and in depth slot (frames % RING): computes the per-image products
+    // optional second stream for the depth-edge kernel (independent of the flow chain); the caller orders it:
+    // forked after the depth upload, joined before enqueue_mask()
+    cudaStream_t edge_stream = nullptr;
     int push_resident(bool gray_done = false);
     float* depth_slot_ptr(int slot) { return depth.as<float>() + (size_t)slot * n_pad; }
     size_t depth_stride_b() const { return (size_t)GD_RING * n_pad; }
