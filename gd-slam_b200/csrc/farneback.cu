@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __r
 // MODE 0: flow of this level read from `fin`; MODE 1: first iteration of a level, flow = 2 * cv::resize(coarser flow)
 // evaluated on the fly from `fin` (pw x ph), same arithmetic as k_fb_upsample; MODE 2: coarsest level, flow = 0.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_fb_matrices(const float* __restrict__ R0, const float* __restrict__ R1, size_t rstride_b,
+__global__ void __launch_bounds__(256, 8) k_fb_matrices(const float* __restrict__ R0, const float* __restrict__ R1, size_t rstride_b,
                                                      const float2* __restrict__ fin, size_t fstride_b, int pw, int ph,
                                                      float* __restrict__ Mout, size_t mstride_b, int w, int h)
 {

@@ -284,7 +284,7 @@ __device__ __forceinline__ float depth2std(float depth, float fu)
     return r;
 }
 
-__global__ void __launch_bounds__(256) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
+__global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
                                                      const float* __restrict__ depth_ref, const float* __restrict__ depth_cur,
                                                      size_t dstride_b, const uint8_t* __restrict__ edge_ref,
                                                      const uint8_t* __restrict__ edge_cur, size_t estride_b,
