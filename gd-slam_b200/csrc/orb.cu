@@ -103,7 +103,7 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
         L.cell_start = cells;
         cells += L.nCols * L.nRows;
         p->max_cells_level = std::max(p->max_cells_level, L.nCols * L.nRows);
-        p->tile_w = std::max(p->tile_w, L.wCell + 6);
+        p->tile_w = std::max(p->tile_w, (int)align_up((size_t)L.wCell + 6 + 3, 4));  // + alignment columns, pitch % 4 == 0
         p->tile_h = std::max(p->tile_h, L.hCell + 6);
         // DistributeOctTree initial nodes, :543-545
         L.nIni = (int)std::round((float)(maxBX - minB) / (maxBY - minB));
@@ -120,6 +120,7 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
     p->pyr_bytes = off;
     p->total_cells = cells;
     p->cell_cap = ((p->tile_w - 6 + 1) / 2) * ((p->tile_h - 6 + 1) / 2);
+    GD_REQUIRE((p->tile_w - 9) * (p->tile_h - 6) <= 128 * 32, "FAST cell larger than the keep bitmap");
     p->cand_total = cand;
     p->kept_total = kept;
     GD_REQUIRE(p->max_N + 8 < 30000 && p->tile_w * p->tile_h * 2 < 200 * 1024, "plan exceeds kernel limits");
@@ -248,15 +249,17 @@ __device__ __forceinline__ int fast_full(const uint8_t* p, int tp)
 }
 
 constexpr int FAST_THREADS = 256;
+constexpr int FAST_KEEP_WORDS = 128;  // keep bitmap: one bit per interior pixel of a cell (cells are < 60 x 60)
+constexpr int FAST_KW = FAST_KEEP_WORDS / 32;
 
 __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __restrict__ pyr, size_t pyr_stride_b, FastArgs a,
                                                           int* __restrict__ cell_cnt, ushort4* __restrict__ slabs)
 {
-    extern __shared__ unsigned char sm[];
-    const int tp = a.tile_w;                       // tile pitch
-    uint8_t* tile = sm;                            // [tile_h][tile_w]
-    uint8_t* sc = sm + a.tile_w * a.tile_h;        // S' (0 when <= minTh)
-    __shared__ int s_warp[FAST_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int tp = a.tile_w;                       // tile pitch (multiple of 4, >= widest cell + 3 alignment columns)
+    uint8_t* tile_base = sm;                       // [tile_h][tp], rows start at the 4-byte aligned column below x0
+    uint8_t* sc_base = sm + tp * a.tile_h;         // S' of the pixels that pass the 4-point test and the threshold, else 0
+    __shared__ unsigned s_keep[FAST_KEEP_WORDS];
     __shared__ int s_nlist;
     const int b = blockIdx.y;
     int cell = blockIdx.x, l = 0;
@@ -281,125 +284,112 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         return;
     }
     // t / d for t * d < 2^20 (tiles are <= ~45 x 45): multiply by ceil-ish reciprocal, exact in that range
-    const unsigned inv_cw = (1u << 20) / (unsigned)cw + 1u, inv_iw = (1u << 20) / (unsigned)iw + 1u;
-    const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off;
-    for (int t = threadIdx.x; t < cw * ch; t += FAST_THREADS) {
-        const int y = (int)(((unsigned)t * inv_cw) >> 20), x = t - y * cw;
-        tile[y * tp + x] = __ldg(img + (size_t)(y0 + y) * L.pitch + x0 + x);
-        sc[y * tp + x] = 0;
+    const unsigned inv_iw = (1u << 20) / (unsigned)iw + 1u;
+    const int xo = x0 & 3;                         // the tile holds image columns [x0 - xo, x1)
+    const int nw = (cw + xo + 3) >> 2;             // 32-bit words per tile row
+    const unsigned inv_nw = (1u << 20) / (unsigned)nw + 1u;
+    const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off + (size_t)y0 * L.pitch + (x0 - xo);
+    for (int t = threadIdx.x; t < nw * ch; t += FAST_THREADS) {
+        const int y = (int)(((unsigned)t * inv_nw) >> 20), k = t - y * nw;
+        reinterpret_cast<unsigned*>(tile_base + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * L.pitch) + k);
     }
-    __syncthreads();
+    for (int t = threadIdx.x; t < (tp * a.tile_h) >> 2; t += FAST_THREADS) reinterpret_cast<unsigned*>(sc_base)[t] = 0u;
+    if (threadIdx.x < FAST_KEEP_WORDS) s_keep[threadIdx.x] = 0u;
+    static_assert(FAST_KEEP_WORDS <= FAST_THREADS, "bitmap is cleared by one pass of the block");
+    const uint8_t* tile = tile_base + xo;
+    uint8_t* sc = sc_base + xo;
     const int npix = iw * ih;
-    // S' pass in two phases so that the 16-point network only runs on pixels that can be corners, densely packed:
-    //   phase 1: 4-point necessary test for every pixel, survivors appended to a shared list (warp-aggregated atomics)
-    //   phase 2: the full network over the list (a warp-divergent early-out would not save anything: in textured images
-    //            nearly every warp holds a survivor)
-    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * a.tile_w * a.tile_h);
-    auto score_pass = [&](int th) {
+    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h);  // raster indices of the survivors
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = FAST_THREADS / 32;
+    const int nwords = (npix + 31) >> 5;
+    int tot = 0;
+    unsigned kw[FAST_KW];  // keep words lane + 32 r (every warp holds the whole bitmap)
+    // first pass at iniThFAST only, like the reference's first cv::FAST call; if no corner survives the NMS the cell is
+    // redone at minThFAST (:812-816).  Per pass:
+    //   1. 4-point necessary test for every pixel, survivors appended to a shared list (warp-aggregated atomics)
+    //   2. the 16-point network over the list (densely packed: in textured images nearly every warp holds a survivor)
+    //   3. cell-local strict NMS over the listed corners only -> one keep bit per interior pixel
+    //   4. raster-ordered compaction straight from the bitmap
+    for (int pass = 0; pass < 2 && tot == 0; ++pass) {
+        const int th = pass == 0 ? a.iniTh : a.minTh;
         if (threadIdx.x == 0) s_nlist = 0;
         __syncthreads();
         for (int base = 0; base < npix; base += FAST_THREADS) {
             const int t = base + threadIdx.x;
-            int pp = 0;
             bool qk = false;
             if (t < npix) {
-                const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
-                pp = y * tp + x;
-                qk = fast_quick(tile + pp, tp, th);
-                if (!qk) sc[pp] = 0;
+                const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
+                qk = fast_quick(tile + (y + 3) * tp + x + 3, tp, th);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, qk);
             int wbase = 0;
-            if ((threadIdx.x & 31) == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
+            if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (qk) plist[wbase + __popc(bal & ((1u << (threadIdx.x & 31)) - 1))] = (unsigned short)pp;
+            if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)t;
         }
         __syncthreads();
         const int nl = s_nlist;
         for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
-            const int pp = plist[q];
+            const int t = plist[q];
+            const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
+            const int pp = (y + 3) * tp + x + 3;
             const int sv = fast_full(tile + pp, tp);
             sc[pp] = (uint8_t)(sv > th ? sv : 0);
         }
         __syncthreads();
-    };
-    // first pass at iniThFAST only, like the reference's first cv::FAST call
-    score_pass(a.iniTh);
-    // NMS at iniTh: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th
-    auto keep_at = [&](int t, int th) -> bool {
-        const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
-        const uint8_t* q = sc + y * tp + x;
-        const int s = q[0];
-        if (s <= th) return false;
-        bool k = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0) continue;
-                const int n = q[dy * tp + dx];
-                k = k && !(n > th && n >= s);
-            }
-        return k;
-    };
-    // raster-ordered compaction with 3 barriers: warp w owns the contiguous pixel range [w*R, (w+1)*R); a lane keeps one
-    // keep-bit per 32-pixel chunk of its warp's range, so the NMS test is evaluated once per threshold
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = FAST_THREADS / 32;
-    const int R = ((npix + NW - 1) / NW + 31) & ~31;  // pixels per warp, multiple of 32 (<= 32 chunks: cells are tiny)
-    const int nchunk = R >> 5;
-    unsigned bits = 0;
-    int wcount = 0;
-    for (int c = 0; c < nchunk; ++c) {
-        const int t = warp * R + c * 32 + lane;
-        const bool k = t < npix && keep_at(t, a.iniTh);
-        const unsigned bal = __ballot_sync(0xffffffffu, k);
-        bits |= (k ? 1u : 0u) << c;
-        wcount += __popc(bal);
-    }
-    if (lane == 0) s_warp[warp] = wcount;
-    __syncthreads();
-    int tot = 0, woff = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < NW; ++w2) {
-        if (w2 < warp) woff += s_warp[w2];
-        tot += s_warp[w2];
-    }
-    if (tot == 0) {  // no corner survived NMS at iniThFAST -> redo the cell at minThFAST (:812-816)
-        __syncthreads();
-        score_pass(a.minTh);
-        bits = 0;
-        wcount = 0;
-        for (int c = 0; c < nchunk; ++c) {
-            const int t = warp * R + c * 32 + lane;
-            const bool k = t < npix && keep_at(t, a.minTh);
-            const unsigned bal = __ballot_sync(0xffffffffu, k);
-            bits |= (k ? 1u : 0u) << c;
-            wcount += __popc(bal);
+        // NMS: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th (sc is 0 otherwise)
+        for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
+            const int t = plist[q];
+            const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
+            const uint8_t* c = sc + (y + 3) * tp + x + 3;
+            const int sv = c[0];
+            if (sv == 0) continue;
+            const int m0 = max(max(c[-tp - 1], c[-tp]), max(c[-tp + 1], c[-1]));
+            const int m1 = max(max(c[tp - 1], c[tp]), max(c[tp + 1], c[1]));
+            if (max(m0, m1) < sv) atomicOr(&s_keep[t >> 5], 1u << (t & 31));
         }
-        if (lane == 0) s_warp[warp] = wcount;
         __syncthreads();
-        tot = 0;
-        woff = 0;
+        int cnt = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) {
-            if (w2 < warp) woff += s_warp[w2];
-            tot += s_warp[w2];
+        for (int r = 0; r < FAST_KW; ++r) {
+            kw[r] = s_keep[lane + 32 * r];
+            cnt += __popc(kw[r]);
         }
+        tot = __reduce_add_sync(0xffffffffu, cnt);
+    }
+    // exclusive prefix of the per-word counts (word k lives in lane k & 31, register k >> 5)
+    int ex[FAST_KW], run = 0;
+#pragma unroll
+    for (int r = 0; r < FAST_KW; ++r) {
+        const int c = __popc(kw[r]);
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        ex[r] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
     ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
-    int pos = woff;
-    for (int c = 0; c < nchunk; ++c) {
-        const bool k = (bits >> c) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, k);
-        const int my = pos + __popc(bal & ((1u << lane) - 1));
-        if (k && my < a.cell_cap) {
-            const int t = warp * R + c * 32 + lane;
-            const int y = (int)(((unsigned)t * inv_iw) >> 20) + 3, x = t - (y - 3) * iw + 3;
-            slab[my] = make_ushort4((unsigned short)(x + j * L.wCell), (unsigned short)(y + i * L.hCell),
-                                    (unsigned short)(sc[y * tp + x] - 1), 0);
+    for (int k = warp; k < nwords; k += NW) {
+        unsigned wsel = kw[0];
+        int esel = ex[0];
+#pragma unroll
+        for (int r = 1; r < FAST_KW; ++r)
+            if ((k >> 5) == r) { wsel = kw[r]; esel = ex[r]; }  // warp-uniform select
+        const unsigned word = __shfl_sync(0xffffffffu, wsel, k & 31);
+        const int off = __shfl_sync(0xffffffffu, esel, k & 31);
+        if ((word >> lane) & 1u) {
+            const int my = off + __popc(word & ((1u << lane) - 1));
+            if (my < a.cell_cap) {
+                const int t = k * 32 + lane;
+                const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
+                slab[my] = make_ushort4((unsigned short)(x + 3 + j * L.wCell), (unsigned short)(y + 3 + i * L.hCell),
+                                        (unsigned short)(sc[(y + 3) * tp + x + 3] - 1), 0);
+            }
         }
-        pos += __popc(bal);
     }
     if (threadIdx.x == 0) *cnt_out = min(tot, a.cell_cap);
 }
