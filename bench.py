@@ -263,7 +263,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device (libgdslam_cuda has no CPU fallback)")
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version at VERSION/INFO)
+        # stdout carries the single JSON line.  NCCL honours NCCL_DEBUG_FILE only above the VERSION level (the image sets
+        # NCCL_DEBUG=VERSION, whose banner goes to stdout), so raise VERSION/unset to WARN and send the log to stderr.
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "NONE", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
 
