@@ -223,6 +223,27 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def bind_host_to_gpu(device):
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the CPUs NVML reports as local
+    to the GPU: the e2e leg moves ~30 GB/s per GPU through host memory, which must not cross the socket interconnect.
+    Best effort: returns the number of CPUs bound to, or None (GD_BENCH_AFFINITY=0 disables)."""
+    if os.environ.get("GD_BENCH_AFFINITY", "1") == "0":
+        return None
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device)
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        print(f"bench.py: host affinity not set ({type(e).__name__}: {e})", file=sys.stderr)
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,6 +283,7 @@ def main():
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (libgdslam_cuda has no CPU fallback)")
     dist = None
+    host_cpus = bind_host_to_gpu(local_rank) if world > 1 else None  # a single rank keeps every core of the box
     if world > 1:
         # stdout carries the single JSON line.  NCCL honours NCCL_DEBUG_FILE only above the VERSION level (the image sets
         # NCCL_DEBUG=VERSION, whose banner goes to stdout), so raise VERSION/unset to WARN and send the log to stderr.
@@ -423,7 +445,8 @@ def main():
                                     "pyramids + staged frames), 126 MB L2" % (B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3) * N_PX / 307200),
                       "sharding": "independent streams per GPU, no collective"},
            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": e2e_s * 1e3 / K_, "handles_per_gpu": NH, "streams_per_handle": Bh},
+                   "ms_per_step": e2e_s * 1e3 / K_, "handles_per_gpu": NH, "streams_per_handle": Bh,
+                   "host_cpus_per_rank": host_cpus},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
