@@ -59,6 +59,14 @@ void make_cam_const(const float K[9], CamConst* c)
     c->fv = K[4];
     c->cu = K[2];
     c->cv = K[5];
+    c->rfu = 1.0f / c->fu;
+    c->rfv = 1.0f / c->fv;
+    {
+        volatile float r = c->rfu * c->rfu;  // same individually rounded f32 products as depth2std()
+        r = r * 0.5f;
+        r = r * 0.5f;
+        c->std_k = r;
+    }
     inv3_cv<float>(K, c->Ki);
     double Kd[9];
     for (int i = 0; i < 9; ++i) Kd[i] = (double)K[i];
@@ -271,17 +279,25 @@ __device__ __forceinline__ float dot3f(float a0, float b0, float a1, float b1, f
     return t;
 }
 
-__device__ __forceinline__ float depth2std(float depth, float fu)
+__device__ __forceinline__ float depth2std(float depth, float std_k)
 {
-    const float inv = 1.0f / fu;
-    float r = inv * inv;
-    r = r * 0.5f;
-    r = r * 0.5f;
+    float r = std_k;  // ((1/fu)^2 * 0.5) * 0.5, rounded product by product on the host
     r = r * depth;
     r = r * depth;
     r = r * depth;
     r = r * depth;
     return r;
+}
+
+// Correctly rounded x / d for a divisor known in advance (Markstein: q = RN(x r), q' = RN(q + RN(x - q d) r) with
+// r = RN(1/d) is RN(x/d) whenever the significand of d is not all ones and nothing over/underflows — focal lengths and
+// metre-scale operands here).  Three FMA-class instructions instead of the IEEE division sequence; the zero it returns for
+// x = -0 is +0, which only feeds products that are added to non-negative-zero sums.
+__device__ __forceinline__ float div_by(float x, float d, float r)
+{
+    const float q = x * r;
+    const float rem = fmaf(-q, d, x);
+    return fmaf(rem, r, q);
 }
 
 __global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
@@ -348,16 +364,18 @@ __global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict
     const float P2 = fmaf(U2, ref_depth, P->T[2]);
     const float e0 = C0 - P0, e1 = C1 - P1, e2 = C2 - P2;
 
-    const float s2 = depth2std(ref_depth, fu);
-    const float s5 = depth2std(cur_depth, fu);
+    const float s2 = depth2std(ref_depth, cam.std_k);
+    const float s5 = depth2std(cur_depth, cam.std_k);
+    const float rfu = cam.rfu, rfv = cam.rfv;
     // J rows (index slips of the reference kept: J(1,1) uses ref_depth, J(1,2) uses x)
     float J[3][6];
-    J[0][0] = cur_depth / fu;      J[0][1] = 0.f;               J[0][2] = (cx - cu) / fu;
-    J[0][3] = -P->R[0] * ref_depth / fu; J[0][4] = -P->R[1] * ref_depth / fv; J[0][5] = -U0;
-    J[1][0] = 0.f;                 J[1][1] = ref_depth / fv;    J[1][2] = (cx - cu) / fv;
-    J[1][3] = -P->R[3] * ref_depth / fu; J[1][4] = -P->R[4] * ref_depth / fv; J[1][5] = -U1;
-    J[2][0] = 0.f;                 J[2][1] = 0.f;               J[2][2] = 1.0f;
-    J[2][3] = -P->R[6] * ref_depth / fu; J[2][4] = -P->R[7] * ref_depth / fv; J[2][5] = -U2;
+    const float dxc = cx - cu;
+    J[0][0] = div_by(cur_depth, fu, rfu);  J[0][1] = 0.f;  J[0][2] = div_by(dxc, fu, rfu);
+    J[0][3] = div_by(-P->R[0] * ref_depth, fu, rfu); J[0][4] = div_by(-P->R[1] * ref_depth, fv, rfv); J[0][5] = -U0;
+    J[1][0] = 0.f;  J[1][1] = div_by(ref_depth, fv, rfv);  J[1][2] = div_by(dxc, fv, rfv);
+    J[1][3] = div_by(-P->R[3] * ref_depth, fu, rfu); J[1][4] = div_by(-P->R[4] * ref_depth, fv, rfv); J[1][5] = -U1;
+    J[2][0] = 0.f;  J[2][1] = 0.f;  J[2][2] = 1.0f;
+    J[2][3] = div_by(-P->R[6] * ref_depth, fu, rfu); J[2][4] = div_by(-P->R[7] * ref_depth, fv, rfv); J[2][5] = -U2;
     // (J S) J^T like cv::gemm: f32 operands, f64 accumulator, k ascending.  The product of two f32 is exact in f64, so
     // fma(a, b, s) rounds exactly like s + a * b; terms with a structural zero of J add +-0 to a sum that is never -0
     // and are skipped (J(0,1) = J(1,0) = J(2,0) = J(2,1) = 0).  Bit-identical to the dense loop, 38 DFMA instead of 108 ops.

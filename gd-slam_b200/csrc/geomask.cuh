@@ -18,6 +18,8 @@ struct PoseDev {
 // camera constants shared by all streams of a handle (kernel argument by value)
 struct CamConst {
     float fu, fv, cu, cv;
+    float rfu, rfv;  // RN(1/fu), RN(1/fv): reciprocals for the correctly rounded division by a constant
+    float std_k;     // ((1/fu)^2 * 0.5) * 0.5, the depth-independent factor of Depth2Std (GeoMaskMaker.cc:1386-1391)
     float Ki[9];    // inv(K) in f32  (GeoMaskMaker.cc:200)
     double Kid[9];  // inv((double)K)  (GeoMaskMaker.cc:888)
 };
