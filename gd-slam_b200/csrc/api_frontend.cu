@@ -101,7 +101,8 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
                             const int* pose_valid)
 {
     GeoMaskCore& g = h->geo;
-    g.prepare_poses(R, T, pose_valid, g.frames + 1);  // the frame of this step is pushed before the mask is evaluated
+    // the frame of this step is pushed before the mask is evaluated; the pose copy stays outside any captured graph
+    GD_TRY(g.upload_poses(R, T, pose_valid, g.frames + 1));
     // graphs only in steady state (every code path has run un-captured at least once: lazy attribute setup, ring full)
     // and never while the per-family event profile is on (events + synchronisation inside the launch scopes)
     if (!h->use_graphs || h->stats.profiling || g.frames < 2 * GD_RING) return frontend_enqueue(h, bgr_dev, bgr_stride_b);

@@ -74,7 +74,8 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
     GD_TRY(poses.alloc(B * sizeof(PoseDev)));
     GD_TRY(mask.alloc(B * n_pad));
     GD_TRY(dist.alloc(B * n_pad * sizeof(float)));
-    GD_TRY(h_poses.alloc(B * sizeof(PoseDev)));
+    GD_TRY(h_poses.alloc(POSE_SLOTS * B * sizeof(PoseDev)));
+    for (int i = 0; i < POSE_SLOTS; ++i) GD_CUDA(cudaEventCreateWithFlags(&pose_ev[i], cudaEventDisableTiming));
     GD_CUDA(cudaMemsetAsync(keys.p, 0, keys.bytes, stream));
     GD_CUDA(cudaMemsetAsync(depth.p, 0, depth.bytes, stream));
     GD_CUDA(cudaMemsetAsync(edge.p, 0, edge.bytes, stream));
@@ -94,6 +95,8 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
 
 GeoMaskCore::~GeoMaskCore()
 {
+    for (int i = 0; i < POSE_SLOTS; ++i)
+        if (pose_ev[i]) cudaEventDestroy(pose_ev[i]);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -117,28 +120,32 @@ int GeoMaskCore::push_resident(bool gray_done)
 
 int GeoMaskCore::compute_mask(const float* Rm, const float* Tm, const int* pose_valid)
 {
-    prepare_poses(Rm, Tm, pose_valid, frames);
+    GD_TRY(upload_poses(Rm, Tm, pose_valid, frames));
     return enqueue_mask();
 }
 
-// host half: pose blocks into the pinned staging buffer (read by the H2D copy enqueue_mask() issues, possibly from a graph)
-void GeoMaskCore::prepare_poses(const float* Rm, const float* Tm, const int* pose_valid, int frames_pushed)
+int GeoMaskCore::upload_poses(const float* Rm, const float* Tm, const int* pose_valid, int frames_pushed)
 {
     const bool started = frames_pushed >= GD_RING;  // start_flag, GeoMaskMaker.cc:419-428
-    PoseDev* hp = h_poses.as<PoseDev>();
+    const int slot = pose_slot;
+    pose_slot = (pose_slot + 1) % POSE_SLOTS;
+    if (pose_pending[slot]) GD_CUDA(cudaEventSynchronize(pose_ev[slot]));  // the copy that last read this slot has run
+    PoseDev* hp = h_poses.as<PoseDev>() + (size_t)slot * batch;
     for (int b = 0; b < batch; ++b) {
         const int valid = started && (!pose_valid || pose_valid[b]) ? 1 : 0;
         static const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
         make_pose(K, Rm ? Rm + 9 * b : I3, Tm ? Tm + 3 * b : Z3, valid, hp + b);
     }
+    GD_CUDA(cudaMemcpyAsync(poses.p, hp, sizeof(PoseDev) * batch, cudaMemcpyHostToDevice, stream));
+    GD_CUDA(cudaEventRecord(pose_ev[slot], stream));
+    pose_pending[slot] = true;
+    return GD_OK;
 }
 
 // device half: everything GetNoGMMmask enqueues on the stream (capturable into a CUDA graph)
 int GeoMaskCore::enqueue_mask()
 {
     const bool started = frames >= GD_RING;
-    PoseDev* hp = h_poses.as<PoseDev>();
-    GD_CUDA(cudaMemcpyAsync(poses.p, hp, sizeof(PoseDev) * batch, cudaMemcpyHostToDevice, stream));
     if (!started) {  // warm-up: all-ones mask (:171-175)
         GD_TRY(launch_fill_u8(mask.as<uint8_t>(), (size_t)batch * n_pad, 1, stream, stats));
         last_flow = nullptr;

@@ -36,7 +36,13 @@ struct GeoMaskCore {
     DevBuf mask;       // [B][n] u8
     DevBuf dist;       // [B][n] f32 (resolved dist image, kept for debug fetch)
     DevBuf lut;        // [n] float2 or empty
-    PinnedBuf h_poses;
+    // pinned staging of the pose blocks: a ring, because the H2D copy reads the buffer when it EXECUTES and a caller of the
+    // device-resident path may enqueue several steps without synchronising (each slot is guarded by an event)
+    static constexpr int POSE_SLOTS = 8;
+    PinnedBuf h_poses;  // [POSE_SLOTS][B] PoseDev
+    cudaEvent_t pose_ev[POSE_SLOTS] = {};
+    bool pose_pending[POSE_SLOTS] = {};
+    int pose_slot = 0;
     const float2* last_flow = nullptr;
     int last_ref_slot = -1, last_cur_slot = -1;
 
@@ -54,9 +60,10 @@ struct GeoMaskCore {
     int cur_slot() const { return frames % GD_RING; }  // slot the NEXT push writes
     // GetNoGMMmask for all streams; result stays in this->mask.  R: [B][9], T: [B][3], valid: [B] (host)
     int compute_mask(const float* R, const float* T, const int* pose_valid);
-    // host half; frames_pushed = number of frames pushed when the mask will be evaluated
-    void prepare_poses(const float* R, const float* T, const int* pose_valid, int frames_pushed);
-    int enqueue_mask();                                                         // device half (graph capturable)
+    // pose blocks -> device (async, never part of a captured graph); frames_pushed = number of frames pushed when the
+    // mask will be evaluated
+    int upload_poses(const float* R, const float* T, const int* pose_valid, int frames_pushed);
+    int enqueue_mask();  // everything GetNoGMMmask launches (graph capturable); expects upload_poses() before it
     int debug_fetch(int what, int stream_idx, void* dst, size_t dst_bytes);
     ~GeoMaskCore();
 };
