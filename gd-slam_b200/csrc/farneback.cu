@@ -77,11 +77,14 @@ static void poly_constants(int n, double sigma, FbPlan* p)
     p->ig55 = 1.0 / G[5][5];
 }
 
+int fb_prepare_device();
+
 int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int poly_n, double poly_sigma, int winsize,
                  FbPlan* plan)
 {
     GD_REQUIRE(poly_n == FB_POLY_N && winsize == FB_WIN, "only poly_n=5 / winsize=15 (the reference's parameters) are built");
     GD_REQUIRE(w >= 16 && h >= 16, "image too small");
+    GD_TRY(fb_prepare_device());
     *plan = FbPlan();
     plan->w = w;
     plan->h = h;
@@ -801,17 +804,19 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
     }
 }
 
+// Function attributes are per device: called from fb_make_plan() with the plan's device current.
+int fb_prepare_device()
+{
+    GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    return GD_OK;
+}
+
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
                    float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_stride_b, const float2** final_flow, cudaStream_t s,
                    LaunchStats* st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-        GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-        attr_set = true;
-    }
     const float2* prev = nullptr;
     int pw = 0, ph = 0;
     for (int k = plan.nlevels - 1; k >= 0; --k) {

@@ -205,3 +205,27 @@ def test_cuda_graph_replay_equals_plain_launches(capi, synth, monkeypatch):
     assert np.array_equal(fa[0][0], fb[0][0])
     plain.close()
     graph.close()
+
+
+def test_handles_on_two_devices_in_one_process(capi, synth):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: a handle on every visible GPU must work from one
+    process and give identical results (multi-GPU = independent handles)."""
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    K = synth.intrinsics()
+    s = synth.SyntheticStream(0)
+    frames = [s.frame(f) for f in range(7)]
+    outs = []
+    for dev in (1, 0):
+        fe = capi.Frontend(K, 640, 480, batch=1, device=dev)
+        for f in range(7):
+            R = T = None
+            if f >= 5:
+                R, T = s.pair_pose(f - 5, f)
+                R, T = R[None], T[None]
+            res = fe.step([frames[f].bgr], [frames[f].depth_m], R, T)
+        outs.append(res[0])
+        fe.close()
+    (m1, k1, d1), (m0, k0, d0) = outs
+    assert np.array_equal(m1, m0) and (m0 == 0).any()
+    _same_kp(k1, d1, k0, d0)
