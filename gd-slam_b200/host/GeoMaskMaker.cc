@@ -57,7 +57,12 @@ void GeoMaskMaker::AddNewImage(cv::Mat new_Image, cv::Mat new_Depth, cv::Mat /*l
     const uint8_t* bgr = new_Image.ptr<uint8_t>(0);
     const float* dep = new_Depth.ptr<float>(0);
     gd_check(gd_geomask_push(handle_, &bgr, (size_t)new_Image.step, &dep, (size_t)new_Depth.step), "gd_geomask_push");
-    // host copies of the last six frames, only for GetRt() (GeoMaskMaker.cc:409-429)
+    // host copies of the last six frames, only for GetRt() (GeoMaskMaker.cc:409-429): not kept while a pose provider is set
+    if (pose_provider_) {
+        if (++pushed_ > inter_frame_size) start_flag = true;
+        return;
+    }
+    ++pushed_;
     cv::Mat rgb, depth;
     new_Image.copyTo(rgb);
     new_Depth.copyTo(depth);

@@ -54,7 +54,8 @@ public:
 private:
     gd_geomask* handle_ = nullptr;
     PoseProvider pose_provider_;
-    std::vector<cv::Mat> host_rgb_, host_depth_;  // last six frames for GetRt()
+    std::vector<cv::Mat> host_rgb_, host_depth_;  // last six frames for GetRt() (not kept while a pose provider is set)
+    int pushed_ = 0;
     void init(int width, int height, int device);
 };
 

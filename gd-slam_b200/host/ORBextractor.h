@@ -35,7 +35,7 @@ public:
     std::vector<cv::Mat> mvImagePyramid;
     bool keepImagePyramid = false;
     // GrabImageRGBD_GD extracts twice from the identical gray image (src/Tracking.cc:238,252): serve the second
-    // call from the first one's result (keyed on size + 64-bit content hash).
+    // call from the first one's result (keyed on the exact image content: memcmp with a kept copy).
     bool memoizeLastImage = true;
 
 protected:
@@ -49,7 +49,7 @@ protected:
 private:
     gd_orb* handle_ = nullptr;
     int handle_w_ = 0, handle_h_ = 0;
-    unsigned long long last_hash_ = 0;
+    std::vector<unsigned char> last_image_;  // copy of the last extracted image (memo key: exact content)
     int last_w_ = 0, last_h_ = 0;
     std::vector<cv::KeyPoint> last_kps_;
     cv::Mat last_desc_;

@@ -2,6 +2,7 @@
 // ORB on the new gray image (twice, second call memoised), AddNewImage, GetNoGMMmask.  Reads a raw sequence file written by
 // tests/test_gpu_shim.py, writes masks / keypoints / descriptors for the test to compare with the oracle.
 //   file: int32 w, h, nframes; per frame: bgr (w*h*3 u8), gray (w*h u8), depth (w*h f32), R (9 f32), T (3 f32)
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -33,6 +34,12 @@ int main(int argc, char** argv)
     ORB_SLAM2::ORBextractor orb(1500, 1.2f, 8, 20, 7);
     std::vector<unsigned char> bgr((size_t)w * h * 3), gray((size_t)w * h);
     std::vector<float> depth((size_t)w * h);
+    double t_orb = 0, t_add = 0, t_mask = 0, t_orb2 = 0;  // steady-state (frame >= 6) wall time per call, ms
+    int n_timed = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
     for (int i = 0; i < nf; ++i) {
         if (std::fread(bgr.data(), 1, bgr.size(), f) != bgr.size() || std::fread(gray.data(), 1, gray.size(), f) != gray.size() ||
             std::fread(depth.data(), 4, depth.size(), f) != depth.size() || std::fread(Rv, 4, 9, f) != 9 || std::fread(Tv, 4, 3, f) != 3)
@@ -40,10 +47,19 @@ int main(int argc, char** argv)
         cv::Mat im(h, w, CV_8UC3, bgr.data()), g(h, w, CV_8UC1, gray.data()), d(h, w, CV_32FC1, depth.data()), label, mask;
         std::vector<cv::KeyPoint> kps, kps2;
         cv::Mat desc, desc2;
+        const auto t0 = now();
         orb(cv::_InputArray(g), cv::_InputArray(label), kps, cv::_OutputArray(desc));    // Frame(), Tracking.cc:238
+        const auto t1 = now();
         gm.AddNewImage(im, d, label, label);                                              // Tracking.cc:242
+        const auto t2 = now();
         gm.GetNoGMMmask(mask);                                                            // Tracking.cc:245
+        const auto t3 = now();
         orb(cv::_InputArray(g), cv::_InputArray(label), kps2, cv::_OutputArray(desc2));  // Frame(), Tracking.cc:252
+        const auto t4 = now();
+        if (i >= 6) {
+            t_orb += ms(t0, t1); t_add += ms(t1, t2); t_mask += ms(t2, t3); t_orb2 += ms(t3, t4);
+            ++n_timed;
+        }
         if (kps2.size() != kps.size()) return 6;
         int n = (int)kps.size();
         std::fwrite(&n, 4, 1, o);
@@ -57,5 +73,10 @@ int main(int argc, char** argv)
     }
     std::fclose(f);
     std::fclose(o);
+    if (n_timed > 0)
+        std::fprintf(stderr, "shim steady state over %d frames, ms per call: ORBextractor() %.3f, AddNewImage %.3f, GetNoGMMmask %.3f, "
+                             "ORBextractor() again (memo) %.3f, frame total %.3f\n",
+                     n_timed, t_orb / n_timed, t_add / n_timed, t_mask / n_timed, t_orb2 / n_timed,
+                     (t_orb + t_add + t_mask + t_orb2) / n_timed);
     return 0;
 }
