@@ -23,6 +23,7 @@ int gd_geomask_create(gd_geomask_t** out, const float K[9], const float* dist, i
         delete h;
         return r;
     }
+    h->core.push_graphs.enabled = h->core.mask_graphs.enabled = GraphCache::env_default(batch);
     *out = h;
     return GD_OK;
 }

@@ -57,6 +57,7 @@ int gd_orb_create(gd_orb_t** out, int nfeatures, float scale_factor, int nlevels
         delete h;
         return r;
     }
+    h->core.graphs.enabled = GraphCache::env_default(batch);
     *out = h;
     return GD_OK;
 }

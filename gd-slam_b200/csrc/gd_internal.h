@@ -6,8 +6,11 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gdslam_cuda.h"
@@ -156,6 +159,60 @@ struct LaunchScope {
             cudaEventElapsedTime(&ms, st->e0, st->e1);
             st->fam[idx].ms += ms;
         }
+    }
+};
+
+// Replays a static launch sequence as a CUDA graph, one executable per key (small batches are launch bound).
+// enqueue() must only enqueue work on `s` (or on streams forked from and joined back into it), must give the same launches
+// for the same key, and must not advance host state.  Never used inside another capture: the batched front-end captures
+// the whole step itself and leaves the caches of its cores disabled.
+struct GraphCache {
+    bool enabled = false;
+    std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> execs;
+    GraphCache() = default;
+    GraphCache(const GraphCache&) = delete;
+    GraphCache& operator=(const GraphCache&) = delete;
+    ~GraphCache()
+    {
+        for (auto& kv : execs)
+            if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+    }
+    static bool env_default(int batch)
+    {
+        const char* e = std::getenv("GD_GRAPHS");
+        return e ? std::atoi(e) != 0 : batch <= 8;
+    }
+    template <class F>
+    int run(unsigned long long key, cudaStream_t s, LaunchStats* st, F&& enqueue)
+    {
+        if (!enabled || (st && st->profiling)) return enqueue();
+        auto it = execs.find(key);
+        if (it == execs.end()) {
+            const long long l0 = st ? st->launches : 0;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                enabled = false;
+                return enqueue();
+            }
+            const int rc = enqueue();
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc != GD_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                enabled = false;  // plain launches for good
+                if (st) st->launches = l0;
+                return enqueue();
+            }
+            cudaGraphDestroy(graph);
+            const long long n = st ? st->launches - l0 : 0;
+            if (st) st->launches = l0;  // the capture issued nothing; the replay below is what runs
+            it = execs.emplace(key, std::make_pair(exec, n)).first;
+        }
+        GD_CUDA(cudaGraphLaunch(it->second.first, s));
+        if (st) st->launches += it->second.second;
+        return GD_OK;
     }
 };
 

@@ -103,6 +103,18 @@ GeoMaskCore::~GeoMaskCore()
 int GeoMaskCore::push_resident(bool gray_done)
 {
     const int slot = frames % GD_RING;
+    // graphs only once every path has run un-captured (lazy set-up) and the ring is in steady state
+    const bool replay = frames >= 2 * GD_RING && !edge_stream;
+    const int rc = replay ? push_graphs.run((unsigned long long)slot * 2 + (gray_done ? 1 : 0), stream, stats,
+                                            [&] { return enqueue_push(slot, gray_done); })
+                          : enqueue_push(slot, gray_done);
+    if (rc != GD_OK) return rc;
+    frames += 1;
+    return GD_OK;
+}
+
+int GeoMaskCore::enqueue_push(int slot, bool gray_done)
+{
     // K0: gray for the flow (the batched front-end computes it together with the ORB gray)
     if (!gray_done)
         GD_TRY(launch_gray(bgr.as<uint8_t>(), (size_t)w * 3, n_pad * 3, w, h, batch, gray.as<uint8_t>(), n_pad, nullptr, 0, 0, 0,
@@ -114,14 +126,16 @@ int GeoMaskCore::push_resident(bool gray_done)
     GD_TRY(launch_depth_edge(depth_slot_ptr(slot), depth_stride_b(), w, h, batch, cam,
                              edge.as<uint8_t>() + (size_t)slot * n_pad, (size_t)GD_RING * n_pad,
                              edge_stream ? edge_stream : stream, stats));
-    frames += 1;
     return GD_OK;
 }
 
 int GeoMaskCore::compute_mask(const float* Rm, const float* Tm, const int* pose_valid)
 {
     GD_TRY(upload_poses(Rm, Tm, pose_valid, frames));
-    return enqueue_mask();
+    if (frames < 2 * GD_RING) return enqueue_mask();
+    last_cur_slot = (frames - 1) % GD_RING;  // host state enqueue_mask() sets; a replay does not run it
+    last_ref_slot = (frames - GD_RING) % GD_RING;
+    return mask_graphs.run((unsigned long long)(frames % GD_RING), stream, stats, [&] { return enqueue_mask(); });
 }
 
 int GeoMaskCore::upload_poses(const float* Rm, const float* Tm, const int* pose_valid, int frames_pushed)

@@ -54,6 +54,9 @@ struct GeoMaskCore {
     // optional second stream for the depth-edge kernel (independent of the flow chain); the caller orders it:
     // forked after the depth upload, joined before enqueue_mask()
     cudaStream_t edge_stream = nullptr;
+    // graph replay of the two launch sequences for stand-alone handles (gd_geomask_*); disabled inside the batched front-end
+    GraphCache push_graphs, mask_graphs;
+    int enqueue_push(int slot, bool gray_done);
     int push_resident(bool gray_done = false);
     float* depth_slot_ptr(int slot) { return depth.as<float>() + (size_t)slot * n_pad; }
     size_t depth_stride_b() const { return (size_t)GD_RING * n_pad; }

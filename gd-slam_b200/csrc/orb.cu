@@ -991,6 +991,7 @@ int OrbCore::set_size(int w, int h)
                    p.total_cells <= big.total_cells,
                "image size needs more memory than the maximum size given at creation");
     plan = p;
+    plain_runs = 0;
     return upload_resize_tables();
 }
 
@@ -1021,6 +1022,16 @@ OrbCore::~OrbCore()
 }
 
 int OrbCore::extract_resident()
+{
+    // stand-alone handles replay the launch sequence as a graph once it has run twice un-captured at this image size
+    if (plain_runs < 2) {
+        ++plain_runs;
+        return enqueue_extract();
+    }
+    return graphs.run(((unsigned long long)plan.w << 20) | (unsigned long long)plan.h, stream, stats, [&] { return enqueue_extract(); });
+}
+
+int OrbCore::enqueue_extract()
 {
     const OrbPlan& P = plan;
     uint8_t* py = pyr.as<uint8_t>();

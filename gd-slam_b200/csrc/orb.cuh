@@ -78,6 +78,9 @@ struct OrbCore {
     uint8_t* level0(int b = 0) { return pyr.as<uint8_t>() + (size_t)b * plan.pyr_bytes; }
     // level 0 of every stream already resident in `pyr` (pitch = plan.lv[0].pitch): run the whole extraction
     int extract_resident();
+    int enqueue_extract();  // the launches of extract_resident() (graph capturable, no host state)
+    GraphCache graphs;      // enabled for stand-alone handles only (the batched front-end captures its whole step)
+    int plain_runs = 0;
     ~OrbCore();
 };
 

@@ -188,3 +188,36 @@ def test_distorted_camera_lut_and_mask(capi, oracle, synth, golden):
     assert np.array_equal(gm.debug(capi.DBG_DIST), dist_o)
     assert np.array_equal(mask, oracle.normalize_threshold(dist_o)[0])
     gm.close()
+
+
+def test_standalone_handles_graph_replay_equals_plain_launches(capi, oracle, synth, monkeypatch):
+    """gd_geomask_* / gd_orb_* (what the C++ drop-in classes call) replay CUDA graphs of their launch sequences in steady
+    state (one stream = launch bound): identical masks, dist images, keypoints and descriptors."""
+    K = synth.intrinsics(320, 240)
+    s = synth.SyntheticStream(5, 320, 240)
+    fr = [s.frame(f) for f in range(8)]
+    monkeypatch.setenv("GD_GRAPHS", "0")
+    gm_p = capi.GeoMask(K, None, 5000.0, 320, 240, 0, batch=1)
+    orb_p = capi.Orb(600, 1.2, 6, 20, 7, 320, 240, 0, 1)
+    monkeypatch.setenv("GD_GRAPHS", "1")
+    gm_g = capi.GeoMask(K, None, 5000.0, 320, 240, 0, batch=1)
+    orb_g = capi.Orb(600, 1.2, 6, 20, 7, 320, 240, 0, 1)
+    R, T = s.pair_pose(0, 5)
+    for i in range(21):  # graphs start at frame 12 (geomask) / the third call (orb)
+        f = fr[i % 8]
+        for gm in (gm_p, gm_g):
+            gm.add_new_image([f.bgr], [f.depth_m])
+        mp = gm_p.get_no_gmm_mask(R[None], T[None])[0]
+        mg = gm_g.get_no_gmm_mask(R[None], T[None])[0]
+        assert np.array_equal(mp, mg), i
+        if i >= 5:
+            assert np.array_equal(gm_p.debug(capi.DBG_DIST), gm_g.debug(capi.DBG_DIST)), i
+            assert (mp == 0).any()
+        gray = oracle.gray(f.bgr, 1)
+        (kp, dp), (kg, dg) = orb_p([gray])[0], orb_g([gray])[0]
+        assert len(kp) == len(kg) > 100
+        for name in kp.dtype.names:
+            assert np.array_equal(kp[name], kg[name]), (i, name)
+        assert np.array_equal(dp, dg)
+    for h in (gm_p, gm_g, orb_p, orb_g):
+        h.close()
