@@ -220,7 +220,7 @@ int gd_stage_farneback(int device, const uint8_t* prev, const uint8_t* next, int
     GD_TRY(fb_launch_pyramid_polyexp(plan, g0.as<uint8_t>(), 0, 1, I.as<float>(), 0, R0.as<float>(), 0, 0, nullptr));
     GD_TRY(fb_launch_pyramid_polyexp(plan, g1.as<uint8_t>(), 0, 1, I.as<float>(), 0, R1.as<float>(), 0, 0, nullptr));
     const float2* fin = nullptr;
-    GD_TRY(fb_launch_flow(plan, R0.as<float>(), R1.as<float>(), 0, 1, fa.as<float2>(), fb.as<float2>(), 0, Mb.as<float>(), 0, &fin, 0, nullptr));
+    GD_TRY(fb_launch_flow(plan, R0.as<float>(), R1.as<float>(), 0, 1, fa.as<float2>(), fb.as<float2>(), 0, Mb.as<float>(), Mb.bytes, &fin, 0, nullptr));
     GD_CUDA(cudaDeviceSynchronize());
     GD_CUDA(cudaMemcpy(flow, fin, n * 8, cudaMemcpyDeviceToHost));
     return GD_OK;

@@ -814,7 +814,7 @@ int fb_prepare_device()
 }
 
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_stride_b, const float2** final_flow, cudaStream_t s,
+                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_bytes, const float2** final_flow, cudaStream_t s,
                    LaunchStats* st)
 {
     const float2* prev = nullptr;
@@ -839,25 +839,35 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
         float2* in = A;
         float2* out = B;
         for (int it = 0; it < plan.iterations; ++it) {
-            if (Mbuf) {  // split form: matrices to HBM once per pixel, then box filter + solve
-                {
-                    LaunchScope ls(st, s, "K1b_matrices", 1);
-                    dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), batch);
-                    if (it > 0)
-                        k_fb_matrices<0><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, in, f_stride_b, 0, 0, Mbuf, m_stride_b, L.w, L.h);
-                    else if (prev)
-                        k_fb_matrices<1><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, prev, f_stride_b, pw, ph, Mbuf, m_stride_b, L.w, L.h);
+            if (Mbuf) {
+                // split form: matrices once per pixel into M, then box filter + solve.  The streams of the batch go through
+                // in groups whose M (packed at the level's own stride) stays inside the L2 window of m_bytes: written by
+                // one kernel, read by the next, overwritten by the following group — M never has to reach HBM.
+                const size_t mstride = 5 * align_up((size_t)L.w * L.h, 64);
+                const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, m_bytes / (mstride * sizeof(float))));
+                for (int b0 = 0; b0 < batch; b0 += group) {
+                    const int nb = std::min(group, batch - b0);
+                    const float* r0 = R0 + L.r_off + (size_t)b0 * r_stride_b;
+                    const float* r1 = R1 + L.r_off + (size_t)b0 * r_stride_b;
+                    {
+                        LaunchScope ls(st, s, "K1b_matrices", 1);
+                        dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), nb);
+                        if (it > 0)
+                            k_fb_matrices<0><<<grid, block, 0, s>>>(r0, r1, r_stride_b, in + (size_t)b0 * f_stride_b, f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h);
+                        else if (prev)
+                            k_fb_matrices<1><<<grid, block, 0, s>>>(r0, r1, r_stride_b, prev + (size_t)b0 * f_stride_b, f_stride_b, pw, ph, Mbuf, mstride, L.w, L.h);
+                        else
+                            k_fb_matrices<2><<<grid, block, 0, s>>>(r0, r1, r_stride_b, nullptr, f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h);
+                        GD_CUDA(cudaGetLastError());
+                    }
+                    LaunchScope ls(st, s, "K1b_box_solve", 1);
+                    dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), nb);
+                    if ((L.w & 3) == 0)
+                        k_fb_box_solve<true><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h);
                     else
-                        k_fb_matrices<2><<<grid, block, 0, s>>>(R0 + L.r_off, R1 + L.r_off, r_stride_b, nullptr, f_stride_b, 0, 0, Mbuf, m_stride_b, L.w, L.h);
+                        k_fb_box_solve<false><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h);
                     GD_CUDA(cudaGetLastError());
                 }
-                LaunchScope ls(st, s, "K1b_box_solve", 1);
-                dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), batch);
-                if ((L.w & 3) == 0)
-                    k_fb_box_solve<true><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
-                else
-                    k_fb_box_solve<false><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, m_stride_b, out, f_stride_b, L.w, L.h);
-                GD_CUDA(cudaGetLastError());
             } else {
                 LaunchScope ls(st, s, "K1b_flow_iter", 1);
                 dim3 grid(cdiv(L.w, FT_W), cdiv(L.h, FT_H), batch);

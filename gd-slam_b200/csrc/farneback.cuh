@@ -47,7 +47,7 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
 // On return *final points at the level-0 flow (inside flowA or flowB).
 // Mbuf: [b][m_floats] scratch for the split form (matrices kernel + box/solve kernel); nullptr selects the fused kernel.
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_stride_b, const float2** final_flow, cudaStream_t s,
+                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_bytes, const float2** final_flow, cudaStream_t s,
                    LaunchStats* st);
 
 }  // namespace gd
