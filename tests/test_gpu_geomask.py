@@ -221,3 +221,28 @@ def test_standalone_handles_graph_replay_equals_plain_launches(capi, oracle, syn
         assert np.array_equal(dp, dg)
     for h in (gm_p, gm_g, orb_p, orb_g):
         h.close()
+
+
+def test_flow_stream_groups_equal_single_launch(capi, synth, monkeypatch):
+    """GD_M_L2_MB bounds the M scratch of the split flow form and runs the batch in stream groups: same flow, dist, mask."""
+    K = synth.intrinsics(320, 240)
+    streams = [synth.SyntheticStream(s, 320, 240) for s in range(3)]
+    fr = [[s.frame(f) for f in range(6)] for s in streams]
+    poses = [s.pair_pose(0, 5) for s in streams]
+    R, T = np.stack([p[0] for p in poses]), np.stack([p[1] for p in poses])
+    out = []
+    for mb in (None, "2"):  # 320x240: M is 1.5 MB per stream -> groups of one stream
+        if mb is None:
+            monkeypatch.delenv("GD_M_L2_MB", raising=False)
+        else:
+            monkeypatch.setenv("GD_M_L2_MB", mb)
+        gm = capi.GeoMask(K, None, 5000.0, 320, 240, 0, batch=3)
+        for f in range(6):
+            gm.add_new_image([fr[b][f].bgr for b in range(3)], [fr[b][f].depth_m for b in range(3)])
+        masks = gm.get_no_gmm_mask(R, T)
+        out.append((masks, [gm.debug(capi.DBG_FLOW, b) for b in range(3)], [gm.debug(capi.DBG_DIST, b) for b in range(3)]))
+        gm.close()
+    for b in range(3):
+        assert np.array_equal(out[0][1][b], out[1][1][b])
+        assert np.array_equal(out[0][2][b], out[1][2][b])
+        assert np.array_equal(out[0][0][b], out[1][0][b]) and (out[0][0][b] == 0).any()
