@@ -83,7 +83,7 @@ int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int
                  FbPlan* plan)
 {
     GD_REQUIRE(poly_n == FB_POLY_N && winsize == FB_WIN, "only poly_n=5 / winsize=15 (the reference's parameters) are built");
-    GD_REQUIRE(w >= 16 && h >= 16, "image too small");
+    GD_REQUIRE(w >= 48 && h >= 48, "image too small (the pyramid blurs reflect at most once at a border)");
     GD_TRY(fb_prepare_device());
     *plan = FbPlan();
     plan->w = w;
@@ -142,6 +142,13 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
+// BORDER_REFLECT_101 for -len < p < 2 len - 1 (blur radius smaller than the image: checked by the plan): no loop, no branch
+__device__ __forceinline__ int reflect101_once(int p, int len)
+{
+    p = abs(p);
+    return p >= len ? 2 * len - 2 - p : p;
+}
+
 struct PyrArgs {
     int W, H, lw, lh, ksize;
     double scale_x, scale_y;
@@ -162,7 +169,7 @@ __device__ __forceinline__ int fb_src_col(int dx, double scale_x, int W, float* 
 
 // Pass A of blur+resample: the row pass of the separable Gaussian on the FULL-RES rows, evaluated only at the two source
 // columns (sx, sx+1) every level column interpolates between.  One thread = one (full-res row, level column).
-__global__ void __launch_bounds__(128) k_fb_rowblur(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
+__global__ void __launch_bounds__(256) k_fb_rowblur(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
                                                     float2* __restrict__ Hrow, size_t hstride_b)
 {
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
@@ -171,21 +178,49 @@ __global__ void __launch_bounds__(128) k_fb_rowblur(const uint8_t* __restrict__ 
     const int sx = fb_src_col(dx, a.scale_x, a.W, &fx);
     const int r = a.ksize >> 1;
     const uint8_t* row = gray + (size_t)b * gstride_b + (size_t)y * a.W;
-    float prev = (float)__ldg(row + reflect101(sx - r, a.W));
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < a.ksize; ++i) {
-        const float nxt = (float)__ldg(row + reflect101(sx - r + i + 1, a.W));
-        acc0 = i == 0 ? a.taps[0] * prev : acc0 + a.taps[i] * prev;
-        acc1 = i == 0 ? a.taps[0] * nxt : acc1 + a.taps[i] * nxt;
+    // one code path for interior and border columns (a divergent border branch would be taken by most warps of the narrow
+    // levels); the first tap is peeled so that the loop body is two FMAs per load
+    const int x0 = sx - r;
+    float prev = (float)__ldg(row + reflect101_once(x0, a.W));
+    float nxt = (float)__ldg(row + reflect101_once(x0 + 1, a.W));
+    float acc0 = a.taps[0] * prev, acc1 = a.taps[0] * nxt;
+#pragma unroll 6
+    for (int i = 1; i < a.ksize; ++i) {
         prev = nxt;
+        nxt = (float)__ldg(row + reflect101_once(x0 + i + 1, a.W));
+        acc0 = acc0 + a.taps[i] * prev;
+        acc1 = acc1 + a.taps[i] * nxt;
     }
     Hrow[(size_t)b * hstride_b + (size_t)y * a.lw + dx] = make_float2(acc0, acc1);
 }
 
+// column pass for an interior level row: rows sy - r .. sy + 1 + r of the row-pass scratch, both windows from one set of loads
+template <int KS>
+__device__ __forceinline__ void fb_colblur_window(const float2* __restrict__ hp, int lw, int sy, const float* taps, float& B00,
+                                                  float& B01, float& B10, float& B11)
+{
+    constexpr int r = KS >> 1;
+    float2 wv[KS + 1];
+    const float2* p = hp + (size_t)(sy - r) * lw;
+#pragma unroll
+    for (int j = 0; j <= KS; ++j) wv[j] = __ldg(p + (size_t)j * lw);
+    B00 = taps[r] * wv[r].x;
+    B01 = taps[r] * wv[r].y;
+    B10 = taps[r] * wv[r + 1].x;
+    B11 = taps[r] * wv[r + 1].y;
+#pragma unroll
+    for (int i = 1; i <= r; ++i) {
+        const float t = taps[r + i];
+        B00 += t * (wv[r + i].x + wv[r - i].x);
+        B01 += t * (wv[r + i].y + wv[r - i].y);
+        B10 += t * (wv[r + 1 + i].x + wv[r + 1 - i].x);
+        B11 += t * (wv[r + 1 + i].y + wv[r + 1 - i].y);
+    }
+}
+
 // Pass B: column pass (symmetric form, REFLECT_101) at the two source rows of every level pixel, then cv::resize's
 // bilinear combination (horizontal first, then vertical).  Reads of Hrow are coalesced across dx.
-__global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restrict__ Hrow, size_t hstride_b, PyrArgs a,
+__global__ void __launch_bounds__(256) k_fb_colblur_resize(const float2* __restrict__ Hrow, size_t hstride_b, PyrArgs a,
                                                            float* __restrict__ I, size_t istride_b)
 {
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
@@ -200,8 +235,20 @@ __global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restr
     sy1 = max(0, min(a.H - 1, sy1));
     const int r = a.ksize >> 1;
     const float2* hp = Hrow + (size_t)b * hstride_b + dx;
+    float B00, B01, B10, B11;
+    // interior rows (all but the first/last few level rows): the two windows centred on sy and sy + 1 share ksize - 1 of
+    // their rows; load the ksize + 1 rows once.  Same products and sums as the general path below.
+    const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < a.H;
+    if (interior && a.ksize == 19) {
+        fb_colblur_window<19>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
+    } else if (interior && a.ksize == 9) {
+        fb_colblur_window<9>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
+    } else if (interior && a.ksize == 3) {
+        fb_colblur_window<3>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
+    } else {
     const float2 c0 = __ldg(hp + (size_t)sy * a.lw);
-    float B00 = a.taps[r] * c0.x, B01 = a.taps[r] * c0.y;
+    B00 = a.taps[r] * c0.x;
+    B01 = a.taps[r] * c0.y;
 #pragma unroll 4
     for (int i = 1; i <= r; ++i) {
         const float t = a.taps[r + i];
@@ -209,7 +256,8 @@ __global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restr
         B00 += t * (u.x + d.x);
         B01 += t * (u.y + d.y);
     }
-    float B10 = B00, B11 = B01;
+    B10 = B00;
+    B11 = B01;
     if (sy1 != sy) {
         const float2 c1 = __ldg(hp + (size_t)sy1 * a.lw);
         B10 = a.taps[r] * c1.x;
@@ -222,6 +270,7 @@ __global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restr
             B11 += t * (u.y + d.y);
         }
     }
+    }
     const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
     const float r0 = B00 * a0 + B01 * a1;
     const float r1 = B10 * a0 + B11 * a1;
@@ -229,17 +278,17 @@ __global__ void __launch_bounds__(128) k_fb_colblur_resize(const float2* __restr
 }
 
 // level 0: the level has the size of the image, cv::resize is a copy -> one 3x3 separable blur per pixel
-__global__ void __launch_bounds__(128) k_fb_blur3_same(const uint8_t* __restrict__ gray, size_t gstride_b, int W, int H, float t0,
+__global__ void __launch_bounds__(256) k_fb_blur3_same(const uint8_t* __restrict__ gray, size_t gstride_b, int W, int H, float t0,
                                                        float t1, float t2, float* __restrict__ I, size_t istride_b)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     const uint8_t* g = gray + (size_t)b * gstride_b;
-    const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    const int xm = reflect101_once(x - 1, W), xp = reflect101_once(x + 1, W);
     float h[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const uint8_t* row = g + (size_t)reflect101(y - 1 + j, H) * W;
+        const uint8_t* row = g + reflect101_once(y - 1 + j, H) * W;
         float acc = t0 * (float)__ldg(row + xm);
         acc = acc + t1 * (float)__ldg(row + x);
         acc = acc + t2 * (float)__ldg(row + xp);
@@ -338,13 +387,17 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
         std::memcpy(pa.taps, L.taps, sizeof(pa.taps));
         {
             LaunchScope ls(st, s, "K1a_blur_resample", (L.w == plan.w && L.h == plan.h && L.ksize == 3) ? 1 : 2);
-            dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
+            // one thread per level column: the block width with the fewest idle lanes for this level (80 -> 96, 160 -> 160)
+            int bs = 128;
+            for (int c = 256, waste = 1 << 30; c >= 64; c -= 32)
+                if (cdiv(L.w, c) * c - L.w < waste) { waste = cdiv(L.w, c) * c - L.w; bs = c; }
+            dim3 block(bs), grid(cdiv(L.w, bs), L.h, batch);
             float* Ik = scratch_I + L.i_off;
             if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
                 k_fb_blur3_same<<<grid, block, 0, s>>>(gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b);
             } else {
                 float2* Hrow = reinterpret_cast<float2*>(scratch_I + plan.hrow_off);
-                dim3 gridA(cdiv(L.w, 128), plan.h, batch);
+                dim3 gridA(cdiv(L.w, bs), plan.h, batch);
                 k_fb_rowblur<<<gridA, block, 0, s>>>(gray, gray_stride_b, pa, Hrow, i_stride_b / 2);
                 GD_CUDA(cudaGetLastError());
                 k_fb_colblur_resize<<<grid, block, 0, s>>>(Hrow, i_stride_b / 2, pa, Ik, i_stride_b);
