@@ -229,3 +229,32 @@ def test_handles_on_two_devices_in_one_process(capi, synth):
     (m1, k1, d1), (m0, k0, d0) = outs
     assert np.array_equal(m1, m0) and (m0 == 0).any()
     _same_kp(k1, d1, k0, d0)
+
+
+def test_degenerate_inputs_match_oracle(capi, oracle, synth):
+    """Edge cases of the domain: no valid depth at all (empty dist image: min == max -> cv::normalize maps everything to 0 ->
+    all-ones mask) and a texture-less image (no FAST corner at either threshold -> zero keypoints, zero flow)."""
+    K = synth.intrinsics(320, 240)
+    s = synth.SyntheticStream(6, 320, 240)
+    fr = [s.frame(f) for f in range(6)]
+    R, T = s.pair_pose(0, 5)
+    # (1) depth missing everywhere
+    fe = capi.Frontend(K, 320, 240, batch=1, nfeatures=600, nlevels=6)
+    zero = np.zeros((240, 320), np.float32)
+    for f in range(6):
+        mask, kp, desc = fe.step([fr[f].bgr], [zero], R[None], T[None])[0]
+    mo = oracle.geomask_pair(fr[0].bgr, fr[5].bgr, zero, zero, K, R, T)
+    assert np.array_equal(mask, mo) and mask.min() == 1
+    assert len(kp) > 100  # ORB does not depend on depth
+    fe.close()
+    # (2) constant image: nothing to detect, nothing to track
+    fe = capi.Frontend(K, 320, 240, batch=1, nfeatures=600, nlevels=6)
+    flat = np.full((240, 320, 3), 117, np.uint8)
+    for f in range(6):
+        mask, kp, desc = fe.step([flat], [fr[f].depth_m], R[None], T[None])[0]
+    rkp, rdesc, _ = oracle.orb_extract(oracle.gray(flat, 1), nfeatures=600, nlevels=6)
+    assert len(kp) == 0 and len(rkp) == 0 and desc.shape[0] == 0
+    mo, flow_o, _ = oracle.geomask_pair(flat, flat, fr[0].depth_m, fr[5].depth_m, K, R, T, want_debug=True)
+    assert np.abs(fe.debug(capi.DBG_FLOW)).max() == 0 and np.abs(flow_o).max() == 0
+    assert (mask == mo).mean() >= 0.999
+    fe.close()
