@@ -235,6 +235,14 @@ def _extract(fn, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, 
     kps = np.zeros(cap, KP_DTYPE)
     desc = np.zeros((cap, 32), np.uint8)
     cfg = orb_config(w, h, nfeatures, scale, nlevels)
+    # the reference has no guards here: a level narrower than one 30-px cell divides by zero at ORBextractor.cc:783-786 and a
+    # portrait level with round(width / height) == 0 indexes an empty node vector at :543-566.  Both sides reject such input.
+    for lw, lh in cfg["level_sizes"]:
+        bw, bh = float(int(lw) - 32 + 3), float(int(lh) - 32 + 3)
+        if int(bw / 30.0) < 1 or int(bh / 30.0) < 1:
+            raise ValueError(f"level {lw}x{lh} too small for one FAST cell")
+        if int(np.round(np.float32(bw) / np.float32(bh))) < 1:
+            raise ValueError(f"level {lw}x{lh}: aspect ratio not supported by DistributeOctTree (nIni = 0)")
     tot = int(sum(int(a) * int(b) for a, b in cfg["level_sizes"]))
     pyr = np.zeros(tot, np.uint8) if want_pyramid else None
     aux = np.zeros(nlevels * 2, np.int32)

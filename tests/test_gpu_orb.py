@@ -110,3 +110,40 @@ def test_capacity_error_is_reported(capi, gray640):
                                      capi._ptr_array([desc]), 10, n)
     assert code == capi.GD_ECAPACITY and n[0] > 1000
     orb.close()
+
+
+def test_random_sizes_parameters_and_rejected_inputs(capi, oracle):
+    """Randomised sizes / feature budgets / level counts / thresholds / corner densities: GPU == oracle bit for bit, and the
+    inputs on which the reference has undefined behaviour (portrait level with nIni == 0, level smaller than one cell) are
+    rejected with an error by both."""
+    rs = np.random.RandomState(20240517)
+    checked = rejected = 0
+    for case in range(10):
+        w, h = int(rs.randint(150, 700)), int(rs.randint(120, 520))
+        nlevels = int(rs.randint(2, 6)) if min(w, h) < 250 else int(rs.randint(4, 9))
+        nf = int(rs.choice([300, 800, 1500, 2500]))
+        ini, mn = [(20, 7), (30, 10), (12, 5)][int(rs.randint(0, 3))]
+        img = rs.rand(h, w).astype(np.float32)
+        k = int(rs.choice([1, 2, 4]))
+        if k > 1:
+            pad = np.pad(img, k, mode="edge")
+            acc = np.zeros_like(img)
+            for dy in range(2 * k + 1):
+                for dx in range(2 * k + 1):
+                    acc += pad[dy:dy + h, dx:dx + w]
+            img = acc
+        img = ((img - img.min()) / (img.max() - img.min()) * rs.choice([255.0, 90.0])).astype(np.uint8)
+        try:
+            rkp, rdesc, _ = oracle.orb_extract(img, nfeatures=nf, nlevels=nlevels, ini_th=ini, min_th=mn)
+        except ValueError:
+            with pytest.raises(capi.GdError):
+                capi.Orb(nf, 1.2, nlevels, ini, mn, w, h, 0, 1)
+            rejected += 1
+            continue
+        orb = capi.Orb(nf, 1.2, nlevels, ini, mn, w, h, 0, 1)
+        for _ in range(3):  # third call replays the CUDA graph of the launch sequence
+            kp, desc = orb([img])[0]
+            _assert_same(kp, desc, rkp, rdesc)
+        orb.close()
+        checked += 1
+    assert checked >= 6 and rejected >= 1

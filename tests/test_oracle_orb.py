@@ -91,3 +91,36 @@ def test_sincos_contract_vs_libm_sweep():
     diff = np.abs(contract.view(np.int32).astype(np.int64) - libm.view(np.int32).astype(np.int64))
     assert diff.max() <= 1  # never more than one ulp apart
     print("cosf vs correctly-rounded: %d / %d differ by 1 ulp" % ((diff > 0).sum(), diff.size))
+
+
+def test_live_reference_random_sizes_and_parameters(oracle):
+    """Randomised pin of the restated ORBextractor against the verbatim-compiled reference: image sizes that are not
+    multiples of anything, different feature budgets / level counts / thresholds, textures from sparse to dense."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/liborbref.so not built")
+    rs = np.random.RandomState(20240517)
+    checked = 0
+    for case in range(10):
+        w, h = int(rs.randint(150, 700)), int(rs.randint(120, 520))
+        nlevels = int(rs.randint(2, 6)) if min(w, h) < 250 else int(rs.randint(4, 9))
+        nf = int(rs.choice([300, 800, 1500, 2500]))
+        ini, mn = [(20, 7), (30, 10), (12, 5)][int(rs.randint(0, 3))]
+        img = rs.rand(h, w).astype(np.float32)
+        k = int(rs.choice([1, 2, 4]))  # box-smooth: controls corner density
+        if k > 1:
+            pad = np.pad(img, k, mode="edge")
+            acc = np.zeros_like(img)
+            for dy in range(2 * k + 1):
+                for dx in range(2 * k + 1):
+                    acc += pad[dy:dy + h, dx:dx + w]
+            img = acc
+        img = ((img - img.min()) / (img.max() - img.min()) * rs.choice([255.0, 90.0])).astype(np.uint8)
+        try:
+            kp, desc, _ = oracle.orb_extract(img, nfeatures=nf, nlevels=nlevels, ini_th=ini, min_th=mn)
+        except ValueError:
+            continue  # level smaller than one cell / portrait level with nIni == 0: the reference has undefined behaviour
+        rkp, rdesc, _ = oracle.orbref_extract(img, nfeatures=nf, nlevels=nlevels, ini_th=ini, min_th=mn)
+        assert len(kp) == len(rkp), (case, w, h, nlevels, nf, len(kp), len(rkp))
+        assert np.array_equal(kp, rkp) and np.array_equal(desc, rdesc), (case, w, h, nlevels, nf)
+        checked += 1
+    assert checked >= 6
