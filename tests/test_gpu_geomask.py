@@ -246,3 +246,26 @@ def test_flow_stream_groups_equal_single_launch(capi, synth, monkeypatch):
         assert np.array_equal(out[0][1][b], out[1][1][b])
         assert np.array_equal(out[0][2][b], out[1][2][b])
         assert np.array_equal(out[0][0][b], out[1][0][b]) and (out[0][0][b] == 0).any()
+
+
+@pytest.mark.parametrize("size", [(322, 246), (401, 303), (218, 166)])
+def test_full_pair_at_ragged_sizes(capi, oracle, synth, size):
+    """Widths that are not multiples of 4 (unaligned gray / depth rows, the scalar tile path of the box filter, odd pyramid
+    levels) with a rolling camera: edges bit-exact, flow within tolerance, mask >= 99.9 %."""
+    w, h = size
+    K = synth.intrinsics(w, h)
+    s = synth.SyntheticStream(7, w, h, roll_deg_per_frame=0.05)
+    fr = [s.frame(f) for f in range(6)]
+    R, T = s.pair_pose(0, 5)
+    gm = capi.GeoMask(K, None, 5000.0, w, h, 0, batch=1)
+    for f in fr:
+        gm.add_new_image([f.bgr], [f.depth_m])
+    mask = gm.get_no_gmm_mask(R[None], T[None])[0]
+    mo, flow_o, dist_o = oracle.geomask_pair(fr[0].bgr, fr[5].bgr, fr[0].depth_m, fr[5].depth_m, K, R, T, want_debug=True)
+    assert np.array_equal(gm.debug(capi.DBG_EDGE_CUR), oracle.depth_edge(fr[5].depth_m, K))
+    assert np.array_equal(gm.debug(capi.DBG_EDGE_REF), oracle.depth_edge(fr[0].depth_m, K))
+    nviol, dmax = flow_tol_violations(gm.debug(capi.DBG_FLOW), flow_o)
+    assert nviol == 0, (size, nviol, dmax)
+    assert (mask == mo).mean() >= 0.999, (size, (mask == mo).mean())
+    assert (mo == 0).any() and (mo == 1).any()
+    gm.close()
