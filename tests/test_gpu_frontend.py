@@ -90,9 +90,10 @@ def test_frontend_profile_families(capi, synth):
     fe.close()
 
 
-def test_frontend_1280x720_pair(capi, oracle, synth):
-    """configs[4] resolution sweep: the same path at 1280x720 (4 Farneback levels of 1280..160 px, ORB cells at 2 initial nodes)."""
-    w, h = 1280, 720
+@pytest.mark.parametrize("size", [(1280, 720), (1920, 1080)])
+def test_frontend_large_resolution_pair(capi, oracle, synth, size):
+    """configs[4] resolution sweep: the same path at 1280x720 and 1920x1080 (4 Farneback levels, ORB cells at 2 initial nodes)."""
+    w, h = size
     K = synth.intrinsics(w, h)
     s = synth.SyntheticStream(0, w, h)
     fr = [s.frame(f) for f in range(6)]
@@ -103,10 +104,11 @@ def test_frontend_1280x720_pair(capi, oracle, synth):
     mask, kp, desc = fe.step([fr[5].bgr], [fr[5].depth_m], R[None], T[None])[0]
     mo, flow_o, _ = oracle.geomask_pair(fr[0].bgr, fr[5].bgr, fr[0].depth_m, fr[5].depth_m, K, R, T, want_debug=True)
     nviol, dmax = flow_tol_violations(fe.debug(capi.DBG_FLOW, 0), flow_o)
-    # At this resolution the occlusion edge of the moving object holds a few ill-conditioned pixels where Farneback is
-    # chaotic: cv2 4.13 with setUseOptimized(True) vs (False) already differs there by 3.3e-4 (12 px over tolerance), the
-    # oracle differs from cv2 at 14 px.  Criterion: tolerance everywhere except <= 0.01 % of the field, bounded excursion.
-    assert nviol <= 1e-4 * flow_o.size and dmax < 5e-3, (nviol, dmax)
+    # At these resolutions the occlusion edge of the moving object holds ill-conditioned pixels where Farneback is chaotic:
+    # cv2 4.13 with setUseOptimized(True) vs (False) already disagrees beyond the tolerance at 12 flow components
+    # (max 3.3e-4) at 1280x720 and at 694 components (max 2.1e-3) at 1920x1080; the oracle differs from cv2 at 14 / 615.
+    # Criterion: tolerance everywhere except <= 0.03 % of the field (the reference's own spread), bounded excursion.
+    assert nviol <= 3e-4 * flow_o.size and dmax < 5e-3, (nviol, dmax)
     assert (mask == mo).mean() >= 0.999
     rkp, rdesc, _ = oracle.orb_extract(oracle.gray(fr[5].bgr, 1))
     _same_kp(kp, desc, rkp, rdesc)
