@@ -172,6 +172,7 @@ __device__ __forceinline__ int fb_src_col(int dx, double scale_x, int W, float* 
 __global__ void __launch_bounds__(256) k_fb_rowblur(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
                                                     float2* __restrict__ Hrow, size_t hstride_b)
 {
+    pdl_wait();
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (dx >= a.lw) return;
     float fx;
@@ -223,6 +224,7 @@ __device__ __forceinline__ void fb_colblur_window(const float2* __restrict__ hp,
 __global__ void __launch_bounds__(256) k_fb_colblur_resize(const float2* __restrict__ Hrow, size_t hstride_b, PyrArgs a,
                                                            float* __restrict__ I, size_t istride_b)
 {
+    pdl_wait();
     const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
     if (dx >= a.lw) return;
     float fx;
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize(const float2* __restr
 __global__ void __launch_bounds__(256) k_fb_blur3_same(const uint8_t* __restrict__ gray, size_t gstride_b, int W, int H, float t0,
                                                        float t1, float t2, float* __restrict__ I, size_t istride_b)
 {
+    pdl_wait();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
     if (x >= W) return;
     const uint8_t* g = gray + (size_t)b * gstride_b;
@@ -311,6 +314,7 @@ constexpr int PT_NT = PT_W * PT_TY;
 __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs a,
                                                             float* __restrict__ R, size_t rstride_b)
 {
+    pdl_wait();
     __shared__ float sI[PT_H + 2 * PN][PT_W + 2 * PN];
     __shared__ float sR[3][PT_H][PT_W + 2 * PN];
     const int b = blockIdx.z;
@@ -394,13 +398,13 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
             dim3 block(bs), grid(cdiv(L.w, bs), L.h, batch);
             float* Ik = scratch_I + L.i_off;
             if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
-                k_fb_blur3_same<<<grid, block, 0, s>>>(gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b);
+                GD_CUDA(launch_pdl(k_fb_blur3_same, grid, block, 0, s, gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b));
             } else {
                 float2* Hrow = reinterpret_cast<float2*>(scratch_I + plan.hrow_off);
                 dim3 gridA(cdiv(L.w, bs), plan.h, batch);
-                k_fb_rowblur<<<gridA, block, 0, s>>>(gray, gray_stride_b, pa, Hrow, i_stride_b / 2);
+                GD_CUDA(launch_pdl(k_fb_rowblur, gridA, block, 0, s, gray, gray_stride_b, pa, Hrow, i_stride_b / 2));
                 GD_CUDA(cudaGetLastError());
-                k_fb_colblur_resize<<<grid, block, 0, s>>>(Hrow, i_stride_b / 2, pa, Ik, i_stride_b);
+                GD_CUDA(launch_pdl(k_fb_colblur_resize, grid, block, 0, s, Hrow, i_stride_b / 2, pa, Ik, i_stride_b));
             }
             GD_CUDA(cudaGetLastError());
         }
@@ -413,7 +417,7 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
             std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
             po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
             dim3 block(PT_W, PT_TY), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
-            k_fb_polyexp<<<grid, block, 0, s>>>(scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b);
+            GD_CUDA(launch_pdl(k_fb_polyexp, grid, block, 0, s, scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b));
             GD_CUDA(cudaGetLastError());
         }
     }
@@ -646,6 +650,8 @@ __global__ void __launch_bounds__(256, 8) k_fb_matrices(const float* __restrict_
                                                      const float2* __restrict__ fin, size_t fstride_b, int pw, int ph,
                                                      float* __restrict__ Mout, size_t mstride_b, int w, int h)
 {
+    pdl_trigger();
+    pdl_wait();
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int b = blockIdx.z;
@@ -731,6 +737,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __restrict__ Min, size_t mstride_b,
                                                                 float2* __restrict__ fout, size_t fstride_b, int w, int h)
 {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sT = reinterpret_cast<float*>(smem_raw);                                        // [2][BXH_H][BXM_P] channel tile
     double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 2 * BXH_H * BXM_P);  // [BXH_H][BXS_P]
@@ -906,19 +914,19 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
                         LaunchScope ls(st, s, "K1b_matrices", 1);
                         dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), nb);
                         if (it > 0)
-                            k_fb_matrices<0><<<grid, block, 0, s>>>(r0, r1, r_stride_b, in + (size_t)b0 * f_stride_b, f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h);
+                            GD_CUDA(launch_pdl(k_fb_matrices<0>, grid, block, 0, s, r0, r1, r_stride_b, (const float2*)(in + (size_t)b0 * f_stride_b), f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h));
                         else if (prev)
-                            k_fb_matrices<1><<<grid, block, 0, s>>>(r0, r1, r_stride_b, prev + (size_t)b0 * f_stride_b, f_stride_b, pw, ph, Mbuf, mstride, L.w, L.h);
+                            GD_CUDA(launch_pdl(k_fb_matrices<1>, grid, block, 0, s, r0, r1, r_stride_b, prev + (size_t)b0 * f_stride_b, f_stride_b, pw, ph, Mbuf, mstride, L.w, L.h));
                         else
-                            k_fb_matrices<2><<<grid, block, 0, s>>>(r0, r1, r_stride_b, nullptr, f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h);
+                            GD_CUDA(launch_pdl(k_fb_matrices<2>, grid, block, 0, s, r0, r1, r_stride_b, (const float2*)nullptr, f_stride_b, 0, 0, Mbuf, mstride, L.w, L.h));
                         GD_CUDA(cudaGetLastError());
                     }
                     LaunchScope ls(st, s, "K1b_box_solve", 1);
                     dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), nb);
                     if ((L.w & 3) == 0)
-                        k_fb_box_solve<true><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h);
+                        GD_CUDA(launch_pdl(k_fb_box_solve<true>, grid, dim3(BX_THREADS), BX_SMEM, s, (const float*)Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h));
                     else
-                        k_fb_box_solve<false><<<grid, BX_THREADS, BX_SMEM, s>>>(Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h);
+                        GD_CUDA(launch_pdl(k_fb_box_solve<false>, grid, dim3(BX_THREADS), BX_SMEM, s, (const float*)Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h));
                     GD_CUDA(cudaGetLastError());
                 }
             } else {

@@ -162,6 +162,41 @@ struct LaunchScope {
     }
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched through launch_pdl() may be scheduled as soon as every CTA of
+// the previous kernel in the stream has executed pdl_trigger() (or exited); its own pdl_wait() then blocks until that
+// kernel has completed and its writes are visible.  Kernels call pdl_trigger(); pdl_wait(); before their first global
+// access, so the launch latency and the tail of the previous kernel overlap with the next kernel's CTAs becoming resident.
+// Both instructions are no-ops for a kernel launched the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+inline bool pdl_enabled()
+{
+    static const bool on = [] {
+        const char* e = std::getenv("GD_PDL");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Replays a static launch sequence as a CUDA graph, one executable per key (small batches are launch bound).
 // enqueue() must only enqueue work on `s` (or on streams forked from and joined back into it), must give the same launches
 // for the same key, and must not advance host state.  Never used inside another capture: the batched front-end captures

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ bgr, s
                                               uint8_t* __restrict__ g_flow, size_t gstride_b, uint8_t* __restrict__ g_orb,
                                               int orb_order, size_t opitch, size_t ostride_b, int aligned)
 {
+    pdl_wait();
     const int b = blockIdx.z;
     const int groups = (w + 3) >> 2;
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +148,7 @@ int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w,
     LaunchScope ls(st, s, "K0_gray", 1);
     const int aligned = ((reinterpret_cast<uintptr_t>(bgr) & 3) == 0 && (bgr_step & 3) == 0 && (bgr_stride_b & 3) == 0) ? 1 : 0;
     dim3 block(128), grid(cdiv((w + 3) / 4, 128), h, batch);
-    k_gray<<<grid, block, 0, s>>>(bgr, bgr_step, bgr_stride_b, w, h, g_flow, gray_stride_b, g_orb, orb_order, orb_pitch, orb_stride_b, aligned);
+    GD_CUDA(launch_pdl(k_gray, grid, block, 0, s, bgr, bgr_step, bgr_stride_b, w, h, g_flow, gray_stride_b, g_orb, orb_order, orb_pitch, orb_stride_b, aligned));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
@@ -160,6 +161,7 @@ constexpr int ET_W = 32, ET_H = 16;
 __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
                                                             CamConst cam, uint8_t* __restrict__ edge, size_t estride_b)
 {
+    pdl_wait();
     __shared__ double sd[ET_H + 4][ET_W + 4];        // clamped depth, halo 2
     __shared__ double sn[ET_H + 2][ET_W + 2][3];     // normals, halo 1
     __shared__ double sv[ET_H + 2][ET_W + 2][3];     // vertices, halo 1
@@ -261,7 +263,7 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
 {
     LaunchScope ls(st, s, "K2a_depth_edge", 1);
     dim3 block(ET_W, ET_H), grid(cdiv(w, ET_W), cdiv(h, ET_H), batch);
-    k_depth_edge<<<grid, block, 0, s>>>(depth, depth_stride_b, w, h, cam, edge, edge_stride_b);
+    GD_CUDA(launch_pdl(k_depth_edge, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict
                                                      const PoseDev* __restrict__ poses, unsigned long long* __restrict__ keys,
                                                      size_t kstride_b)
 {
+    pdl_wait();
     const int b = blockIdx.z;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -425,8 +428,8 @@ int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* de
 {
     LaunchScope ls(st, s, "K2b_mahalanobis", 1);
     dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), batch);
-    k_mahalanobis<<<grid, block, 0, s>>>(flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
-                                          edge_stride_b, lut, w, h, cam, poses, keys, keys_stride_b);
+    GD_CUDA(launch_pdl(k_mahalanobis, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
+                                          edge_stride_b, lut, w, h, cam, poses, keys, keys_stride_b));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
@@ -437,6 +440,7 @@ int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* de
 __global__ void __launch_bounds__(256) k_minmax(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
                                                 unsigned int* __restrict__ minmax_bits)
 {
+    pdl_wait();
     const int b = blockIdx.y;
     const unsigned long long* kp = keys + (size_t)b * kstride_b;
     unsigned mn = 0xFFFFFFFFu, mx = 0u;
@@ -492,7 +496,7 @@ int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px
     int blocks = cdiv(n_px / 2, 256 * 4);
     if (blocks < 1) blocks = 1;
     dim3 grid(blocks, batch);
-    k_minmax<<<grid, 256, 0, s>>>(keys, keys_stride_b, n_px, minmax_bits);
+    GD_CUDA(launch_pdl(k_minmax, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(256) k_normalize_mask(unsigned long long* __re
                                                         const PoseDev* __restrict__ poses, uint8_t* __restrict__ mask,
                                                         size_t mstride_b, float* __restrict__ dist_out, size_t dstride_b)
 {
+    pdl_wait();
     const int b = blockIdx.y;
     unsigned long long* kp = keys + (size_t)b * kstride_b;
     uint8_t* mp = mask + (size_t)b * mstride_b;
@@ -553,8 +558,8 @@ int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_
 {
     LaunchScope ls(st, s, "K3b_normalize_mask", 1);
     dim3 grid(cdiv(cdiv(n_px, 4), 256), batch);
-    k_normalize_mask<<<grid, 256, 0, s>>>(keys, keys_stride_b, n_px, minmax_bits, poses, mask, mask_stride_b, dist_out,
-                                          dist_stride_b);
+    GD_CUDA(launch_pdl(k_normalize_mask, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits, poses, mask, mask_stride_b, dist_out,
+                                          dist_stride_b));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

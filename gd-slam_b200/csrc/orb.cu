@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) k_orb_resize(const uint8_t* __restrict__ 
                                                     int dh, int dpitch, size_t stride_b, const ushort4* __restrict__ xt,
                                                     const ushort4* __restrict__ yt)
 {
+    pdl_wait();
     const int dx = blockIdx.x * 32 + threadIdx.x;
     if (dx >= dw) return;
     const uint8_t* s = src + (size_t)blockIdx.z * stride_b;
@@ -255,6 +256,7 @@ constexpr int FAST_KW = FAST_KEEP_WORDS / 32;
 __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __restrict__ pyr, size_t pyr_stride_b, FastArgs a,
                                                           int* __restrict__ cell_cnt, ushort4* __restrict__ slabs)
 {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char sm[];
     const int tp = a.tile_w;                       // tile pitch (multiple of 4, >= widest cell + 3 alignment columns)
     uint8_t* tile_base = sm;                       // [tile_h][tp], rows start at the 4-byte aligned column below x0
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_orb_quadtree(QtArgs a, const int
                                                              int* __restrict__ kept_cnt, int* __restrict__ cand_cnt,
                                                              int* __restrict__ err)
 {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char qsm[];
     const int LN = a.LN;
     // shared arrays (ints unless noted)
@@ -745,6 +748,7 @@ __device__ __forceinline__ int reflect101i(int p, int len)
 __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ out, size_t stride_b,
                                                   BlurArgs a)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     int t = blockIdx.x * 8 + (threadIdx.x >> 5), l = 0;
     if (t >= a.total_tiles) return;  // warp-uniform
@@ -849,6 +853,7 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
                                                       gd_keypoint* __restrict__ out_kp, uint8_t* __restrict__ out_desc,
                                                       int* __restrict__ out_n)
 {
+    pdl_wait();
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1040,8 +1045,8 @@ int OrbCore::enqueue_extract()
         LaunchScope ls(stats, stream, "K4a_pyramid_resize", 1);
         const OrbLevel &S = P.lv[l - 1], &D = P.lv[l];
         dim3 block(32, 8), grid(cdiv(D.w, 32), cdiv(D.h, 8 * RS_ROWS), batch);
-        k_orb_resize<<<grid, block, 0, stream>>>(py + S.off, S.pitch, py + D.off, D.w, D.h, D.pitch, P.pyr_bytes,
-                                                 rs_tab.as<ushort4>() + rs_x_off[l], rs_tab.as<ushort4>() + rs_y_off[l]);
+        GD_CUDA(launch_pdl(k_orb_resize, grid, block, 0, stream, py + S.off, S.pitch, py + D.off, D.w, D.h, D.pitch, P.pyr_bytes,
+                                                 rs_tab.as<ushort4>() + rs_x_off[l], rs_tab.as<ushort4>() + rs_y_off[l]));
         GD_CUDA(cudaGetLastError());
     }
     {  // K4b: FAST over every cell of every level
@@ -1054,8 +1059,8 @@ int OrbCore::enqueue_extract()
             fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start};
         }
         dim3 grid(P.total_cells, batch);
-        k_orb_fast<<<grid, FAST_THREADS, (size_t)P.tile_w * P.tile_h * 4, stream>>>(py, P.pyr_bytes, fa, cell_cnt.as<int>(),
-                                                                                      slabs.as<ushort4>());
+        GD_CUDA(launch_pdl(k_orb_fast, grid, dim3(FAST_THREADS), (size_t)P.tile_w * P.tile_h * 4, stream, py, P.pyr_bytes, fa, cell_cnt.as<int>(),
+                                                                                      slabs.as<ushort4>()));
         GD_CUDA(cudaGetLastError());
     }
     {  // K4c: quadtree, one CTA per (level, stream)
@@ -1069,9 +1074,9 @@ int OrbCore::enqueue_extract()
                         L.w - ORB_EDGE + 3 - ORB_BORDER, L.h - ORB_EDGE + 3 - ORB_BORDER, L.hX};
         }
         dim3 grid(P.nlevels, batch);
-        k_orb_quadtree<<<grid, QT_THREADS, qt_smem_bytes(qa.LN, qa.max_cells), stream>>>(
+        GD_CUDA(launch_pdl(k_orb_quadtree, grid, dim3(QT_THREADS), qt_smem_bytes(qa.LN, qa.max_cells), stream, 
             qa, cell_cnt.as<int>(), slabs.as<ushort4>(), cand.as<ushort4>(), cand_q.as<uint8_t>(), kept.as<int>(),
-            kept_cnt.as<int>(), cand_cnt.as<int>(), err.as<int>());
+            kept_cnt.as<int>(), cand_cnt.as<int>(), err.as<int>()));
         GD_CUDA(cudaGetLastError());
     }
     {  // K4e: 7x7 Gaussian of every level
@@ -1086,7 +1091,7 @@ int OrbCore::enqueue_extract()
         }
         ba.total_tiles = tiles;
         dim3 grid(cdiv(tiles, 8), batch);  // one warp per 120 x 32 block
-        k_orb_blur<<<grid, 256, 0, stream>>>(py, blur.as<uint8_t>(), P.pyr_bytes, ba);
+        GD_CUDA(launch_pdl(k_orb_blur, grid, dim3(256), 0, stream, py, blur.as<uint8_t>(), P.pyr_bytes, ba));
         GD_CUDA(cudaGetLastError());
     }
     {  // K4d/e: orientation + descriptors + output records
@@ -1099,9 +1104,9 @@ int OrbCore::enqueue_extract()
             da.lv[l] = {L.pitch, L.cand_off, L.kept_off, (unsigned long long)L.off, L.scale, L.kp_size};
         }
         dim3 grid(cdiv(P.kp_capacity, 8), batch);
-        k_orb_describe<<<grid, 256, 0, stream>>>(py, blur.as<uint8_t>(), P.pyr_bytes, da, cand.as<ushort4>(), kept.as<int>(),
+        GD_CUDA(launch_pdl(k_orb_describe, grid, dim3(256), 0, stream, py, blur.as<uint8_t>(), P.pyr_bytes, da, cand.as<ushort4>(), kept.as<int>(),
                                                  kept_cnt.as<int>(), out_kp.as<gd_keypoint>(), out_desc.as<uint8_t>(),
-                                                 out_n.as<int>());
+                                                 out_n.as<int>()));
         GD_CUDA(cudaGetLastError());
     }
     return GD_OK;
