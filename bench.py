@@ -250,7 +250,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("GD_BENCH_BATCH", "32")), help="streams per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("GD_BENCH_BATCH", "64")), help="streams per GPU")
     ap.add_argument("--streams-total", type=int, default=0,
                     help="strong-scaling variant of SURVEY 8d config 4: this many streams in total, split evenly over the GPUs "
                          "(overrides --batch; e.g. 8 -> 8/4/2/1 streams per GPU on 1/2/4/8 GPUs)")
@@ -432,7 +432,10 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom_name)
+            tj = json.load(open(tp))
+            traffic = tj.get(dom_name)
+            if traffic is not None:  # captured at tj["_streams"] streams of 640x480 per launch; per-launch traffic scales with batch and pixels
+                traffic = traffic * B / float(tj.get("_streams", B)) * (N_PX / float(640 * 480))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
