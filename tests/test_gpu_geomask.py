@@ -269,3 +269,22 @@ def test_full_pair_at_ragged_sizes(capi, oracle, synth, size):
     assert (mask == mo).mean() >= 0.999, (size, (mask == mo).mean())
     assert (mo == 0).any() and (mo == 1).any()
     gm.close()
+
+
+def test_fused_flow_form_still_matches_oracle(capi, oracle, synth, monkeypatch):
+    """GD_FLOW_FUSED=1 selects the single-kernel form of a flow iteration (matrices only in shared memory); kept for comparison
+    with the split pair, so it stays under the same tolerance."""
+    monkeypatch.setenv("GD_FLOW_FUSED", "1")
+    K = synth.intrinsics(320, 240)
+    s = synth.SyntheticStream(8, 320, 240)
+    fr = [s.frame(f) for f in range(6)]
+    R, T = s.pair_pose(0, 5)
+    gm = capi.GeoMask(K, None, 5000.0, 320, 240, 0, batch=1)
+    for f in fr:
+        gm.add_new_image([f.bgr], [f.depth_m])
+    mask = gm.get_no_gmm_mask(R[None], T[None])[0]
+    mo, flow_o, _ = oracle.geomask_pair(fr[0].bgr, fr[5].bgr, fr[0].depth_m, fr[5].depth_m, K, R, T, want_debug=True)
+    nviol, dmax = flow_tol_violations(gm.debug(capi.DBG_FLOW), flow_o)
+    assert nviol == 0, (nviol, dmax)
+    assert (mask == mo).mean() >= 0.999
+    gm.close()
