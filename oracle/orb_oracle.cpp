@@ -362,6 +362,12 @@ int gdo_orb_distribute(const float* cand, int n, int minX, int maxX, int minY, i
     return (int)r.size();
 }
 
+// rBRIEF descriptor of one keypoint on an already blurred image (computeOrbDescriptor, ORBextractor.cc:108-147)
+void gdo_orb_descriptor(const uint8_t* blurred, int cols, int x, int y, float angle_deg, uint8_t* desc32)
+{
+    orb_descriptor(blurred, cols, x, y, angle_deg, desc32);
+}
+
 float gdo_ic_angle(const uint8_t* img, int cols, int x, int y)
 {
     OrbCfg cfg(1500, 1.2f, 8, 20, 7);

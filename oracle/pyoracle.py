@@ -167,6 +167,8 @@ def _orb():
         L.gdo_orb_distribute.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int]
         L.gdo_ic_angle.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
         L.gdo_ic_angle.restype = C.c_float
+        L.gdo_orb_descriptor.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_float, u8p]
+        L.gdo_orb_descriptor.restype = None
         L.gdo_orb_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _ORB_BOUND = True
@@ -226,6 +228,14 @@ def orb_distribute(cand, minX, maxX, minY, maxY, N):
 def ic_angle(img, x, y):
     img = _c(img, np.uint8)
     return _orb().gdo_ic_angle(img.reshape(-1), img.shape[1], int(x), int(y))
+
+
+def orb_descriptor(blurred, x, y, angle_deg):
+    """rBRIEF descriptor of one keypoint at integer (x, y) of an already blurred level image (32 bytes)."""
+    blurred = _c(blurred, np.uint8)
+    out = np.zeros(32, np.uint8)
+    _orb().gdo_orb_descriptor(blurred.reshape(-1), blurred.shape[1], int(x), int(y), float(angle_deg), out)
+    return out
 
 
 def _extract(fn, gray, nfeatures, scale, nlevels, ini_th, min_th, want_pyramid, has_nlevel):
