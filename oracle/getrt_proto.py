@@ -20,12 +20,16 @@ Findings (probed against cv2 4.13.0, bit-exact unless stated):
     cv::ORB blurs a submatrix of its pyramid buffer, and cv::GaussianBlur only takes the 8-bit fixed-point path
     ([18 34 48 56 48 34 18] / 256, what ORBextractor's blur of a cloned level gets) for non-submatrix inputs — 2.5 % of the
     pixels differ by one grey level between the two; the pattern and the rotation arithmetic equal ORB_SLAM2's;
-  * the ORDER of the returned keypoints is the permutation std::nth_element leaves behind inside retainBest: reproducible
-    only by calling the same libstdc++ routine on the same sequence (sets are compared here);
+  * the ORDER of the returned keypoints is the permutation std::nth_element + std::partition leave behind inside the two
+    retainBest calls, applied to the raster-ordered FAST output: calling the same libstdc++ routines on the same sequence
+    (oracle gdo_retain_best_order) reproduces cv2's order exactly;
   * BFMatcher cross-check: query q pairs with its nearest train t (smallest index on ties) iff q is the nearest query of
     t (smallest index on ties); results come ordered by query index;
   * sort(matches) is an unstable std::sort on the distance: which of several equal-distance matches make the first 100 is
-    implementation defined (GeoMaskMaker.cc:96-97 also reads past the end when fewer than 100 matches exist).
+    implementation defined; oracle gdo_sort_matches_order runs libstdc++'s std::sort on the same sequence
+    (GeoMaskMaker.cc:96-97 also reads past the end when fewer than 100 matches exist);
+  * solvePnPRansac + Rodrigues (:143-150) have no restatement: cv2 itself is the oracle for that step (fixed-seed RNG, EPnP
+    on 5-point samples, LM refinement on the inliers).
 """
 from __future__ import annotations
 
@@ -114,10 +118,13 @@ def features_per_level(nfeatures: int, scale_factor: float, nlevels: int):
     return out
 
 
-def cv_orb_detect_and_compute(img, fast_detect, ic_angle, orb_descriptor, nfeatures=2000, scale_factor=1.2, nlevels=8, edge=31):
-    """cv::ORB (HARRIS_SCORE, WTA_K 2, patch 31, FAST 20) as a set of (octave, x, y, response, angle, descriptor).
-    fast_detect(img, th) -> [(x, y, response)], ic_angle(img, x, y), orb_descriptor(blurred, x, y, angle): the cv2-pinned
-    primitives of oracle/pyoracle.py."""
+def cv_orb_detect_and_compute(img, fast_detect, ic_angle, orb_descriptor, nfeatures=2000, scale_factor=1.2, nlevels=8, edge=31,
+                              retain_best_order=None):
+    """cv::ORB (HARRIS_SCORE, WTA_K 2, patch 31, FAST 20): list of (octave, x, y, response, angle, descriptor).
+    fast_detect(img, th) -> [(x, y, response)] in raster order, ic_angle(img, x, y), orb_descriptor(blurred, x, y, angle):
+    the cv2-pinned primitives of oracle/pyoracle.py.  With retain_best_order = pyoracle.retain_best_order the list has
+    cv2's own order, otherwise only the set is meaningful."""
+    rb = retain_best_order if retain_best_order is not None else (lambda r, n: retain_best(np.asarray(r), n))
     nper = features_per_level(nfeatures, scale_factor, nlevels)
     levels, scales = [img], [f32(1.0)]
     for l in range(1, nlevels):
@@ -132,10 +139,10 @@ def cv_orb_detect_and_compute(img, fast_detect, ic_angle, orb_descriptor, nfeatu
         pts = np.asarray(fast_detect(im, 20), np.float32).reshape(-1, 3)
         keep = (pts[:, 0] >= edge) & (pts[:, 0] < w - edge) & (pts[:, 1] >= edge) & (pts[:, 1] < h - edge)
         pts = pts[keep]
-        pts = pts[retain_best(pts[:, 2], 2 * nper[l])]
+        pts = pts[rb(pts[:, 2], 2 * nper[l])]
         hr = harris_responses(im, pts[:, 0].astype(int), pts[:, 1].astype(int))
         blurred = gaussian7_float(im)
-        for i in retain_best(hr, nper[l]):
+        for i in rb(hr, nper[l]):
             x, y = int(pts[i, 0]), int(pts[i, 1])
             ang = f32(ic_angle(im, x, y))
             out.append((l, f32(f32(x) * scales[l]), f32(f32(y) * scales[l]), hr[i], ang, orb_descriptor(blurred, x, y, ang)))
@@ -151,10 +158,14 @@ def bf_match_hamming_crosscheck(d1: np.ndarray, d2: np.ndarray):
     return [(q, int(t), int(dist[q, t])) for q, t in enumerate(nn12) if nn21[t] == q]
 
 
-def back_project_matches(matches, kp1_xy, kp2_xy, depth1, K, ntop=100):
-    """GeoMaskMaker.cc:95-141 for an undistorted camera: the `ntop` best matches (stable order on ties: the reference's
-    std::sort leaves that undefined), depth of the first image at the truncated pixel, K^-1 [x y 1] * d in f32."""
-    order = sorted(range(len(matches)), key=lambda i: (matches[i][2], i))[:ntop]
+def back_project_matches(matches, kp1_xy, kp2_xy, depth1, K, ntop=100, sort_order=None):
+    """GeoMaskMaker.cc:95-141 for an undistorted camera: the `ntop` best matches (sort_order = pyoracle.sort_matches_order
+    gives the reference's std::sort order, otherwise a stable order), depth of the first image at the truncated pixel,
+    K^-1 [x y 1] * d in f32."""
+    if sort_order is not None:
+        order = [int(i) for i in sort_order(np.asarray([m[2] for m in matches], np.float32))][:ntop]
+    else:
+        order = sorted(range(len(matches)), key=lambda i: (matches[i][2], i))[:ntop]
     Ki = np.linalg.inv(K.astype(np.float64)).astype(f32)  # cv::Mat::inv of a 3x3 f32: f64 cofactors (oracle gdo_inv3_f32)
     obj, pix = [], []
     for i in order:
@@ -168,3 +179,22 @@ def back_project_matches(matches, kp1_xy, kp2_xy, depth1, K, ntop=100):
         obj.append(P * f32(d))
         pix.append(kp2_xy[t])
     return np.asarray(obj, f32).reshape(-1, 3), np.asarray(pix, f32).reshape(-1, 2)
+
+
+def get_rt(img1, img2, depth1, K, prims, solve_pnp_ransac):
+    """GeoMaskMaker::GetRt (GeoMaskMaker.cc:77-156) for an undistorted camera: (ok, R 3x3 f32, T 3 f32).
+    prims: oracle.pyoracle (fast_detect in raster order via cv2-pinned gdo_fast_detect, ic_angle, orb_descriptor,
+    retain_best_order, sort_matches_order); solve_pnp_ransac(obj, pix, K) -> (rvec, tvec) = cv2.solvePnPRansac (the oracle
+    of that step) followed by cv2.Rodrigues."""
+    def fast(im, th):
+        return prims.fast_detect(im, th)
+    feats = [cv_orb_detect_and_compute(im, fast, prims.ic_angle, prims.orb_descriptor, retain_best_order=prims.retain_best_order)
+             for im in (img1, img2)]
+    desc = [np.stack([f[5] for f in fs]) for fs in feats]
+    xy = [[(f[1], f[2]) for f in fs] for fs in feats]
+    matches = bf_match_hamming_crosscheck(desc[0], desc[1])
+    obj, pix = back_project_matches(matches, xy[0], xy[1], depth1, K, 100, prims.sort_matches_order)
+    if len(obj) < 20:
+        return False, None, None
+    R, T = solve_pnp_ransac(obj, pix, K)
+    return True, np.asarray(R, np.float32), np.asarray(T, np.float32).reshape(3)

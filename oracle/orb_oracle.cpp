@@ -362,6 +362,43 @@ int gdo_orb_distribute(const float* cand, int n, int minX, int maxX, int minY, i
     return (int)r.size();
 }
 
+// cv::KeyPointsFilter::retainBest as OpenCV writes it (std::nth_element + std::partition on the responses): returns the
+// number kept and the permutation the routine leaves behind (perm[i] = original index of the i-th kept element).  The
+// order is whatever libstdc++'s introselect produces; it is what cv::ORB's output order consists of.
+int gdo_retain_best_order(const float* resp, int n, int n_points, int* perm)
+{
+    struct E {
+        float r;
+        int i;
+    };
+    std::vector<E> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[i] = {resp[i], i};
+    if (n_points >= 0 && n > n_points) {
+        if (n_points == 0) return 0;
+        std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(), [](const E& a, const E& b) { return a.r > b.r; });
+        const float amb = v[n_points - 1].r;
+        auto e = std::partition(v.begin() + n_points, v.end(), [amb](const E& a) { return a.r >= amb; });
+        v.resize((size_t)(e - v.begin()));
+    }
+    for (size_t i = 0; i < v.size(); ++i) perm[i] = v[i].i;
+    return (int)v.size();
+}
+
+// std::sort(matches.begin(), matches.end()) of GeoMaskMaker.cc:95 (cv::DMatch::operator< compares the distance only): the
+// order among equal distances is whatever libstdc++'s introsort produces; perm[i] = original index of the i-th match.
+void gdo_sort_matches_order(const float* dist, int n, int* perm)
+{
+    struct E {
+        float d;
+        int i;
+        bool operator<(const E& o) const { return d < o.d; }
+    };
+    std::vector<E> v((size_t)n);
+    for (int i = 0; i < n; ++i) v[i] = {dist[i], i};
+    std::sort(v.begin(), v.end());
+    for (int i = 0; i < n; ++i) perm[i] = v[i].i;
+}
+
 // rBRIEF descriptor of one keypoint on an already blurred image (computeOrbDescriptor, ORBextractor.cc:108-147)
 void gdo_orb_descriptor(const uint8_t* blurred, int cols, int x, int y, float angle_deg, uint8_t* desc32)
 {

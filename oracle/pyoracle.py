@@ -169,6 +169,10 @@ def _orb():
         L.gdo_ic_angle.restype = C.c_float
         L.gdo_orb_descriptor.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_float, u8p]
         L.gdo_orb_descriptor.restype = None
+        L.gdo_retain_best_order.argtypes = [f32p, C.c_int, C.c_int, i32p]
+        L.gdo_retain_best_order.restype = C.c_int
+        L.gdo_sort_matches_order.argtypes = [f32p, C.c_int, i32p]
+        L.gdo_sort_matches_order.restype = None
         L.gdo_orb_extract.argtypes = [u8p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _ORB_BOUND = True
@@ -228,6 +232,22 @@ def orb_distribute(cand, minX, maxX, minY, maxY, N):
 def ic_angle(img, x, y):
     img = _c(img, np.uint8)
     return _orb().gdo_ic_angle(img.reshape(-1), img.shape[1], int(x), int(y))
+
+
+def retain_best_order(resp, n_points):
+    """cv::KeyPointsFilter::retainBest: indices kept, in the order std::nth_element + std::partition leave them."""
+    resp = _c(resp, np.float32)
+    perm = np.zeros(len(resp), np.int32)
+    n = _orb().gdo_retain_best_order(resp, len(resp), int(n_points), perm)
+    return perm[:n].copy()
+
+
+def sort_matches_order(dist):
+    """Order std::sort leaves a vector<DMatch> in (comparison on the distance only)."""
+    dist = _c(dist, np.float32)
+    perm = np.zeros(len(dist), np.int32)
+    _orb().gdo_sort_matches_order(dist, len(dist), perm)
+    return perm
 
 
 def orb_descriptor(blurred, x, y, angle_deg):
