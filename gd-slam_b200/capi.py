@@ -100,6 +100,10 @@ SYMBOLS = {
     "gd_stage_orb_pyramid": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, ip]),
     "gd_stage_fast_cells": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]),
     "gd_stage_gaussian7": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+    "gd_stage_resize_linear_exact": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
+    "gd_stage_gaussian7_float": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+    "gd_stage_harris": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
+    "gd_stage_hamming_crosscheck": (C.c_int, [C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, ip]),
 }
 
 
@@ -325,6 +329,38 @@ def stage_gaussian7(gray, device=0):
 
 
 # ---------------------------------------------------------------------------------------------- ORBextractor
+# ---- GetRt building blocks
+def stage_resize_linear_exact(src, dw, dh, device=0):
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    check(lib().gd_stage_resize_linear_exact(device, _vptr(src), src.shape[1], src.shape[0], _vptr(out), dw, dh))
+    return out
+
+
+def stage_gaussian7_float(src, device=0):
+    src = np.ascontiguousarray(src, np.uint8)
+    out = np.empty_like(src)
+    check(lib().gd_stage_gaussian7_float(device, _vptr(src), src.shape[1], src.shape[0], _vptr(out)))
+    return out
+
+
+def stage_harris(img, xs, ys, device=0):
+    img = np.ascontiguousarray(img, np.uint8)
+    xs, ys = np.ascontiguousarray(xs, np.int32), np.ascontiguousarray(ys, np.int32)
+    out = np.empty(len(xs), np.float32)
+    check(lib().gd_stage_harris(device, _vptr(img), img.shape[1], img.shape[0], _vptr(xs), _vptr(ys), len(xs), _vptr(out)))
+    return out
+
+
+def stage_hamming_crosscheck(d1, d2, device=0):
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    cap = len(d1)
+    q, t, d = (np.empty(cap, np.int32) for _ in range(3))
+    n = C.c_int(0)
+    check(lib().gd_stage_hamming_crosscheck(device, _vptr(d1), len(d1), _vptr(d2), len(d2), _vptr(q), _vptr(t), _vptr(d), cap, C.byref(n)))
+    return [(int(q[i]), int(t[i]), int(d[i])) for i in range(n.value)]
+
+
 class Orb:
     """Mirror of ORB_SLAM2::ORBextractor (include/ORBextractor.h:45-111) for `batch` images per call."""
 

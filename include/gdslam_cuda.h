@@ -219,6 +219,19 @@ GD_API int gd_stage_fast_cells(int device, const uint8_t* gray, int w, int h, in
 /* GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image (ORBextractor.cc:1086) */
 GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uint8_t* out);
 
+/* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1: single kernels with host buffers,
+ * each bit-exact against the cv2-pinned restatement oracle/getrt_proto.py.  The GetRt entry point itself is not built yet. */
+/* cv::resize(INTER_LINEAR_EXACT) between the pyramid levels of cv::ORB (GeoMaskMaker.cc:82, cv::ORB::detectAndCompute) */
+GD_API int gd_stage_resize_linear_exact(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+/* GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as cv::ORB gets it on a pyramid submatrix: the float separable path */
+GD_API int gd_stage_gaussian7_float(int device, const uint8_t* src, int w, int h, uint8_t* dst);
+/* HarrisResponses(blockSize 7, k 0.04) of cv::ORB at integer level coordinates (at least 4 px from the border) */
+GD_API int gd_stage_harris(int device, const uint8_t* img, int w, int h, const int* xs, const int* ys, int n, float* out);
+/* BFMatcher(NORM_HAMMING, crossCheck = true)->match(des_first, des_second) (GeoMaskMaker.cc:92-94): 32-byte descriptors,
+ * matches ordered by query index, distance = number of differing bits */
+GD_API int gd_stage_hamming_crosscheck(int device, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* query_idx,
+                                       int* train_idx, int* distance, int capacity, int* n_matches);
+
 #ifdef __cplusplus
 }
 #endif
