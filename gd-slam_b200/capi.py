@@ -100,6 +100,7 @@ SYMBOLS = {
     "gd_stage_orb_pyramid": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, ip]),
     "gd_stage_fast_cells": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]),
     "gd_stage_gaussian7": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+    "gd_stage_fast_whole": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "gd_stage_resize_linear_exact": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
     "gd_stage_gaussian7_float": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
     "gd_stage_harris": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
@@ -330,6 +331,15 @@ def stage_gaussian7(gray, device=0):
 
 # ---------------------------------------------------------------------------------------------- ORBextractor
 # ---- GetRt building blocks
+def stage_fast_whole(gray, threshold=20, device=0):
+    """cv::FAST(threshold, nonmax) on the whole image -> int array of (x, y, S') in raster order."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    kept = np.empty_like(gray)
+    check(lib().gd_stage_fast_whole(device, _vptr(gray), gray.shape[1], gray.shape[0], threshold, _vptr(kept)))
+    ys, xs = np.nonzero(kept)
+    return np.stack([xs, ys, kept[ys, xs].astype(np.int64)], 1).astype(np.int32)
+
+
 def stage_resize_linear_exact(src, dw, dh, device=0):
     src = np.ascontiguousarray(src, np.uint8)
     out = np.empty((dh, dw), np.uint8)

@@ -175,4 +175,21 @@ int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uint8_t* o
     return GD_OK;
 }
 
+
+int gd_stage_fast_whole(int device, const uint8_t* gray, int w, int h, int threshold, uint8_t* kept)
+{
+    GD_REQUIRE(gray && kept && w >= 7 && h >= 7, "bad argument");
+    GD_TRY(select_device(device));
+    DevBuf im, sc, kp;
+    const size_t n = (size_t)w * h;
+    GD_TRY(im.alloc(n));
+    GD_TRY(sc.alloc(n));
+    GD_TRY(kp.alloc(n));
+    GD_CUDA(cudaMemcpy(im.p, gray, n, cudaMemcpyHostToDevice));
+    GD_TRY(orb_fast_whole(im.as<uint8_t>(), w, h, w, threshold, sc.as<uint8_t>(), kp.as<uint8_t>(), 0));
+    GD_CUDA(cudaDeviceSynchronize());
+    GD_CUDA(cudaMemcpy(kept, kp.p, n, cudaMemcpyDeviceToHost));
+    return GD_OK;
+}
+
 }  // extern "C"

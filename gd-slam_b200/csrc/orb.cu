@@ -396,6 +396,82 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     if (threadIdx.x == 0) *cnt_out = min(tot, a.cell_cap);
 }
 
+// ------------------------------------------------------------------------------------------------ whole-level FAST (GetRt)
+// cv::FAST(threshold, nonmaxSuppression = true) on a whole image, as cv::ORB runs it per pyramid level (GetRt):
+// (1) score map S' (0 unless S' > th) on regular 64 x 16 tiles, 4-point test -> compacted list -> 16-point network;
+// (2) strict 8-neighbour NMS over the map (pixels closer than 3 to the border have no score).  The second kernel writes a
+// map that holds S' at the surviving corners and 0 elsewhere; raster order of its non-zeros = cv::FAST's output order.
+constexpr int FW_W = 64, FW_H = 16, FW_P = 72;
+
+__global__ void __launch_bounds__(256) k_fast_whole_score(const uint8_t* __restrict__ img, int w, int h, int pitch, int th,
+                                                          uint8_t* __restrict__ score)
+{
+    __shared__ __align__(16) uint8_t tile[(FW_H + 6) * FW_P];
+    __shared__ __align__(16) uint8_t sc[FW_H * FW_W];
+    __shared__ unsigned short plist[FW_H * FW_W];
+    __shared__ int s_nlist;
+    const int X0 = FW_W * blockIdx.x, Y0 = FW_H * blockIdx.y;  // first scored pixel of the tile
+    const int tid = threadIdx.x;
+    for (int q = tid; q < (FW_H + 6) * FW_P; q += 256) {  // rows Y0 - 3 .. Y0 + 18, columns X0 - 4 .. X0 + 67
+        const int row = q / FW_P, col = q - row * FW_P;
+        const int gy = Y0 - 3 + row, gx = X0 - 4 + col;
+        tile[q] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? img[(size_t)gy * pitch + gx] : (uint8_t)0;
+    }
+    reinterpret_cast<unsigned*>(sc)[tid] = 0u;
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    const int lane = tid & 31;
+#pragma unroll
+    for (int base = 0; base < FW_H * FW_W; base += 256) {
+        const int q = base + tid, ly = q >> 6, lx = q & 63;
+        const int gx = X0 + lx, gy = Y0 + ly;
+        bool qk = gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3;
+        if (qk) qk = fast_quick(tile + (ly + 3) * FW_P + lx + 4, FW_P, th);
+        const unsigned bal = __ballot_sync(0xffffffffu, qk);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)q;
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    for (int e = tid; e < nl; e += 256) {
+        const int q = plist[e], ly = q >> 6, lx = q & 63;
+        const int sv = fast_full(tile + (ly + 3) * FW_P + lx + 4, FW_P);
+        sc[q] = (uint8_t)(sv > th ? sv : 0);
+    }
+    __syncthreads();
+    for (int q = tid; q < FW_H * FW_W; q += 256) {
+        const int ly = q >> 6, lx = q & 63, gx = X0 + lx, gy = Y0 + ly;
+        if (gx < w && gy < h) score[(size_t)gy * pitch + gx] = sc[q];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fast_whole_nms(const uint8_t* __restrict__ score, int w, int h, int pitch,
+                                                        uint8_t* __restrict__ kept)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t* c = score + (size_t)y * pitch + x;
+    const int s = c[0];
+    int out = 0;
+    if (s > 0) {  // scored pixels are at least 3 from the border: the 8 neighbours exist
+        const int m0 = max(max(c[-pitch - 1], c[-pitch]), max(c[-pitch + 1], c[-1]));
+        const int m1 = max(max(c[pitch - 1], c[pitch]), max(c[pitch + 1], c[1]));
+        if (max(m0, m1) < s) out = s;
+    }
+    kept[(size_t)y * pitch + x] = (uint8_t)out;
+}
+
+int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_t* d_score, uint8_t* d_kept, cudaStream_t s)
+{
+    k_fast_whole_score<<<dim3(cdiv(w, FW_W), cdiv(h, FW_H)), 256, 0, s>>>(d_img, w, h, pitch, th, d_score);
+    GD_CUDA(cudaGetLastError());
+    k_fast_whole_nms<<<dim3(cdiv(w, 32), cdiv(h, 8)), dim3(32, 8), 0, s>>>(d_score, w, h, pitch, d_kept);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ K4c quadtree
 // DistributeOctTree restated for one CTA.  The reference keeps a std::list of nodes: every pass of its first loop
 // splits ALL nodes holding more than one key (children are push_front'ed, the parent erased); once another full pass

@@ -84,4 +84,7 @@ struct OrbCore {
     ~OrbCore();
 };
 
+// cv::FAST(th, nonmax) on a whole image (cv::ORB per level, GetRt): kept[y][x] = S' at surviving corners, else 0
+int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_t* d_score, uint8_t* d_kept, cudaStream_t s);
+
 }  // namespace gd

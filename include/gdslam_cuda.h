@@ -221,6 +221,9 @@ GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uin
 
 /* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1: single kernels with host buffers,
  * each bit-exact against the cv2-pinned restatement oracle/getrt_proto.py.  The GetRt entry point itself is not built yet. */
+/* cv::FAST(threshold, nonmaxSuppression) on a whole 8-bit image as cv::ORB runs it per level: kept[y*w+x] = S' (= response + 1)
+ * at the corners that survive the 8-neighbour suppression, 0 elsewhere; raster order of the non-zeros = cv::FAST's output order */
+GD_API int gd_stage_fast_whole(int device, const uint8_t* gray, int w, int h, int threshold, uint8_t* kept);
 /* cv::resize(INTER_LINEAR_EXACT) between the pyramid levels of cv::ORB (GeoMaskMaker.cc:82, cv::ORB::detectAndCompute) */
 GD_API int gd_stage_resize_linear_exact(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 /* GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as cv::ORB gets it on a pyramid submatrix: the float separable path */

@@ -70,3 +70,14 @@ def test_hamming_crosscheck_matcher(capi, proto):
     d2[1::97] = d2[0]  # duplicated train descriptors: ties resolved to the smallest index
     ref = proto.bf_match_hamming_crosscheck(d1, d2)
     assert capi.stage_hamming_crosscheck(d1, d2) == ref and 800 < len(ref) < 1200
+
+
+def test_fast_whole_level_with_nms(capi, oracle, gray):
+    """cv::FAST(20, nonmax) on a whole level: same corners, same order, response = S' - 1 (oracle.fast_detect == cv2)."""
+    for img in (gray, np.ascontiguousarray(gray[3:200, 5:278]), np.ascontiguousarray(gray[::2, ::2])):
+        ref = oracle.fast_detect(img, 20)
+        out = capi.stage_fast_whole(img, 20)
+        out[:, 2] -= 1
+        assert len(ref) > 200 and np.array_equal(out, ref)
+    flat = np.full((64, 80), 90, np.uint8)
+    assert len(capi.stage_fast_whole(flat, 20)) == 0
