@@ -100,6 +100,7 @@ SYMBOLS = {
     "gd_stage_orb_pyramid": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, ip]),
     "gd_stage_fast_cells": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]),
     "gd_stage_gaussian7": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+    "gd_stage_cvorb_detect_and_compute": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip]),
     "gd_stage_fast_whole": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "gd_stage_resize_linear_exact": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
     "gd_stage_gaussian7_float": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
@@ -331,6 +332,18 @@ def stage_gaussian7(gray, device=0):
 
 # ---------------------------------------------------------------------------------------------- ORBextractor
 # ---- GetRt building blocks
+def stage_cvorb_detect_and_compute(gray, nfeatures=2000, device=0):
+    """cv::ORB(nfeatures, 1.2, 8, 31, 0, 2).detectAndCompute -> (keypoints[KP_DTYPE], descriptors[n, 32]) in cv2's order."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    cap = nfeatures + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int(0)
+    check(lib().gd_stage_cvorb_detect_and_compute(device, _vptr(gray), gray.shape[1], gray.shape[0], nfeatures, _vptr(kps), _vptr(desc),
+                                                  cap, C.byref(n)))
+    return kps[: n.value].copy(), desc[: n.value].copy()
+
+
 def stage_fast_whole(gray, threshold=20, device=0):
     """cv::FAST(threshold, nonmax) on the whole image -> int array of (x, y, S') in raster order."""
     gray = np.ascontiguousarray(gray, np.uint8)

@@ -6,7 +6,9 @@
 //   gd_stage_harris                HarrisResponses (blockSize 7, k 0.04)
 //   gd_stage_hamming_crosscheck    BFMatcher(NORM_HAMMING, crossCheck = true)::match
 #include "gd_internal.h"
+#include "orb.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -132,6 +134,164 @@ __global__ void __launch_bounds__(128) k_hamming_nn(const uint4* __restrict__ q,
     dist[i] = best;
 }
 
+
+// cv::KeyPointsFilter::retainBest as OpenCV writes it: std::nth_element + std::partition on the responses.  The order it
+// leaves behind IS the order of cv::ORB's output, so the same libstdc++ routines run here on the same sequence.
+static void retain_best_order(const std::vector<float>& resp, int n_points, std::vector<int>* perm)
+{
+    struct E {
+        float r;
+        int i;
+    };
+    std::vector<E> v(resp.size());
+    for (size_t i = 0; i < resp.size(); ++i) v[i] = {resp[i], (int)i};
+    if (n_points >= 0 && (int)v.size() > n_points) {
+        if (n_points == 0) {
+            perm->clear();
+            return;
+        }
+        std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(), [](const E& a, const E& b) { return a.r > b.r; });
+        const float amb = v[n_points - 1].r;
+        auto e = std::partition(v.begin() + n_points, v.end(), [amb](const E& a) { return a.r >= amb; });
+        v.resize((size_t)(e - v.begin()));
+    }
+    perm->resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) (*perm)[i] = v[i].i;
+}
+
+static Gauss7 gauss7_taps()
+{
+    Gauss7 G;  // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, then rounded to float
+    double g[7], sum = 0;
+    for (int i = 0; i < 7; ++i) {
+        const double x = i - 3;
+        g[i] = std::exp(-(x * x) / (2.0 * 2.0 * 2.0));
+        sum += g[i];
+    }
+    for (int k = 0; k <= 3; ++k) G.g[k] = (float)(g[3 + k] / sum);
+    return G;
+}
+
+static float harris_scale4()
+{
+    const float scale = 1.0f / (float)((1 << 2) * 7 * 255.0f);
+    volatile float s4 = scale * scale;  // (s * s * s * s) as three individually rounded products
+    s4 = s4 * scale;
+    s4 = s4 * scale;
+    return s4;
+}
+
+// cv::ORB::create(nfeatures, 1.2f, 8, 31, 0, 2, HARRIS_SCORE, 31, 20)->detectAndCompute on one 8-bit image: pyramid, FAST,
+// Harris, blur, orientation and descriptors on the device; the two retainBest orderings on the host (tiny arrays).
+static int cvorb_detect_and_compute(const uint8_t* gray, int w, int h, int nfeatures, std::vector<gd_keypoint>* kps,
+                                    std::vector<uint8_t>* desc)
+{
+    constexpr int NL = 8, EDGE = 31;
+    const float sf = 1.2f;
+    int nper[NL];
+    {
+        const double factor = 1.0 / (double)sf;
+        double nd = nfeatures * (1 - factor) / (1 - std::pow(factor, (double)NL));
+        int sum = 0;
+        for (int l = 0; l < NL - 1; ++l) {
+            nper[l] = (int)std::nearbyint(nd);
+            sum += nper[l];
+            nd *= factor;
+        }
+        nper[NL - 1] = std::max(nfeatures - sum, 0);
+    }
+    const Gauss7 G = gauss7_taps();
+    const float s4 = harris_scale4();
+    DevBuf lvl[NL], blur, score, kept, dx, dy, dresp, dang, ddesc, tab;
+    int lw[NL], lh[NL];
+    float scale[NL];
+    lw[0] = w; lh[0] = h; scale[0] = 1.0f;
+    GD_TRY(lvl[0].alloc((size_t)w * h));
+    GD_TRY(blur.alloc((size_t)w * h));
+    GD_TRY(score.alloc((size_t)w * h));
+    GD_TRY(kept.alloc((size_t)w * h));
+    GD_CUDA(cudaMemcpy(lvl[0].p, gray, (size_t)w * h, cudaMemcpyHostToDevice));
+    std::vector<uint8_t> hk((size_t)w * h);
+    kps->clear();
+    desc->clear();
+    for (int l = 0; l < NL; ++l) {
+        if (l > 0) {
+            scale[l] = (float)std::pow((double)sf, (double)l);
+            lw[l] = (int)std::nearbyint((float)w / scale[l]);
+            lh[l] = (int)std::nearbyint((float)h / scale[l]);
+            if (lw[l] < 2 || lh[l] < 2) break;
+            GD_TRY(lvl[l].alloc((size_t)lw[l] * lh[l]));
+            std::vector<ushort4> t((size_t)lw[l] + lh[l]);
+            linear_exact_axis_table(lw[l], lw[l - 1], t.data());
+            linear_exact_axis_table(lh[l], lh[l - 1], t.data() + lw[l]);
+            GD_TRY(tab.alloc(t.size() * sizeof(ushort4)));
+            GD_CUDA(cudaMemcpy(tab.p, t.data(), t.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
+            k_resize_linear_exact<<<dim3(cdiv(lw[l], 32), cdiv(lh[l], 8)), dim3(32, 8)>>>(lvl[l - 1].as<uint8_t>(), lw[l - 1], lvl[l].as<uint8_t>(),
+                                                                                    lw[l], lh[l], tab.as<ushort4>(), tab.as<ushort4>() + lw[l]);
+            GD_CUDA(cudaGetLastError());
+        }
+        const int W = lw[l], H = lh[l];
+        if (std::min(W, H) <= 2 * EDGE) continue;
+        const uint8_t* img = lvl[l].as<uint8_t>();
+        GD_TRY(orb_fast_whole(img, W, H, W, 20, score.as<uint8_t>(), kept.as<uint8_t>(), 0));
+        GD_CUDA(cudaMemcpy(hk.data(), kept.p, (size_t)W * H, cudaMemcpyDeviceToHost));
+        // raster-ordered FAST output inside the 31-px border (KeyPointsFilter::runByImageBorder), response = S' - 1
+        std::vector<int> xs, ys;
+        std::vector<float> resp;
+        for (int y = EDGE; y < H - EDGE; ++y)
+            for (int x = EDGE; x < W - EDGE; ++x)
+                if (hk[(size_t)y * W + x]) {
+                    xs.push_back(x);
+                    ys.push_back(y);
+                    resp.push_back((float)(hk[(size_t)y * W + x] - 1));
+                }
+        std::vector<int> perm;
+        retain_best_order(resp, 2 * nper[l], &perm);
+        std::vector<int> x2(perm.size()), y2(perm.size());
+        for (size_t i = 0; i < perm.size(); ++i) { x2[i] = xs[perm[i]]; y2[i] = ys[perm[i]]; }
+        const int n2 = (int)perm.size();
+        if (n2 == 0) continue;
+        GD_TRY(dx.alloc(sizeof(int) * n2));
+        GD_TRY(dy.alloc(sizeof(int) * n2));
+        GD_TRY(dresp.alloc(sizeof(float) * n2));
+        GD_CUDA(cudaMemcpy(dx.p, x2.data(), sizeof(int) * n2, cudaMemcpyHostToDevice));
+        GD_CUDA(cudaMemcpy(dy.p, y2.data(), sizeof(int) * n2, cudaMemcpyHostToDevice));
+        k_harris<<<cdiv(n2, 128), 128>>>(img, W, dx.as<int>(), dy.as<int>(), n2, s4, dresp.as<float>());
+        GD_CUDA(cudaGetLastError());
+        std::vector<float> hr((size_t)n2);
+        GD_CUDA(cudaMemcpy(hr.data(), dresp.p, sizeof(float) * n2, cudaMemcpyDeviceToHost));
+        retain_best_order(hr, nper[l], &perm);
+        const int n3 = (int)perm.size();
+        if (n3 == 0) continue;
+        std::vector<int> x3(n3), y3(n3);
+        for (int i = 0; i < n3; ++i) { x3[i] = x2[perm[i]]; y3[i] = y2[perm[i]]; }
+        GD_CUDA(cudaMemcpy(dx.p, x3.data(), sizeof(int) * n3, cudaMemcpyHostToDevice));
+        GD_CUDA(cudaMemcpy(dy.p, y3.data(), sizeof(int) * n3, cudaMemcpyHostToDevice));
+        k_gaussian7_float<<<dim3(cdiv(W, GF_W), cdiv(H, GF_H)), dim3(GF_W, GF_H)>>>(img, W, H, G, blur.as<uint8_t>());
+        GD_CUDA(cudaGetLastError());
+        GD_TRY(dang.alloc(sizeof(float) * n3));
+        GD_TRY(ddesc.alloc((size_t)32 * n3));
+        GD_TRY(orb_cv_describe(img, blur.as<uint8_t>(), W, dx.as<int>(), dy.as<int>(), n3, dang.as<float>(), ddesc.as<uint8_t>(), 0));
+        std::vector<float> ang((size_t)n3);
+        const size_t d0 = desc->size();
+        desc->resize(d0 + (size_t)32 * n3);
+        GD_CUDA(cudaMemcpy(ang.data(), dang.p, sizeof(float) * n3, cudaMemcpyDeviceToHost));
+        GD_CUDA(cudaMemcpy(desc->data() + d0, ddesc.p, (size_t)32 * n3, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n3; ++i) {
+            gd_keypoint k;
+            k.x = (float)x3[i] * scale[l];
+            k.y = (float)y3[i] * scale[l];
+            k.size = 31.0f * scale[l];
+            k.angle = ang[i];
+            k.response = hr[perm[i]];
+            k.octave = l;
+            k.class_id = -1;
+            kps->push_back(k);
+        }
+    }
+    return GD_OK;
+}
+
 }  // namespace gd
 
 using namespace gd;
@@ -241,6 +401,22 @@ int gd_stage_hamming_crosscheck(int device, const uint8_t* d1, int n1, const uin
     }
     *n_matches = m;
     GD_REQUIRE(m <= capacity, "match capacity too small");
+    return GD_OK;
+}
+
+
+int gd_stage_cvorb_detect_and_compute(int device, const uint8_t* gray, int w, int h, int nfeatures, gd_keypoint* kps, uint8_t* desc,
+                                      int capacity, int* n)
+{
+    GD_REQUIRE(gray && kps && desc && n && w > 0 && h > 0 && nfeatures > 0, "bad argument");
+    GD_TRY(select_device(device));
+    std::vector<gd_keypoint> k;
+    std::vector<uint8_t> d;
+    GD_TRY(cvorb_detect_and_compute(gray, w, h, nfeatures, &k, &d));
+    *n = (int)k.size();
+    GD_REQUIRE(*n <= capacity, "keypoint capacity too small");
+    std::memcpy(kps, k.data(), sizeof(gd_keypoint) * k.size());
+    std::memcpy(desc, d.data(), d.size());
     return GD_OK;
 }
 

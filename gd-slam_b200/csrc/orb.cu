@@ -1007,6 +1007,73 @@ __global__ void __launch_bounds__(256) k_orb_describe(const uint8_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ core
+// IC_Angle + steered BRIEF of cv::ORB for a list of keypoints at integer level coordinates (one warp per keypoint; the same
+// arithmetic as k_orb_describe, cv::ORB only differs in the image the tests read: its float-blurred level)
+struct CvDescArgs {
+    int umax[ORB_HALF + 1];
+};
+__global__ void __launch_bounds__(256) k_cvorb_describe(const uint8_t* __restrict__ img, const uint8_t* __restrict__ blur, int pitch,
+                                                        const int* __restrict__ xs, const int* __restrict__ ys, int n, CvDescArgs a,
+                                                        float* __restrict__ angle_out, uint8_t* __restrict__ desc_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    const int x = xs[g], y = ys[g];
+    const uint8_t* center = img + (size_t)y * pitch + x;
+    int m01 = 0, m10 = 0;
+    const int u = lane - ORB_HALF;
+    if (lane < 2 * ORB_HALF + 1) {
+        m10 = u * center[u];
+        const int au = abs(u);
+#pragma unroll
+        for (int v = 1; v <= ORB_HALF; ++v) {
+            if (au <= a.umax[v]) {
+                const int vp = center[u + v * pitch], vm = center[u - v * pitch];
+                m01 += v * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    const float angle = fast_atan2_dev((float)m01, (float)m10);
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ar = angle * factorPI;
+    const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+    const uint8_t* bc = blur + (size_t)y * pitch + x;
+    int val = 0;
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2);
+    const int4 q1 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2 + 1);
+    const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int wd = words[k];
+        const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff),
+                    x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+        const int t0 = bc[__float2int_rn(x0 * sa + y0 * ca) * pitch + __float2int_rn(x0 * ca - y0 * sa)];
+        const int t1 = bc[__float2int_rn(x1 * sa + y1 * ca) * pitch + __float2int_rn(x1 * ca - y1 * sa)];
+        val |= (t0 < t1) << k;
+    }
+    desc_out[(size_t)g * 32 + lane] = (uint8_t)val;
+    if (lane == 0) angle_out[g] = angle;
+}
+
+int orb_cv_describe(const uint8_t* d_img, const uint8_t* d_blur, int pitch, const int* d_xs, const int* d_ys, int n, float* d_angle,
+                    uint8_t* d_desc, cudaStream_t s)
+{
+    if (n <= 0) return GD_OK;
+    static const int umax[ORB_HALF + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:456-469
+    CvDescArgs a;
+    for (int i = 0; i <= ORB_HALF; ++i) a.umax[i] = umax[i];
+    k_cvorb_describe<<<cdiv(n, 8), 256, 0, s>>>(d_img, d_blur, pitch, d_xs, d_ys, n, a, d_angle, d_desc);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 int OrbCore::init(int nfeatures_, float scale_factor_, int nlevels_, int ini_th, int min_th, int max_width, int max_height,
                   int device_, int batch_, cudaStream_t s, LaunchStats* st)
 {

@@ -84,6 +84,9 @@ struct OrbCore {
     ~OrbCore();
 };
 
+// IC_Angle + rBRIEF for keypoints at integer coordinates of one level (cv::ORB: d_blur = the float-blurred level)
+int orb_cv_describe(const uint8_t* d_img, const uint8_t* d_blur, int pitch, const int* d_xs, const int* d_ys, int n, float* d_angle,
+                    uint8_t* d_desc, cudaStream_t s);
 // cv::FAST(th, nonmax) on a whole image (cv::ORB per level, GetRt): kept[y][x] = S' at surviving corners, else 0
 int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_t* d_score, uint8_t* d_kept, cudaStream_t s);
 

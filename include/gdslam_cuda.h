@@ -221,6 +221,11 @@ GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uin
 
 /* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1: single kernels with host buffers,
  * each bit-exact against the cv2-pinned restatement oracle/getrt_proto.py.  The GetRt entry point itself is not built yet. */
+/* cv::ORB::create(nfeatures, 1.2f, 8, 31, 0, 2)->detectAndCompute(gray) of GeoMaskMaker.cc:82-90: keypoints (cv::KeyPoint layout) and
+ * 32-byte descriptors in OpenCV's own order.  Pyramid, FAST, Harris, blur, orientation, descriptors on the device; the two
+ * KeyPointsFilter::retainBest orderings (std::nth_element) on the host */
+GD_API int gd_stage_cvorb_detect_and_compute(int device, const uint8_t* gray, int w, int h, int nfeatures, gd_keypoint* kps,
+                                             uint8_t* desc, int capacity, int* n);
 /* cv::FAST(threshold, nonmaxSuppression) on a whole 8-bit image as cv::ORB runs it per level: kept[y*w+x] = S' (= response + 1)
  * at the corners that survive the 8-neighbour suppression, 0 elsewhere; raster order of the non-zeros = cv::FAST's output order */
 GD_API int gd_stage_fast_whole(int device, const uint8_t* gray, int w, int h, int threshold, uint8_t* kept);

@@ -81,3 +81,46 @@ def test_fast_whole_level_with_nms(capi, oracle, gray):
         assert len(ref) > 200 and np.array_equal(out, ref)
     flat = np.full((64, 80), 90, np.uint8)
     assert len(capi.stage_fast_whole(flat, 20)) == 0
+
+
+def _proto_features(proto, oracle, img, nf):
+    feats = proto.cv_orb_detect_and_compute(img, oracle.fast_detect, oracle.ic_angle, oracle.orb_descriptor, nfeatures=nf,
+                                            retain_best_order=oracle.retain_best_order)
+    return feats
+
+
+def test_cvorb_detect_and_compute_in_opencv_order(capi, proto, oracle, synth):
+    """cv::ORB::detectAndCompute of GetRt on the GPU blocks (+ host retainBest ordering): keypoints, responses, angles,
+    descriptors and their ORDER equal the cv2-pinned restatement."""
+    for (w, h, nf, stream) in ((320, 240, 500, 0), (640, 480, 2000, 1)):
+        img = oracle.gray(synth.SyntheticStream(stream, w, h).frame(2).bgr, 0)
+        ref = _proto_features(proto, oracle, img, nf)
+        kp, desc = capi.stage_cvorb_detect_and_compute(img, nf)
+        assert len(kp) == len(ref) > 0.8 * nf
+        assert [int(o) for o in kp["octave"]] == [r[0] for r in ref]
+        for name, col in (("x", 1), ("y", 2), ("response", 3), ("angle", 4)):
+            assert np.array_equal(kp[name].view(np.uint32), np.array([r[col] for r in ref], np.float32).view(np.uint32)), name
+        assert np.array_equal(desc, np.stack([r[5] for r in ref]))
+        sc = np.power(float(np.float32(1.2)), kp["octave"].astype(np.float64)).astype(np.float32)
+        assert np.array_equal(kp["size"], np.float32(31.0) * sc) and (kp["class_id"] == -1).all()
+
+
+def test_getrt_front_half_gives_the_oracle_point_sets(capi, proto, oracle, synth):
+    """Features of both frames and the cross-check matcher on the GPU, then the reference's first-100 selection and
+    back-projection: the object / image points handed to solvePnPRansac equal the all-CPU restatement bit for bit."""
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = synth.intrinsics()
+    g0, g5 = oracle.gray(f0.bgr, 0), oracle.gray(f5.bgr, 0)
+    k1, d1 = capi.stage_cvorb_detect_and_compute(g0, 2000)
+    k2, d2 = capi.stage_cvorb_detect_and_compute(g5, 2000)
+    m_gpu = capi.stage_hamming_crosscheck(d1, d2)
+    obj, pix = proto.back_project_matches(m_gpu, list(zip(k1["x"], k1["y"])), list(zip(k2["x"], k2["y"])), f0.depth_m, K, 100,
+                                          oracle.sort_matches_order)
+    feats = [_proto_features(proto, oracle, g, 2000) for g in (g0, g5)]
+    dd = [np.stack([f[5] for f in fs]) for fs in feats]
+    xy = [[(f[1], f[2]) for f in fs] for fs in feats]
+    m_ref = proto.bf_match_hamming_crosscheck(dd[0], dd[1])
+    obj_r, pix_r = proto.back_project_matches(m_ref, xy[0], xy[1], f0.depth_m, K, 100, oracle.sort_matches_order)
+    assert m_gpu == m_ref and len(obj_r) >= 20
+    assert np.array_equal(obj, obj_r) and np.array_equal(pix, pix_r)
