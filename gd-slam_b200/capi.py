@@ -100,6 +100,7 @@ SYMBOLS = {
     "gd_stage_orb_pyramid": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, ip]),
     "gd_stage_fast_cells": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]),
     "gd_stage_gaussian7": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp]),
+    "gd_getrt_points": (C.c_int, [C.c_int, vp, vp, C.c_int, C.c_int, vp, fp, fp, C.c_int, vp, vp, ip]),
     "gd_stage_cvorb_detect_and_compute": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, ip]),
     "gd_stage_fast_whole": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "gd_stage_resize_linear_exact": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
@@ -332,6 +333,19 @@ def stage_gaussian7(gray, device=0):
 
 # ---------------------------------------------------------------------------------------------- ORBextractor
 # ---- GetRt building blocks
+def getrt_points(gray_first, gray_second, depth_first_m, K, dist=None, device=0):
+    """GeoMaskMaker::GetRt up to (not including) solvePnPRansac: (object_points [n,3], image_pixels [n,2]) f32."""
+    g1, g2 = np.ascontiguousarray(gray_first, np.uint8), np.ascontiguousarray(gray_second, np.uint8)
+    dep = np.ascontiguousarray(depth_first_m, np.float32)
+    Kf = np.ascontiguousarray(K, np.float32).reshape(9)
+    d = None if dist is None else np.ascontiguousarray(dist, np.float32).reshape(-1)
+    obj, pix = np.zeros((100, 3), np.float32), np.zeros((100, 2), np.float32)
+    n = C.c_int(0)
+    check(lib().gd_getrt_points(device, _vptr(g1), _vptr(g2), g1.shape[1], g1.shape[0], _vptr(dep), _fptr(Kf),
+                                _fptr(d) if d is not None else None, 0 if d is None else len(d), _vptr(obj), _vptr(pix), C.byref(n)))
+    return obj[: n.value].copy(), pix[: n.value].copy()
+
+
 def stage_cvorb_detect_and_compute(gray, nfeatures=2000, device=0):
     """cv::ORB(nfeatures, 1.2, 8, 31, 0, 2).detectAndCompute -> (keypoints[KP_DTYPE], descriptors[n, 32]) in cv2's order."""
     gray = np.ascontiguousarray(gray, np.uint8)

@@ -6,6 +6,7 @@
 //   gd_stage_harris                HarrisResponses (blockSize 7, k 0.04)
 //   gd_stage_hamming_crosscheck    BFMatcher(NORM_HAMMING, crossCheck = true)::match
 #include "gd_internal.h"
+#include "geomask.cuh"
 #include "orb.cuh"
 
 #include <algorithm>
@@ -417,6 +418,58 @@ int gd_stage_cvorb_detect_and_compute(int device, const uint8_t* gray, int w, in
     GD_REQUIRE(*n <= capacity, "keypoint capacity too small");
     std::memcpy(kps, k.data(), sizeof(gd_keypoint) * k.size());
     std::memcpy(desc, d.data(), d.size());
+    return GD_OK;
+}
+
+
+int gd_getrt_points(int device, const uint8_t* gray_first, const uint8_t* gray_second, int w, int h, const float* depth_first_m,
+                    const float K[9], const float* dist, int ndist, float* object_points, float* image_pixels, int* n_points)
+{
+    GD_REQUIRE(gray_first && gray_second && depth_first_m && K && object_points && image_pixels && n_points, "null argument");
+    for (int i = 0; i < ndist; ++i) GD_REQUIRE(!dist || dist[i] == 0.f, "distorted cameras are not built for GetRt yet (undistortPoints on the matches)");
+    GD_TRY(select_device(device));
+    *n_points = 0;
+    std::vector<gd_keypoint> k1, k2;
+    std::vector<uint8_t> d1, d2;
+    GD_TRY(cvorb_detect_and_compute(gray_first, w, h, 2000, &k1, &d1));    // GeoMaskMaker.cc:82-90
+    GD_TRY(cvorb_detect_and_compute(gray_second, w, h, 2000, &k2, &d2));
+    if (k1.empty() || k2.empty()) return GD_OK;
+    const int n1 = (int)k1.size(), n2 = (int)k2.size();
+    std::vector<int> mq(n1), mt(n1), md(n1);
+    int nm = 0;
+    GD_TRY(gd_stage_hamming_crosscheck(device, d1.data(), n1, d2.data(), n2, mq.data(), mt.data(), md.data(), n1, &nm));  // :92-94
+    // sort(matches.begin(), matches.end()) (:95): DMatch::operator< looks at the distance only; the same libstdc++ introsort
+    // on the same sequence leaves equal distances in the same order as the reference
+    struct M {
+        float d;
+        int i;
+        bool operator<(const M& o) const { return d < o.d; }
+    };
+    std::vector<M> ms((size_t)nm);
+    for (int i = 0; i < nm; ++i) ms[i] = {(float)md[i], i};
+    std::sort(ms.begin(), ms.end());
+    const int ntop = std::min(nm, 100);  // the reference takes begin()+100 unconditionally (:97); fewer matches are undefined there
+    CamConst cam;
+    make_cam_const(K, &cam);
+    int n = 0;
+    for (int r = 0; r < ntop; ++r) {
+        const int i = ms[r].i;
+        const float x = k1[mq[i]].x, y = k1[mq[i]].y;      // undistortPoints with D = 0, P = K is the identity in f32
+        const int dx = (int)x, dy = (int)y;                 // :122-123
+        if (dx < 0 || dy < 0 || dx >= w || dy >= h) continue;
+        const float depth = depth_first_m[(size_t)dy * w + dx];
+        if (depth == 0.f) continue;                         // :125-128
+        for (int c = 0; c < 3; ++c) {                       // (inv(K) * [x y 1]^T) * depth, f32 gemm of inner length 3 (:133)
+            volatile float t = cam.Ki[3 * c] * x;
+            t = t + cam.Ki[3 * c + 1] * y;
+            t = t + cam.Ki[3 * c + 2] * 1.0f;
+            object_points[3 * n + c] = t * depth;
+        }
+        image_pixels[2 * n] = k2[mt[i]].x;                  // :139
+        image_pixels[2 * n + 1] = k2[mt[i]].y;
+        ++n;
+    }
+    *n_points = n;
     return GD_OK;
 }
 

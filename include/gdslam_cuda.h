@@ -221,6 +221,13 @@ GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uin
 
 /* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1: single kernels with host buffers,
  * each bit-exact against the cv2-pinned restatement oracle/getrt_proto.py.  The GetRt entry point itself is not built yet. */
+/* Everything GeoMaskMaker::GetRt does before solvePnPRansac (GeoMaskMaker.cc:82-141) for an undistorted camera: cv::ORB features
+ * of both gray images and the Hamming cross-check matcher on the device, the reference's sort / first-100 / depth look-up /
+ * back-projection on the host.  object_points: up to 100 x 3 floats (metres, first camera), image_pixels: up to 100 x 2 floats
+ * (second image), in the reference's order.  GetRt then returns false when *n_points < 20 (:143-146) and otherwise calls
+ * cv::solvePnPRansac(objectPoints, imagePixels, K, D, rvec, T) + cv::Rodrigues (:148-150), which stay in the caller. */
+GD_API int gd_getrt_points(int device, const uint8_t* gray_first, const uint8_t* gray_second, int w, int h, const float* depth_first_m,
+                           const float K[9], const float* dist, int ndist, float* object_points, float* image_pixels, int* n_points);
 /* cv::ORB::create(nfeatures, 1.2f, 8, 31, 0, 2)->detectAndCompute(gray) of GeoMaskMaker.cc:82-90: keypoints (cv::KeyPoint layout) and
  * 32-byte descriptors in OpenCV's own order.  Pyramid, FAST, Harris, blur, orientation, descriptors on the device; the two
  * KeyPointsFilter::retainBest orderings (std::nth_element) on the host */

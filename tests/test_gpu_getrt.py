@@ -124,3 +124,31 @@ def test_getrt_front_half_gives_the_oracle_point_sets(capi, proto, oracle, synth
     obj_r, pix_r = proto.back_project_matches(m_ref, xy[0], xy[1], f0.depth_m, K, 100, oracle.sort_matches_order)
     assert m_gpu == m_ref and len(obj_r) >= 20
     assert np.array_equal(obj, obj_r) and np.array_equal(pix, pix_r)
+
+
+def test_getrt_points_entry_point_and_final_pose(capi, proto, oracle, synth):
+    """gd_getrt_points = GeoMaskMaker::GetRt up to solvePnPRansac: the point sets equal the all-CPU restatement, hence the
+    pose cv2.solvePnPRansac + Rodrigues returns for them is the reference's (checked where cv2 is installed)."""
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = synth.intrinsics()
+    g0, g5 = oracle.gray(f0.bgr, 0), oracle.gray(f5.bgr, 0)
+    obj, pix = capi.getrt_points(g0, g5, f0.depth_m, K, np.zeros(4, np.float32))
+    seen = {}
+
+    def solve(o, p, Kf):
+        seen["obj"], seen["pix"] = o.copy(), p.copy()
+        try:
+            import cv2
+        except ImportError:
+            return np.eye(3), np.zeros(3)
+        ok, rvec, tvec, _ = cv2.solvePnPRansac(o, p, Kf, np.zeros((4, 1), np.float32))
+        return cv2.Rodrigues(rvec)[0], tvec
+
+    ok, R_ref, T_ref = proto.get_rt(g0, g5, f0.depth_m, K, oracle, solve)
+    assert ok and len(obj) >= 20
+    assert np.array_equal(obj, seen["obj"]) and np.array_equal(pix, seen["pix"])
+    R, T = solve(obj, pix, K)
+    assert np.array_equal(np.asarray(R, np.float32), R_ref) and np.array_equal(np.asarray(T, np.float32).reshape(3), T_ref)
+    with pytest.raises(capi.GdError):  # distorted cameras: not built yet, rejected loudly
+        capi.getrt_points(g0, g5, f0.depth_m, K, np.array([0.1, 0, 0, 0], np.float32))
