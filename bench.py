@@ -10,8 +10,10 @@ min-max/threshold mask).  Streams are sharded across ranks with no collective on
 
   value : frames/s, inputs already resident in HBM (gd_frontend_step_staged), CUDA events on the handle's stream,
           max over ranks.
-  e2e   : the same through the reference-facing C ABI with pinned HOST buffers (gd_frontend_step): H2D of BGR+depth and
-          D2H of mask + keypoints + descriptors inside the timed region.
+  e2e   : the same through the reference-facing C ABI with pinned HOST buffers: H2D of BGR + the raw 16-bit depth image
+          (gd_frontend_step_u16, what Tracking.cc:234-235 receives) and D2H of mask + keypoints + descriptors inside the
+          timed region; `e2e.f32_depth` repeats it with the depth already converted to metres on the host (gd_frontend_step).
+  parity_checked : after the timed region one stream's results of the LAST timed step are compared with the CPU oracle.
 torch is used only for the multi-rank barrier / max-reduce (torch.distributed, NCCL); the product path is the C ABI.
 """
 from __future__ import annotations
@@ -56,6 +58,28 @@ FAMILY_BYTES = {
     "K4c_quadtree": 8 * 8000 * 4,
     "K4e_blur7": 2 * 3.094 * N_PX,
     "K4de_orient_describe": 1500 * (749 + 512 + 60),
+}
+
+
+# what actually bounds each kernel family on B200 (ncu, profiles/): reported beside the HBM fraction so that a low HBM
+# fraction of a compute-bound kernel is not misread
+FAMILY_LIMITER = {
+    "K0_gray": "hbm",
+    "K1a_blur_resample": "issue slots / L2 (narrow levels)",
+    "K1a_polyexp": "shared-memory pipe + fp64 horizontal pass",
+    "K1b_matrices": "hbm",
+    "K1b_box_solve": "shared-memory data pipe (fp64 running sums) + barriers",
+    "K1b_box_matrices": "hbm + shared-memory data pipe",
+    "K2a_depth_edge": "issue slots (f32 interval test; fp64 only for undecided pixels)",
+    "K2b_mahalanobis": "fp64 pipe + f32<->f64 conversions (bit-exact OpenCV accumulation widths)",
+    "K3a_minmax": "hbm",
+    "K3b_normalize_mask": "hbm",
+    "K3_minmax_mask": "hbm",
+    "K4a_pyramid_resize": "issue slots (byte gathers), L2 resident",
+    "K4b_fast_cells": "issue slots (16-point score network), L2 resident",
+    "K4c_quadtree": "latency (one CTA per level and stream)",
+    "K4e_blur7": "issue slots, L2 resident",
+    "K4de_orient_describe": "latency / gathers",
 }
 
 
@@ -120,9 +144,9 @@ class ClockSampler:
 
 
 def _gen_frame(args):
-    stream, f = args
+    stream, f, res = args
     synth = importlib.import_module("gd-slam_b200.synth")
-    s = synth.SyntheticStream(stream, W, H)
+    s = synth.SyntheticStream(stream, res[0], res[1])
     fr = s.frame(f)
     return stream, f, fr.bgr, fr.depth_m
 
@@ -132,7 +156,7 @@ def make_data(n_distinct, n_frames, seed0):
     from concurrent.futures import ProcessPoolExecutor
 
     synth = importlib.import_module("gd-slam_b200.synth")
-    jobs = [(seed0 + s, f) for s in range(n_distinct) for f in range(n_frames)]
+    jobs = [(seed0 + s, f, (W, H)) for s in range(n_distinct) for f in range(n_frames)]
     bgr = np.empty((n_distinct, n_frames, H, W, 3), np.uint8)
     dep = np.empty((n_distinct, n_frames, H, W), np.float32)
     with ProcessPoolExecutor(max_workers=min(os.cpu_count() or 1, 16)) as ex:
@@ -150,6 +174,33 @@ def make_data(n_distinct, n_frames, seed0):
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 _CPU = {}
+
+
+def workload_name():
+    """config.workload: identical in both arms (the driver compares the strings)."""
+    return f"synthetic {W}x{H} RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7)"
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def use_native_oracle():
+    """Point the CPU legs at an -O3 -march=native build of the oracle made on THIS machine; the
+    portable -O2 parity build is the fallback.  Returns the description that goes into the JSON line."""
+    from oracle import pyoracle as po
+
+    p = po.build_native()
+    if p:
+        os.environ["GD_ORACLE_LIB"] = p  # inherited by the worker processes
+        return "-O3 -march=native -ffp-contract=off (built on this host)"
+    return "-O2 -ffp-contract=off (portable parity build; the native build failed)"
 
 
 def _cpu_init(res):
@@ -175,12 +226,34 @@ def _cpu_step(n_frames):
     return n_frames, time.perf_counter() - t0
 
 
+def _cpu_stage_split(_):
+    """ms per frame of each stage of the CPU path on ONE core."""
+    po, K, a, b, (R, T) = _CPU["po"], _CPU["K"], _CPU["a"], _CPU["b"], _CPU["pose"]
+    out = {}
+
+    def t(name, fn):
+        t0 = time.perf_counter()
+        r = fn()
+        out[name] = (time.perf_counter() - t0) * 1e3
+        return r
+
+    g0 = t("gray_x2", lambda: (po.gray(a.bgr, 0), po.gray(b.bgr, 0)))
+    flow = t("farneback_pair", lambda: po.farneback(g0[0], g0[1]))
+    e = t("depth_edge_x2", lambda: (po.depth_edge(a.depth_m, K), po.depth_edge(b.depth_m, K)))
+    dist = t("mahalanobis_loop", lambda: po.mahalanobis(flow, a.depth_m, b.depth_m, e[0], e[1], K, R, T)[0])
+    t("normalize_threshold", lambda: po.normalize_threshold(dist))
+    go = po.gray(b.bgr, 1)
+    t("orb_extract", lambda: po.orb_extract(go))
+    return out
+
+
 class CpuReference:
     """The reference's CPU path (oracle port) on all host cores: one worker process per core, kept alive across steps."""
 
     def __init__(self, procs=None):
         from concurrent.futures import ProcessPoolExecutor
 
+        self.build = use_native_oracle()
         self.procs = procs or (os.cpu_count() or 1)
         self.ex = ProcessPoolExecutor(max_workers=self.procs, initializer=_cpu_init, initargs=((W, H),))
         list(self.ex.map(_cpu_step, [0] * self.procs))  # start the workers, build their frames
@@ -188,6 +261,12 @@ class CpuReference:
     def step(self, frames_per_proc):
         res = list(self.ex.map(_cpu_step, [frames_per_proc] * self.procs))
         return sum(r[0] for r in res) / max(r[1] for r in res)
+
+    def stage_split(self):
+        return {k: round(v, 2) for k, v in list(self.ex.map(_cpu_stage_split, [0]))[0].items()}
+
+    def describe(self):
+        return {"cpu_model": cpu_model(), "nproc": os.cpu_count(), "oracle_build": self.build}
 
     def close(self):
         self.ex.shutdown()
@@ -207,6 +286,8 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         rates.append(ref.step(per_step))
     ms = (time.perf_counter() - t_all) * 1e3 / max(1, args.steps)
+    split = ref.stage_split()
+    desc = ref.describe()
     ref.close()
     v = float(statistics.median(rates))
     sample = (f"{procs} host processes x {per_step} frame(s) per step ({W}x{H} pair (t-5,t) + ORB on the new frame), oracle port "
@@ -214,10 +295,12 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"synthetic {W}x{H} RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7)",
+           "config": {"workload": workload_name(),
                       "note": "reference's CPU path restated (oracle/): OpenCV-4.13 semantics, one process per host core, "
-                              "reference-structured (both pyramids / edge maps recomputed per call)"},
-           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
+                              "reference-structured (both pyramids / edge maps recomputed per call); the real reference "
+                              "additionally allocates cv::Mat temporaries and calls Mat::inv() per pixel, so it is slower than this"},
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
+                            "stage_ms_one_core": split, **desc},
            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -244,6 +327,19 @@ def bind_host_to_gpu(device):
         return None
 
 
+def check_last_step_against_oracle(res, bgr_ref, bgr_cur, dep_ref, dep_cur, K, R, T):
+    """One stream of the last timed step against the CPU oracle: ORB exact, mask agreement >= 99.9 %."""
+    from oracle import pyoracle as po
+
+    mask, kp, desc = res
+    rkp, rdesc, _ = po.orb_extract(po.gray(bgr_cur, 1))
+    orb_ok = len(kp) == len(rkp) and all(np.array_equal(kp[f], rkp[f]) for f in kp.dtype.names) and np.array_equal(desc, rdesc)
+    mo = po.geomask_pair(bgr_ref, bgr_cur, dep_ref, dep_cur, K, R, T)
+    agree = float((mask == mo).mean())
+    return {"orb_bit_exact": bool(orb_ok), "mask_agreement": agree, "n_keypoints": int(len(kp)),
+            "dynamic_fraction": float((mask == 0).mean()), "ok": bool(orb_ok and agree >= 0.999)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -259,6 +355,9 @@ def main():
     ap.add_argument("--ref-frames-per-proc", type=int, default=3)
     ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles (host threads) the e2e leg drives per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the 8-streams-in-total (config 4 as written) side measurement")
+    ap.add_argument("--probe-pcie", action="store_true",
+                    help="only time bare pinned cudaMemcpyAsync H2D / D2H on all ranks at once and print the rates")
     ap.add_argument("--res", default="640x480", help="WxH of the synthetic streams (configs[4]: 1280x720, 1920x1080)")
     args = ap.parse_args()
     global W, H, N_PX, ALGO_BYTES_PER_FRAME, METRIC
@@ -314,6 +413,28 @@ def main():
     def max_over_ranks(x):
         return sharding.max_over_ranks(x, dist, f"cuda:{local_rank}" if dist is not None else None)
 
+    def min_over_ranks(x):
+        return -max_over_ranks(-x)
+
+    # ---- host-side copy ceiling: bare pinned cudaMemcpyAsync on every rank at the same time (no kernel involved)
+    def probe():
+        barrier()
+        h2d = capi.probe_copy(device, 256 << 20, 8, True)
+        barrier()
+        d2h = capi.probe_copy(device, 256 << 20, 8, False)
+        barrier()
+        return min_over_ranks(h2d), min_over_ranks(d2h)
+
+    if args.probe_pcie:
+        h2d, d2h = probe()
+        if rank == 0:
+            print(json.dumps({"probe": "pinned cudaMemcpyAsync, 8 x 256 MiB per direction, all ranks at once, slowest rank",
+                              "n_gpus": world, "h2d_gbs_per_gpu": h2d, "d2h_gbs_per_gpu": d2h,
+                              "h2d_gbs_box": h2d * world, "d2h_gbs_box": d2h * world, "host_cpus_per_rank": host_cpus}), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # ---- data: every rank owns its own `B` streams (weak scaling); `distinct` seeded streams are generated per rank and
     #      replicated over the batch with a frame offset
     D = min(args.distinct, B)
@@ -322,28 +443,32 @@ def main():
     fe = capi.Frontend(K, W, H, batch=B, device=device, staged_slots=S)
     hb = capi.pinned_empty((S, B, H, W, 3), np.uint8)
     hd = capi.pinned_empty((S, B, H, W), np.float32)
+    hd16 = capi.pinned_empty((S, B, H, W), np.uint16)  # the raw TUM depth image: metres = u16 * (1 / 5000.f), exactly
     Rs = np.zeros((S, B, 3, 3), np.float32)
     Ts = np.zeros((S, B, 3), np.float32)
+    d16 = np.rint(dep.astype(np.float64) * 5000.0).astype(np.uint16)
+    assert np.array_equal(d16.astype(np.float32) * np.float32(1.0 / 5000.0), dep)
     for s in range(S):
         for b in range(B):
             src, off = b % D, (b // D) % S
             f = (s + off) % S
             hb[s, b] = bgr[src, f]
             hd[s, b] = dep[src, f]
+            hd16[s, b] = d16[src, f]
             Rs[s, b], Ts[s, b] = poses[(src, f)]
         fe.stage(s, hb[s], hd[s])
-    del bgr, dep
+    del bgr, dep, d16
 
+    # L2 hygiene: the default batch streams far more than the 126 MB L2 per step; small batches flush it before every step
+    ws_mb = B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3) * N_PX / 307200
+    flush = ws_mb < 2 * 126
     step_i = [0]
 
     def step_staged():
         s = step_i[0] % S
+        if flush:
+            fe.flush_l2()
         fe.step_staged(s, Rs[s], Ts[s])
-        step_i[0] += 1
-
-    def step_host():
-        s = step_i[0] % S
-        fe.step(hb[s], hd[s], Rs[s], Ts[s])
         step_i[0] += 1
 
     # ---- device-resident throughput (value)
@@ -365,9 +490,20 @@ def main():
     ms_total = max_over_ranks(ms_total)
     value = world * B * K_ / (ms_total * 1e-3)
 
+    # ---- parity of what was just timed: stream 0 (and the last stream) of the LAST timed step against the CPU oracle
+    parity = None
+    if rank == 0:
+        last = (step_i[0] - 1) % S
+        ref_slot = (step_i[0] - 1 - 5) % S
+        res = fe.fetch()
+        checks = [check_last_step_against_oracle(res[b], hb[ref_slot, b], hb[last, b], hd[ref_slot, b], hd[last, b], K,
+                                                 Rs[last, b], Ts[last, b]) for b in sorted({0, B - 1})]
+        parity = {"ok": all(c["ok"] for c in checks), "streams": sorted({0, B - 1}), "checks": checks,
+                  "what": "ORB keypoints/descriptors bit-exact and mask agreement >= 0.999 vs the CPU oracle on the last timed step"}
+
     # ---- end to end through the C ABI with pinned host buffers (e2e)
     #      The batch is driven as `args.e2e_handles` independent handles (B / handles streams each) from as many host
-    #      threads: gd_frontend_step is synchronous per handle (the reference's contract), so one handle's PCIe copies
+    #      threads: gd_frontend_step* is synchronous per handle (the reference's contract), so one handle's PCIe copies
     #      overlap the other's kernels.  Every step still moves all B frames host->device and all results device->host.
     NH = max(1, min(args.e2e_handles, B))
     while B % NH:
@@ -378,17 +514,21 @@ def main():
         fes = [capi.Frontend(K, W, H, batch=B // NH, device=device) for _ in range(NH)]
     Bh = B // NH
 
-    def host_loop(i, nsteps, start_evt):
+    def host_loop(i, nsteps, start_evt, u16):
         f = fes[i]
+        sl = slice(i * Bh, (i + 1) * Bh)
         start_evt.wait()
         for k in range(nsteps):
             s = k % S
-            f.step(hb[s, i * Bh:(i + 1) * Bh], hd[s, i * Bh:(i + 1) * Bh], Rs[s, i * Bh:(i + 1) * Bh], Ts[s, i * Bh:(i + 1) * Bh])
+            if u16:
+                f.step_u16(hb[s, sl], hd16[s, sl], Rs[s, sl], Ts[s, sl])
+            else:
+                f.step(hb[s, sl], hd[s, sl], Rs[s, sl], Ts[s, sl])
         f.sync()
 
-    def run_host(nsteps):
+    def run_host(nsteps, u16):
         ev = threading.Event()
-        th = [threading.Thread(target=host_loop, args=(i, nsteps, ev)) for i in range(NH)]
+        th = [threading.Thread(target=host_loop, args=(i, nsteps, ev, u16)) for i in range(NH)]
         for t in th:
             t.start()
         t0 = time.perf_counter()
@@ -397,18 +537,45 @@ def main():
             t.join()
         return time.perf_counter() - t0
 
-    run_host(6 + 3)  # fill the rings of the e2e handles + warm-up
+    run_host(6 + 3, True)  # fill the rings of the e2e handles + warm-up
     barrier()
-    e2e_s = run_host(K_)
-    clocks = sampler.stop()
+    e2e_s = run_host(K_, True)
     barrier()
     e2e_s = max_over_ranks(e2e_s)
+    run_host(3, False)
+    barrier()
+    e2e32_s = run_host(K_, False)
+    clocks = sampler.stop()
+    barrier()
+    e2e32_s = max_over_ranks(e2e32_s)
     e2e_value = world * B * K_ / e2e_s
-    h2d = B * (N_PX * 3 + N_PX * 4)
     d2h = B * (N_PX + fe.cap * (28 + 32) + 4)
+    h2d_u16 = B * (N_PX * 3 + N_PX * 2)
+    h2d_f32 = B * (N_PX * 3 + N_PX * 4)
     if NH > 1:
         for f in fes:
             f.close()
+    ceil_h2d, ceil_d2h = probe()
+
+    # ---- SURVEY 8d config 4 as written: 8 streams in total over the GPUs (strong scaling, latency-bound regime)
+    strong = None
+    if not args.no_strong and args.streams_total == 0 and 8 % world == 0 and B >= 8 // world:
+        bs = 8 // world
+        fs = capi.Frontend(K, W, H, batch=bs, device=device, staged_slots=S)
+        for s in range(S):
+            fs.stage(s, hb[s, :bs], hd[s, :bs])
+        for k in range(6 + 2 * 6 + Wm):  # ring, graph capture of the six ring phases, warm-up
+            fs.step_staged(k % S, Rs[k % S, :bs], Ts[k % S, :bs])
+        fs.sync()
+        barrier()
+        fs.timer_begin()
+        for k in range(K_):
+            fs.step_staged(k % S, Rs[k % S, :bs], Ts[k % S, :bs])
+        ms_s = max_over_ranks(fs.timer_end())
+        fs.close()
+        strong = {"streams_total": 8, "streams_per_gpu": bs, "value": 8 * K_ / (ms_s * 1e-3), "unit": "frames/s",
+                  "ms_per_step": ms_s / K_, "scaling": "strong",
+                  "note": "BASELINE configs[3] as written; per-step working set below the L2 size, not flushed"}
 
     # ---- per-kernel-family device time (events on the handle's stream, serialised) -> dominant kernel + roofline
     fe.profile(True)
@@ -422,8 +589,10 @@ def main():
     families = {}
     for name, ms, ln in fam:
         by = FAMILY_BYTES.get(name, 0.0) * B * PSTEPS
+        gbs = by / (ms * 1e-3) / 1e9 if ms > 0 else None
         families[name] = {"ms_per_step": ms / PSTEPS, "launches_per_step": ln / PSTEPS, "share": ms / tot_ms,
-                          "achieved_gbs": by / (ms * 1e-3) / 1e9 if ms > 0 else None}
+                          "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak if gbs else None,
+                          "limiter": FAMILY_LIMITER.get(name)}
     dom = max(fam, key=lambda x: x[1])
     dom_name, dom_ms, dom_ln = dom
     dom_bytes_per_launch = FAMILY_BYTES.get(dom_name, 0.0) * B * PSTEPS / max(1, dom_ln)
@@ -445,30 +614,48 @@ def main():
                              "achieved": value / world * ALGO_BYTES_PER_FRAME / 1e9, "frac": value / world * ALGO_BYTES_PER_FRAME / 1e9 / peak},
                 "families": families}
 
+    if flush:
+        l2 = ("L2 flushed by a 256 MiB memset before every step, inside the timed region (per-step working set %.0f MB per GPU "
+              "is not larger than twice the 126 MB L2)" % ws_mb)
+    else:
+        l2 = ("inputs larger than L2: per-step working set %.0f MB per GPU (ring of polynomial-expansion pyramids + staged "
+              "frames), 126 MB L2" % ws_mb)
     out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K_, "warmup": Wm,
            "ms_per_step": ms_total / K_, "higher_is_better": True, "scaling": "strong" if args.streams_total > 0 else "weak",
            "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": f"synthetic {W}x{H} RGB-D streams, full GeoMaskMaker + ORB (TUM3 intrinsics, ORB 1500/1.2/8/20/7), "
-                                  "steady state (per-image products cached in the 6-deep device ring)",
+           "config": {"workload": workload_name(),
+                      "note": "steady state: per-image products cached in the 6-deep device ring",
                       "streams_per_gpu": B, "frames_per_step": B * world, "resident_frames_per_stream": S,
-                      "l2_hygiene": "inputs larger than L2: per-step working set %.0f MB per GPU (ring of polynomial-expansion "
-                                    "pyramids + staged frames), 126 MB L2" % (B * (2 * 8.2 + 2.2 + 2 * 2.5 + 2.5 + 3.3) * N_PX / 307200),
-                      "sharding": "independent streams per GPU, no collective"},
-           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "l2_hygiene": l2, "sharding": "independent streams per GPU, no collective"},
+           "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_u16, "d2h_bytes_per_step": d2h,
                    "ms_per_step": e2e_s * 1e3 / K_, "handles_per_gpu": NH, "streams_per_handle": Bh,
+                   "depth_input": "raw 16-bit TUM depth, converted on the device (gd_frontend_step_u16)",
+                   "h2d_gbs": h2d_u16 * K_ / e2e_s / 1e9, "d2h_gbs": d2h * K_ / e2e_s / 1e9,
+                   "h2d_ceiling_gbs": ceil_h2d, "d2h_ceiling_gbs": ceil_d2h,
+                   "ceiling_note": "per GPU: bare pinned cudaMemcpyAsync (8 x 256 MiB) on all ranks at once, slowest rank",
+                   "f32_depth": {"value": world * B * K_ / e2e32_s, "ms_per_step": e2e32_s * 1e3 / K_,
+                                 "h2d_bytes_per_step": h2d_f32, "h2d_gbs": h2d_f32 * K_ / e2e32_s / 1e9},
                    "host_cpus_per_rank": host_cpus},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if parity is not None:
+        out["parity_checked"] = parity["ok"]
+        out["parity"] = parity
+    if strong is not None:
+        out["strong_scaling_8_streams"] = strong
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.perf_counter()
         ref = CpuReference()
         per = 3
         v = ref.step(per)
+        split = ref.stage_split()
+        desc = ref.describe()
         ref.close()
         out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": ref.procs, "kind": "port",
                                "sample": f"{ref.procs} host processes x {per} frames of the same workload through the oracle "
-                                         f"(reference-structured: both pyramids/edge maps per call), {time.perf_counter() - t0:.1f} s wall"}
+                                         f"(reference-structured: both pyramids/edge maps per call), {time.perf_counter() - t0:.1f} s wall",
+                               "stage_ms_one_core": split, **desc}
     fe.close()
     if dist is not None:
         dist.barrier()

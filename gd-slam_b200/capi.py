@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgdslam_cuda.so")
 
-GD_OK, GD_EINVAL, GD_ENODEVICE, GD_ECUDA, GD_ENOMEM, GD_ECAPACITY = 0, -1, -2, -3, -4, -5
+GD_OK, GD_EINVAL, GD_ENODEVICE, GD_ECUDA, GD_ENOMEM, GD_ECAPACITY, GD_EINTERNAL = 0, -1, -2, -3, -4, -5, -6
 DBG_FLOW, DBG_DIST, DBG_EDGE_REF, DBG_EDGE_CUR, DBG_GRAY_CUR, DBG_MINMAX, DBG_LUT = range(7)
 
 
@@ -58,6 +58,7 @@ SYMBOLS = {
     "gd_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int, ip, C.POINTER(C.c_size_t)]),
     "gd_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
     "gd_host_free": (C.c_int, [vp]),
+    "gd_probe_copy": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "gd_geomask_create": (C.c_int, [C.POINTER(vp), fp, fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gd_geomask_destroy": (None, [vp]),
     "gd_geomask_push": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
@@ -162,6 +163,13 @@ def device_info(device=0):
     mem = C.c_size_t(0)
     check(lib().gd_device_info(device, name, 256, C.byref(sm), C.byref(mem)))
     return name.value.decode(), sm.value, mem.value
+
+
+def probe_copy(device=0, nbytes=256 << 20, iters=8, to_device=True) -> float:
+    """GB/s of bare pinned-memory copies on one device (gd_probe_copy)."""
+    g = C.c_double(0)
+    check(lib().gd_probe_copy(device, nbytes, iters, 1 if to_device else 0, C.byref(g)))
+    return g.value
 
 
 def pinned_empty(shape, dtype):
@@ -527,9 +535,9 @@ class Frontend:
         """Same as step() with the raw 16-bit TUM depth (row f-4: converted on the device like Tracking.cc:234-235)."""
         B = self.batch
         R, T, pv = self._pose(R, T, pose_valid, B)
-        bp = _ptr_array([np.ascontiguousarray(bgr[b], np.uint8) for b in range(B)])
+        bl = [np.ascontiguousarray(bgr[b], np.uint8) for b in range(B)]  # views of a packed (pinned) batch stay views
         dl = [np.ascontiguousarray(depth_u16[b], np.uint16) for b in range(B)]
-        check(lib().gd_frontend_step_u16(self._h, bp, self.w * 3, _ptr_array(dl), self.w * 2, _fptr(R), _fptr(T),
+        check(lib().gd_frontend_step_u16(self._h, _ptr_array(bl), self.w * 3, _ptr_array(dl), self.w * 2, _fptr(R), _fptr(T),
                                          pv.ctypes.data_as(ip), self._mask_ptrs, self.w, self._kp_ptrs, self._desc_ptrs,
                                          self.n_kp.ctypes.data_as(ip)))
         return self.results()

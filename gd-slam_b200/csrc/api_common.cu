@@ -92,4 +92,45 @@ int gd_host_free(void* ptr)
     return GD_OK;
 }
 
+// Bare pinned-memory copy rate of one device: `iters` back-to-back cudaMemcpyAsync of `bytes` in the given direction, timed with
+// CUDA events on a private stream.  bench.py runs it on every rank at the same time to measure what the box's host side can
+// deliver (the ceiling of the end-to-end leg), independently of any kernel.
+int gd_probe_copy(int device, size_t bytes, int iters, int to_device, double* gb_per_s)
+{
+    if (!gb_per_s || bytes == 0 || iters <= 0) return GD_EINVAL;
+    GD_TRY(gd::select_device(device));
+    gd::PinnedBuf hb;
+    gd::DevBuf db;
+    GD_TRY(hb.alloc(bytes));
+    GD_TRY(db.alloc(bytes));
+    std::memset(hb.p, 1, bytes);
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GD_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = GD_OK;
+    float ms = 0.f;
+    for (int pass = 0; pass < 2 && rc == GD_OK; ++pass) {  // pass 0 warms up
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < (pass ? iters : 1); ++i) {
+            const cudaError_t e = to_device ? cudaMemcpyAsync(db.p, hb.p, bytes, cudaMemcpyHostToDevice, s)
+                                            : cudaMemcpyAsync(hb.p, db.p, bytes, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) {
+                gd::set_error("gd_probe_copy: %s", cudaGetErrorString(e));
+                rc = GD_ECUDA;
+                break;
+            }
+        }
+        cudaEventRecord(e1, s);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = GD_ECUDA;
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    if (rc == GD_OK) *gb_per_s = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    return rc;
+}
+
 }  // extern "C"

@@ -42,6 +42,7 @@ struct gd_frontend {
     };
     std::map<std::tuple<int, const void*, size_t>, GraphEntry> graphs;
     bool use_graphs = false;
+    int graph_fallbacks = 0;  // captures / instantiations that failed (the reason is left in gd_last_error)
     ~gd_frontend()
     {
         if (ev0) cudaEventDestroy(ev0);
@@ -117,8 +118,12 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
         const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
         if (rc != GD_OK || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
+            // not fatal, but recorded: gd_last_error() tells why this handle runs plain launches from now on
+            set_error("CUDA graph capture of the front-end step failed (enqueue rc %d, %s): falling back to plain launches", rc,
+                      cudaGetErrorString(ce));
             cudaGetLastError();
             h->use_graphs = false;  // fall back to plain launches for good
+            h->graph_fallbacks += 1;
             g.frames = frames0;
             h->stats.launches = l0;
             return frontend_enqueue(h, bgr_dev, bgr_stride_b);
@@ -128,8 +133,10 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
         const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) {
+            set_error("cudaGraphInstantiate of the front-end step failed (%s): falling back to plain launches", cudaGetErrorString(ie));
             cudaGetLastError();
             h->use_graphs = false;
+            h->graph_fallbacks += 1;
             g.frames = frames0;
             h->stats.launches = l0;
             return frontend_enqueue(h, bgr_dev, bgr_stride_b);
@@ -170,6 +177,8 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
         if ((r = h->orb.init(cfg->nfeatures, cfg->scale_factor, cfg->nlevels, cfg->ini_th_fast, cfg->min_th_fast, cfg->width,
                              cfg->height, cfg->device, cfg->batch, h->stream, &h->stats)) != GD_OK)
             break;
+        // the front-end captures its whole step itself: the per-core graph caches must never capture inside that capture
+        h->geo.push_graphs.enabled = h->geo.mask_graphs.enabled = h->orb.graphs.enabled = false;
         if (cfg->staged_slots > 0) {
             const size_t B = (size_t)cfg->batch, S = (size_t)cfg->staged_slots;
             if ((r = h->staged_bgr.alloc(S * B * h->geo.n_pad * 3)) != GD_OK) break;
@@ -284,14 +293,15 @@ int gd_frontend_fetch(gd_frontend_t* h, uint8_t* const* mask_out, size_t mask_st
     GD_CUDA(cudaMemcpyAsync(hn, o.out_n.p, sizeof(int) * g.batch, cudaMemcpyDeviceToHost, h->stream));
     GD_CUDA(cudaMemcpyAsync(hn + g.batch, o.err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     GD_CUDA(cudaStreamSynchronize(h->stream));
-    if (hn[g.batch] != 0) {
-        set_error("ORB kernel reported an internal capacity overflow (flags %d)", hn[g.batch]);
-        return GD_ECAPACITY;
-    }
     int rc = GD_OK;
+    if (hn[g.batch] != 0) {  // reported once, then cleared; counts and (clamped) records are still delivered
+        set_error("ORB kernel reported an internal capacity overflow (flags %d): results are truncated", hn[g.batch]);
+        GD_CUDA(cudaMemsetAsync(o.err.p, 0, sizeof(int), h->stream));
+        rc = GD_EINTERNAL;
+    }
     for (int b = 0; b < g.batch; ++b) {
         if (n_kp) n_kp[b] = hn[b];
-        if (hn[b] > cap && ((kps && kps[b]) || (desc && desc[b]))) {
+        if (rc == GD_OK && hn[b] > cap && ((kps && kps[b]) || (desc && desc[b]))) {
             set_error("keypoint capacity %d too small for %d keypoints", cap, hn[b]);
             rc = GD_ECAPACITY;
         }
@@ -323,12 +333,28 @@ int gd_frontend_step_u16(gd_frontend_t* h, const uint8_t* const* bgr, size_t bgr
     GD_REQUIRE(h->cfg.depth_factor != 0.f, "depth_factor is zero");
     if (!h->raw_depth.p) GD_TRY(h->raw_depth.alloc((size_t)g.batch * g.n_pad * sizeof(uint16_t)));
     const int slot = g.cur_slot();
+    // one copy per plane for the whole batch when the caller's frames are densely packed back to back (pinned batch buffers)
+    bool packed_bgr = bgr_step == (size_t)g.w * 3 && g.n_pad == g.n, packed_d = depth_step == (size_t)g.w * 2 && g.n_pad == g.n;
     for (int b = 0; b < g.batch; ++b) {
         GD_REQUIRE(bgr[b] && depth_raw[b], "null image pointer");
-        GD_CUDA(cudaMemcpy2DAsync(g.bgr.as<uint8_t>() + (size_t)b * g.n_pad * 3, (size_t)g.w * 3, bgr[b], bgr_step, (size_t)g.w * 3, g.h,
-                                  cudaMemcpyHostToDevice, h->stream));
-        GD_CUDA(cudaMemcpy2DAsync(h->raw_depth.as<uint16_t>() + (size_t)b * g.n_pad, (size_t)g.w * 2, depth_raw[b], depth_step,
-                                  (size_t)g.w * 2, g.h, cudaMemcpyHostToDevice, h->stream));
+        if (b > 0) {
+            packed_bgr = packed_bgr && bgr[b] == bgr[b - 1] + g.n * 3;
+            packed_d = packed_d && depth_raw[b] == depth_raw[b - 1] + g.n;
+        }
+    }
+    if (packed_bgr) {
+        GD_CUDA(cudaMemcpyAsync(g.bgr.p, bgr[0], (size_t)g.batch * g.n * 3, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int b = 0; b < g.batch; ++b)
+            GD_CUDA(cudaMemcpy2DAsync(g.bgr.as<uint8_t>() + (size_t)b * g.n_pad * 3, (size_t)g.w * 3, bgr[b], bgr_step, (size_t)g.w * 3,
+                                      g.h, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (packed_d) {
+        GD_CUDA(cudaMemcpyAsync(h->raw_depth.p, depth_raw[0], (size_t)g.batch * g.n * 2, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int b = 0; b < g.batch; ++b)
+            GD_CUDA(cudaMemcpy2DAsync(h->raw_depth.as<uint16_t>() + (size_t)b * g.n_pad, (size_t)g.w * 2, depth_raw[b], depth_step,
+                                      (size_t)g.w * 2, g.h, cudaMemcpyHostToDevice, h->stream));
     }
     const float inv_factor = 1.0f / h->cfg.depth_factor;  // mDepthMapFactor = 1.0f/mDepthMapFactor, Tracking.cc:130-134
     GD_TRY(launch_depth_u16_to_m(h->raw_depth.as<uint16_t>(), g.n_pad, g.depth_slot_ptr(slot), g.depth_stride_b(), g.n, g.batch,

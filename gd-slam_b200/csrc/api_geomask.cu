@@ -132,7 +132,7 @@ int gd_stage_mahalanobis(int device, const float* flow, const float* depth_ref, 
     GD_TRY(er.alloc(n));
     GD_TRY(ec.alloc(n));
     GD_TRY(keys.alloc(np * 8));
-    GD_TRY(mm.alloc(8));
+    GD_TRY(mm.alloc(GD_MM_WORDS * 4));
     GD_TRY(pose.alloc(sizeof(PoseDev)));
     GD_TRY(dmask.alloc(np));
     GD_TRY(ddist.alloc(np * 4));
@@ -149,22 +149,25 @@ int gd_stage_mahalanobis(int device, const float* flow, const float* depth_ref, 
     CamConst cam;
     make_cam_const(K, &cam);
     PoseDev p;
-    make_pose(K, R, T, 1, &p);
+    make_pose(K, R, T, 1, 1, &p);
+    const KeyFormat kf = make_key_format(n);
     GD_CUDA(cudaMemcpy(pose.p, &p, sizeof(p), cudaMemcpyHostToDevice));
     GD_TRY(launch_mahalanobis(dflow.as<float2>(), 0, dr.as<float>(), dc.as<float>(), 0, er.as<uint8_t>(), ec.as<uint8_t>(), 0,
-                              lut ? dl.as<float2>() : nullptr, w, h, 1, cam, pose.as<PoseDev>(),
+                              lut ? dl.as<float2>() : nullptr, w, h, 1, cam, pose.as<PoseDev>(), kf,
                               keys.as<unsigned long long>(), 0, 0, nullptr));
     GD_TRY(launch_minmax_reset(mm.as<unsigned>(), 1, 0));
-    GD_TRY(launch_minmax(keys.as<unsigned long long>(), 0, (int)n, 1, mm.as<unsigned>(), 0, nullptr));
-    GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), 0, (int)n, 1, mm.as<unsigned>(), pose.as<PoseDev>(),
-                                 dmask.as<uint8_t>(), 0, ddist.as<float>(), 0, 0, nullptr));
+    GD_TRY(launch_minmax(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, mm.as<unsigned>(), 0, nullptr));
+    GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), 0, (int)n, 1, mm.as<unsigned>(), pose.as<PoseDev>(), kf,
+                                 dmask.as<uint8_t>(), 0, 0, nullptr));
+    GD_TRY(launch_resolve_dist(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, ddist.as<float>(), 0, 0));
     GD_CUDA(cudaDeviceSynchronize());
     if (dist) GD_CUDA(cudaMemcpy(dist, ddist.p, n * 4, cudaMemcpyDeviceToHost));
     if (mask) GD_CUDA(cudaMemcpy(mask, dmask.p, n, cudaMemcpyDeviceToHost));
     if (minmax) {
-        unsigned bits[2];
-        GD_CUDA(cudaMemcpy(bits, mm.p, 8, cudaMemcpyDeviceToHost));
+        unsigned bits[GD_MM_WORDS];
+        GD_CUDA(cudaMemcpy(bits, mm.p, sizeof(bits), cudaMemcpyDeviceToHost));
         bits[1] = ~bits[1];
+        if (bits[2] == 0u) bits[0] = bits[1] = 0x7FC00000u;
         std::memcpy(minmax, bits, 8);
     }
     return GD_OK;

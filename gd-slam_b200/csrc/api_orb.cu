@@ -16,19 +16,23 @@ int orb_fetch_results(OrbCore& c, gd_keypoint* const* kps, uint8_t* const* desc,
     GD_CUDA(cudaMemcpyAsync(hn, c.out_n.p, sizeof(int) * c.batch, cudaMemcpyDeviceToHost, c.stream));
     GD_CUDA(cudaMemcpyAsync(hn + c.batch, c.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     GD_CUDA(cudaStreamSynchronize(c.stream));
-    if (hn[c.batch] != 0) {
-        set_error("ORB kernel reported an internal capacity overflow (flags %d)", hn[c.batch]);
-        return GD_ECAPACITY;
-    }
     int rc = GD_OK;
+    if (hn[c.batch] != 0) {
+        // reported once, then cleared: the flag must not poison later extractions.  The clamped results are still delivered.
+        set_error("ORB kernel reported an internal capacity overflow (flags %d): results are truncated", hn[c.batch]);
+        GD_CUDA(cudaMemsetAsync(c.err.p, 0, sizeof(int), c.stream));
+        rc = GD_EINTERNAL;
+    }
     for (int b = 0; b < c.batch; ++b) {
         const int n = hn[b];
         if (n_out) n_out[b] = n;
         int m = n;
         if (n > capacity) {
             m = capacity;
-            rc = GD_ECAPACITY;
-            set_error("keypoint capacity %d too small for %d keypoints", capacity, n);
+            if (rc == GD_OK) {
+                rc = GD_ECAPACITY;
+                set_error("keypoint capacity %d too small for %d keypoints", capacity, n);
+            }
         }
         if (kps && kps[b] && m > 0)
             GD_CUDA(cudaMemcpyAsync(kps[b], c.out_kp.as<gd_keypoint>() + (size_t)b * c.plan.kp_capacity, sizeof(gd_keypoint) * m,

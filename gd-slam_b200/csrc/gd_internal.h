@@ -225,7 +225,9 @@ struct GraphCache {
         if (it == execs.end()) {
             const long long l0 = st ? st->launches : 0;
             cudaGraph_t graph = nullptr;
-            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            const cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            if (be != cudaSuccess) {
+                set_error("cudaStreamBeginCapture failed (%s): this handle runs plain launches from now on", cudaGetErrorString(be));
                 cudaGetLastError();
                 enabled = false;
                 return enqueue();
@@ -235,6 +237,8 @@ struct GraphCache {
             cudaGraphExec_t exec = nullptr;
             if (rc != GD_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
                 if (graph) cudaGraphDestroy(graph);
+                set_error("CUDA graph capture / instantiation failed (enqueue rc %d, %s): this handle runs plain launches from now on",
+                          rc, cudaGetErrorString(ce));
                 cudaGetLastError();
                 enabled = false;  // plain launches for good
                 if (st) st->launches = l0;

@@ -73,7 +73,18 @@ void make_cam_const(const float K[9], CamConst* c)
     inv3_cv<double>(Kd, c->Kid);
 }
 
-void make_pose(const float K[9], const float R[9], const float T[3], int valid, PoseDev* p)
+KeyFormat make_key_format(size_t n_px)
+{
+    int idx_bits = 1;
+    while (((size_t)1 << idx_bits) <= n_px + 1) ++idx_bits;  // source index + 1 fits
+    KeyFormat kf;
+    kf.shift = 32 + idx_bits;
+    const int epoch_bits = 64 - kf.shift > 20 ? 20 : 64 - kf.shift;
+    kf.epoch_max = (1 << epoch_bits) - 1;
+    return kf;
+}
+
+void make_pose(const float K[9], const float R[9], const float T[3], int valid, int epoch, PoseDev* p)
 {
     float Ki[9];
     inv3_cv<float>(K, Ki);
@@ -83,7 +94,8 @@ void make_pose(const float K[9], const float R[9], const float T[3], int valid, 
         for (int j = 0; j < 3; ++j)
             p->RK[3 * i + j] = h_dot3(R[3 * i], Ki[j], R[3 * i + 1], Ki[3 + j], R[3 * i + 2], Ki[6 + j]);
     p->valid = valid;
-    p->pad[0] = p->pad[1] = 0;
+    p->epoch = epoch;
+    p->pad = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,8 +319,8 @@ __global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict
                                                      size_t dstride_b, const uint8_t* __restrict__ edge_ref,
                                                      const uint8_t* __restrict__ edge_cur, size_t estride_b,
                                                      const float2* __restrict__ lut, int w, int h, CamConst cam,
-                                                     const PoseDev* __restrict__ poses, unsigned long long* __restrict__ keys,
-                                                     size_t kstride_b)
+                                                     const PoseDev* __restrict__ poses, int key_shift,
+                                                     unsigned long long* __restrict__ keys, size_t kstride_b)
 {
     pdl_wait();
     const int b = blockIdx.z;
@@ -417,44 +429,66 @@ __global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict
     l = fma((double)q[2], (double)e2, l);
     float value = sqrtf((float)l);
     value = value + 0.0f;  // -0 -> +0 so that the bit pattern orders like the value
-    const unsigned long long key = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned long long)__float_as_uint(value);
+    const unsigned long long key = ((unsigned long long)(unsigned)P->epoch << key_shift) | ((unsigned long long)(unsigned)(i + 1) << 32) |
+                                   (unsigned long long)__float_as_uint(value);
     atomicMax(keys + (size_t)b * kstride_b + (size_t)icy * w + icx, key);
 }
 
 int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* depth_ref, const float* depth_cur,
                        size_t depth_stride_b, const uint8_t* edge_ref, const uint8_t* edge_cur, size_t edge_stride_b,
-                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses,
+                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses, KeyFormat kf,
                        unsigned long long* keys, size_t keys_stride_b, cudaStream_t s, LaunchStats* st)
 {
     LaunchScope ls(st, s, "K2b_mahalanobis", 1);
     dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), batch);
     GD_CUDA(launch_pdl(k_mahalanobis, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
-                                          edge_stride_b, lut, w, h, cam, poses, keys, keys_stride_b));
+                                          edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 pass 1: min / max over the resolved low words (unwritten pixels contribute 0.0f)
+// K3 pass 1: min / max over the resolved low words.  Unwritten pixels (stale epoch) contribute 0.0f; NaN values are
+// skipped like cv::normalize's min/max scan skips them — except at pixel 0, where the scan starts (flag word [2]).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned key_value_bits(unsigned long long key, int key_shift, unsigned epoch)
+{
+    return (unsigned)(key >> key_shift) == epoch ? (unsigned)key : 0u;
+}
+__device__ __forceinline__ bool bits_is_nan(unsigned b) { return (b & 0x7FFFFFFFu) > 0x7F800000u; }
+
 __global__ void __launch_bounds__(256) k_minmax(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
+                                                const PoseDev* __restrict__ poses, int key_shift,
                                                 unsigned int* __restrict__ minmax_bits)
 {
     pdl_wait();
     const int b = blockIdx.y;
     const unsigned long long* kp = keys + (size_t)b * kstride_b;
+    const unsigned epoch = (unsigned)poses[b].epoch;
     unsigned mn = 0xFFFFFFFFu, mx = 0u;
     const int n2 = n_px >> 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
         const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(kp) + i);
-        const unsigned a = (unsigned)v.x, c = (unsigned)v.y;
-        mn = min(mn, min(a, c));
-        mx = max(mx, max(a, c));
+        const unsigned a = key_value_bits(v.x, key_shift, epoch), c = key_value_bits(v.y, key_shift, epoch);
+        if (!bits_is_nan(a)) {
+            mn = min(mn, a);
+            mx = max(mx, a);
+        } else if (i == 0) {
+            minmax_bits[GD_MM_WORDS * b + 2] = 0u;
+        }
+        if (!bits_is_nan(c)) {
+            mn = min(mn, c);
+            mx = max(mx, c);
+        }
     }
     if ((n_px & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned a = (unsigned)kp[n_px - 1];
-        mn = min(mn, a);
-        mx = max(mx, a);
+        const unsigned a = key_value_bits(kp[n_px - 1], key_shift, epoch);
+        if (!bits_is_nan(a)) {
+            mn = min(mn, a);
+            mx = max(mx, a);
+        } else if (n_px == 1) {
+            minmax_bits[GD_MM_WORDS * b + 2] = 0u;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -477,32 +511,32 @@ __global__ void __launch_bounds__(256) k_minmax(const unsigned long long* __rest
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         }
         if (lane == 0) {
-            atomicMin(minmax_bits + 2 * b, mn);
-            atomicMin(minmax_bits + 2 * b + 1, ~mx);
+            atomicMin(minmax_bits + GD_MM_WORDS * b, mn);
+            atomicMin(minmax_bits + GD_MM_WORDS * b + 1, ~mx);
         }
     }
 }
 
 int launch_minmax_reset(unsigned int* minmax_bits, int batch, cudaStream_t s)
 {
-    GD_CUDA(cudaMemsetAsync(minmax_bits, 0xFF, sizeof(unsigned) * 2 * batch, s));
+    GD_CUDA(cudaMemsetAsync(minmax_bits, 0xFF, sizeof(unsigned) * GD_MM_WORDS * batch, s));
     return GD_OK;
 }
 
-int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, unsigned int* minmax_bits,
-                  cudaStream_t s, LaunchStats* st)
+int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses, KeyFormat kf,
+                  unsigned int* minmax_bits, cudaStream_t s, LaunchStats* st)
 {
     LaunchScope ls(st, s, "K3a_minmax", 1);
     int blocks = cdiv(n_px / 2, 256 * 4);
     if (blocks < 1) blocks = 1;
     dim3 grid(blocks, batch);
-    GD_CUDA(launch_pdl(k_minmax, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits));
+    GD_CUDA(launch_pdl(k_minmax, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, poses, kf.shift, minmax_bits));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 pass 2: v*a+b (fused, like cv convertTo), round half even, saturate, (<20) -> {1,0}; clear keys
+// K3 pass 2: v*a+b (fused, like cv convertTo), round half even, saturate, (<20) -> {1,0}
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned mask_of(float d, float a, float bsh)
 {
@@ -512,18 +546,20 @@ __device__ __forceinline__ unsigned mask_of(float d, float a, float bsh)
     return r < 20 ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_normalize_mask(unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
+__global__ void __launch_bounds__(256) k_normalize_mask(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
                                                         const unsigned int* __restrict__ minmax_bits,
-                                                        const PoseDev* __restrict__ poses, uint8_t* __restrict__ mask,
-                                                        size_t mstride_b, float* __restrict__ dist_out, size_t dstride_b)
+                                                        const PoseDev* __restrict__ poses, int key_shift,
+                                                        uint8_t* __restrict__ mask, size_t mstride_b)
 {
     pdl_wait();
     const int b = blockIdx.y;
-    unsigned long long* kp = keys + (size_t)b * kstride_b;
+    const unsigned long long* kp = keys + (size_t)b * kstride_b;
     uint8_t* mp = mask + (size_t)b * mstride_b;
-    const bool valid = poses[b].valid != 0;
-    const float smin_f = __uint_as_float(minmax_bits[2 * b]);
-    const float smax_f = __uint_as_float(~minmax_bits[2 * b + 1]);
+    const unsigned epoch = (unsigned)poses[b].epoch;
+    // invalid pose -> all ones (:179-185); NaN at pixel 0 -> cv::normalize turns the whole image into NaN -> 8-bit 0 -> all ones
+    const bool valid = poses[b].valid != 0 && minmax_bits[GD_MM_WORDS * b + 2] != 0u;
+    const float smin_f = __uint_as_float(minmax_bits[GD_MM_WORDS * b]);
+    const float smax_f = __uint_as_float(~minmax_bits[GD_MM_WORDS * b + 1]);
     const double smin = (double)smin_f, smax = (double)smax_f;
     const double scale = 255.0 * ((smax - smin) > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
     const double shift = 0.0 - smin * scale;
@@ -532,34 +568,47 @@ __global__ void __launch_bounds__(256) k_normalize_mask(unsigned long long* __re
     const int i0 = g * 4;
     if (i0 >= n_px) return;
     if (i0 + 4 <= n_px && (mstride_b & 3) == 0 && (kstride_b & 1) == 0) {
-        ulonglong2* k2 = reinterpret_cast<ulonglong2*>(kp + i0);
-        const ulonglong2 v0 = k2[0], v1 = k2[1];
-        const float d0 = __uint_as_float((unsigned)v0.x), d1 = __uint_as_float((unsigned)v0.y);
-        const float d2 = __uint_as_float((unsigned)v1.x), d3 = __uint_as_float((unsigned)v1.y);
+        const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(kp + i0);
+        const ulonglong2 v0 = __ldg(k2), v1 = __ldg(k2 + 1);
+        const float d0 = __uint_as_float(key_value_bits(v0.x, key_shift, epoch)), d1 = __uint_as_float(key_value_bits(v0.y, key_shift, epoch));
+        const float d2 = __uint_as_float(key_value_bits(v1.x, key_shift, epoch)), d3 = __uint_as_float(key_value_bits(v1.y, key_shift, epoch));
         unsigned m = 0x01010101u;
         if (valid) m = mask_of(d0, a, bsh) | (mask_of(d1, a, bsh) << 8) | (mask_of(d2, a, bsh) << 16) | (mask_of(d3, a, bsh) << 24);
         *reinterpret_cast<unsigned*>(mp + i0) = m;
-        if (dist_out) *reinterpret_cast<float4*>(dist_out + (size_t)b * dstride_b + i0) = make_float4(d0, d1, d2, d3);
-        k2[0] = make_ulonglong2(0ull, 0ull);
-        k2[1] = make_ulonglong2(0ull, 0ull);
     } else {
         for (int i = i0; i < min(i0 + 4, n_px); ++i) {
-            const float d = __uint_as_float((unsigned)kp[i]);
+            const float d = __uint_as_float(key_value_bits(kp[i], key_shift, epoch));
             mp[i] = valid ? (uint8_t)mask_of(d, a, bsh) : (uint8_t)1;
-            if (dist_out) dist_out[(size_t)b * dstride_b + i] = d;
-            kp[i] = 0ull;
         }
     }
 }
 
-int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
-                          const unsigned int* minmax_bits, const PoseDev* poses, uint8_t* mask, size_t mask_stride_b,
-                          float* dist_out, size_t dist_stride_b, cudaStream_t s, LaunchStats* st)
+int launch_normalize_mask(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
+                          const unsigned int* minmax_bits, const PoseDev* poses, KeyFormat kf, uint8_t* mask, size_t mask_stride_b,
+                          cudaStream_t s, LaunchStats* st)
 {
     LaunchScope ls(st, s, "K3b_normalize_mask", 1);
     dim3 grid(cdiv(cdiv(n_px, 4), 256), batch);
-    GD_CUDA(launch_pdl(k_normalize_mask, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits, poses, mask, mask_stride_b, dist_out,
-                                          dist_stride_b));
+    GD_CUDA(launch_pdl(k_normalize_mask, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits, poses, kf.shift, mask, mask_stride_b));
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_dist(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px,
+                                                      const PoseDev* __restrict__ poses, int key_shift, float* __restrict__ dist,
+                                                      size_t dstride_b)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    dist[(size_t)b * dstride_b + i] = __uint_as_float(key_value_bits(keys[(size_t)b * kstride_b + i], key_shift, (unsigned)poses[b].epoch));
+}
+
+int launch_resolve_dist(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses, KeyFormat kf,
+                        float* dist_out, size_t dist_stride_b, cudaStream_t s)
+{
+    dim3 grid(cdiv(n_px, 256), batch);
+    k_resolve_dist<<<grid, 256, 0, s>>>(keys, keys_stride_b, n_px, poses, kf.shift, dist_out, dist_stride_b);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

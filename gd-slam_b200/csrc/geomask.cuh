@@ -12,8 +12,20 @@ struct PoseDev {
     float T[3];
     float RK[9];  // R * inv(K), f32 gemm semantics of OpenCV (GeoMaskMaker.cc:241)
     int valid;    // 0 -> all-ones mask (GetRt failure path / warm-up)
-    int pad[2];
+    int epoch;    // scatter-key epoch of this step (see KeyFormat); uploaded with the pose, never part of a captured graph
+    int pad;
 };
+
+// 64-bit scatter key of K2b/K3: [ epoch | source index + 1 | bits(value) ].  The source index orders the writers of one
+// target by raster position (atomicMax = last raster-order writer wins, GeoMaskMaker.cc:269); the epoch in the top bits
+// makes every key of an earlier step smaller than any key of this step and lets the readers treat stale entries as
+// "not written" (0.0f), so the key image is never cleared between frames (it was 8 bytes/pixel of stores per frame).
+// When the epoch wraps (every 2^epoch_bits - 1 steps) the host clears the image once.
+struct KeyFormat {
+    int shift;      // 32 + index bits
+    int epoch_max;  // 2^(64 - shift) - 1
+};
+KeyFormat make_key_format(size_t n_px);
 
 // camera constants shared by all streams of a handle (kernel argument by value)
 struct CamConst {
@@ -25,7 +37,7 @@ struct CamConst {
 };
 
 void make_cam_const(const float K[9], CamConst* c);
-void make_pose(const float K[9], const float R[9], const float T[3], int valid, PoseDev* p);
+void make_pose(const float K[9], const float R[9], const float T[3], int valid, int epoch, PoseDev* p);
 
 // K0: 8UC3 -> 8UC1 (cv::cvtColor 8-bit, 15-bit fixed point).  Either output may be null.
 // gray_bgr2gray: rows of w bytes, stream stride gray_stride_b.  gray_orb: row pitch orb_pitch, stream stride orb_stride_b.
@@ -40,19 +52,23 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
 // K2b: fused back-projection + J S J^T + 3x3 inverse + Mahalanobis + scatter (64-bit atomicMax keys)
 int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* depth_ref, const float* depth_cur,
                        size_t depth_stride_b, const uint8_t* edge_ref, const uint8_t* edge_cur, size_t edge_stride_b,
-                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses,
+                       const float2* lut, int w, int h, int batch, const CamConst& cam, const PoseDev* poses, KeyFormat kf,
                        unsigned long long* keys, size_t keys_stride_b, cudaStream_t s, LaunchStats* st);
 
-// K3 pass 1: per-stream min / max of the resolved dist image.  minmax_bits: [batch][2] u32, must hold 0xFFFFFFFF
-// on entry (launch_minmax_reset).  Encoding: [0] = min(bits(v)), [1] = min(~bits(v)).
+// K3 pass 1: per-stream min / max of the resolved dist image.  minmax_bits: [batch][GD_MM_WORDS] u32, must hold 0xFFFFFFFF
+// on entry (launch_minmax_reset).  Encoding: [0] = min(bits(v)), [1] = min(~bits(v)), [2] = 0 when pixel 0 holds a NaN
+// (cv::normalize's min/max scan starts from element 0 and ignores NaN everywhere else: a NaN there poisons the whole image).
+constexpr int GD_MM_WORDS = 4;
 int launch_minmax_reset(unsigned int* minmax_bits, int batch, cudaStream_t s);
-int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, unsigned int* minmax_bits,
-                  cudaStream_t s, LaunchStats* st);
-// K3 pass 2: normalise (0..255), round half even, < 20 -> mask {1,0}; clears the keys for the next frame.
-// dist_out (optional) receives the resolved f32 dist image.
-int launch_normalize_mask(unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
-                          const unsigned int* minmax_bits, const PoseDev* poses, uint8_t* mask, size_t mask_stride_b,
-                          float* dist_out, size_t dist_stride_b, cudaStream_t s, LaunchStats* st);
+int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses, KeyFormat kf,
+                  unsigned int* minmax_bits, cudaStream_t s, LaunchStats* st);
+// K3 pass 2: normalise (0..255), round half even, < 20 -> mask {1,0}.  The keys are left alone (epoch tagged).
+int launch_normalize_mask(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
+                          const unsigned int* minmax_bits, const PoseDev* poses, KeyFormat kf, uint8_t* mask,
+                          size_t mask_stride_b, cudaStream_t s, LaunchStats* st);
+// debug / parity only: the resolved f32 dist image of the last step (GeoMaskMaker.cc:269, before normalize)
+int launch_resolve_dist(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses,
+                        KeyFormat kf, float* dist_out, size_t dist_stride_b, cudaStream_t s);
 // "next" row (f)-2: Frame ctor erosion + keypoint filter (src/Frame.cc:258-282)
 struct EllipseSE {
     int j1[31], j2[31];  // [j1, j2) columns of each row of cv::getStructuringElement(MORPH_ELLIPSE, 31x31)

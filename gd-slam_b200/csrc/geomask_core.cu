@@ -67,7 +67,10 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
     GD_TRY(scratchI.alloc(B * plan.i_floats * sizeof(float)));
     GD_TRY(flowA.alloc(B * plan.f_float2 * sizeof(float2)));
     GD_TRY(flowB.alloc(B * plan.f_float2 * sizeof(float2)));
-    split_flow = std::getenv("GD_FLOW_FUSED") == nullptr;  // default: split form (matrices + box/solve)
+    {  // GD_FLOW_FUSED=1 selects the older single-kernel flow iteration; default (0 / unset): split form (matrices + box/solve)
+        const char* e = std::getenv("GD_FLOW_FUSED");
+        split_flow = !(e && std::atoi(e) != 0);
+    }
     if (split_flow) {
         // M scratch of the split flow form.  GD_M_L2_MB=<n> processes the streams in groups whose M fits n MB (so that it
         // could stay L2 resident between the two kernels); measured on B200 at batch 32: 24/48/96 MB groups are 12/5/2 %
@@ -78,10 +81,10 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
         GD_TRY(Mbuf.alloc(std::max(one, std::min(B * one, budget / one * one))));
     }
     GD_TRY(keys.alloc(B * n_pad * sizeof(unsigned long long)));
-    GD_TRY(minmax.alloc(B * 2 * sizeof(unsigned)));
+    GD_TRY(minmax.alloc(B * GD_MM_WORDS * sizeof(unsigned)));
+    keyfmt = make_key_format(n);
     GD_TRY(poses.alloc(B * sizeof(PoseDev)));
     GD_TRY(mask.alloc(B * n_pad));
-    GD_TRY(dist.alloc(B * n_pad * sizeof(float)));
     GD_TRY(h_poses.alloc(POSE_SLOTS * B * sizeof(PoseDev)));
     for (int i = 0; i < POSE_SLOTS; ++i) GD_CUDA(cudaEventCreateWithFlags(&pose_ev[i], cudaEventDisableTiming));
     GD_CUDA(cudaMemsetAsync(keys.p, 0, keys.bytes, stream));
@@ -153,10 +156,14 @@ int GeoMaskCore::upload_poses(const float* Rm, const float* Tm, const int* pose_
     pose_slot = (pose_slot + 1) % POSE_SLOTS;
     if (pose_pending[slot]) GD_CUDA(cudaEventSynchronize(pose_ev[slot]));  // the copy that last read this slot has run
     PoseDev* hp = h_poses.as<PoseDev>() + (size_t)slot * batch;
+    // scatter-key epoch of this step (KeyFormat): 1 .. epoch_max, the key image is cleared once per wrap-around
+    epoch = epoch % keyfmt.epoch_max + 1;
+    if (epoch == 1 && epoch_used) GD_CUDA(cudaMemsetAsync(keys.p, 0, keys.bytes, stream));
+    epoch_used = true;
     for (int b = 0; b < batch; ++b) {
         const int valid = started && (!pose_valid || pose_valid[b]) ? 1 : 0;
         static const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
-        make_pose(K, Rm ? Rm + 9 * b : I3, Tm ? Tm + 3 * b : Z3, valid, hp + b);
+        make_pose(K, Rm ? Rm + 9 * b : I3, Tm ? Tm + 3 * b : Z3, valid, epoch, hp + b);
     }
     GD_CUDA(cudaMemcpyAsync(poses.p, hp, sizeof(PoseDev) * batch, cudaMemcpyHostToDevice, stream));
     GD_CUDA(cudaEventRecord(pose_ev[slot], stream));
@@ -184,11 +191,12 @@ int GeoMaskCore::enqueue_mask()
     GD_TRY(launch_mahalanobis(last_flow, plan.f_float2, depth_slot_ptr(ref), depth_slot_ptr(cur), depth_stride_b(),
                               edge.as<uint8_t>() + (size_t)ref * n_pad, edge.as<uint8_t>() + (size_t)cur * n_pad,
                               (size_t)GD_RING * n_pad, has_lut ? lut.as<float2>() : nullptr, w, h, batch, cam,
-                              poses.as<PoseDev>(), keys.as<unsigned long long>(), n_pad, stream, stats));
+                              poses.as<PoseDev>(), keyfmt, keys.as<unsigned long long>(), n_pad, stream, stats));
     GD_TRY(launch_minmax_reset(minmax.as<unsigned>(), batch, stream));
-    GD_TRY(launch_minmax(keys.as<unsigned long long>(), n_pad, (int)n, batch, minmax.as<unsigned>(), stream, stats));
-    GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), n_pad, (int)n, batch, minmax.as<unsigned>(),
-                                 poses.as<PoseDev>(), mask.as<uint8_t>(), n_pad, dist.as<float>(), n_pad, stream, stats));
+    GD_TRY(launch_minmax(keys.as<unsigned long long>(), n_pad, (int)n, batch, poses.as<PoseDev>(), keyfmt, minmax.as<unsigned>(),
+                         stream, stats));
+    GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), n_pad, (int)n, batch, minmax.as<unsigned>(), poses.as<PoseDev>(),
+                                 keyfmt, mask.as<uint8_t>(), n_pad, stream, stats));
     return GD_OK;
 }
 
@@ -204,6 +212,11 @@ int GeoMaskCore::debug_fetch(int what, int b, void* dst, size_t dst_bytes)
             bytes = n * sizeof(float2);
             break;
         case GD_DBG_DIST:
+            // resolved on demand from the key image of the last step (the per-frame path only writes the mask)
+            GD_REQUIRE(last_cur_slot >= 0, "no pair evaluated yet");
+            if (!dist.p) GD_TRY(dist.alloc((size_t)batch * n_pad * sizeof(float)));
+            GD_TRY(launch_resolve_dist(keys.as<unsigned long long>(), n_pad, (int)n, batch, poses.as<PoseDev>(), keyfmt,
+                                       dist.as<float>(), n_pad, stream));
             src = dist.as<float>() + (size_t)b * n_pad;
             bytes = n * sizeof(float);
             break;
@@ -226,10 +239,11 @@ int GeoMaskCore::debug_fetch(int what, int b, void* dst, size_t dst_bytes)
             break;
         case GD_DBG_MINMAX: {
             GD_REQUIRE(dst_bytes >= 2 * sizeof(float), "dst too small");
-            unsigned bits[2];
+            unsigned bits[GD_MM_WORDS];
             GD_CUDA(cudaStreamSynchronize(stream));
-            GD_CUDA(cudaMemcpy(bits, minmax.as<unsigned>() + 2 * b, sizeof(bits), cudaMemcpyDeviceToHost));
+            GD_CUDA(cudaMemcpy(bits, minmax.as<unsigned>() + GD_MM_WORDS * b, sizeof(bits), cudaMemcpyDeviceToHost));
             unsigned mn = bits[0], mx = ~bits[1];
+            if (bits[2] == 0u) mn = mx = 0x7FC00000u;  // NaN at pixel 0: cv's scan returns NaN for both
             std::memcpy(dst, &mn, 4);
             std::memcpy((char*)dst + 4, &mx, 4);
             return GD_OK;

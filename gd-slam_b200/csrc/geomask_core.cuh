@@ -30,11 +30,14 @@ struct GeoMaskCore {
     DevBuf flowA, flowB;  // [B][f_float2]
     DevBuf Mbuf;          // [B][m_floats] UpdateMatrices output of the current level (split flow form)
     bool split_flow = true;
-    DevBuf keys;       // [B][n] u64 scatter keys (zero between frames)
-    DevBuf minmax;     // [B][2] u32
+    DevBuf keys;       // [B][n] u64 scatter keys, epoch tagged (KeyFormat): never cleared between frames
+    KeyFormat keyfmt;
+    int epoch = 0;     // epoch of the last uploaded pose block
+    bool epoch_used = false;
+    DevBuf minmax;     // [B][GD_MM_WORDS] u32
     DevBuf poses;      // [B] PoseDev
     DevBuf mask;       // [B][n] u8
-    DevBuf dist;       // [B][n] f32 (resolved dist image, kept for debug fetch)
+    DevBuf dist;       // [B][n] f32 resolved dist image: allocated and filled by debug_fetch(GD_DBG_DIST) only
     DevBuf lut;        // [n] float2 or empty
     // pinned staging of the pose blocks: a ring, because the H2D copy reads the buffer when it EXECUTES and a caller of the
     // device-resident path may enqueue several steps without synchronising (each slot is guarded by an event)

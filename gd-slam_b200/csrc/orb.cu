@@ -110,7 +110,9 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
         GD_REQUIRE(L.nIni >= 1, "aspect ratio not supported by DistributeOctTree (nIni = 0)");
         L.hX = (float)(maxBX - minB) / L.nIni;
         L.cand_off = cand;
-        L.cand_cap = ((maxBX - minB + 1) / 2 + 1) * ((maxBY - minB + 1) / 2 + 1);  // NMS: no two 8-adjacent survivors
+        // non-maximum suppression runs per cell: no two 8-adjacent survivors INSIDE a cell, but survivors of neighbouring
+        // cells can touch across the cell border -> the bound is the sum of the per-cell bounds
+        L.cand_cap = L.nCols * L.nRows * ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
         cand += (int)align_up((size_t)L.cand_cap, 64);
         L.kept_off = kept;
         kept += L.N + 8;
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_orb_quadtree(QtArgs a, const int
     const int* cc_in = cell_cnt + (size_t)b * a.total_cells + L.cell_start;
     for (int c = tid; c < ncell; c += QT_THREADS) sA[c] = cc_in[c];
     int n = block_excl_scan(sA, ncell, &s_total);
-    if (n > L.cand_cap) {  // cannot happen (NMS density bound); flag instead of corrupting memory
+    if (n > L.cand_cap) {  // per-cell NMS density bound; flag instead of corrupting memory
         if (tid == 0) atomicOr(err, 1);
         n = L.cand_cap;
     }

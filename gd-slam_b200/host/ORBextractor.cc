@@ -11,6 +11,8 @@ namespace ORB_SLAM2 {
 
 static void gd_check(int code, const char* what)
 {
+    // GD_ECAPACITY = more keypoints than the caller's buffer holds (clamped, like the reference's retainBest would);
+    // everything else, including the internal-overflow report GD_EINTERNAL, is an error
     if (code != GD_OK && code != GD_ECAPACITY) throw std::runtime_error(std::string(what) + ": " + gd_last_error());
 }
 

@@ -50,7 +50,8 @@ extern "C" {
 #define GD_ENODEVICE (-2) /* no CUDA device / device index out of range */
 #define GD_ECUDA (-3)     /* a CUDA runtime call or kernel failed */
 #define GD_ENOMEM (-4)
-#define GD_ECAPACITY (-5) /* an output buffer given by the caller is too small */
+#define GD_ECAPACITY (-5) /* an output buffer given by the caller is too small (results clamped, counts set) */
+#define GD_EINTERNAL (-6) /* an internal device-side capacity bound was exceeded (results truncated; reported once) */
 
 #define GD_ABI_VERSION 1
 
@@ -83,6 +84,9 @@ GD_API int gd_device_info(int device, char* name, int len, int* sm_count, size_t
 /* page-locked host memory for callers that want true asynchronous H2D/D2H (bench e2e leg) */
 GD_API int gd_host_alloc(void** ptr, size_t bytes);
 GD_API int gd_host_free(void* ptr);
+/* measurement aid: rate of `iters` back-to-back pinned cudaMemcpyAsync of `bytes` (to_device != 0: host->device) on `device`,
+ * CUDA-event timed.  Run on all GPUs of a box at once it gives the host-side ceiling of the end-to-end (host buffer) path. */
+GD_API int gd_probe_copy(int device, size_t bytes, int iters, int to_device, double* gb_per_s);
 
 /* ------------------------------------------------------------------ GeoMaskMaker ------------------ */
 /* K: 3x3 row-major; dist: k1,k2,p1,p2[,k3] or NULL (ndist 0).  Non-zero distortion builds the undistorted-pixel

@@ -24,10 +24,21 @@ def build() -> None:
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
+def build_native() -> str | None:
+    """-O3 -march=native build for bench.py's CPU timing legs, compiled on the machine it runs on; None if that fails."""
+    try:
+        subprocess.run(["make", "-s", "-C", _HERE, "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+    p = os.path.join(_HERE, "_native", "liboracle_native.so")
+    return p if os.path.exists(p) else None
+
+
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+        # GD_ORACLE_LIB: bench.py's CPU legs point this at the native timing build; the parity tests never set it
+        path = os.environ.get("GD_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
         if not os.path.exists(path):
             build()
         _LIB = C.CDLL(path)

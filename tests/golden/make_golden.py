@@ -194,6 +194,27 @@ def make_geomask_small():
           "max", dist.max())
 
 
+def make_geomask_640():
+    """The per-pixel loop (GeoMaskMaker.cc:208-272) + normalise/threshold at the BASELINE size 640x480: the literal cv2
+    transcription over every source pixel; the fixture keeps every 4th row of dist, the packed mask and min/max.  Inputs are
+    reproducible from the seeded generator: flow = the oracle's Farneback of frames (0, 5) of stream 0 (pinned against
+    cv2 by farneback.npz), edges = the oracle's GetEdge (pinned bit-exact against literal_get_edge by geomask_small.npz)."""
+    from oracle import pyoracle as po
+
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = synth.intrinsics()
+    R, T = s.pair_pose(0, 5)
+    flow = po.farneback(po.gray(f0.bgr), po.gray(f5.bgr))
+    e0, e5 = po.depth_edge(f0.depth_m, K), po.depth_edge(f5.depth_m, K)
+    dist, d8, mask = literal_mahalanobis(flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T)
+    np.savez_compressed(os.path.join(HERE, "geomask_640.npz"), K=K, R=R, T=T,
+                        crc=np.array([synth.frame_crc(f0), synth.frame_crc(f5)], np.uint64),
+                        flow_crc=np.uint64(__import__("zlib").crc32(flow.tobytes())), dist_rows4=dist[::4].copy(),
+                        mask=np.packbits(mask), minmax=np.array([dist.min(), dist.max()], np.float32))
+    print("geomask_640: written", (dist > 0).mean(), "dynamic", (mask == 0).mean(), "max", dist.max())
+
+
 def make_farneback():
     out = {}
     s = synth.SyntheticStream(0)
@@ -269,7 +290,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "erode":
         make_erode()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "geomask_640":
+        make_geomask_640()
+        sys.exit(0)
     make_geomask_small()
+    make_geomask_640()
     make_farneback()
     make_erode()
     make_undistort()

@@ -60,11 +60,18 @@ def test_frontend_stream_of_frames_host_and_staged(capi, oracle, synth):
                 assert nviol == 0, (f, b, nviol, dmax)
                 agree = (mask == mo).mean()
                 assert agree >= 0.999, (f, b, agree)
-                # Mahalanobis values within tolerance wherever both wrote the same target
+                # Mahalanobis image: sub-tolerance flow differences move a few integer targets, so the comparison with
+                # the oracle's own dist is not pixel-wise meaningful; the per-pixel loop is exact given the flow -> feed
+                # the front-end's flow (and its edge maps) to the oracle loop and require bit equality
                 dg = fe.debug(capi.DBG_DIST, b)
-                both = (dg > 0) & (dist_o > 0)
-                rel = np.abs(dg[both] - dist_o[both]) / np.maximum(1.0, np.abs(dist_o[both]))
-                assert np.quantile(rel, 0.999) <= 1e-4 * 50, float(rel.max())  # flow differences move a few targets
+                e_ref, e_cur = fe.debug(capi.DBG_EDGE_REF, b), fe.debug(capi.DBG_EDGE_CUR, b)
+                assert np.array_equal(e_ref, oracle.depth_edge(frames[b][f - 5].depth_m, K))
+                assert np.array_equal(e_cur, oracle.depth_edge(dep[b], K))
+                dist_x, _, _ = oracle.mahalanobis(fe.debug(capi.DBG_FLOW, b), frames[b][f - 5].depth_m, dep[b], e_ref, e_cur, K,
+                                                  R[b], T[b])
+                assert np.array_equal(dg, dist_x, equal_nan=True), (f, b)
+                same_target = (dg > 0) == (dist_o > 0)
+                assert same_target.mean() >= 0.999
     assert fe.launch_count() > launches0
     fe.close()
     fe2.close()

@@ -1,7 +1,7 @@
 """Oracle vs the committed golden fixtures (CPU only): GeoMaskMaker arithmetic."""
 import numpy as np
 
-from conftest import flow_tol_violations
+from conftest import flow_tol_violations  # noqa: F401
 
 
 def test_gray_matches_cv2_golden(oracle, golden):
@@ -26,6 +26,76 @@ def test_mahalanobis_vs_literal_cv2(oracle, golden):
     # the restatement follows OpenCV's accumulation widths, so it is in fact bit-exact here
     assert np.array_equal(dist, g["dist"])
     assert np.array_equal(written == 1, g["dist"] > 0) or (written.sum() >= (g["dist"] > 0).sum())
+
+
+def _inputs_640(oracle, synth, g):
+    """Inputs of geomask_640.npz, regenerated from the seeded generator (checked by CRC)."""
+    import zlib
+
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    assert [synth.frame_crc(f0), synth.frame_crc(f5)] == [int(v) for v in g["crc"]]
+    K = synth.intrinsics()
+    flow = oracle.farneback(oracle.gray(f0.bgr), oracle.gray(f5.bgr))
+    assert zlib.crc32(flow.tobytes()) == int(g["flow_crc"]), "oracle Farneback is not reproducible on this machine"
+    e0, e5 = oracle.depth_edge(f0.depth_m, K), oracle.depth_edge(f5.depth_m, K)
+    return flow, f0.depth_m, f5.depth_m, e0, e5
+
+
+def test_mahalanobis_640x480_vs_literal_cv2(oracle, synth, golden):
+    """The BASELINE size: the per-pixel loop of GeoMaskMaker.cc:208-272 over all 307 200 source pixels against the literal
+    cv2 transcription (every 4th row of dist kept in the fixture, the whole mask, min/max)."""
+    g = golden("geomask_640.npz")
+    flow, d0, d5, e0, e5 = _inputs_640(oracle, synth, g)
+    dist, _, _ = oracle.mahalanobis(flow, d0, d5, e0, e5, g["K"], g["R"], g["T"])
+    assert np.array_equal(dist[::4], g["dist_rows4"])
+    mask, _, mm = oracle.normalize_threshold(dist)
+    assert np.array_equal(mask, np.unpackbits(g["mask"])[: 480 * 640].reshape(480, 640))
+    assert np.array_equal(mm, g["minmax"])
+
+
+def test_nan_value_is_skipped_by_minmax_like_cv(oracle):
+    """A slightly negative quadratic form gives sqrt -> NaN.  cv::normalize's min/max scan ignores NaN (except at element 0,
+    where the scan starts): only that pixel is affected (8-bit 0 -> mask 1), not the whole image."""
+    import cv2
+
+    dist, wr = nan_case(oracle)
+    assert np.isnan(dist[wr > 0]).sum() >= 1 and not np.isnan(dist.flat[0])
+    mask, d8, mm = oracle.normalize_threshold(dist)
+    n = cv2.normalize(dist, None, 0.0, 255.0, cv2.NORM_MINMAX)
+    with np.errstate(invalid="ignore"):
+        ref8 = np.where(np.isnan(n), 0, np.clip(np.rint(n), 0, 255)).astype(np.uint8)
+    assert np.array_equal(d8, ref8) and 0 < (mask == 0).sum()
+    assert mm[0] == np.nanmin(dist) and mm[1] == np.nanmax(dist)
+    d2 = dist.copy()
+    d2.flat[0] = np.nan  # the scan starts here: everything becomes NaN -> 0 -> all ones
+    assert oracle.normalize_threshold(d2)[0].min() == 1
+    assert np.isnan(cv2.normalize(d2, None, 0.0, 255.0, cv2.NORM_MINMAX)).all()
+
+
+def nan_case(oracle, want_inputs=False):
+    """Seeded random pair (64x48, strong rotation) on which one Mahalanobis value is NaN (found by search)."""
+    import importlib
+
+    import cv2
+
+    synth = importlib.import_module("gd-slam_b200.synth")
+    K = synth.intrinsics(640, 480)
+    rng = np.random.default_rng(1)
+    h, w = 48, 64
+    for trial in range(114):
+        scale = 10 ** rng.uniform(-4, 0.5)
+        dref = (rng.random((h, w)) * scale).astype(np.float32)
+        dcur = (rng.random((h, w)) * scale).astype(np.float32)
+        flow = (rng.normal(0, 1.0, (h, w, 2))).astype(np.float32)
+        ang = rng.normal(0, 0.3, 3)
+        R = cv2.Rodrigues(ang)[0].astype(np.float32)
+        T = rng.normal(0, 0.05, 3).astype(np.float32)
+    e = np.zeros((h, w), np.uint8)
+    dist, wr, _ = oracle.mahalanobis(flow, dref, dcur, e, e, K, R, T)
+    if want_inputs:
+        return flow, dref, dcur, e, K, R, T, dist
+    return dist, wr
 
 
 def test_normalize_threshold_vs_cv2(oracle, golden):
