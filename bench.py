@@ -48,6 +48,9 @@ FAMILY_BYTES = {
     "K1b_flow_iter": 3 * 56 * FB_LEVEL_SUM * N_PX,      # fused form (GD_FLOW_FUSED=1)
     "K1b_matrices": 3 * 68 * FB_LEVEL_SUM * N_PX,       # split form: R0 20 + R1 20 + flow 8 in, M 20 out
     "K1b_box_solve": 3 * 28 * FB_LEVEL_SUM * N_PX,      # split form: M 20 in, flow 8 out
+    # M ping-pong form (default): per level matrices once (R0 20 + R1 20 + coarse flow 2, M 20 out), two fused
+    # box/solve + next-matrices launches (M 20 in, R0 20 + R1 20, M 20 out) and a last box/solve (M 20 in, flow 8 out)
+    "K1b_box_matrices": 2 * 80 * FB_LEVEL_SUM * N_PX,
     "K1b_flow_upsample": (8 * 0.328125 / 4 + 8 * 0.328125) * N_PX,
     "K2a_depth_edge": 5 * N_PX,
     "K2b_mahalanobis": 22 * N_PX,
@@ -585,6 +588,9 @@ def main():
     fe.profile(False)
     fam = fe.profile_read()
     peak, peak_src = load_peaks()
+    if any(name == "K1b_box_matrices" for name, _, _ in fam):  # M ping-pong form: one launch of each per level
+        FAMILY_BYTES["K1b_matrices"] = 62 * FB_LEVEL_SUM * N_PX
+        FAMILY_BYTES["K1b_box_solve"] = 28 * FB_LEVEL_SUM * N_PX
     tot_ms = sum(ms for _, ms, _ in fam) or 1.0
     families = {}
     for name, ms, ln in fam:

@@ -209,7 +209,7 @@ int gd_stage_farneback(int device, const uint8_t* prev, const uint8_t* next, int
     FbPlan plan;
     GD_TRY(fb_make_plan(w, h, 0.5, 3, 3, 5, 1.2, 15, &plan));
     const size_t n = (size_t)w * h;
-    DevBuf g0, g1, I, R0, R1, fa, fb, Mb;
+    DevBuf g0, g1, I, R0, R1, fa, fb, Mb, Mb2;
     GD_TRY(g0.alloc(n));
     GD_TRY(g1.alloc(n));
     GD_TRY(I.alloc(plan.i_floats * 4));
@@ -218,12 +218,15 @@ int gd_stage_farneback(int device, const uint8_t* prev, const uint8_t* next, int
     GD_TRY(fa.alloc(plan.f_float2 * 8));
     GD_TRY(fb.alloc(plan.f_float2 * 8));
     GD_TRY(Mb.alloc(plan.m_floats * 4));
+    GD_TRY(Mb2.alloc(plan.m_floats * 4));
+    FbFlowBuffers fbuf;
+    GD_TRY(fb_prepare_flow_buffers(plan, 1, Mb.as<float>(), Mb2.as<float>(), Mb.bytes, &fbuf));
     GD_CUDA(cudaMemcpy(g0.p, prev, n, cudaMemcpyHostToDevice));
     GD_CUDA(cudaMemcpy(g1.p, next, n, cudaMemcpyHostToDevice));
     GD_TRY(fb_launch_pyramid_polyexp(plan, g0.as<uint8_t>(), 0, 1, I.as<float>(), 0, R0.as<float>(), 0, 0, nullptr));
     GD_TRY(fb_launch_pyramid_polyexp(plan, g1.as<uint8_t>(), 0, 1, I.as<float>(), 0, R1.as<float>(), 0, 0, nullptr));
     const float2* fin = nullptr;
-    GD_TRY(fb_launch_flow(plan, R0.as<float>(), R1.as<float>(), 0, 1, fa.as<float2>(), fb.as<float2>(), 0, Mb.as<float>(), Mb.bytes, &fin, 0, nullptr));
+    GD_TRY(fb_launch_flow(plan, R0.as<float>(), R1.as<float>(), 0, 1, fa.as<float2>(), fb.as<float2>(), 0, &fbuf, &fin, 0, nullptr));
     GD_CUDA(cudaDeviceSynchronize());
     GD_CUDA(cudaMemcpy(flow, fin, n * 8, cudaMemcpyDeviceToHost));
     return GD_OK;

@@ -11,6 +11,8 @@
 // memory, runs the 15x15 box sums in FP64 (like OpenCV's double vsum) and solves the 2x2 system.
 #include "farneback.cuh"
 
+#include <cuda.h>  // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through the CUDA runtime, no libcuda link)
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -638,6 +640,26 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_fb_flow_iter(const float* __r
     }
 }
 
+// FarnebackUpdateMatrices of pixel (x, y) for the flow fl: loads of R0 at the pixel and the bilinear gather of R1 at the
+// displaced position, then fb_um_compute.
+__device__ __forceinline__ void fb_matrices_pixel(const float4* __restrict__ R0A, const float* __restrict__ R0B,
+                                                  const float4* __restrict__ R1A, const float* __restrict__ R1B, int w, int h, int x,
+                                                  int y, float2 fl, float M[5])
+{
+    const int o = y * w + x;
+    const float4 a0 = __ldg(R0A + o);
+    const float a04 = __ldg(R0B + o);
+    float fx = x + fl.x, fy = y + fl.y;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= x1;
+    fy -= y1;
+    const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int q = inside ? y1 * w + x1 : 0;
+    const float4 p00 = __ldg(R1A + q), p01 = __ldg(R1A + q + 1), p10 = __ldg(R1A + q + w), p11 = __ldg(R1A + q + w + 1);
+    const float e00 = __ldg(R1B + q), e01 = __ldg(R1B + q + 1), e10 = __ldg(R1B + q + w), e11 = __ldg(R1B + q + w + 1);
+    fb_um_compute(a0, a04, p00, p01, p10, p11, e00, e01, e10, e11, inside, fx, fy, fl, x, y, w, h, M);
+}
+
 // ------------------------------------------------------------------------------------------------ K1b, split form
 // (a) k_fb_matrices: FarnebackUpdateMatrices for every pixel exactly once -> M (5 f32 planes) in HBM.  Embarrassingly
 //     parallel, no shared memory, full occupancy: the dependent bilinear gathers are hidden by ~40 resident warps.
@@ -690,18 +712,8 @@ __global__ void __launch_bounds__(256, 8) k_fb_matrices(const float* __restrict_
     } else {
         fl = make_float2(0.f, 0.f);
     }
-    const float4 a0 = __ldg(R0A + o);
-    const float a04 = __ldg(R0B + o);
-    float fx = x + fl.x, fy = y + fl.y;
-    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= x1;
-    fy -= y1;
-    const bool inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-    const int q = inside ? y1 * w + x1 : 0;
-    const float4 p00 = __ldg(R1A + q), p01 = __ldg(R1A + q + 1), p10 = __ldg(R1A + q + w), p11 = __ldg(R1A + q + w + 1);
-    const float e00 = __ldg(R1B + q), e01 = __ldg(R1B + q + 1), e10 = __ldg(R1B + q + w), e11 = __ldg(R1B + q + w + 1);
     float M[5];
-    fb_um_compute(a0, a04, p00, p01, p10, p11, e00, e01, e10, e11, inside, fx, fy, fl, x, y, w, h, M);
+    fb_matrices_pixel(R0A, R0B, R1A, R1B, w, h, x, y, fl, M);
     float* mo = Mout + (size_t)b * mstride_b + o;
 #pragma unroll
     for (int c = 0; c < 5; ++c) mo[(size_t)c * npad] = M[c];
@@ -715,7 +727,9 @@ constexpr int BXM_P = 84;                    // smem row pitch (floats): 16-byte
 constexpr int BXS_P = BX_W + 1;              // 65 doubles
 constexpr int BX_THREADS = 256;
 constexpr int BX_ROWS = BX_H / (BX_THREADS / BX_W);  // 8 rows per thread in the vertical pass
-constexpr size_t BX_SMEM = sizeof(float) * 2 * BXH_H * BXM_P + sizeof(double) * BXH_H * BXS_P;
+constexpr int BX_TILE_BYTES = BXH_H * BXM_P * (int)sizeof(float);                    // 15 456: one channel tile (TMA box 84 x 46)
+constexpr int BX_TILE_STRIDE = (BX_TILE_BYTES + 127) / 128 * 128;                    // 128-byte aligned tile buffers (TMA)
+constexpr size_t BX_SMEM = 2 * (size_t)BX_TILE_STRIDE + sizeof(double) * BXH_H * BXS_P + 16;  // + two mbarriers
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 {
@@ -731,17 +745,67 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- TMA (cp.async.bulk.tensor, SASS UTMALDG) + mbarrier helpers
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+// one box of a rank-3 tensor (x, y, plane) -> shared memory; out-of-bounds elements are written as zeros
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+// what the kernel does with the solved flow: NEXT = false -> store it (last iteration of a level); NEXT = true -> never store
+// it: UpdateMatrices of the NEXT iteration only needs the flow of the pixel itself, so the same thread evaluates it right
+// away and stores M for the following launch (R0 20 + R1 20 + M 20 bytes per pixel instead of flow 8 out + 8 in and a launch)
+struct BoxNext {
+    const float* R0;
+    const float* R1;
+    size_t rstride_b;
+    float* Mout;  // same per-stream stride as Min
+};
+
 // VEC: the row stride is a multiple of 4 floats -> every 16-byte chunk is either fully inside or fully outside the image;
 //      outside chunks are skipped and the replicated border columns are filled in shared memory afterwards (edge tiles only).
-template <bool VEC>
-__global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __restrict__ Min, size_t mstride_b,
-                                                                float2* __restrict__ fout, size_t fstride_b, int w, int h)
+// TMA (needs VEC): the whole 84 x 46 channel tile is ONE cp.async.bulk.tensor issued by one thread, completion counted in
+//      bytes on an mbarrier; the unit zero-fills outside the image, so edge tiles replicate the border rows as well.
+template <bool VEC, bool TMA, bool NEXT>
+__global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ Min,
+                                                                size_t mstride_b, float2* __restrict__ fout, size_t fstride_b, int w,
+                                                                int h, BoxNext nx)
 {
     pdl_trigger();
     pdl_wait();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sT = reinterpret_cast<float*>(smem_raw);                                        // [2][BXH_H][BXM_P] channel tile
-    double* sH = reinterpret_cast<double*>(smem_raw + sizeof(float) * 2 * BXH_H * BXM_P);  // [BXH_H][BXS_P]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* sT = reinterpret_cast<float*>(smem_raw);                                    // [2] channel tiles of [BXH_H][BXM_P]
+    double* sH = reinterpret_cast<double*>(smem_raw + 2 * BX_TILE_STRIDE);             // [BXH_H][BXS_P]
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * BX_TILE_STRIDE + sizeof(double) * BXH_H * BXS_P);
+    constexpr int TS = BX_TILE_STRIDE / (int)sizeof(float);
     const int b = blockIdx.z;
     const size_t npad = align_up_dev((size_t)w * h, 64);
     const float* Mb = Min + (size_t)b * mstride_b;
@@ -751,19 +815,38 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
     constexpr int CH = BXT_W / 4;                                       // 20 chunks per row
     constexpr int NCHUNK = (BXH_H * CH + BX_THREADS - 1) / BX_THREADS;  // 4 per thread
     int c_src[NCHUNK], c_dst[NCHUNK];  // element offsets in the plane / in the smem tile; c_src < 0: nothing to copy
+    if (VEC && !TMA) {
 #pragma unroll
-    for (int k = 0; k < NCHUNK; ++k) {
-        const int i = tid + k * BX_THREADS;
-        const int ly = i / CH, ch = i - ly * CH;
-        const int y = min(max(y0 + ly - FHALO, 0), h - 1);
-        const int xs = x0 - BX_LEFT + 4 * ch;
-        c_dst[k] = ly * BXM_P + 4 * ch;
-        c_src[k] = (i < BXH_H * CH && xs >= 0 && xs + 3 < w) ? y * w + xs : -1;
+        for (int k = 0; k < NCHUNK; ++k) {
+            const int i = tid + k * BX_THREADS;
+            const int ly = i / CH, ch = i - ly * CH;
+            const int y = min(max(y0 + ly - FHALO, 0), h - 1);
+            const int xs = x0 - BX_LEFT + 4 * ch;
+            c_dst[k] = ly * BXM_P + 4 * ch;
+            c_src[k] = (i < BXH_H * CH && xs >= 0 && xs + 3 < w) ? y * w + xs : -1;
+        }
     }
-    const bool edge_l = x0 == 0, edge_r = x0 + BX_W + BX_LEFT > w;  // tile reaches beyond the left / right image border
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // tile reaches beyond the left / right (top / bottom: only the TMA path zero-fills rows, the others clamp the row index)
+    const bool edge_l = x0 == 0, edge_r = x0 + BX_W + BX_LEFT > w;
+    const bool edge_t = TMA && y0 == 0, edge_b = TMA && y0 + BX_H + FHALO > h;
     auto load_tile = [&](int c, int buf) {
+        float* dst = sT + buf * TS;
+        if (TMA) {
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar[buf], (unsigned)BX_TILE_BYTES);
+                tma_load_3d(dst, &tmap, x0 - BX_LEFT, y0 - FHALO, b * 5 + c, &s_bar[buf]);
+            }
+            return;
+        }
         const float* plane = Mb + (size_t)c * npad;
-        float* dst = sT + buf * BXH_H * BXM_P;
         if (VEC) {
 #pragma unroll
             for (int k = 0; k < NCHUNK; ++k)
@@ -777,9 +860,10 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
         }
         cp_async_commit();
     };
-    // replicate the border pixel into the tile columns that lie outside the image (VEC path, edge tiles only)
+    // replicate the border pixel into the tile cells that lie outside the image (edge tiles only): columns first (on the
+    // rows that exist), then whole rows
     auto fix_border = [&](int buf) {
-        float* t = sT + buf * BXH_H * BXM_P;
+        float* t = sT + buf * TS;
         if (edge_l)
             for (int i = tid; i < BXH_H * BX_LEFT; i += BX_THREADS) {
                 const int ly = i / BX_LEFT, lx = i - ly * BX_LEFT;
@@ -792,6 +876,16 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
                 if (lx > last) t[ly * BXM_P + lx] = t[ly * BXM_P + last];
             }
         }
+        if (edge_t || edge_b) {
+            __syncthreads();
+            const int first = edge_t ? FHALO : 0;                              // tile row of image row 0
+            const int lastr = min(BXH_H - 1, h - 1 - (y0 - FHALO));            // tile row of the last image row
+            for (int i = tid; i < BXH_H * BXT_W; i += BX_THREADS) {
+                const int ly = i / BXT_W, lx = i - ly * BXT_W;
+                if (ly < first) t[ly * BXM_P + lx] = t[first * BXM_P + lx];
+                if (ly > lastr) t[ly * BXM_P + lx] = t[lastr * BXM_P + lx];
+            }
+        }
     };
     constexpr int NTASK = (BX_W / FT_SEG) * BXH_H;  // 184 horizontal tasks: (segment of 16 columns) x (tile row)
     const int hseg = tid / BXH_H, hrow = tid - hseg * BXH_H;
@@ -800,20 +894,22 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
     load_tile(0, 0);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        if (c + 1 < 5) {
-            load_tile(c + 1, (c + 1) & 1);
+        if (c + 1 < 5) load_tile(c + 1, (c + 1) & 1);
+        if (TMA) {
+            mbar_wait(&s_bar[c & 1], (unsigned)((c >> 1) & 1));  // buffer c & 1 is filled for the (c >> 1)-th time
+        } else if (c + 1 < 5) {
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();
-        if (VEC && (edge_l || edge_r)) {  // block-uniform
+        __syncthreads();  // tile c visible to everyone; the V pass of channel c - 1 is done with sH
+        if ((VEC || TMA) && (edge_l || edge_r || edge_t || edge_b)) {  // block-uniform
             fix_border(c & 1);
             __syncthreads();
         }
         if (tid < NTASK) {
             // window of output column j (tile-local) = tile floats [j + 1, j + 15]; the segment reads floats [16 seg, 16 seg + 32)
-            const float4* m4 = reinterpret_cast<const float4*>(sT + (c & 1) * BXH_H * BXM_P + hrow * BXM_P + hseg * FT_SEG);
+            const float4* m4 = reinterpret_cast<const float4*>(sT + (c & 1) * TS + hrow * BXM_P + hseg * FT_SEG);
             float m[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -849,19 +945,40 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
     }
     const int x = x0 + cx;
     if (x >= w) return;
-    float2* fo = fout + (size_t)b * fstride_b;
+    float2 o[BX_ROWS];
 #pragma unroll
     for (int j = 0; j < BX_ROWS; ++j) {
-        const int y = y0 + vr0 + j;
-        if (y >= h) break;
         const double scale = 1. / (FB_WIN * FB_WIN);
         const double g11 = acc[0][j] * scale, g12 = acc[1][j] * scale, g22 = acc[2][j] * scale, h1 = acc[3][j] * scale,
                      h2 = acc[4][j] * scale;
         const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
-        float2 o;
-        o.x = (float)((g11 * h2 - g12 * h1) * idet);
-        o.y = (float)((g22 * h1 - g12 * h2) * idet);
-        fo[(size_t)y * w + x] = o;
+        o[j].x = (float)((g11 * h2 - g12 * h1) * idet);
+        o[j].y = (float)((g22 * h1 - g12 * h2) * idet);
+    }
+    if (!NEXT) {
+        float2* fo = fout + (size_t)b * fstride_b;
+#pragma unroll
+        for (int j = 0; j < BX_ROWS; ++j) {
+            const int y = y0 + vr0 + j;
+            if (y < h) fo[(size_t)y * w + x] = o[j];
+        }
+    } else {
+        const float* r0 = nx.R0 + (size_t)b * nx.rstride_b;
+        const float* r1 = nx.R1 + (size_t)b * nx.rstride_b;
+        const float4* R0A = reinterpret_cast<const float4*>(r0);
+        const float4* R1A = reinterpret_cast<const float4*>(r1);
+        const float* R0B = r0 + 4 * npad;
+        const float* R1B = r1 + 4 * npad;
+        float* mo = nx.Mout + (size_t)b * mstride_b;
+#pragma unroll
+        for (int j = 0; j < BX_ROWS; ++j) {
+            const int y = y0 + vr0 + j;
+            if (y >= h) break;
+            float M[5];
+            fb_matrices_pixel(R0A, R0B, R1A, R1B, w, h, x, y, o[j], M);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) mo[(size_t)c * npad + (size_t)y * w + x] = M[c];
+        }
     }
 }
 
@@ -869,21 +986,134 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const float* __r
 int fb_prepare_device()
 {
     GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
     return GD_OK;
 }
 
+static int env_flag(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links the CUDA runtime only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int fb_prepare_flow_buffers(const FbPlan& plan, int batch, float* M0, float* M1, size_t m_bytes_each, FbFlowBuffers* fb)
+{
+    *fb = FbFlowBuffers();
+    fb->M[0] = M0;
+    fb->M[1] = M1;
+    fb->m_bytes = m_bytes_each;
+    const bool whole_batch = m_bytes_each >= (size_t)batch * plan.m_floats * sizeof(float);
+    fb->fuse_next = M1 != nullptr && whole_batch && env_flag("GD_FLOW_NEXT", 1) != 0;
+    fb->use_tma = false;
+    if (!whole_batch || env_flag("GD_FLOW_TMA", 1) == 0) return GD_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return GD_OK;  // no driver entry point: the cp.async tile load is used
+    for (int k = 0; k < plan.nlevels; ++k) {
+        const FbLevel& L = plan.lv[k];
+        if (L.w & 3) continue;  // rows not 16-byte aligned: that level takes the scalar path
+        const size_t npad = align_up((size_t)L.w * L.h, 64);
+        for (int i = 0; i < 2; ++i) {
+            if (!fb->M[i]) continue;
+            const cuuint64_t dims[3] = {(cuuint64_t)L.w, (cuuint64_t)L.h, (cuuint64_t)5 * batch};
+            const cuuint64_t strides[2] = {(cuuint64_t)L.w * sizeof(float), (cuuint64_t)npad * sizeof(float)};
+            const cuuint32_t box[3] = {(cuuint32_t)BXM_P, (cuuint32_t)BXH_H, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = enc(&fb->tmap[k][i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, fb->M[i], dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled failed (%d) for level %d (%d x %d)", (int)r, k, L.w, L.h);
+                return GD_ECUDA;
+            }
+            fb->tmap_ok[k][i] = true;
+        }
+    }
+    fb->use_tma = true;
+    return GD_OK;
+}
+
+template <bool NEXT>
+static cudaError_t launch_box(const FbFlowBuffers& fb, int level, int src, dim3 grid, cudaStream_t s, const float* Min, size_t mstride,
+                              float2* fout, size_t fstride, int w, int h, BoxNext nx)
+{
+    static const CUtensorMap no_map = {};
+    if ((w & 3) != 0)
+        return launch_pdl(k_fb_box_solve<false, false, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, no_map, Min, mstride, fout, fstride, w, h, nx);
+    if (fb.use_tma && fb.tmap_ok[level][src])
+        return launch_pdl(k_fb_box_solve<true, true, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, fb.tmap[level][src], Min, mstride, fout, fstride, w, h, nx);
+    return launch_pdl(k_fb_box_solve<true, false, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, no_map, Min, mstride, fout, fstride, w, h, nx);
+}
+
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_bytes, const float2** final_flow, cudaStream_t s,
+                   float2* flowB, size_t f_stride_b, const FbFlowBuffers* fbuf, const float2** final_flow, cudaStream_t s,
                    LaunchStats* st)
 {
     const float2* prev = nullptr;
     int pw = 0, ph = 0;
+    float* Mbuf = fbuf ? fbuf->M[0] : nullptr;
+    const size_t m_bytes = fbuf ? fbuf->m_bytes : 0;
     for (int k = plan.nlevels - 1; k >= 0; --k) {
         const FbLevel& L = plan.lv[k];
         float2* A = flowA + L.f_off;
         float2* B = flowB + L.f_off;
+        const size_t mstride = 5 * align_up((size_t)L.w * L.h, 64);
+        if (fbuf && fbuf->fuse_next) {
+            // M ping-pong: matrices(level entry) -> M[0]; box/solve + next matrices: M[0] -> M[1], M[1] -> M[0], ...;
+            // the last iteration stores the flow of the level.  4 launches per level instead of 6, no intermediate flow.
+            const float* r0 = R0 + L.r_off;
+            const float* r1 = R1 + L.r_off;
+            {
+                LaunchScope ls(st, s, "K1b_matrices", 1);
+                dim3 block(32, 8), grid(cdiv(L.w, 32), cdiv(L.h, 8), batch);
+                if (prev)
+                    GD_CUDA(launch_pdl(k_fb_matrices<1>, grid, block, 0, s, r0, r1, r_stride_b, prev, f_stride_b, pw, ph, fbuf->M[0], mstride, L.w, L.h));
+                else
+                    GD_CUDA(launch_pdl(k_fb_matrices<2>, grid, block, 0, s, r0, r1, r_stride_b, (const float2*)nullptr, f_stride_b, 0, 0, fbuf->M[0], mstride, L.w, L.h));
+                GD_CUDA(cudaGetLastError());
+            }
+            dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), batch);
+            int src = 0;
+            for (int it = 0; it < plan.iterations; ++it) {
+                const bool last = it + 1 == plan.iterations;
+                BoxNext nx = {r0, r1, r_stride_b, fbuf->M[src ^ 1]};
+                if (last) {
+                    LaunchScope ls(st, s, "K1b_box_solve", 1);
+                    GD_CUDA(launch_box<false>(*fbuf, k, src, grid, s, fbuf->M[src], mstride, A, f_stride_b, L.w, L.h, nx));
+                } else {
+                    LaunchScope ls(st, s, "K1b_box_matrices", 1);
+                    GD_CUDA(launch_box<true>(*fbuf, k, src, grid, s, fbuf->M[src], mstride, A, f_stride_b, L.w, L.h, nx));
+                }
+                GD_CUDA(cudaGetLastError());
+                src ^= 1;
+            }
+            prev = A;
+            pw = L.w;
+            ph = L.h;
+            continue;
+        }
         if (Mbuf) {
             // split form: the first matrices launch of a level takes its flow from the coarser level (or zero) on the fly
         } else if (!prev) {
@@ -904,7 +1134,6 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
                 // split form: matrices once per pixel into M, then box filter + solve.  The streams of the batch go through
                 // in groups whose M (packed at the level's own stride) stays inside the L2 window of m_bytes: written by
                 // one kernel, read by the next, overwritten by the following group — M never has to reach HBM.
-                const size_t mstride = 5 * align_up((size_t)L.w * L.h, 64);
                 const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)batch, m_bytes / (mstride * sizeof(float))));
                 for (int b0 = 0; b0 < batch; b0 += group) {
                     const int nb = std::min(group, batch - b0);
@@ -923,10 +1152,10 @@ int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t 
                     }
                     LaunchScope ls(st, s, "K1b_box_solve", 1);
                     dim3 grid(cdiv(L.w, BX_W), cdiv(L.h, BX_H), nb);
-                    if ((L.w & 3) == 0)
-                        GD_CUDA(launch_pdl(k_fb_box_solve<true>, grid, dim3(BX_THREADS), BX_SMEM, s, (const float*)Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h));
-                    else
-                        GD_CUDA(launch_pdl(k_fb_box_solve<false>, grid, dim3(BX_THREADS), BX_SMEM, s, (const float*)Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h));
+                    // the tensor maps describe the whole batch from stream 0: the TMA path needs un-grouped launches
+                    FbFlowBuffers one = *fbuf;
+                    if (group < batch) one.use_tma = false;
+                    GD_CUDA(launch_box<false>(one, k, 0, grid, s, (const float*)Mbuf, mstride, out + (size_t)b0 * f_stride_b, f_stride_b, L.w, L.h, BoxNext{}));
                     GD_CUDA(cudaGetLastError());
                 }
             } else {

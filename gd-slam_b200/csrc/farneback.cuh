@@ -1,6 +1,8 @@
 // farneback.cuh — dense optical flow (cv::calcOpticalFlowFarneback, flags = 0) as a batched CUDA pipeline.
 // Same algorithm and parameters the reference invokes at src/GeoMaskMaker.cc:165: (0.5, 3, 15, 3, 5, 1.2, 0).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only)
+
 #include "gd_internal.h"
 
 namespace gd {
@@ -43,11 +45,27 @@ int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int
 int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gray_stride_b, int batch, float* scratch_I,
                               size_t i_stride_b, float* R, size_t r_stride_b, cudaStream_t s, LaunchStats* st);
 
+// M scratch of the split flow form and how the box/solve kernel reads it.
+//   M[0]            [batch][m_floats] (or a smaller group window of m_bytes): UpdateMatrices output
+//   M[1]            second buffer of the same size: enables the fused "box/solve + next iteration's matrices" kernel
+//                   (M ping-pong, no intermediate flow, 4 launches per level instead of 6); nullptr = plain split form
+//   tmap[level][i]  rank-3 TMA descriptors (x, y, plane) of M[i] at every level whose rows are 16-byte aligned: the
+//                   84 x 46 channel tile of the box filter arrives by one cp.async.bulk.tensor per channel
+// GD_FLOW_NEXT=0 / GD_FLOW_TMA=0 switch the two features off (A/B measurements).
+struct FbFlowBuffers {
+    float* M[2] = {nullptr, nullptr};
+    size_t m_bytes = 0;
+    bool fuse_next = false, use_tma = false;
+    bool tmap_ok[FB_MAX_LEVELS][2] = {};
+    alignas(64) CUtensorMap tmap[FB_MAX_LEVELS][2];
+};
+int fb_prepare_flow_buffers(const FbPlan& plan, int batch, float* M0, float* M1, size_t m_bytes_each, FbFlowBuffers* fb);
+
 // per-pair half: R0, R1 -> flow (level 0, float2 [b][h][w]).  flow scratch: two buffers [b][f_float2].
 // On return *final points at the level-0 flow (inside flowA or flowB).
-// Mbuf: [b][m_floats] scratch for the split form (matrices kernel + box/solve kernel); nullptr selects the fused kernel.
+// fbuf: the M scratch (split form); nullptr selects the older single-kernel flow iteration.
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,
-                   float2* flowB, size_t f_stride_b, float* Mbuf, size_t m_bytes, const float2** final_flow, cudaStream_t s,
+                   float2* flowB, size_t f_stride_b, const FbFlowBuffers* fbuf, const float2** final_flow, cudaStream_t s,
                    LaunchStats* st);
 
 }  // namespace gd

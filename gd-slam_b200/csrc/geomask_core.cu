@@ -79,6 +79,9 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
         const size_t one = plan.m_floats * sizeof(float);
         const size_t budget = e ? (size_t)std::max(1, std::atoi(e)) << 20 : B * one;
         GD_TRY(Mbuf.alloc(std::max(one, std::min(B * one, budget / one * one))));
+        const bool whole = Mbuf.bytes >= B * one;
+        if (whole) GD_TRY(Mbuf2.alloc(Mbuf.bytes));
+        GD_TRY(fb_prepare_flow_buffers(plan, batch, Mbuf.as<float>(), whole ? Mbuf2.as<float>() : nullptr, Mbuf.bytes, &flow_bufs));
     }
     GD_TRY(keys.alloc(B * n_pad * sizeof(unsigned long long)));
     GD_TRY(minmax.alloc(B * GD_MM_WORDS * sizeof(unsigned)));
@@ -186,8 +189,8 @@ int GeoMaskCore::enqueue_mask()
     last_cur_slot = cur;
     const size_t rs = (size_t)GD_RING * plan.r_floats;
     GD_TRY(fb_launch_flow(plan, R.as<float>() + (size_t)ref * plan.r_floats, R.as<float>() + (size_t)cur * plan.r_floats, rs,
-                          batch, flowA.as<float2>(), flowB.as<float2>(), plan.f_float2, split_flow ? Mbuf.as<float>() : nullptr, Mbuf.bytes,
-                          &last_flow, stream, stats));
+                          batch, flowA.as<float2>(), flowB.as<float2>(), plan.f_float2, split_flow ? &flow_bufs : nullptr, &last_flow,
+                          stream, stats));
     GD_TRY(launch_mahalanobis(last_flow, plan.f_float2, depth_slot_ptr(ref), depth_slot_ptr(cur), depth_stride_b(),
                               edge.as<uint8_t>() + (size_t)ref * n_pad, edge.as<uint8_t>() + (size_t)cur * n_pad,
                               (size_t)GD_RING * n_pad, has_lut ? lut.as<float2>() : nullptr, w, h, batch, cam,

@@ -28,7 +28,8 @@ struct GeoMaskCore {
     DevBuf R;          // [B][RING][r_floats]  Farnebäck polynomial expansion pyramid
     DevBuf scratchI;   // [B][i_floats]
     DevBuf flowA, flowB;  // [B][f_float2]
-    DevBuf Mbuf;          // [B][m_floats] UpdateMatrices output of the current level (split flow form)
+    DevBuf Mbuf, Mbuf2;   // [B][m_floats] UpdateMatrices output of the current level (split flow form), ping-pong pair
+    FbFlowBuffers flow_bufs;
     bool split_flow = true;
     DevBuf keys;       // [B][n] u64 scatter keys, epoch tagged (KeyFormat): never cleared between frames
     KeyFormat keyfmt;
