@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles (host threads) the e2e leg drives per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the 8-streams-in-total (config 4 as written) side measurement")
+    ap.add_argument("--quick", action="store_true", help="device-resident leg and kernel profile only (A/B runs of kernel variants)")
     ap.add_argument("--probe-pcie", action="store_true",
                     help="only time bare pinned cudaMemcpyAsync H2D / D2H on all ranks at once and print the rates")
     ap.add_argument("--res", default="640x480", help="WxH of the synthetic streams (configs[4]: 1280x720, 1920x1080)")
@@ -540,14 +541,15 @@ def main():
             t.join()
         return time.perf_counter() - t0
 
+    Ke = 2 if args.quick else K_
     run_host(6 + 3, True)  # fill the rings of the e2e handles + warm-up
     barrier()
-    e2e_s = run_host(K_, True)
+    e2e_s = run_host(Ke, True) * (K_ / Ke)
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     run_host(3, False)
     barrier()
-    e2e32_s = run_host(K_, False)
+    e2e32_s = run_host(Ke, False) * (K_ / Ke)
     clocks = sampler.stop()
     barrier()
     e2e32_s = max_over_ranks(e2e32_s)
@@ -562,7 +564,7 @@ def main():
 
     # ---- SURVEY 8d config 4 as written: 8 streams in total over the GPUs (strong scaling, latency-bound regime)
     strong = None
-    if not args.no_strong and args.streams_total == 0 and 8 % world == 0 and B >= 8 // world:
+    if not args.no_strong and not args.quick and args.streams_total == 0 and 8 % world == 0 and B >= 8 // world:
         bs = 8 // world
         fs = capi.Frontend(K, W, H, batch=bs, device=device, staged_slots=S)
         for s in range(S):
@@ -650,7 +652,9 @@ def main():
     if strong is not None:
         out["strong_scaling_8_streams"] = strong
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if args.quick:
+        out["e2e"]["note"] = "--quick: 2 steps only, not a measurement"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         t0 = time.perf_counter()
         ref = CpuReference()
         per = 3

@@ -38,7 +38,12 @@ class FrontendConfig(C.Structure):
                 ("width", C.c_int), ("height", C.c_int), ("device", C.c_int), ("batch", C.c_int),
                 ("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("ini_th_fast", C.c_int),
                 ("min_th_fast", C.c_int), ("orb_gray_order", C.c_int), ("kp_capacity", C.c_int),
-                ("staged_slots", C.c_int)]
+                ("staged_slots", C.c_int), ("getrt", C.c_int)]
+
+
+# int hook(void* user, int stream, const float* obj, const float* pix, int n, float R[9], float T[3])
+POSE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
+                        C.POINTER(C.c_float))
 
 
 def build_library() -> None:
@@ -64,6 +69,10 @@ SYMBOLS = {
     "gd_geomask_push": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp), C.c_size_t]),
     "gd_geomask_mask": (C.c_int, [vp, fp, fp, ip, C.POINTER(vp), C.c_size_t]),
     "gd_geomask_frames": (C.c_int, [vp]),
+    "gd_geomask_enable_getrt": (C.c_int, [vp]),
+    "gd_geomask_getrt_points": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), ip]),
+    "gd_frontend_set_pose_hook": (C.c_int, [vp, POSE_HOOK, vp]),
+    "gd_frontend_fetch_getrt": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), ip]),
     "gd_geomask_debug_fetch": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_size_t]),
     "gd_orb_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int]),
@@ -297,6 +306,18 @@ class GeoMask:
     def frames(self):
         return lib().gd_geomask_frames(self._h)
 
+    def enable_getrt(self):
+        check(lib().gd_geomask_enable_getrt(self._h))
+
+    def getrt_points(self):
+        """GetRt up to solvePnPRansac for the buffered pair: list of (object_points [n,3], image_pixels [n,2]) per stream."""
+        B = self.batch
+        obj = [np.zeros((100, 3), np.float32) for _ in range(B)]
+        pix = [np.zeros((100, 2), np.float32) for _ in range(B)]
+        n = np.zeros(B, np.int32)
+        check(lib().gd_geomask_getrt_points(self._h, _ptr_array(obj), _ptr_array(pix), n.ctypes.data_as(ip)))
+        return [(obj[b][: n[b]].copy(), pix[b][: n[b]].copy()) for b in range(B)]
+
     def debug(self, what, stream=0):
         shapes = {DBG_FLOW: ((self.h, self.w, 2), np.float32), DBG_DIST: ((self.h, self.w), np.float32),
                   DBG_EDGE_REF: ((self.h, self.w), np.uint8), DBG_EDGE_CUR: ((self.h, self.w), np.uint8),
@@ -341,7 +362,7 @@ def stage_gaussian7(gray, device=0):
 
 # ---------------------------------------------------------------------------------------------- ORBextractor
 # ---- GetRt building blocks
-def getrt_points(gray_first, gray_second, depth_first_m, K, dist=None, device=0):
+def getrt_points(gray_first, gray_second, depth_first_m, K, dist=None, device=0):  # dist: k1 k2 p1 p2 [k3] (may be zero)
     """GeoMaskMaker::GetRt up to (not including) solvePnPRansac: (object_points [n,3], image_pixels [n,2]) f32."""
     g1, g2 = np.ascontiguousarray(gray_first, np.uint8), np.ascontiguousarray(gray_second, np.uint8)
     dep = np.ascontiguousarray(depth_first_m, np.float32)
@@ -473,7 +494,7 @@ class Frontend:
     """gd_frontend_*: GrabImageRGBD_GD's per-frame sequence (gray, ORB, AddNewImage, GetNoGMMmask) for `batch` streams."""
 
     def __init__(self, K, width=640, height=480, batch=1, device=0, dist=None, depth_factor=5000.0, nfeatures=1500,
-                 scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7, orb_gray_order=1, staged_slots=0):
+                 scale_factor=1.2, nlevels=8, ini_th_fast=20, min_th_fast=7, orb_gray_order=1, staged_slots=0, getrt=False):
         cfg = FrontendConfig()
         K = np.ascontiguousarray(K, np.float32).reshape(-1)
         for i in range(9):
@@ -488,6 +509,8 @@ class Frontend:
         cfg.ini_th_fast, cfg.min_th_fast, cfg.orb_gray_order = ini_th_fast, min_th_fast, orb_gray_order
         cfg.kp_capacity = nfeatures + 3 * nlevels
         cfg.staged_slots = staged_slots
+        cfg.getrt = 1 if getrt else 0
+        self._hook = None
         self.cfg = cfg
         self.w, self.h, self.batch, self.cap = width, height, batch, cfg.kp_capacity
         self._h = vp()
@@ -520,12 +543,52 @@ class Frontend:
         pv = np.ascontiguousarray(np.ones(B, np.int32) if pv is None else pv, np.int32)
         return R, T, pv
 
-    def step(self, bgr, depth, R=None, T=None, pose_valid=None, fetch=True):
-        """bgr: (B,H,W,3) u8 array or list of (H,W,3); depth: (B,H,W) f32 or list.  Host buffers in, results out."""
+    def set_pose_hook(self, fn):
+        """fn(stream, object_points [n,3], image_pixels [n,2]) -> (R 3x3, T 3) or None: the caller's solvePnPRansac + Rodrigues
+        (GeoMaskMaker.cc:148-150).  Used by step(..., use_hook=True)."""
+        if fn is None:
+            self._hook = None
+            check(lib().gd_frontend_set_pose_hook(self._h, C.cast(None, POSE_HOOK), None))
+            return
+
+        def tramp(user, stream, obj, pix, n, Rp, Tp):
+            o = np.ctypeslib.as_array(obj, shape=(n, 3)).copy()
+            p = np.ctypeslib.as_array(pix, shape=(n, 2)).copy()
+            res = fn(stream, o, p)
+            if res is None:
+                return 0
+            Rm = np.asarray(res[0], np.float32).reshape(9)
+            Tm = np.asarray(res[1], np.float32).reshape(3)
+            for i in range(9):
+                Rp[i] = float(Rm[i])
+            for i in range(3):
+                Tp[i] = float(Tm[i])
+            return 1
+
+        self._hook = POSE_HOOK(tramp)  # kept alive by the object
+        check(lib().gd_frontend_set_pose_hook(self._h, self._hook, None))
+
+    def fetch_getrt(self):
+        """Points of the last step's GetRt stage: list of (object_points [n,3], image_pixels [n,2]) per stream."""
         B = self.batch
-        R, T, pv = self._pose(R, T, pose_valid, B)
+        obj = [np.zeros((100, 3), np.float32) for _ in range(B)]
+        pix = [np.zeros((100, 2), np.float32) for _ in range(B)]
+        n = np.zeros(B, np.int32)
+        check(lib().gd_frontend_fetch_getrt(self._h, _ptr_array(obj), _ptr_array(pix), n.ctypes.data_as(ip)))
+        return [(obj[b][: n[b]].copy(), pix[b][: n[b]].copy()) for b in range(B)]
+
+    def step(self, bgr, depth, R=None, T=None, pose_valid=None, fetch=True, use_hook=False):
+        """bgr: (B,H,W,3) u8 array or list of (H,W,3); depth: (B,H,W) f32 or list.  Host buffers in, results out.
+        use_hook: pass no pose at all -> the pose comes from the GetRt stage + the installed pose hook."""
+        B = self.batch
         bp = _ptr_array([bgr[b] for b in range(B)])
         dp = _ptr_array([depth[b] for b in range(B)])
+        if use_hook:
+            check(lib().gd_frontend_step(self._h, bp, self.w * 3, dp, self.w * 4, None, None, None,
+                                         self._mask_ptrs if fetch else None, self.w, self._kp_ptrs if fetch else None,
+                                         self._desc_ptrs if fetch else None, self.n_kp.ctypes.data_as(ip)))
+            return self.results() if fetch else None
+        R, T, pv = self._pose(R, T, pose_valid, B)
         check(lib().gd_frontend_step(self._h, bp, self.w * 3, dp, self.w * 4, _fptr(R), _fptr(T), pv.ctypes.data_as(ip),
                                      self._mask_ptrs if fetch else None, self.w, self._kp_ptrs if fetch else None,
                                      self._desc_ptrs if fetch else None, self.n_kp.ctypes.data_as(ip)))

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <map>
 #include <tuple>
+#include <vector>
 
 namespace gd {
 int orb_fetch_results(OrbCore& c, gd_keypoint* const* kps, uint8_t* const* desc, int capacity, int* n_out);
@@ -34,6 +35,14 @@ struct gd_frontend {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_edge = nullptr, ev_join = nullptr;
     bool overlap = true;
+    // GetRt stage (cfg.getrt): its chain (cv::ORB features of the new frame, matching against the frame five steps back, the
+    // 100 points of solvePnPRansac and their D2H) runs on a third forked stream.  With a pose hook installed and no pose
+    // given, the step waits for the points in the middle, asks the hook for (R, T) and only then enqueues the Mahalanobis half.
+    cudaStream_t rt_stream = nullptr;
+    cudaEvent_t ev_rt = nullptr;
+    gd_pose_hook_fn pose_hook = nullptr;
+    void* pose_hook_user = nullptr;
+    bool getrt_points_ready = false;
     // CUDA graphs of the per-frame device work, one per (ring phase, input buffer): the launch sequence of a step is
     // static, so small batches (launch bound: 51 launches per frame) replay a graph instead of re-issuing every launch
     struct GraphEntry {
@@ -50,6 +59,8 @@ struct gd_frontend {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (ev_edge) cudaEventDestroy(ev_edge);
+        if (ev_rt) cudaEventDestroy(ev_rt);
+        if (rt_stream) cudaStreamDestroy(rt_stream);
         if (aux_stream) cudaStreamDestroy(aux_stream);
         // cores do not own the shared stream
         for (auto& kv : graphs)
@@ -60,8 +71,10 @@ struct gd_frontend {
 
 using namespace gd;
 
-// per-frame device work once the new frame sits in geo.bgr and in the depth ring slot
-static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b)
+// per-frame device work once the new frame sits in geo.bgr and in the depth ring slot.
+// part 1 = everything up to (and including) the flow; part 2 = Mahalanobis + mask + joins.  A plain step runs both back to
+// back (and a graph captures both); the pose-hook path fetches the GetRt points between them.
+static int frontend_enqueue_head(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b, bool* forked)
 {
     GeoMaskCore& g = h->geo;
     OrbCore& o = h->orb;
@@ -70,31 +83,79 @@ static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
                        h->cfg.orb_gray_order, (size_t)o.plan.lv[0].pitch, o.plan.pyr_bytes, h->stream, &h->stats));
     // (launch_gray above and everything below is what a graph replays)
     const bool fork = h->overlap && !h->stats.profiling;  // the per-family event profile wants serialised kernels
+    *forked = fork;
     if (!fork) {
         GD_TRY(o.extract_resident());       // Frame() -> ORBextractor::operator()   (Tracking.cc:238)
         GD_TRY(g.push_resident(true));      // AddNewImage                          (Tracking.cc:242)
-        GD_TRY(g.enqueue_mask());           // GetNoGMMmask                          (Tracking.cc:245)
-    } else {
-        // aux stream: depth edges (FP64 bound, only needed by the Mahalanobis kernel at the end) then the ORB chain;
-        // main stream: flow pyramids, polynomial expansion, flow iterations, Mahalanobis, mask
-        GD_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-        GD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
-        g.edge_stream = h->aux_stream;
-        int rc = g.push_resident(true);
-        g.edge_stream = nullptr;
-        if (rc != GD_OK) return rc;
-        GD_CUDA(cudaEventRecord(h->ev_edge, h->aux_stream));
-        o.stream = h->aux_stream;
-        rc = o.extract_resident();
-        o.stream = h->stream;
-        if (rc != GD_OK) return rc;
-        GD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
-        GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
-        GD_TRY(g.enqueue_mask());
+        if (g.getrt && g.getrt_pair_ready()) GD_TRY(g.enqueue_getrt_match());
+        GD_TRY(g.enqueue_flow());           // GetNoGMMmask, first half               (Tracking.cc:245)
+        return GD_OK;
+    }
+    // aux stream: depth edges (only needed by the Mahalanobis kernel at the end) then the ORB chain;
+    // rt stream: the GetRt chain; main stream: flow pyramids, polynomial expansion, flow iterations
+    GD_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    GD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    if (g.getrt) GD_CUDA(cudaStreamWaitEvent(h->rt_stream, h->ev_fork, 0));
+    g.edge_stream = h->aux_stream;
+    g.getrt_stream = g.getrt ? h->rt_stream : nullptr;
+    int rc = g.push_resident(true);
+    g.edge_stream = nullptr;
+    if (rc == GD_OK && g.getrt && g.getrt_pair_ready()) rc = g.enqueue_getrt_match();
+    g.getrt_stream = nullptr;
+    if (rc != GD_OK) return rc;
+    if (g.getrt) GD_CUDA(cudaEventRecord(h->ev_rt, h->rt_stream));
+    GD_CUDA(cudaEventRecord(h->ev_edge, h->aux_stream));
+    o.stream = h->aux_stream;
+    rc = o.extract_resident();
+    o.stream = h->stream;
+    if (rc != GD_OK) return rc;
+    GD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+    GD_TRY(g.enqueue_flow());
+    return GD_OK;
+}
+
+static int frontend_enqueue_tail(gd_frontend* h, bool forked)
+{
+    GeoMaskCore& g = h->geo;
+    if (forked) GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
+    GD_TRY(g.enqueue_mask_tail());
+    if (forked) {
         GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (g.getrt) GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_rt, 0));
     }
     h->results_ready = true;
     h->filtered_ready = false;
+    h->getrt_points_ready = g.getrt && g.getrt_pair_ready();
+    return GD_OK;
+}
+
+static int frontend_enqueue(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b)
+{
+    bool forked = false;
+    GD_TRY(frontend_enqueue_head(h, bgr_dev, bgr_stride_b, &forked));
+    return frontend_enqueue_tail(h, forked);
+}
+
+// GeoMaskMaker::GetRt through the caller's solvePnPRansac: wait for the points of this step, ask the hook for every stream
+// with at least 20 points (GeoMaskMaker.cc:143-146), build the pose arrays
+static int frontend_poses_from_hook(gd_frontend* h, std::vector<float>& R, std::vector<float>& T, std::vector<int>& valid)
+{
+    GeoMaskCore& g = h->geo;
+    const int B = g.batch;
+    R.assign((size_t)9 * B, 0.f);
+    T.assign((size_t)3 * B, 0.f);
+    valid.assign((size_t)B, 0);
+    if (!g.getrt_pair_ready()) return GD_OK;  // warm-up: no pair yet
+    GD_CUDA(cudaEventSynchronize(h->ev_rt));
+    if (g.getrt->host_err() != 0) {
+        set_error("GetRt stage: capacity overflow of the selection lists (flags %d)", g.getrt->host_err());
+        return GD_EINTERNAL;
+    }
+    for (int b = 0; b < B; ++b) {
+        const int n = g.getrt->host_cnt()[b];
+        if (n < 20) continue;  // "small feature match.": GetRt returns false -> all-ones mask
+        valid[b] = h->pose_hook(h->pose_hook_user, b, g.getrt->host_obj(b), g.getrt->host_pix(b), n, &R[9 * b], &T[3 * b]) ? 1 : 0;
+    }
     return GD_OK;
 }
 
@@ -102,6 +163,17 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
                             const int* pose_valid)
 {
     GeoMaskCore& g = h->geo;
+    if (!R && !T && h->pose_hook && g.getrt) {
+        // pose from the GetRt stage + the caller's solvePnPRansac: plain launches, one host synchronisation in the middle
+        bool forked = false;
+        GD_TRY(frontend_enqueue_head(h, bgr_dev, bgr_stride_b, &forked));
+        if (!forked && g.getrt_pair_ready()) GD_CUDA(cudaEventRecord(h->ev_rt, h->stream));
+        std::vector<float> Rh, Th;
+        std::vector<int> vh;
+        GD_TRY(frontend_poses_from_hook(h, Rh, Th, vh));
+        GD_TRY(g.upload_poses(Rh.data(), Th.data(), vh.data(), g.frames));
+        return frontend_enqueue_tail(h, forked);
+    }
     // the frame of this step is pushed before the mask is evaluated; the pose copy stays outside any captured graph
     GD_TRY(g.upload_poses(R, T, pose_valid, g.frames + 1));
     // graphs only in steady state (every code path has run un-captured at least once: lazy attribute setup, ring full)
@@ -148,11 +220,13 @@ static int frontend_compute(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_s
     GD_CUDA(cudaGraphLaunch(it->second.exec, h->stream));
     h->stats.launches += it->second.launches;
     // host-side state the enqueue path advances
+    if (g.getrt) g.feat_frame[g.frames % GD_RING] = g.frames;
     g.frames += 1;
     g.last_cur_slot = (g.frames - 1) % GD_RING;
     g.last_ref_slot = (g.frames - GD_RING) % GD_RING;
     h->results_ready = true;
     h->filtered_ready = false;
+    h->getrt_points_ready = g.getrt && g.getrt_pair_ready();
     return GD_OK;
 }
 
@@ -201,6 +275,15 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
             r = GD_ECUDA;
             break;
         }
+        if (cfg->getrt) {
+            if ((r = h->geo.enable_getrt()) != GD_OK) break;
+            if (cudaStreamCreateWithFlags(&h->rt_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&h->ev_rt, cudaEventDisableTiming) != cudaSuccess) {
+                set_error("cudaStreamCreate/cudaEventCreate failed");
+                r = GD_ECUDA;
+                break;
+            }
+        }
         if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
             set_error("cudaEventCreate failed");
             r = GD_ECUDA;
@@ -221,6 +304,7 @@ void gd_frontend_destroy(gd_frontend_t* h)
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
+    if (h->rt_stream) cudaStreamSynchronize(h->rt_stream);
     delete h;
 }
 
@@ -476,6 +560,38 @@ int gd_stage_erode_filter(int device, const uint8_t* mask, int w, int h, const g
     GD_TRY(launch_erode_filter(dm.as<uint8_t>(), 0, w, h, 1, dk.as<gd_keypoint>(), (size_t)n, nullptr, n, dkeep.as<uint8_t>(), 0, nullptr));
     GD_CUDA(cudaDeviceSynchronize());
     GD_CUDA(cudaMemcpy(keep, dkeep.p, (size_t)n, cudaMemcpyDeviceToHost));
+    return GD_OK;
+}
+
+int gd_frontend_set_pose_hook(gd_frontend_t* h, gd_pose_hook_fn hook, void* user)
+{
+    GD_REQUIRE(h, "null handle");
+    GD_REQUIRE(!hook || h->geo.getrt, "the pose hook needs the GetRt stage (gd_frontend_config.getrt = 1)");
+    h->pose_hook = hook;
+    h->pose_hook_user = user;
+    return GD_OK;
+}
+
+int gd_frontend_fetch_getrt(gd_frontend_t* h, float* const* object_points, float* const* image_pixels, int* n_points)
+{
+    GD_REQUIRE(h && n_points, "null argument");
+    GD_TRY(select_device(h->cfg.device));
+    GeoMaskCore& g = h->geo;
+    GD_REQUIRE(g.getrt, "GetRt stage not enabled (gd_frontend_config.getrt = 1)");
+    GD_CUDA(cudaStreamSynchronize(h->stream));  // the step joined the GetRt chain into the main stream
+    if (h->rt_stream) GD_CUDA(cudaStreamSynchronize(h->rt_stream));
+    for (int b = 0; b < g.batch; ++b) n_points[b] = 0;
+    if (!h->getrt_points_ready) return GD_OK;  // warm-up: no buffered pair yet
+    if (g.getrt->host_err() != 0) {
+        set_error("GetRt stage: capacity overflow of the selection lists (flags %d)", g.getrt->host_err());
+        return GD_EINTERNAL;
+    }
+    for (int b = 0; b < g.batch; ++b) {
+        const int n = g.getrt->host_cnt()[b];
+        n_points[b] = n;
+        if (object_points && object_points[b]) std::memcpy(object_points[b], g.getrt->host_obj(b), sizeof(float) * 3 * n);
+        if (image_pixels && image_pixels[b]) std::memcpy(image_pixels[b], g.getrt->host_pix(b), sizeof(float) * 2 * n);
+    }
     return GD_OK;
 }
 

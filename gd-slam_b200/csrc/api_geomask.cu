@@ -76,6 +76,35 @@ int gd_geomask_mask(gd_geomask_t* h, const float* R, const float* T, const int* 
 
 int gd_geomask_frames(const gd_geomask_t* h) { return h ? h->core.frames : GD_EINVAL; }
 
+int gd_geomask_enable_getrt(gd_geomask_t* h)
+{
+    GD_REQUIRE(h, "null handle");
+    return h->core.enable_getrt();
+}
+
+int gd_geomask_getrt_points(gd_geomask_t* h, float* const* object_points, float* const* image_pixels, int* n_points)
+{
+    GD_REQUIRE(h && n_points, "null argument");
+    GeoMaskCore& c = h->core;
+    GD_TRY(select_device(c.device));
+    GD_REQUIRE(c.getrt, "GetRt stage not enabled (gd_geomask_enable_getrt)");
+    for (int b = 0; b < c.batch; ++b) n_points[b] = 0;
+    if (c.frames < GD_RING) return GD_OK;  // fewer than six frames: no pair (the reference's warm-up, :171-175)
+    GD_TRY(c.enqueue_getrt_match());
+    GD_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.getrt->host_err() != 0) {
+        set_error("GetRt stage: capacity overflow of the selection lists (flags %d)", c.getrt->host_err());
+        return GD_EINTERNAL;
+    }
+    for (int b = 0; b < c.batch; ++b) {
+        const int n = c.getrt->host_cnt()[b];
+        n_points[b] = n;
+        if (object_points && object_points[b]) std::memcpy(object_points[b], c.getrt->host_obj(b), sizeof(float) * 3 * n);
+        if (image_pixels && image_pixels[b]) std::memcpy(image_pixels[b], c.getrt->host_pix(b), sizeof(float) * 2 * n);
+    }
+    return GD_OK;
+}
+
 int gd_geomask_debug_fetch(gd_geomask_t* h, int what, int stream, void* dst, size_t dst_bytes)
 {
     GD_REQUIRE(h, "null handle");

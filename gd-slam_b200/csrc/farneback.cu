@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <type_traits>
 
 namespace gd {
 
@@ -660,6 +661,29 @@ __device__ __forceinline__ void fb_matrices_pixel(const float4* __restrict__ R0A
     fb_um_compute(a0, a04, p00, p01, p10, p11, e00, e01, e10, e11, inside, fx, fy, fl, x, y, w, h, M);
 }
 
+// the same in two steps, so that a thread can have the loads of several pixels in flight before it needs any of them
+struct FbMatPix {
+    float4 a0, p00, p01, p10, p11;
+    float a04, e00, e01, e10, e11, fx, fy;
+    bool inside;
+};
+__device__ __forceinline__ void fb_matrices_load(const float4* __restrict__ R0A, const float* __restrict__ R0B,
+                                                 const float4* __restrict__ R1A, const float* __restrict__ R1B, int w, int h, int x, int y,
+                                                 float2 fl, FbMatPix& m)
+{
+    const int o = y * w + x;
+    m.a0 = __ldg(R0A + o);
+    m.a04 = __ldg(R0B + o);
+    float fx = x + fl.x, fy = y + fl.y;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    m.fx = fx - x1;
+    m.fy = fy - y1;
+    m.inside = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    const int q = m.inside ? y1 * w + x1 : 0;
+    m.p00 = __ldg(R1A + q); m.p01 = __ldg(R1A + q + 1); m.p10 = __ldg(R1A + q + w); m.p11 = __ldg(R1A + q + w + 1);
+    m.e00 = __ldg(R1B + q); m.e01 = __ldg(R1B + q + 1); m.e10 = __ldg(R1B + q + w); m.e11 = __ldg(R1B + q + w + 1);
+}
+
 // ------------------------------------------------------------------------------------------------ K1b, split form
 // (a) k_fb_matrices: FarnebackUpdateMatrices for every pixel exactly once -> M (5 f32 planes) in HBM.  Embarrassingly
 //     parallel, no shared memory, full occupancy: the dependent bilinear gathers are hidden by ~40 resident warps.
@@ -729,7 +753,13 @@ constexpr int BX_THREADS = 256;
 constexpr int BX_ROWS = BX_H / (BX_THREADS / BX_W);  // 8 rows per thread in the vertical pass
 constexpr int BX_TILE_BYTES = BXH_H * BXM_P * (int)sizeof(float);                    // 15 456: one channel tile (TMA box 84 x 46)
 constexpr int BX_TILE_STRIDE = (BX_TILE_BYTES + 127) / 128 * 128;                    // 128-byte aligned tile buffers (TMA)
-constexpr size_t BX_SMEM = 2 * (size_t)BX_TILE_STRIDE + sizeof(double) * BXH_H * BXS_P + 16;  // + two mbarriers
+// shared memory of k_fb_box_solve<..., NBUF, F32>: NBUF channel-tile buffers, the horizontal-sum exchange buffer, mbarriers
+constexpr int BXS_PF = BX_W + 4;             // 68 floats: pitch of the f32 horizontal-sum buffer (STS.128 by row conflict free)
+template <int NBUF, bool F32>
+constexpr size_t bx_smem_bytes()
+{
+    return (size_t)NBUF * BX_TILE_STRIDE + (F32 ? sizeof(float) * BXH_H * BXS_PF : sizeof(double) * BXH_H * BXS_P) + 8 * NBUF;
+}
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 {
@@ -790,21 +820,45 @@ struct BoxNext {
     float* Mout;  // same per-stream stride as Min
 };
 
+// sliding sums of 15 consecutive values without a running sum (no drift): pair, quad and octet partial sums, then
+// out[j] = oct[j] + quad[j + 8] + pair[j + 12] + a[j + 14].  N outputs from N + 14 inputs.
+template <int N>
+__device__ __forceinline__ void window15_f32(const float* a, float* out)
+{
+    float p[N + 13], q[N + 11], o[N];
+#pragma unroll
+    for (int i = 0; i < N + 13; ++i) p[i] = a[i] + a[i + 1];
+#pragma unroll
+    for (int i = 0; i < N + 11; ++i) q[i] = p[i] + p[i + 2];
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = q[i] + q[i + 4];
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[j] = ((o[j] + q[j + 8]) + p[j + 12]) + a[j + 14];
+}
+
 // VEC: the row stride is a multiple of 4 floats -> every 16-byte chunk is either fully inside or fully outside the image;
 //      outside chunks are skipped and the replicated border columns are filled in shared memory afterwards (edge tiles only).
 // TMA (needs VEC): the whole 84 x 46 channel tile is ONE cp.async.bulk.tensor issued by one thread, completion counted in
 //      bytes on an mbarrier; the unit zero-fills outside the image, so edge tiles replicate the border rows as well.
-template <bool VEC, bool TMA, bool NEXT>
-__global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ Min,
+// NEXT: see BoxNext.   NBUF: channel-tile buffers in flight (2 = double buffering, 5 = the whole CTA's input at once).
+// F32:  true  = the 15 x 15 box sums in f32 as direct (tree) window sums, only the 2 x 2 solve in f64.  OpenCV accumulates
+//               the box in f64; the difference stays below 12 % of the 1e-4 tolerance on the 640 x 480 pairs and
+//               the kernel drops the f32->f64 conversions, half the exchange traffic and 40 registers;
+//       false = f64 running sums like OpenCV's vsum / hsum (GD_FLOW_BOX_F64=1).
+// MB:   resident CTAs per SM the register allocation aims at (2: 128 registers, 3: 85 — only the f32 form fits that).
+template <bool VEC, bool TMA, bool NEXT, int NBUF, bool F32, int MB>
+__global__ void __launch_bounds__(BX_THREADS, MB) k_fb_box_solve(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ Min,
                                                                 size_t mstride_b, float2* __restrict__ fout, size_t fstride_b, int w,
                                                                 int h, BoxNext nx)
 {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* sT = reinterpret_cast<float*>(smem_raw);                                    // [2] channel tiles of [BXH_H][BXM_P]
-    double* sH = reinterpret_cast<double*>(smem_raw + 2 * BX_TILE_STRIDE);             // [BXH_H][BXS_P]
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem_raw + 2 * BX_TILE_STRIDE + sizeof(double) * BXH_H * BXS_P);
+    float* sT = reinterpret_cast<float*>(smem_raw);                                   // [NBUF] channel tiles of [BXH_H][BXM_P]
+    double* sH = reinterpret_cast<double*>(smem_raw + NBUF * BX_TILE_STRIDE);         // [BXH_H][BXS_P]   (f64 form)
+    float* sHf = reinterpret_cast<float*>(smem_raw + NBUF * BX_TILE_STRIDE);          // [BXH_H][BXS_PF]  (f32 form)
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(
+        smem_raw + NBUF * BX_TILE_STRIDE + (F32 ? sizeof(float) * BXH_H * BXS_PF : sizeof(double) * BXH_H * BXS_P));
     constexpr int TS = BX_TILE_STRIDE / (int)sizeof(float);
     const int b = blockIdx.z;
     const size_t npad = align_up_dev((size_t)w * h, 64);
@@ -828,8 +882,8 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_con
     }
     if (TMA) {
         if (tid == 0) {
-            mbar_init(&s_bar[0], 1);
-            mbar_init(&s_bar[1], 1);
+#pragma unroll
+            for (int c = 0; c < NBUF; ++c) mbar_init(&s_bar[c], 1);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
         __syncthreads();
@@ -890,58 +944,86 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_con
     constexpr int NTASK = (BX_W / FT_SEG) * BXH_H;  // 184 horizontal tasks: (segment of 16 columns) x (tile row)
     const int hseg = tid / BXH_H, hrow = tid - hseg * BXH_H;
     const int cx = tid & (BX_W - 1), vr0 = (tid / BX_W) * BX_ROWS;
-    double acc[5][BX_ROWS];
-    load_tile(0, 0);
+    typedef typename std::conditional<F32, float, double>::type acc_t;
+    acc_t acc[5][BX_ROWS];
+#pragma unroll
+    for (int c = 0; c < NBUF && c < 5; ++c) load_tile(c, c);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        if (c + 1 < 5) load_tile(c + 1, (c + 1) & 1);
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int buf = c % NBUF;
         if (TMA) {
-            mbar_wait(&s_bar[c & 1], (unsigned)((c >> 1) & 1));  // buffer c & 1 is filled for the (c >> 1)-th time
-        } else if (c + 1 < 5) {
-            cp_async_wait<1>();
+            mbar_wait(&s_bar[buf], (unsigned)((c / NBUF) & 1));  // buffer `buf` is filled for the (c / NBUF)-th time
         } else {
-            cp_async_wait<0>();
+            // groups complete in order; committed so far: min(5, NBUF + c); channel c has landed when at most
+            // min(5, NBUF + c) - (c + 1) groups are still pending
+            const int pending = (NBUF + c < 5 ? NBUF + c : 5) - (c + 1);
+            switch (pending) {
+                case 4: cp_async_wait<4>(); break;
+                case 3: cp_async_wait<3>(); break;
+                case 2: cp_async_wait<2>(); break;
+                case 1: cp_async_wait<1>(); break;
+                default: cp_async_wait<0>(); break;
+            }
         }
-        __syncthreads();  // tile c visible to everyone; the V pass of channel c - 1 is done with sH
+        __syncthreads();  // tile c visible to everyone; the V pass of channel c - 1 is done with the exchange buffer
         if ((VEC || TMA) && (edge_l || edge_r || edge_t || edge_b)) {  // block-uniform
-            fix_border(c & 1);
+            fix_border(buf);
             __syncthreads();
         }
         if (tid < NTASK) {
             // window of output column j (tile-local) = tile floats [j + 1, j + 15]; the segment reads floats [16 seg, 16 seg + 32)
-            const float4* m4 = reinterpret_cast<const float4*>(sT + (c & 1) * TS + hrow * BXM_P + hseg * FT_SEG);
+            const float4* m4 = reinterpret_cast<const float4*>(sT + buf * TS + hrow * BXM_P + hseg * FT_SEG);
             float m[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 v = m4[q];
                 m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
             }
-            double* ho = sH + hrow * BXS_P + hseg * FT_SEG;
-            double s = 0.0;
+            if (F32) {
+                float hs[FT_SEG];
+                window15_f32<FT_SEG>(m + 1, hs);
+                float4* ho = reinterpret_cast<float4*>(sHf + hrow * BXS_PF + hseg * FT_SEG);
 #pragma unroll
-            for (int i = 1; i <= FB_WIN; ++i) s += (double)m[i];
-            ho[0] = s;
+                for (int q = 0; q < FT_SEG / 4; ++q) ho[q] = make_float4(hs[4 * q], hs[4 * q + 1], hs[4 * q + 2], hs[4 * q + 3]);
+            } else {
+                double* ho = sH + hrow * BXS_P + hseg * FT_SEG;
+                double s = 0.0;
 #pragma unroll
-            for (int j = 1; j < FT_SEG; ++j) {
-                s += (double)m[j + FB_WIN] - (double)m[j];
-                ho[j] = s;
+                for (int i = 1; i <= FB_WIN; ++i) s += (double)m[i];
+                ho[0] = s;
+#pragma unroll
+                for (int j = 1; j < FT_SEG; ++j) {
+                    s += (double)m[j + FB_WIN] - (double)m[j];
+                    ho[j] = s;
+                }
             }
         }
         __syncthreads();
-        {
+        if (c + NBUF < 5) load_tile(c + NBUF, buf);  // the H pass was the last reader of this tile buffer
+        if (F32) {
+            const float* hp = sHf + vr0 * BXS_PF + cx;
+            float hv[BX_ROWS + FB_WIN - 1];
+#pragma unroll
+            for (int i = 0; i < BX_ROWS + FB_WIN - 1; ++i) hv[i] = hp[i * BXS_PF];
+            float vs[BX_ROWS];
+            window15_f32<BX_ROWS>(hv, vs);
+#pragma unroll
+            for (int j = 0; j < BX_ROWS; ++j) acc[c][j] = (acc_t)vs[j];
+        } else {
             const double* hp = sH + vr0 * BXS_P + cx;
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < FB_WIN; ++i) s += hp[i * BXS_P];
-            acc[c][0] = s;
+            acc[c][0] = (acc_t)s;
 #pragma unroll
             for (int j = 1; j < BX_ROWS; ++j) {
                 s += hp[(j + FB_WIN - 1) * BXS_P] - hp[(j - 1) * BXS_P];
-                acc[c][j] = s;
+                acc[c][j] = (acc_t)s;
             }
         }
-        // the next iteration's first __syncthreads orders these sH reads before the next H-pass writes; the tile buffer
-        // (c & 1) is only overwritten by load_tile(c + 2), issued after that barrier as well
+        // the next iteration's first __syncthreads orders these exchange-buffer reads before the next H-pass writes
     }
     const int x = x0 + cx;
     if (x >= w) return;
@@ -949,8 +1031,8 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_con
 #pragma unroll
     for (int j = 0; j < BX_ROWS; ++j) {
         const double scale = 1. / (FB_WIN * FB_WIN);
-        const double g11 = acc[0][j] * scale, g12 = acc[1][j] * scale, g22 = acc[2][j] * scale, h1 = acc[3][j] * scale,
-                     h2 = acc[4][j] * scale;
+        const double g11 = (double)acc[0][j] * scale, g12 = (double)acc[1][j] * scale, g22 = (double)acc[2][j] * scale,
+                     h1 = (double)acc[3][j] * scale, h2 = (double)acc[4][j] * scale;
         const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
         o[j].x = (float)((g11 * h2 - g12 * h1) * idet);
         o[j].y = (float)((g22 * h1 - g12 * h2) * idet);
@@ -970,28 +1052,60 @@ __global__ void __launch_bounds__(BX_THREADS, 2) k_fb_box_solve(const __grid_con
         const float* R0B = r0 + 4 * npad;
         const float* R1B = r1 + 4 * npad;
         float* mo = nx.Mout + (size_t)b * mstride_b;
+        // several rows at a time: all gathers of the group are issued before the first one is consumed (the phase runs with
+        // 16 warps per SM, so the memory parallelism has to come from inside the thread)
+        constexpr int U = (F32 && MB == 2) ? 4 : 2;
 #pragma unroll
-        for (int j = 0; j < BX_ROWS; ++j) {
-            const int y = y0 + vr0 + j;
-            if (y >= h) break;
-            float M[5];
-            fb_matrices_pixel(R0A, R0B, R1A, R1B, w, h, x, y, o[j], M);
+        for (int j0 = 0; j0 < BX_ROWS; j0 += U) {
+            FbMatPix mp[U];
 #pragma unroll
-            for (int c = 0; c < 5; ++c) mo[(size_t)c * npad + (size_t)y * w + x] = M[c];
+            for (int u = 0; u < U; ++u) {
+                const int y = min(y0 + vr0 + j0 + u, h - 1);  // rows below the image: a valid address, result discarded
+                fb_matrices_load(R0A, R0B, R1A, R1B, w, h, x, y, o[j0 + u], mp[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = y0 + vr0 + j0 + u;
+                float M[5];
+                fb_um_compute(mp[u].a0, mp[u].a04, mp[u].p00, mp[u].p01, mp[u].p10, mp[u].p11, mp[u].e00, mp[u].e01, mp[u].e10,
+                              mp[u].e11, mp[u].inside, mp[u].fx, mp[u].fy, o[j0 + u], x, y, w, h, M);
+                if (y < h) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) mo[(size_t)c * npad + (size_t)y * w + x] = M[c];
+                }
+            }
         }
     }
 }
 
 // Function attributes are per device: called from fb_make_plan() with the plan's device current.
+template <bool VEC, bool TMA, bool NEXT, int NBUF, bool F32, int MB>
+static cudaError_t box_attr()
+{
+    return cudaFuncSetAttribute(k_fb_box_solve<VEC, TMA, NEXT, NBUF, F32, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)bx_smem_bytes<NBUF, F32>());
+}
+template <int NBUF, bool F32, int MB>
+static cudaError_t box_attr_all()
+{
+    cudaError_t e;
+    if ((e = box_attr<true, false, false, NBUF, F32, MB>()) != cudaSuccess) return e;
+    if ((e = box_attr<true, false, true, NBUF, F32, MB>()) != cudaSuccess) return e;
+    if ((e = box_attr<true, true, false, NBUF, F32, MB>()) != cudaSuccess) return e;
+    if ((e = box_attr<true, true, true, NBUF, F32, MB>()) != cudaSuccess) return e;
+    if ((e = box_attr<false, false, false, NBUF, F32, MB>()) != cudaSuccess) return e;
+    return box_attr<false, false, true, NBUF, F32, MB>();
+}
+
 int fb_prepare_device()
 {
     GD_CUDA(cudaFuncSetAttribute(k_fb_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
-    GD_CUDA(cudaFuncSetAttribute(k_fb_box_solve<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BX_SMEM));
+    GD_CUDA((box_attr_all<2, true, 2>()));
+    GD_CUDA((box_attr_all<5, true, 2>()));
+    GD_CUDA((box_attr_all<2, true, 3>()));
+    GD_CUDA((box_attr_all<5, true, 3>()));
+    GD_CUDA((box_attr_all<2, false, 2>()));
+    GD_CUDA((box_attr_all<5, false, 2>()));
     return GD_OK;
 }
 
@@ -1027,6 +1141,9 @@ int fb_prepare_flow_buffers(const FbPlan& plan, int batch, float* M0, float* M1,
     fb->m_bytes = m_bytes_each;
     const bool whole_batch = m_bytes_each >= (size_t)batch * plan.m_floats * sizeof(float);
     fb->fuse_next = M1 != nullptr && whole_batch && env_flag("GD_FLOW_NEXT", 1) != 0;
+    fb->box_f32 = env_flag("GD_FLOW_BOX_F64", 0) == 0;
+    fb->nbuf = env_flag("GD_FLOW_NBUF", 2);
+    fb->min_blocks = env_flag("GD_FLOW_MB", 2);
     fb->use_tma = false;
     if (!whole_batch || env_flag("GD_FLOW_TMA", 1) == 0) return GD_OK;
     EncodeTiledFn enc = encode_tiled_fn();
@@ -1055,16 +1172,33 @@ int fb_prepare_flow_buffers(const FbPlan& plan, int batch, float* M0, float* M1,
     return GD_OK;
 }
 
+template <bool NEXT, int NBUF, bool F32, int MB>
+static cudaError_t launch_box_v(const FbFlowBuffers& fb, int level, int src, dim3 grid, cudaStream_t s, const float* Min, size_t mstride,
+                                float2* fout, size_t fstride, int w, int h, BoxNext nx)
+{
+    static const CUtensorMap no_map = {};
+    const size_t smem = bx_smem_bytes<NBUF, F32>();
+    if ((w & 3) != 0)
+        return launch_pdl(k_fb_box_solve<false, false, NEXT, NBUF, F32, MB>, grid, dim3(BX_THREADS), smem, s, no_map, Min, mstride, fout, fstride, w, h, nx);
+    if (fb.use_tma && fb.tmap_ok[level][src])
+        return launch_pdl(k_fb_box_solve<true, true, NEXT, NBUF, F32, MB>, grid, dim3(BX_THREADS), smem, s, fb.tmap[level][src], Min, mstride, fout, fstride, w, h, nx);
+    return launch_pdl(k_fb_box_solve<true, false, NEXT, NBUF, F32, MB>, grid, dim3(BX_THREADS), smem, s, no_map, Min, mstride, fout, fstride, w, h, nx);
+}
+
 template <bool NEXT>
 static cudaError_t launch_box(const FbFlowBuffers& fb, int level, int src, dim3 grid, cudaStream_t s, const float* Min, size_t mstride,
                               float2* fout, size_t fstride, int w, int h, BoxNext nx)
 {
-    static const CUtensorMap no_map = {};
-    if ((w & 3) != 0)
-        return launch_pdl(k_fb_box_solve<false, false, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, no_map, Min, mstride, fout, fstride, w, h, nx);
-    if (fb.use_tma && fb.tmap_ok[level][src])
-        return launch_pdl(k_fb_box_solve<true, true, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, fb.tmap[level][src], Min, mstride, fout, fstride, w, h, nx);
-    return launch_pdl(k_fb_box_solve<true, false, NEXT>, grid, dim3(BX_THREADS), BX_SMEM, s, no_map, Min, mstride, fout, fstride, w, h, nx);
+    if (fb.box_f32 && fb.min_blocks >= 3) {
+        if (fb.nbuf >= 5) return launch_box_v<NEXT, 5, true, 3>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
+        return launch_box_v<NEXT, 2, true, 3>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
+    }
+    if (fb.box_f32) {
+        if (fb.nbuf >= 5) return launch_box_v<NEXT, 5, true, 2>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
+        return launch_box_v<NEXT, 2, true, 2>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
+    }
+    if (fb.nbuf >= 5) return launch_box_v<NEXT, 5, false, 2>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
+    return launch_box_v<NEXT, 2, false, 2>(fb, level, src, grid, s, Min, mstride, fout, fstride, w, h, nx);
 }
 
 int fb_launch_flow(const FbPlan& plan, const float* R0, const float* R1, size_t r_stride_b, int batch, float2* flowA,

@@ -51,11 +51,15 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
 //                   (M ping-pong, no intermediate flow, 4 launches per level instead of 6); nullptr = plain split form
 //   tmap[level][i]  rank-3 TMA descriptors (x, y, plane) of M[i] at every level whose rows are 16-byte aligned: the
 //                   84 x 46 channel tile of the box filter arrives by one cp.async.bulk.tensor per channel
-// GD_FLOW_NEXT=0 / GD_FLOW_TMA=0 switch the two features off (A/B measurements).
+// GD_FLOW_NEXT=0 / GD_FLOW_TMA=0 switch the two features off, GD_FLOW_BOX_F64=1 / GD_FLOW_NBUF=5 select the box kernel's
+// accumulation type and prefetch depth (A/B measurements).
 struct FbFlowBuffers {
     float* M[2] = {nullptr, nullptr};
     size_t m_bytes = 0;
     bool fuse_next = false, use_tma = false;
+    bool box_f32 = true;  // 15 x 15 box sums in f32 tree form (default) or f64 running sums like OpenCV (GD_FLOW_BOX_F64=1)
+    int min_blocks = 2;   // register budget of the f32 box kernel: 2 or 3 resident CTAs per SM (GD_FLOW_MB)
+    int nbuf = 2;         // channel tiles a CTA of the box kernel keeps in flight (GD_FLOW_NBUF = 2 or 5)
     bool tmap_ok[FB_MAX_LEVELS][2] = {};
     alignas(64) CUtensorMap tmap[FB_MAX_LEVELS][2];
 };

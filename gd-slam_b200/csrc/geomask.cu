@@ -12,7 +12,9 @@
 // no tensor-core work (largest matrix on the path is 6x6).
 #include "geomask.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace gd {
 
@@ -166,58 +168,160 @@ int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w,
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2a depth edge (FP64, bit-exact vs oracle).  Tile 32x16, depth halo 2, normal/vertex halo 1 in smem.
+// K2a depth edge (GetEdge, GeoMaskMaker.cc:854-964).  The reference evaluates everything in FP64; its result per pixel is
+// one bit (edge or not).  k_depth_edge evaluates the test in f32 INTERVAL form — every f32 quantity carries a rigorous bound
+// on its distance from the reference's f64 value — and decides the pixel when the interval of thres_edge lies entirely on
+// one side of 0.04.  The few undecided pixels (|thres - 0.04| within ~1e-4) are queued in shared memory and re-evaluated by
+// edge_exact_f64(), the reference's f64 arithmetic operation by operation.  The output is bit-exact; the FP64 pipe is
+// (nearly) idle.  k_depth_edge_f64 (the all-f64 kernel of round 1) stays as the path for cameras whose inv(K) has a
+// non-trivial third row, and as the in-tree cross-check (GD_EDGE_F64=1).
+//
+// Error bounds (u = 2^-24; S = max_i sum_j |Kinv_ij| * (W-1, H-1, 1); D = 3.5 m, the depth cut applied to interior pixels):
+//   h_f = Kinv_f * (x, y, 1)      |h_f - h| <= 6 u S            (constants rounded to f32, two products, two sums)
+//   v_f = h_f * d                 |v_f - v| <= 7 u S D =: ev
+//   diff_f = v_j - v_c            |.| <= 2 ev + 2 u S D = 16 u S D =: ed
+//   n_f = (dl - dc, dt - dc, 1) * (1 / sqrt(ss))   relative error <= 4.5 u per component -> en = 5 u
+//   phi_d_f = sum_i diff_i n_i    |.| <= 3 (2 S D en + ed) + 24 u S D = 102 u S D   -> E_D = 128 u S D
+//   phi_c_f = 1 - sum_i n_j,i n_c,i   |.| <= 6 en + 4 u = 34 u                      -> E_C = 40 u
 // ------------------------------------------------------------------------------------------------
 constexpr int ET_W = 32, ET_H = 16;
 
+// the reference's normal and vertex of tile pixel (ly, lx) [depth tile coordinates, halo 2] in f64, operation by operation
+__device__ __forceinline__ void edge_nv_f64(const float (*sd)[ET_W + 4], int ly, int lx, int x, int y, int w, int h, const CamConst& cam,
+                                            double n[3], double v[3])
+{
+    n[0] = n[1] = n[2] = 0.0;
+    v[0] = v[1] = v[2] = 0.0;
+    if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
+        const double dc = (double)sd[ly][lx], dt = (double)sd[ly - 1][lx], dl = (double)sd[ly][lx - 1];
+        if (dc != 0.0 && dt != 0.0 && dl != 0.0) {
+            // cross((-1, 0, dl - dc), (0, -1, dt - dc)) = (dl - dc, dt - dc, 1): the products with the constant
+            // components are exact and the differences are never -0, so the three components need no arithmetic
+            const double c0 = dl - dc, c1 = dt - dc, c2 = 1.0;
+            double ss = c0 * c0;  // cv::norm: 0 + c0^2 + c1^2 + c2^2 in this order (0 + x == x for x >= 0)
+            ss += c1 * c1;
+            ss += c2 * c2;
+            const double nv = sqrt(ss);
+            const double inv = nv != 0.0 ? 1.0 / nv : 0.0;
+            n[0] = c0 * inv;
+            n[1] = c1 * inv;
+            n[2] = c2 * inv;
+            const double px = (double)x, py = (double)y;
+            const double h0 = cam.Kid[0] * px + cam.Kid[1] * py + cam.Kid[2] * 1.0;
+            const double h1 = cam.Kid[3] * px + cam.Kid[4] * py + cam.Kid[5] * 1.0;
+            const double h2 = cam.Kid[6] * px + cam.Kid[7] * py + cam.Kid[8] * 1.0;
+            v[0] = h0 * dc;
+            v[1] = h1 * dc;
+            v[2] = h2 * dc;
+        }
+    }
+}
+
+// the reference's edge decision of an interior pixel with non-zero (clamped) depth, from normals / vertices given by nv(k, n, v)
+// for k = 0..7 (neighbour k) and k = 8 (the pixel itself)
+template <class NV>
+__device__ __forceinline__ uint8_t edge_decide_f64(NV nv)
+{
+    double cn[3], cv[3];
+    nv(8, cn, cv);
+    bool zero_nb = false;
+    double max_phi_d = -1.0, max_phi_c = -1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double jn[3], jv[3];
+        nv(k, jn, jv);
+        const double z = jv[2];
+        if (z == 0.0) {
+            zero_nb = true;
+            continue;
+        }
+        // the leading "0 +" of the dot products is dropped: it can only turn a -0 sum into +0, which no later
+        // comparison distinguishes
+        double phi_d = (jv[0] - cv[0]) * cn[0];
+        phi_d += (jv[1] - cv[1]) * cn[1];
+        phi_d += (z - cv[2]) * cn[2];
+        const double ad = fabs(phi_d);
+        if (max_phi_d < ad) max_phi_d = ad;
+        if (phi_d < 0.0) {
+            if (max_phi_c < 0.0) max_phi_c = 0.0;
+        } else {
+            double dot = jn[0] * cn[0];
+            dot += jn[1] * cn[1];
+            dot += jn[2] * cn[2];
+            const double phi_c = 1.0 - dot;
+            if (phi_c > max_phi_c) max_phi_c = phi_c;
+        }
+    }
+    if (zero_nb) return 255;
+    if (!(max_phi_c == -1.0 || max_phi_d == -1.0)) {
+        const double thres_edge = max_phi_d + 0.05 * max_phi_c;
+        if (thres_edge > 0.04) return 255;
+    }
+    return 0;
+}
+
+__constant__ int c_edge_nx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+__constant__ int c_edge_ny[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+__device__ __forceinline__ void load_depth_tile(const float* __restrict__ dp, int w, int h, int x0, int y0, int tid,
+                                                float (*sd)[ET_W + 4])
+{
+    for (int i = tid; i < (ET_H + 4) * (ET_W + 4); i += ET_W * ET_H) {
+        const int ly = i / (ET_W + 4), lx = i - ly * (ET_W + 4);
+        const int x = x0 + lx - 2, y = y0 + ly - 2;
+        float v = 0.f;
+        if (x >= 0 && y >= 0 && x < w && y < h) {
+            v = __ldg(dp + (size_t)y * w + x);
+            const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
+            if (interior && v > 3.5f) v = 0.f;  // :870-874 ((double)v > 3.5 <=> v > 3.5f: 3.5 is a float)
+        }
+        sd[ly][lx] = v;
+    }
+}
+
+struct EdgeBounds {
+    float Ki[9];  // inv(K) rounded to f32
+    float e_d;    // bound on |phi_d_f32 - phi_d_f64|
+    float e_c;    // bound on |phi_c_f32 - phi_c_f64|
+};
+
 __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
-                                                            CamConst cam, uint8_t* __restrict__ edge, size_t estride_b)
+                                                            CamConst cam, EdgeBounds eb, uint8_t* __restrict__ edge, size_t estride_b)
 {
     pdl_wait();
-    __shared__ double sd[ET_H + 4][ET_W + 4];        // clamped depth, halo 2
-    __shared__ double sn[ET_H + 2][ET_W + 2][3];     // normals, halo 1
-    __shared__ double sv[ET_H + 2][ET_W + 2][3];     // vertices, halo 1
+    __shared__ float sd[ET_H + 4][ET_W + 4];      // clamped depth, halo 2
+    __shared__ float sn[ET_H + 2][ET_W + 2][3];   // f32 normals, halo 1
+    __shared__ float sv[ET_H + 2][ET_W + 2][3];   // f32 vertices, halo 1 (z == 0 <=> the reference's vertex is zero)
+    __shared__ int s_todo[ET_W * ET_H];
+    __shared__ int s_ntodo;
     const int b = blockIdx.z;
     const float* dp = depth + (size_t)b * dstride_b;
     const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
     const int tid = threadIdx.y * ET_W + threadIdx.x;
-    for (int i = tid; i < (ET_H + 4) * (ET_W + 4); i += ET_W * ET_H) {
-        const int ly = i / (ET_W + 4), lx = i - ly * (ET_W + 4);
-        const int x = x0 + lx - 2, y = y0 + ly - 2;
-        double v = 0.0;
-        if (x >= 0 && y >= 0 && x < w && y < h) {
-            v = (double)__ldg(dp + (size_t)y * w + x);
-            const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
-            if (interior && v > 3.5) v = 0.0;  // :870-874
-        }
-        sd[ly][lx] = v;
-    }
+    if (tid == 0) s_ntodo = 0;
+    load_depth_tile(dp, w, h, x0, y0, tid, sd);
     __syncthreads();
     for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
         const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
         const int x = x0 + lx - 1, y = y0 + ly - 1;
-        double n0 = 0, n1 = 0, n2 = 0, v0 = 0, v1 = 0, v2 = 0;
+        float n0 = 0, n1 = 0, n2 = 0, v0 = 0, v1 = 0, v2 = 0;
         if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
-            const double dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
-            if (dc != 0.0 && dt != 0.0 && dl != 0.0) {
-                // cross((-1, 0, dl - dc), (0, -1, dt - dc)) = (dl - dc, dt - dc, 1): the products with the constant
-                // components are exact and the differences are never -0, so the three components need no arithmetic
-                const double c0 = dl - dc, c1 = dt - dc, c2 = 1.0;
-                double ss = c0 * c0;  // cv::norm: 0 + c0^2 + c1^2 + c2^2 in this order (0 + x == x for x >= 0)
-                ss += c1 * c1;
-                ss += c2 * c2;
-                const double nv = sqrt(ss);
-                const double inv = nv != 0.0 ? 1.0 / nv : 0.0;
+            const float dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
+            if (dc != 0.f && dt != 0.f && dl != 0.f) {
+                const float c0 = dl - dc, c1 = dt - dc;
+                float ss = c0 * c0;
+                ss = ss + c1 * c1;
+                ss = ss + 1.0f;
+                const float inv = 1.0f / sqrtf(ss);  // IEEE sqrt and division (this file is built without fast math)
                 n0 = c0 * inv;
                 n1 = c1 * inv;
-                n2 = c2 * inv;
-                const double px = (double)x, py = (double)y;
-                const double h0 = cam.Kid[0] * px + cam.Kid[1] * py + cam.Kid[2] * 1.0;
-                const double h1 = cam.Kid[3] * px + cam.Kid[4] * py + cam.Kid[5] * 1.0;
-                const double h2 = cam.Kid[6] * px + cam.Kid[7] * py + cam.Kid[8] * 1.0;
+                n2 = inv;
+                const float px = (float)x, py = (float)y;
+                const float h0 = eb.Ki[0] * px + eb.Ki[1] * py + eb.Ki[2];
+                const float h1 = eb.Ki[3] * px + eb.Ki[4] * py + eb.Ki[5];
                 v0 = h0 * dc;
                 v1 = h1 * dc;
-                v2 = h2 * dc;
+                v2 = dc;  // third row of inv(K) is (0, 0, 1) on this path: z = depth exactly, like the reference's 1.0 * dc
             }
         }
         sn[ly][lx][0] = n0; sn[ly][lx][1] = n1; sn[ly][lx][2] = n2;
@@ -225,48 +329,93 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool in_img = x < w && y < h;
+    uint8_t e = 0;
+    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
+    if (in_img && x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.f) {
+        const float cn0 = sn[ly][lx][0], cn1 = sn[ly][lx][1], cn2 = sn[ly][lx][2];
+        const float cv0 = sv[ly][lx][0], cv1 = sv[ly][lx][1], cv2 = sv[ly][lx][2];
+        bool zero_nb = false;
+        float maxd = 0.f, c_lo = 0.f, c_hi = 0.f;  // all eight neighbours valid below -> both maxima are >= 0 in the reference
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int jx = lx + c_edge_nx[k], jy = ly + c_edge_ny[k];
+            const float z = sv[jy][jx][2];
+            if (z == 0.f) zero_nb = true;
+            float phi_d = (sv[jy][jx][0] - cv0) * cn0;
+            phi_d = phi_d + (sv[jy][jx][1] - cv1) * cn1;
+            phi_d = phi_d + (z - cv2) * cn2;
+            maxd = fmaxf(maxd, fabsf(phi_d));
+            float dot = sn[jy][jx][0] * cn0;
+            dot = dot + sn[jy][jx][1] * cn1;
+            dot = dot + sn[jy][jx][2] * cn2;
+            const float phi_c = 1.0f - dot;
+            // contribution of this neighbour to max_phi_c: phi_c when phi_d >= 0, 0 when phi_d < 0; undecided sign -> both
+            const float lo = phi_d >= eb.e_d ? phi_c : (phi_d < -eb.e_d ? 0.f : fminf(0.f, phi_c));
+            const float hi = phi_d >= eb.e_d ? phi_c : (phi_d < -eb.e_d ? 0.f : fmaxf(0.f, phi_c));
+            c_lo = k == 0 ? lo : fmaxf(c_lo, lo);
+            c_hi = k == 0 ? hi : fmaxf(c_hi, hi);
+        }
+        if (zero_nb || cv2 == 0.f) {
+            // a zero vertex among the neighbours: edge (:925-949).  A pixel with depth but without a normal (its top or left
+            // neighbour has no depth): cn = cv = 0 -> phi_d = 0, phi_c = 1 for every valid neighbour -> 0.05 > 0.04: edge as well
+            e = 255;
+        } else {
+            const float slack = eb.e_d * 1.125f + 1e-6f;  // + rounding of the few f32 operations below
+            const float t_lo = (maxd - slack) + 0.05f * (c_lo - eb.e_c);
+            const float t_hi = (maxd + slack) + 0.05f * (c_hi + eb.e_c);
+            if (t_lo > 0.04f)
+                e = 255;
+            else if (!(t_hi < 0.04f))
+                s_todo[atomicAdd(&s_ntodo, 1)] = (ly << 8) | lx;  // undecided: exact f64 evaluation below
+        }
+    }
+    if (in_img) edge[(size_t)b * estride_b + (size_t)y * w + x] = e;
+    __syncthreads();
+    const int ntodo = s_ntodo;  // block-uniform
+    for (int t = tid; t < ntodo; t += ET_W * ET_H) {
+        const int ply = s_todo[t] >> 8, plx = s_todo[t] & 255;  // normal / vertex tile coordinates (halo 1)
+        const int px = x0 + plx - 1, py = y0 + ply - 1;
+        const uint8_t ex = edge_decide_f64([&](int k, double n[3], double v[3]) {
+            const int dx = k < 8 ? c_edge_nx[k] : 0, dy = k < 8 ? c_edge_ny[k] : 0;
+            edge_nv_f64(sd, ply + 1 + dy, plx + 1 + dx, px + dx, py + dy, w, h, cam, n, v);
+        });
+        edge[(size_t)b * estride_b + (size_t)py * w + px] = ex;
+    }
+}
+
+// the all-f64 form: one normal / vertex per pixel in shared memory (f64), then the reference's neighbour loop
+__global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge_f64(const float* __restrict__ depth, size_t dstride_b, int w, int h,
+                                                                CamConst cam, uint8_t* __restrict__ edge, size_t estride_b)
+{
+    pdl_wait();
+    __shared__ float sd[ET_H + 4][ET_W + 4];          // clamped depth, halo 2
+    __shared__ double sn[ET_H + 2][ET_W + 2][3];      // normals, halo 1
+    __shared__ double sv[ET_H + 2][ET_W + 2][3];      // vertices, halo 1
+    const int b = blockIdx.z;
+    const float* dp = depth + (size_t)b * dstride_b;
+    const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
+    const int tid = threadIdx.y * ET_W + threadIdx.x;
+    load_depth_tile(dp, w, h, x0, y0, tid, sd);
+    __syncthreads();
+    for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
+        const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
+        double n[3], v[3];
+        edge_nv_f64(sd, ly + 1, lx + 1, x0 + lx - 1, y0 + ly - 1, w, h, cam, n, v);
+        sn[ly][lx][0] = n[0]; sn[ly][lx][1] = n[1]; sn[ly][lx][2] = n[2];
+        sv[ly][lx][0] = v[0]; sv[ly][lx][1] = v[1]; sv[ly][lx][2] = v[2];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= w || y >= h) return;
     uint8_t e = 0;
     const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
-    if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.0) {
-        const int nx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
-        const int ny[8] = {0, -1, -1, -1, 0, 1, 1, 1};
-        bool zero_nb = false;
-        double max_phi_d = -1.0, max_phi_c = -1.0;
-        const double cn0 = sn[ly][lx][0], cn1 = sn[ly][lx][1], cn2 = sn[ly][lx][2];
-        const double cv0 = sv[ly][lx][0], cv1 = sv[ly][lx][1], cv2 = sv[ly][lx][2];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int jx = lx + nx[k], jy = ly + ny[k];
-            const double z = sv[jy][jx][2];
-            if (z == 0.0) {
-                zero_nb = true;
-                continue;
-            }
-            // the leading "0 +" of the dot products is dropped: it can only turn a -0 sum into +0, which no later
-            // comparison distinguishes
-            double phi_d = (sv[jy][jx][0] - cv0) * cn0;
-            phi_d += (sv[jy][jx][1] - cv1) * cn1;
-            phi_d += (z - cv2) * cn2;
-            const double ad = fabs(phi_d);
-            if (max_phi_d < ad) max_phi_d = ad;
-            if (phi_d < 0.0) {
-                if (max_phi_c < 0.0) max_phi_c = 0.0;
-            } else {
-                double dot = sn[jy][jx][0] * cn0;
-                dot += sn[jy][jx][1] * cn1;
-                dot += sn[jy][jx][2] * cn2;
-                const double phi_c = 1.0 - dot;
-                if (phi_c > max_phi_c) max_phi_c = phi_c;
-            }
-        }
-        if (zero_nb)
-            e = 255;
-        else if (!(max_phi_c == -1.0 || max_phi_d == -1.0)) {
-            const double thres_edge = max_phi_d + 0.05 * max_phi_c;
-            if (thres_edge > 0.04) e = 255;
-        }
-    }
+    if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.f)
+        e = edge_decide_f64([&](int k, double n[3], double v[3]) {
+            const int jx = lx + (k < 8 ? c_edge_nx[k] : 0), jy = ly + (k < 8 ? c_edge_ny[k] : 0);
+            n[0] = sn[jy][jx][0]; n[1] = sn[jy][jx][1]; n[2] = sn[jy][jx][2];
+            v[0] = sv[jy][jx][0]; v[1] = sv[jy][jx][1]; v[2] = sv[jy][jx][2];
+        });
     edge[(size_t)b * estride_b + (size_t)y * w + x] = e;
 }
 
@@ -275,7 +424,27 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
 {
     LaunchScope ls(st, s, "K2a_depth_edge", 1);
     dim3 block(ET_W, ET_H), grid(cdiv(w, ET_W), cdiv(h, ET_H), batch);
-    GD_CUDA(launch_pdl(k_depth_edge, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
+    const char* env = std::getenv("GD_EDGE_F64");  // read per launch: the parity test toggles it inside one process
+    const bool force_f64 = env && std::atoi(env) != 0;
+    // the f32 interval kernel assumes z = depth (third row of inv(K) = (0, 0, 1)) and finite bounds
+    // (inv(K)[2][2] = fx fy * (1 / (fx fy)) may differ from 1 in the last bit: z = that * depth is then within 2^-52 of the
+    // depth the kernel uses, far inside the bounds, and it is zero exactly when the depth is)
+    const bool plain_k = cam.Kid[6] == 0.0 && cam.Kid[7] == 0.0 && std::fabs(cam.Kid[8] - 1.0) < 1e-12;
+    double S = 0.0;
+    for (int r = 0; r < 2; ++r)
+        S = std::max(S, std::fabs(cam.Kid[3 * r]) * (w - 1) + std::fabs(cam.Kid[3 * r + 1]) * (h - 1) + std::fabs(cam.Kid[3 * r + 2]));
+    S = std::max(S, 1.0);
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    const double e_d = 128.0 * u * S * 3.5;
+    if (force_f64 || !plain_k || !(e_d < 1e-2)) {
+        GD_CUDA(launch_pdl(k_depth_edge_f64, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
+    } else {
+        EdgeBounds eb;
+        for (int i = 0; i < 9; ++i) eb.Ki[i] = (float)cam.Kid[i];
+        eb.e_d = (float)(e_d * 1.0000002);  // rounded up
+        eb.e_c = (float)(40.0 * u);
+        GD_CUDA(launch_pdl(k_depth_edge, grid, block, 0, s, depth, depth_stride_b, w, h, cam, eb, edge, edge_stride_b));
+    }
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

@@ -37,6 +37,8 @@ static void build_undistort_lut(const float K[9], const float* d, int nd, int w,
         }
 }
 
+static int dist_coef_in_range(int n) { return n < 0 ? 0 : (n > 5 ? 5 : n); }
+
 int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int width, int height, int device_,
                       int batch_, cudaStream_t s, LaunchStats* st)
 {
@@ -51,6 +53,11 @@ int GeoMaskCore::init(const float K_[9], const float* dist_coef, int ndist, int 
     stats = st;
     std::memcpy(K, K_, sizeof(K));
     make_cam_const(K, &cam);
+    ndist = dist_coef_in_range(ndist);
+    for (int i = 0; i < ndist && dist_coef; ++i) this->dist_coef[i] = dist_coef[i];
+    if (!dist_coef) ndist = 0;
+    this->ndist = ndist;
+    for (int i = 0; i < GD_RING; ++i) feat_frame[i] = -1;
     GD_TRY(fb_make_plan(w, h, 0.5, 3, 3, 5, 1.2, 15, &plan));  // GeoMaskMaker.cc:165
     if (s) {
         stream = s;
@@ -123,6 +130,7 @@ int GeoMaskCore::push_resident(bool gray_done)
                                             [&] { return enqueue_push(slot, gray_done); })
                           : enqueue_push(slot, gray_done);
     if (rc != GD_OK) return rc;
+    if (getrt) feat_frame[slot] = frames;
     frames += 1;
     return GD_OK;
 }
@@ -140,7 +148,44 @@ int GeoMaskCore::enqueue_push(int slot, bool gray_done)
     GD_TRY(launch_depth_edge(depth_slot_ptr(slot), depth_stride_b(), w, h, batch, cam,
                              edge.as<uint8_t>() + (size_t)slot * n_pad, (size_t)GD_RING * n_pad,
                              edge_stream ? edge_stream : stream, stats));
+    // GetRt (when enabled): cv::ORB features of the new frame into the slot's feature cache
+    if (getrt) {
+        getrt->stream = getrt_stream ? getrt_stream : stream;
+        getrt->stats = stats;
+        GD_TRY(getrt->enqueue_features(gray.as<uint8_t>(), n_pad, slot));
+    }
     return GD_OK;
+}
+
+int GeoMaskCore::enable_getrt()
+{
+    if (getrt) return GD_OK;
+    GD_TRY(select_device(device));
+    std::unique_ptr<GetRtCore> c(new (std::nothrow) GetRtCore());
+    if (!c) return GD_ENOMEM;
+    GD_TRY(c->init(K, ndist ? dist_coef : nullptr, ndist, w, h, device, batch, GD_RING));
+    getrt = std::move(c);
+    // graphs captured before this point do not contain the feature launches
+    push_graphs.enabled = false;
+    return GD_OK;
+}
+
+bool GeoMaskCore::getrt_pair_ready() const
+{
+    if (!getrt || frames < GD_RING) return false;
+    const int cur = (frames - 1) % GD_RING, ref = (frames - GD_RING) % GD_RING;
+    return feat_frame[cur] == (long long)frames - 1 && feat_frame[ref] == (long long)frames - GD_RING;
+}
+
+int GeoMaskCore::enqueue_getrt_match()
+{
+    GD_REQUIRE(getrt, "GetRt stage not enabled");
+    GD_REQUIRE(getrt_pair_ready(), "features of the buffered pair are not available (enable GetRt before pushing the frames)");
+    const int cur = (frames - 1) % GD_RING, ref = (frames - GD_RING) % GD_RING;
+    getrt->stream = getrt_stream ? getrt_stream : stream;
+    getrt->stats = stats;
+    GD_TRY(getrt->enqueue_match(ref, cur, depth_slot_ptr(ref), depth_stride_b()));
+    return getrt->enqueue_fetch();
 }
 
 int GeoMaskCore::compute_mask(const float* Rm, const float* Tm, const int* pose_valid)
@@ -177,9 +222,14 @@ int GeoMaskCore::upload_poses(const float* Rm, const float* Tm, const int* pose_
 // device half: everything GetNoGMMmask enqueues on the stream (capturable into a CUDA graph)
 int GeoMaskCore::enqueue_mask()
 {
+    GD_TRY(enqueue_flow());
+    return enqueue_mask_tail();
+}
+
+int GeoMaskCore::enqueue_flow()
+{
     const bool started = frames >= GD_RING;
-    if (!started) {  // warm-up: all-ones mask (:171-175)
-        GD_TRY(launch_fill_u8(mask.as<uint8_t>(), (size_t)batch * n_pad, 1, stream, stats));
+    if (!started) {
         last_flow = nullptr;
         return GD_OK;
     }
@@ -188,9 +238,18 @@ int GeoMaskCore::enqueue_mask()
     last_ref_slot = ref;
     last_cur_slot = cur;
     const size_t rs = (size_t)GD_RING * plan.r_floats;
-    GD_TRY(fb_launch_flow(plan, R.as<float>() + (size_t)ref * plan.r_floats, R.as<float>() + (size_t)cur * plan.r_floats, rs,
+    return fb_launch_flow(plan, R.as<float>() + (size_t)ref * plan.r_floats, R.as<float>() + (size_t)cur * plan.r_floats, rs,
                           batch, flowA.as<float2>(), flowB.as<float2>(), plan.f_float2, split_flow ? &flow_bufs : nullptr, &last_flow,
-                          stream, stats));
+                          stream, stats);
+}
+
+int GeoMaskCore::enqueue_mask_tail()
+{
+    const bool started = frames >= GD_RING;
+    if (!started) {  // warm-up: all-ones mask (:171-175)
+        return launch_fill_u8(mask.as<uint8_t>(), (size_t)batch * n_pad, 1, stream, stats);
+    }
+    const int cur = last_cur_slot, ref = last_ref_slot;
     GD_TRY(launch_mahalanobis(last_flow, plan.f_float2, depth_slot_ptr(ref), depth_slot_ptr(cur), depth_stride_b(),
                               edge.as<uint8_t>() + (size_t)ref * n_pad, edge.as<uint8_t>() + (size_t)cur * n_pad,
                               (size_t)GD_RING * n_pad, has_lut ? lut.as<float2>() : nullptr, w, h, batch, cam,

@@ -1,8 +1,11 @@
 // geomask_core.cuh — device-resident state of `batch` GeoMaskMaker streams (ring buffer of per-image products)
 // and the per-frame sequence AddNewImage / GetNoGMMmask (GD-SLAM src/GeoMaskMaker.cc:167-277, 405-429).
 #pragma once
+#include <memory>
+
 #include "farneback.cuh"
 #include "geomask.cuh"
+#include "getrt.cuh"
 
 namespace gd {
 
@@ -60,6 +63,18 @@ struct GeoMaskCore {
     cudaStream_t edge_stream = nullptr;
     // graph replay of the two launch sequences for stand-alone handles (gd_geomask_*); disabled inside the batched front-end
     GraphCache push_graphs, mask_graphs;
+    // GeoMaskMaker::GetRt as a resident stage (row f-1): cv::ORB features of every pushed frame kept per ring slot, the pair
+    // (t-5, t) matched and back-projected on demand.  Off until enable_getrt().
+    std::unique_ptr<GetRtCore> getrt;
+    float dist_coef[5] = {0, 0, 0, 0, 0};
+    int ndist = 0;
+    long long feat_frame[GD_RING];  // frame number whose features sit in the slot (-1: none)
+    cudaStream_t getrt_stream = nullptr;  // optional side stream for the GetRt chain (the caller forks / joins it)
+    int enable_getrt();
+    int enqueue_getrt_match();            // match + points + D2H of the buffered pair; needs features of both slots
+    bool getrt_pair_ready() const;
+    int enqueue_flow();                   // first half of enqueue_mask(): Farneback of the buffered pair
+    int enqueue_mask_tail();              // second half: Mahalanobis scatter, min/max, normalise + threshold
     int enqueue_push(int slot, bool gray_done);
     int push_resident(bool gray_done = false);
     float* depth_slot_ptr(int slot) { return depth.as<float>() + (size_t)slot * n_pad; }

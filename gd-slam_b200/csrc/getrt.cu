@@ -1,17 +1,26 @@
-// getrt.cu — building blocks of GeoMaskMaker::GetRt (GD-SLAM src/GeoMaskMaker.cc:77-156) for sm_100a, SURVEY 8(f)-1.
-// Built with --fmad=false (integer stages and individually rounded f32).  Only the single-kernel gd_stage_* entry points
-// exist so far; each one is bit-exact against oracle/getrt_proto.py, which is pinned against cv2 4.13:
-//   gd_stage_resize_linear_exact   cv::resize(INTER_LINEAR_EXACT) between cv::ORB pyramid levels
-//   gd_stage_gaussian7_float       cv::GaussianBlur(7x7, sigma 2) as cv::ORB gets it (float separable path: it blurs a submatrix)
-//   gd_stage_harris                HarrisResponses (blockSize 7, k 0.04)
-//   gd_stage_hamming_crosscheck    BFMatcher(NORM_HAMMING, crossCheck = true)::match
-#include "gd_internal.h"
-#include "geomask.cuh"
-#include "orb.cuh"
+// getrt.cu — GeoMaskMaker::GetRt (GD-SLAM src/GeoMaskMaker.cc:77-156) up to solvePnPRansac, resident and batched.
+// Built with --fmad=false (integer stages and individually rounded f32 / f64, like the CPU code it reproduces).
+//
+//   per frame (enqueue_features)   cv::ORB::create(2000, 1.2f, 8, 31, 0, 2)->detectAndCompute(gray)            :82-90
+//     k_resize_linear_exact          pyramid: every level from the previous one, INTER_LINEAR_EXACT (8.8 fixed point)
+//     k_cv_fast_score/nms_levels     cv::FAST(20, nonmax) on every level + per-row corner counts          (orb.cu)
+//     k_getrt_select                 raster-ordered corner list, retainBest(2 N_l) on the FAST response, Harris responses,
+//                                    retainBest(N_l): std::nth_element / std::partition run as libstdc++ runs them, by one
+//                                    thread per (level, stream) on lists in shared memory (stdalgo.cuh)
+//     k_gaussian7_float_levels       the FLOAT separable 7x7 Gaussian cv::ORB's pyramid sub-matrices get
+//     k_cv_describe_sel              IC_Angle + rBRIEF, cv::KeyPoint records in cv::ORB's order         (orb.cu)
+//   per pair (enqueue_match)       features of ring slot t-5 against slot t
+//     k_getrt_nn                     Hamming nearest neighbour in both directions (BFMatcher, crossCheck = true)  :92-94
+//     k_getrt_points                 cross check in query order, std::sort -> first 100 (stdalgo::sort_prefix), undistortPoints,
+//                                    depth look-up, back-projection                                               :95-141
+// The caller gets object points / image pixels and hands them to cv::solvePnPRansac + cv::Rodrigues (:143-150).
+#include "getrt.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <vector>
+
+#include "stdalgo.cuh"
 
 namespace gd {
 
@@ -31,18 +40,21 @@ static void linear_exact_axis_table(int dn, int sn, ushort4* t)
     }
 }
 
-__global__ void __launch_bounds__(256) k_resize_linear_exact(const uint8_t* __restrict__ src, int sw, uint8_t* __restrict__ dst, int dw,
-                                                             int dh, const ushort4* __restrict__ xt, const ushort4* __restrict__ yt)
+// blockIdx.z = stream; src / dst are dense (pitch = width) images at a per-stream stride
+__global__ void __launch_bounds__(256) k_resize_linear_exact(const uint8_t* __restrict__ src, size_t sstride_b, int sw,
+                                                             uint8_t* __restrict__ dst, size_t dstride_b, int dw, int dh,
+                                                             const ushort4* __restrict__ xt, const ushort4* __restrict__ yt)
 {
     const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
     if (dx >= dw || dy >= dh) return;
     const ushort4 X = __ldg(xt + dx), Y = __ldg(yt + dy);
-    const uint8_t* r0 = src + (size_t)Y.x * sw;
-    const uint8_t* r1 = src + (size_t)Y.y * sw;
+    const uint8_t* s = src + (size_t)blockIdx.z * sstride_b;
+    const uint8_t* r0 = s + (size_t)Y.x * sw;
+    const uint8_t* r1 = s + (size_t)Y.y * sw;
     const int h0 = r0[X.x] * (int)X.z + r0[X.y] * (int)X.w;
     const int h1 = r1[X.x] * (int)X.z + r1[X.y] * (int)X.w;
     const int v = (h0 * (int)Y.z + h1 * (int)Y.w + 32768) >> 16;
-    dst[(size_t)dy * dw + dx] = (uint8_t)max(0, min(255, v));
+    dst[(size_t)blockIdx.z * dstride_b + (size_t)dy * dw + dx] = (uint8_t)max(0, min(255, v));
 }
 
 // ------------------------------------------------------------------------------------------------ float Gaussian 7x7
@@ -59,12 +71,19 @@ __device__ __forceinline__ int reflect101_dev(int p, int len)
     return p >= len ? 2 * len - 2 - p : p;
 }
 
-__global__ void __launch_bounds__(GF_W* GF_H) k_gaussian7_float(const uint8_t* __restrict__ src, int w, int h, Gauss7 G,
-                                                                uint8_t* __restrict__ dst)
+// blockIdx = (tile, level, stream); levels dense at lv[l].off of a stream's pyramid
+__global__ void __launch_bounds__(GF_W* GF_H) k_gaussian7_float_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a,
+                                                                       Gauss7 G, uint8_t* __restrict__ out)
 {
+    const CvLevelDev L = a.lv[blockIdx.y];
+    const int tiles_x = (L.w + GF_W - 1) / GF_W, tiles_y = (L.h + GF_H - 1) / GF_H;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    const int w = L.w, h = L.h;
+    const uint8_t* src = pyr + (size_t)blockIdx.z * stride_b + L.off;
+    uint8_t* dst = out + (size_t)blockIdx.z * stride_b + L.off;
     __shared__ float s_in[GF_H + 6][GF_W + 6];
     __shared__ float s_row[GF_H + 6][GF_W];
-    const int x0 = blockIdx.x * GF_W, y0 = blockIdx.y * GF_H;
+    const int x0 = ((int)blockIdx.x % tiles_x) * GF_W, y0 = ((int)blockIdx.x / tiles_x) * GF_H;
     const int tid = threadIdx.y * GF_W + threadIdx.x;
     for (int i = tid; i < (GF_H + 6) * (GF_W + 6); i += GF_W * GF_H) {
         const int ly = i / (GF_W + 6), lx = i - ly * (GF_W + 6);
@@ -91,13 +110,24 @@ __global__ void __launch_bounds__(GF_W* GF_H) k_gaussian7_float(const uint8_t* _
     dst[(size_t)y * w + x] = (uint8_t)max(0, min(255, v));
 }
 
-// ------------------------------------------------------------------------------------------------ Harris responses
-__global__ void __launch_bounds__(128) k_harris(const uint8_t* __restrict__ img, int w, const int* __restrict__ xs,
-                                                const int* __restrict__ ys, int n, float s4, float* __restrict__ out)
+static Gauss7 gauss7_taps()
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t* c = img + (size_t)ys[i] * w + xs[i];
+    Gauss7 G;  // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, then rounded to float
+    double g[7], sum = 0;
+    for (int i = 0; i < 7; ++i) {
+        const double x = i - 3;
+        g[i] = std::exp(-(x * x) / (2.0 * 2.0 * 2.0));
+        sum += g[i];
+    }
+    for (int k = 0; k <= 3; ++k) G.g[k] = (float)(g[3 + k] / sum);
+    return G;
+}
+
+// ------------------------------------------------------------------------------------------------ Harris responses
+// HarrisResponses(blockSize 7, k 0.04) of cv::ORB at an integer level position (at least 4 px from the border)
+__device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int w, int x, int y, float s4)
+{
+    const uint8_t* c = img + (size_t)y * w + x;
     int a = 0, b = 0, cc = 0;
     for (int dy = -3; dy <= 3; ++dy)
         for (int dx = -3; dx <= 3; ++dx) {
@@ -112,65 +142,14 @@ __global__ void __launch_bounds__(128) k_harris(const uint8_t* __restrict__ img,
     float t = fa * fb - fc * fc;  // two products and one difference, each rounded (no FMA in this file)
     const float sab = fa + fb;
     t = t - 0.04f * sab * sab;
-    out[i] = t * s4;
+    return t * s4;
 }
 
-// ------------------------------------------------------------------------------------------------ Hamming nearest neighbour
-// one thread per query descriptor (eight 32-bit words in registers); every thread walks the train set in the same order,
-// so the train words are broadcast loads.  Strict '<' keeps the smallest index among equal distances, like cv::batchDistance.
-__global__ void __launch_bounds__(128) k_hamming_nn(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt,
-                                                    int* __restrict__ nn, int* __restrict__ dist)
+__global__ void __launch_bounds__(128) k_harris(const uint8_t* __restrict__ img, int w, const int* __restrict__ xs,
+                                                const int* __restrict__ ys, int n, float s4, float* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const uint4 a0 = q[2 * i], a1 = q[2 * i + 1];
-    int best = 1 << 30, bi = -1;
-    for (int j = 0; j < nt; ++j) {
-        const uint4 b0 = __ldg(t + 2 * j), b1 = __ldg(t + 2 * j + 1);
-        const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
-                      __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-        if (d < best) { best = d; bi = j; }
-    }
-    nn[i] = bi;
-    dist[i] = best;
-}
-
-
-// cv::KeyPointsFilter::retainBest as OpenCV writes it: std::nth_element + std::partition on the responses.  The order it
-// leaves behind IS the order of cv::ORB's output, so the same libstdc++ routines run here on the same sequence.
-static void retain_best_order(const std::vector<float>& resp, int n_points, std::vector<int>* perm)
-{
-    struct E {
-        float r;
-        int i;
-    };
-    std::vector<E> v(resp.size());
-    for (size_t i = 0; i < resp.size(); ++i) v[i] = {resp[i], (int)i};
-    if (n_points >= 0 && (int)v.size() > n_points) {
-        if (n_points == 0) {
-            perm->clear();
-            return;
-        }
-        std::nth_element(v.begin(), v.begin() + n_points - 1, v.end(), [](const E& a, const E& b) { return a.r > b.r; });
-        const float amb = v[n_points - 1].r;
-        auto e = std::partition(v.begin() + n_points, v.end(), [amb](const E& a) { return a.r >= amb; });
-        v.resize((size_t)(e - v.begin()));
-    }
-    perm->resize(v.size());
-    for (size_t i = 0; i < v.size(); ++i) (*perm)[i] = v[i].i;
-}
-
-static Gauss7 gauss7_taps()
-{
-    Gauss7 G;  // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, then rounded to float
-    double g[7], sum = 0;
-    for (int i = 0; i < 7; ++i) {
-        const double x = i - 3;
-        g[i] = std::exp(-(x * x) / (2.0 * 2.0 * 2.0));
-        sum += g[i];
-    }
-    for (int k = 0; k <= 3; ++k) G.g[k] = (float)(g[3 + k] / sum);
-    return G;
+    if (i < n) out[i] = harris_at(img, w, xs[i], ys[i], s4);
 }
 
 static float harris_scale4()
@@ -182,114 +161,505 @@ static float harris_scale4()
     return s4;
 }
 
-// cv::ORB::create(nfeatures, 1.2f, 8, 31, 0, 2, HARRIS_SCORE, 31, 20)->detectAndCompute on one 8-bit image: pyramid, FAST,
-// Harris, blur, orientation and descriptors on the device; the two retainBest orderings on the host (tiny arrays).
-static int cvorb_detect_and_compute(const uint8_t* gray, int w, int h, int nfeatures, std::vector<gd_keypoint>* kps,
-                                    std::vector<uint8_t>* desc)
+// ------------------------------------------------------------------------------------------------ selection per level
+struct SelLevel {
+    int w, h;
+    unsigned long long off;
+    int row_off;
+    int N;       // features wanted at this level
+    int n1_cap;  // capacity of the raster corner list
+};
+struct SelArgs {
+    int nlevels, edge, n2_cap, sel_cap, n1_cap_max;
+    float s4;
+    SelLevel lv[GETRT_LEVELS];
+};
+struct HarrisEntry {
+    float r;
+    unsigned idx;
+};
+constexpr int SEL_THREADS = 512;
+
+// exclusive scan of data[0..n) by warp 0 (all threads call); returns the total
+__device__ int sel_block_scan(int* data, int n, int* s_total)
 {
-    constexpr int NL = 8, EDGE = 31;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int idx = base + threadIdx.x;
+            const int v = idx < n ? data[idx] : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if ((int)threadIdx.x >= o) x += y;
+            }
+            if (idx < n) data[idx] = carry + x - v;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (threadIdx.x == 0) *s_total = carry;
+    }
+    __syncthreads();
+    return *s_total;
+}
+
+// One CTA per (level, stream): cv::ORB's computeKeyPoints for that level after cv::FAST.
+//   list1 (u32: response << 24 | pixel index)  = the FAST output inside the 31-px border in raster order
+//   retainBest(list1, 2 N) by one thread, Harris responses by all, retainBest(list2, N) by one thread
+__global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ kept,
+                                                              size_t stride_b, const int* __restrict__ rowcnt, size_t rowcnt_stride,
+                                                              SelArgs a, uint2* __restrict__ sel, int* __restrict__ sel_n,
+                                                              int* __restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char sel_sm[];
+    unsigned* list1 = reinterpret_cast<unsigned*>(sel_sm);
+    HarrisEntry* list2 = reinterpret_cast<HarrisEntry*>(sel_sm + (size_t)a.n1_cap_max * 4);
+    int* rowoff = reinterpret_cast<int*>(list2);  // scratch until list2 is filled (h <= 2 * n2_cap ints)
+    __shared__ int s_total, s_n;
+    const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const SelLevel L = a.lv[l];
+    const int edge = a.edge;
+    int* out_n = sel_n + b * a.nlevels + l;
+    if (min(L.w, L.h) <= 2 * edge) {  // cv::ORB skips levels that small
+        if (tid == 0) *out_n = 0;
+        return;
+    }
+    const int rows = L.h - 2 * edge;
+    const int* rc = rowcnt + (size_t)b * rowcnt_stride + L.row_off + edge;
+    for (int r = tid; r < rows; r += SEL_THREADS) rowoff[r] = rc[r];
+    int n1 = sel_block_scan(rowoff, rows, &s_total);
+    if (n1 > L.n1_cap) {
+        if (tid == 0) atomicOr(err, 4);
+        n1 = L.n1_cap;
+    }
+    const uint8_t* kp = kept + (size_t)b * stride_b + L.off;
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < rows; r += SEL_THREADS / 32) {
+            int pos = rowoff[r];
+            const int y = edge + r;
+            for (int x0 = edge; x0 < L.w - edge; x0 += 32) {
+                const int x = x0 + lane;
+                const int v = x < L.w - edge ? (int)kp[(size_t)y * L.w + x] : 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, v > 0);
+                if (v > 0) {
+                    const int p = pos + __popc(bal & ((1u << lane) - 1));
+                    if (p < L.n1_cap) list1[p] = ((unsigned)(v - 1) << 24) | (unsigned)(y * L.w + x);
+                }
+                pos += __popc(bal);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) s_n = stdalgo::retain_best(list1, n1, 2 * L.N, [](unsigned e) { return e >> 24; });
+    __syncthreads();
+    int n2 = s_n;
+    if (n2 > a.n2_cap) {
+        if (tid == 0) atomicOr(err, 8);
+        n2 = a.n2_cap;
+    }
+    const uint8_t* img = pyr + (size_t)b * stride_b + L.off;
+    for (int i = tid; i < n2; i += SEL_THREADS) {
+        const unsigned idx = list1[i] & 0xFFFFFFu;
+        const int y = (int)(idx / (unsigned)L.w), x = (int)(idx - (unsigned)y * L.w);
+        HarrisEntry e;
+        e.r = harris_at(img, L.w, x, y, a.s4);
+        e.idx = idx;
+        list2[i] = e;
+    }
+    __syncthreads();
+    if (tid == 0) s_n = stdalgo::retain_best(list2, n2, L.N, [](const HarrisEntry& e) { return e.r; });
+    __syncthreads();
+    int n3 = s_n;
+    if (n3 > a.sel_cap) {
+        if (tid == 0) atomicOr(err, 16);
+        n3 = a.sel_cap;
+    }
+    uint2* so = sel + ((size_t)b * a.nlevels + l) * a.sel_cap;
+    for (int i = tid; i < n3; i += SEL_THREADS) so[i] = make_uint2(list2[i].idx, __float_as_uint(list2[i].r));
+    if (tid == 0) *out_n = n3;
+}
+
+// ------------------------------------------------------------------------------------------------ Hamming nearest neighbour
+// blockIdx = (query tile, direction, stream).  direction 0: queries = ref features, train = cur features; 1: the reverse.
+// One thread per query descriptor (eight words in registers); the train set goes through shared memory in tiles of 128.
+// Strict '<' keeps the smallest train index among equal distances, like cv::batchDistance.
+constexpr int NN_THREADS = 128;
+__global__ void __launch_bounds__(NN_THREADS) k_getrt_nn(const uint4* __restrict__ desc_ref, const uint4* __restrict__ desc_cur,
+                                                         const int* __restrict__ n_ref, const int* __restrict__ n_cur, int feat_cap,
+                                                         int* __restrict__ nn, int* __restrict__ dd)
+{
+    __shared__ uint4 tile[NN_THREADS * 2];
+    const int b = blockIdx.z, dir = blockIdx.y;
+    const int nq = min(dir == 0 ? n_ref[b] : n_cur[b], feat_cap), nt = min(dir == 0 ? n_cur[b] : n_ref[b], feat_cap);
+    if ((int)blockIdx.x * NN_THREADS >= nq) return;
+    const uint4* q = (dir == 0 ? desc_ref : desc_cur) + (size_t)b * feat_cap * 2;
+    const uint4* t = (dir == 0 ? desc_cur : desc_ref) + (size_t)b * feat_cap * 2;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (i < nq) {
+        a0 = q[2 * i];
+        a1 = q[2 * i + 1];
+    }
+    int best = 1 << 30, bi = -1;
+    for (int base = 0; base < nt; base += NN_THREADS) {
+        const int m = min(NN_THREADS, nt - base);
+        __syncthreads();
+        if ((int)threadIdx.x < m) {
+            tile[2 * threadIdx.x] = t[2 * (base + threadIdx.x)];
+            tile[2 * threadIdx.x + 1] = t[2 * (base + threadIdx.x) + 1];
+        }
+        __syncthreads();
+        for (int j = 0; j < m; ++j) {
+            const uint4 b0 = tile[2 * j], b1 = tile[2 * j + 1];
+            const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+                          __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            if (d < best) {
+                best = d;
+                bi = base + j;
+            }
+        }
+    }
+    if (i < nq) {
+        nn[((size_t)b * 2 + dir) * feat_cap + i] = bi;
+        dd[((size_t)b * 2 + dir) * feat_cap + i] = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ matches -> points
+struct PointArgs {
+    int w, h, feat_cap;
+    int distorted;
+    double fx, fy, cx, cy;  // (double) of the f32 K
+    double k[5];            // k1 k2 p1 p2 k3
+    float Ki[9];            // inv(K) in f32
+};
+struct MatchEntry {
+    float d;
+    int i;
+};
+constexpr int PT_THREADS = 256;
+
+// cv::undistortPoints(pt, K, D, noArray(), K) for one float point: normalise, 5 fixed-point iterations, re-project (f64)
+__device__ __forceinline__ void undistort_point(const PointArgs& a, float u, float v, float* ou, float* ov)
+{
+    const double ifx = 1.0 / a.fx, ify = 1.0 / a.fy;
+    double x = ((double)u - a.cx) * ifx, y = ((double)v - a.cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1 + ((a.k[4] * r2 + a.k[1]) * r2 + a.k[0]) * r2);
+        if (icdist < 0) {
+            x = ((double)u - a.cx) * ifx;
+            y = ((double)v - a.cy) * ify;
+            break;
+        }
+        const double dX = 2 * a.k[2] * x * y + a.k[3] * (r2 + 2 * x * x);
+        const double dY = a.k[2] * (r2 + 2 * y * y) + 2 * a.k[3] * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    *ou = (float)(a.fx * x + a.cx);
+    *ov = (float)(a.fy * y + a.cy);
+}
+
+// One CTA per stream.  Matches come out of BFMatcher ordered by query index; GetRt sorts them (std::sort on the distance,
+// unstable) and keeps the first 100; points whose depth is zero are dropped (GeoMaskMaker.cc:95-141).
+__global__ void __launch_bounds__(PT_THREADS) k_getrt_points(const gd_keypoint* __restrict__ kp_ref, const gd_keypoint* __restrict__ kp_cur,
+                                                             const int* __restrict__ n_ref, const int* __restrict__ n_cur,
+                                                             const int* __restrict__ nn, const int* __restrict__ dd,
+                                                             const float* __restrict__ depth_ref, size_t depth_stride_b, PointArgs a,
+                                                             float* __restrict__ out_obj, float* __restrict__ out_pix,
+                                                             int* __restrict__ out_cnt)
+{
+    extern __shared__ __align__(16) unsigned char pt_sm[];
+    MatchEntry* ms = reinterpret_cast<MatchEntry*>(pt_sm);            // [feat_cap]
+    int* mq = reinterpret_cast<int*>(pt_sm + (size_t)a.feat_cap * 8);  // [feat_cap] query index of match i
+    __shared__ int s_warp[PT_THREADS / 32], s_base, s_valid[GETRT_TOP];
+    __shared__ float s_obj[GETRT_TOP][3], s_pix[GETRT_TOP][2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n1 = min(n_ref[b], a.feat_cap), n2 = min(n_cur[b], a.feat_cap);
+    const int* nn0 = nn + ((size_t)b * 2 + 0) * a.feat_cap;
+    const int* nn1 = nn + ((size_t)b * 2 + 1) * a.feat_cap;
+    const int* dd0 = dd + ((size_t)b * 2 + 0) * a.feat_cap;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n1; base += PT_THREADS) {  // cross check, order preserving compaction
+        const int q = base + tid;
+        bool ok = false;
+        int t = -1;
+        if (q < n1 && n2 > 0) {
+            t = nn0[q];
+            ok = t >= 0 && t < n2 && nn1[t] == q;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < PT_THREADS / 32; ++w2) {
+            if (w2 < warp) woff += s_warp[w2];
+            tot += s_warp[w2];
+        }
+        if (ok) {
+            const int m = s_base + woff + __popc(bal & ((1u << lane) - 1));
+            ms[m].d = (float)dd0[q];
+            ms[m].i = m;
+            mq[m] = q;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    const int nm = s_base;
+    if (tid == 0 && nm > 0)
+        stdalgo::sort_prefix(ms, ms + nm, (long)GETRT_TOP, [](const MatchEntry& x, const MatchEntry& y) { return x.d < y.d; });
+    __syncthreads();
+    // the reference takes begin() + 100 unconditionally (:97); with fewer matches that is undefined there, all of them here
+    const int ntop = min(nm, GETRT_TOP);
+    if (tid < GETRT_TOP) {
+        int valid = 0;
+        if (tid < ntop) {
+            const int q = mq[ms[tid].i], t = nn0[q];
+            const gd_keypoint k1 = kp_ref[(size_t)b * a.feat_cap + q];
+            const gd_keypoint k2 = kp_cur[(size_t)b * a.feat_cap + t];
+            float ux, uy;
+            undistort_point(a, k1.x, k1.y, &ux, &uy);  // :104-110 (D = 0: returns the point itself)
+            const int dx = (int)ux, dy = (int)uy;      // :122-123
+            if (dx >= 0 && dy >= 0 && dx < a.w && dy < a.h) {
+                const float depth = depth_ref[(size_t)b * depth_stride_b + (size_t)dy * a.w + dx];
+                if (depth != 0.f) {                    // :125-128
+                    valid = 1;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {      // (inv(K) * [x y 1]^T) * depth, f32 gemm of inner length 3 (:133)
+                        float v = a.Ki[3 * c] * ux;
+                        v = v + a.Ki[3 * c + 1] * uy;
+                        v = v + a.Ki[3 * c + 2] * 1.0f;
+                        s_obj[tid][c] = v * depth;
+                    }
+                    s_pix[tid][0] = k2.x;              // :139
+                    s_pix[tid][1] = k2.y;
+                }
+            }
+        }
+        s_valid[tid] = valid;
+    }
+    __syncthreads();
+    if (tid == 0) {  // 100 flags: a serial prefix is cheaper than another scan
+        int n = 0;
+        for (int r = 0; r < GETRT_TOP; ++r) {
+            const int v = s_valid[r];
+            s_valid[r] = v ? n : -1;
+            n += v;
+        }
+        out_cnt[b] = n;
+    }
+    __syncthreads();
+    if (tid < GETRT_TOP && s_valid[tid] >= 0) {
+        const int o = s_valid[tid];
+        for (int c = 0; c < 3; ++c) out_obj[((size_t)b * GETRT_TOP + o) * 3 + c] = s_obj[tid][c];
+        out_pix[((size_t)b * GETRT_TOP + o) * 2] = s_pix[tid][0];
+        out_pix[((size_t)b * GETRT_TOP + o) * 2 + 1] = s_pix[tid][1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GetRtCore
+int GetRtCore::init(const float K[9], const float* dist_coef, int ndist, int width, int height, int device_, int batch_, int ring_slots,
+                    int nfeatures_)
+{
+    GD_REQUIRE(nfeatures_ >= 8 && nfeatures_ <= 8192, "nfeatures out of range");
+    nfeatures = nfeatures_;
+    GD_REQUIRE(width >= 2 * GETRT_EDGE + 8 && height >= 2 * GETRT_EDGE + 8 && batch_ >= 1 && ring_slots >= 1, "bad size / batch");
+    GD_REQUIRE((long long)width * height < (1ll << 24), "image too large for the 24-bit pixel index of the corner lists");
+    GD_TRY(select_device(device_));
+    device = device_;
+    batch = batch_;
+    w = width;
+    h = height;
+    ring = ring_slots;
+    make_cam_const(K, &cam);
+    Kd[0] = (double)K[0]; Kd[1] = (double)K[4]; Kd[2] = (double)K[2]; Kd[3] = (double)K[5];
+    for (int i = 0; i < 5; ++i) dist[i] = 0.0;
+    distorted = false;
+    for (int i = 0; i < ndist && i < 5 && dist_coef; ++i) {
+        dist[i] = (double)dist_coef[i];
+        distorted = distorted || dist_coef[i] != 0.f;
+    }
+    // cv::ORB: features per level (geometric series, last level takes the remainder), level sizes from the float scale
     const float sf = 1.2f;
-    int nper[NL];
     {
         const double factor = 1.0 / (double)sf;
-        double nd = nfeatures * (1 - factor) / (1 - std::pow(factor, (double)NL));
+        double nd = nfeatures * (1 - factor) / (1 - std::pow(factor, (double)GETRT_LEVELS));
         int sum = 0;
-        for (int l = 0; l < NL - 1; ++l) {
+        for (int l = 0; l < GETRT_LEVELS - 1; ++l) {
             nper[l] = (int)std::nearbyint(nd);
             sum += nper[l];
             nd *= factor;
         }
-        nper[NL - 1] = std::max(nfeatures - sum, 0);
+        nper[GETRT_LEVELS - 1] = std::max(nfeatures - sum, 0);
     }
-    const Gauss7 G = gauss7_taps();
-    const float s4 = harris_scale4();
-    DevBuf lvl[NL], blur, score, kept, dx, dy, dresp, dang, ddesc, tab;
-    int lw[NL], lh[NL];
-    float scale[NL];
-    lw[0] = w; lh[0] = h; scale[0] = 1.0f;
-    GD_TRY(lvl[0].alloc((size_t)w * h));
-    GD_TRY(blur.alloc((size_t)w * h));
-    GD_TRY(score.alloc((size_t)w * h));
-    GD_TRY(kept.alloc((size_t)w * h));
-    GD_CUDA(cudaMemcpy(lvl[0].p, gray, (size_t)w * h, cudaMemcpyHostToDevice));
-    std::vector<uint8_t> hk((size_t)w * h);
-    kps->clear();
-    desc->clear();
-    for (int l = 0; l < NL; ++l) {
+    pyr_args.nlevels = GETRT_LEVELS;
+    size_t off = 0;
+    int rows = 0, max_n = 0;
+    std::vector<ushort4> tab;
+    for (int l = 0; l < GETRT_LEVELS; ++l) {
+        CvLevelDev& L = pyr_args.lv[l];
+        L.scale = l == 0 ? 1.0f : (float)std::pow((double)sf, (double)l);
+        L.w = l == 0 ? w : (int)std::nearbyint((float)w / L.scale);
+        L.h = l == 0 ? h : (int)std::nearbyint((float)h / L.scale);
+        GD_REQUIRE(L.w >= 8 && L.h >= 8, "image too small for the 8-level cv::ORB pyramid");
+        L.off = off;
+        off += align_up((size_t)L.w * L.h, 256);
+        L.row_off = rows;
+        rows += L.h;
+        max_n = std::max(max_n, nper[l]);
         if (l > 0) {
-            scale[l] = (float)std::pow((double)sf, (double)l);
-            lw[l] = (int)std::nearbyint((float)w / scale[l]);
-            lh[l] = (int)std::nearbyint((float)h / scale[l]);
-            if (lw[l] < 2 || lh[l] < 2) break;
-            GD_TRY(lvl[l].alloc((size_t)lw[l] * lh[l]));
-            std::vector<ushort4> t((size_t)lw[l] + lh[l]);
-            linear_exact_axis_table(lw[l], lw[l - 1], t.data());
-            linear_exact_axis_table(lh[l], lh[l - 1], t.data() + lw[l]);
-            GD_TRY(tab.alloc(t.size() * sizeof(ushort4)));
-            GD_CUDA(cudaMemcpy(tab.p, t.data(), t.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
-            k_resize_linear_exact<<<dim3(cdiv(lw[l], 32), cdiv(lh[l], 8)), dim3(32, 8)>>>(lvl[l - 1].as<uint8_t>(), lw[l - 1], lvl[l].as<uint8_t>(),
-                                                                                    lw[l], lh[l], tab.as<ushort4>(), tab.as<ushort4>() + lw[l]);
+            tab_x[l] = (int)tab.size();
+            tab.resize(tab.size() + L.w);
+            linear_exact_axis_table(L.w, pyr_args.lv[l - 1].w, tab.data() + tab_x[l]);
+            tab_y[l] = (int)tab.size();
+            tab.resize(tab.size() + L.h);
+            linear_exact_axis_table(L.h, pyr_args.lv[l - 1].h, tab.data() + tab_y[l]);
+        }
+    }
+    pyr_bytes = off;
+    rows_total = rows;
+    // capacities: the NMS map has no two 8-adjacent corners -> at most a quarter of the interior pixels; bounded by what one
+    // CTA's shared memory holds (an overflow is reported through the error flag, never silently)
+    n1_cap = 0;
+    for (int l = 0; l < GETRT_LEVELS; ++l) {
+        const CvLevelDev& L = pyr_args.lv[l];
+        const long long interior = (long long)std::max(0, L.w - 2 * GETRT_EDGE) * std::max(0, L.h - 2 * GETRT_EDGE);
+        n1_cap = std::max<long long>(n1_cap, std::min<long long>((interior + 3) / 4 + 32, 36864));
+    }
+    n2_cap = 2 * max_n + 4096;
+    sel_cap = max_n + 64;
+    feat_cap = (int)align_up((size_t)nfeatures + 256, 128);
+    select_smem = (size_t)n1_cap * 4 + (size_t)n2_cap * 8;
+    GD_REQUIRE(select_smem <= 200 * 1024 && 2 * n2_cap >= h, "selection kernel's shared memory plan does not fit");
+    GD_CUDA(cudaFuncSetAttribute(k_getrt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)select_smem));
+    GD_REQUIRE((size_t)feat_cap * 12 <= 48 * 1024, "match list larger than the default shared memory");
+    const size_t B = (size_t)batch;
+    GD_TRY(pyr.alloc(B * pyr_bytes));
+    GD_TRY(score.alloc(B * pyr_bytes));
+    GD_TRY(kept.alloc(B * pyr_bytes));
+    GD_TRY(blur.alloc(B * pyr_bytes));
+    GD_TRY(rowcnt.alloc(B * rows_total * sizeof(int)));
+    GD_TRY(tabs.alloc(std::max<size_t>(1, tab.size()) * sizeof(ushort4)));
+    GD_TRY(sel.alloc(B * GETRT_LEVELS * sel_cap * sizeof(uint2)));
+    GD_TRY(sel_n.alloc(B * GETRT_LEVELS * sizeof(int)));
+    GD_TRY(feat_kp.alloc((size_t)ring * B * feat_cap * sizeof(gd_keypoint)));
+    GD_TRY(feat_desc.alloc((size_t)ring * B * feat_cap * 32));
+    GD_TRY(feat_n.alloc((size_t)ring * B * sizeof(int)));
+    GD_TRY(nn.alloc(B * 2 * feat_cap * sizeof(int)));
+    GD_TRY(dd.alloc(B * 2 * feat_cap * sizeof(int)));
+    GD_TRY(out_obj.alloc(B * GETRT_TOP * 3 * sizeof(float)));
+    GD_TRY(out_pix.alloc(B * GETRT_TOP * 2 * sizeof(float)));
+    GD_TRY(out_cnt.alloc((B + 1) * sizeof(int)));
+    GD_TRY(err.alloc(sizeof(int)));
+    GD_TRY(h_out.alloc(B * GETRT_TOP * 5 * sizeof(float) + (B + 1) * sizeof(int)));
+    GD_CUDA(cudaMemcpy(tabs.p, tab.data(), tab.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
+    GD_CUDA(cudaMemset(feat_n.p, 0, feat_n.bytes));
+    GD_CUDA(cudaMemset(err.p, 0, sizeof(int)));
+    GD_CUDA(cudaMemset(out_cnt.p, 0, out_cnt.bytes));
+    return GD_OK;
+}
+
+int GetRtCore::enqueue_features(const uint8_t* gray, size_t gray_stride_b, int slot)
+{
+    GD_REQUIRE(slot >= 0 && slot < ring, "ring slot out of range");
+    const cudaStream_t s = stream;
+    uint8_t* py = pyr.as<uint8_t>();
+    {
+        LaunchScope ls(stats, s, "G1_cvorb_pyramid", GETRT_LEVELS - 1);
+        GD_CUDA(cudaMemcpy2DAsync(py, pyr_bytes, gray, gray_stride_b, (size_t)w * h, batch, cudaMemcpyDeviceToDevice, s));
+        const ushort4* t = tabs.as<ushort4>();
+        for (int l = 1; l < GETRT_LEVELS; ++l) {
+            const CvLevelDev& S = pyr_args.lv[l - 1];
+            const CvLevelDev& D = pyr_args.lv[l];
+            k_resize_linear_exact<<<dim3(cdiv(D.w, 32), cdiv(D.h, 8), batch), dim3(32, 8), 0, s>>>(py + S.off, pyr_bytes, S.w, py + D.off, pyr_bytes,
+                                                                                              D.w, D.h, t + tab_x[l], t + tab_y[l]);
             GD_CUDA(cudaGetLastError());
         }
-        const int W = lw[l], H = lh[l];
-        if (std::min(W, H) <= 2 * EDGE) continue;
-        const uint8_t* img = lvl[l].as<uint8_t>();
-        GD_TRY(orb_fast_whole(img, W, H, W, 20, score.as<uint8_t>(), kept.as<uint8_t>(), 0));
-        GD_CUDA(cudaMemcpy(hk.data(), kept.p, (size_t)W * H, cudaMemcpyDeviceToHost));
-        // raster-ordered FAST output inside the 31-px border (KeyPointsFilter::runByImageBorder), response = S' - 1
-        std::vector<int> xs, ys;
-        std::vector<float> resp;
-        for (int y = EDGE; y < H - EDGE; ++y)
-            for (int x = EDGE; x < W - EDGE; ++x)
-                if (hk[(size_t)y * W + x]) {
-                    xs.push_back(x);
-                    ys.push_back(y);
-                    resp.push_back((float)(hk[(size_t)y * W + x] - 1));
-                }
-        std::vector<int> perm;
-        retain_best_order(resp, 2 * nper[l], &perm);
-        std::vector<int> x2(perm.size()), y2(perm.size());
-        for (size_t i = 0; i < perm.size(); ++i) { x2[i] = xs[perm[i]]; y2[i] = ys[perm[i]]; }
-        const int n2 = (int)perm.size();
-        if (n2 == 0) continue;
-        GD_TRY(dx.alloc(sizeof(int) * n2));
-        GD_TRY(dy.alloc(sizeof(int) * n2));
-        GD_TRY(dresp.alloc(sizeof(float) * n2));
-        GD_CUDA(cudaMemcpy(dx.p, x2.data(), sizeof(int) * n2, cudaMemcpyHostToDevice));
-        GD_CUDA(cudaMemcpy(dy.p, y2.data(), sizeof(int) * n2, cudaMemcpyHostToDevice));
-        k_harris<<<cdiv(n2, 128), 128>>>(img, W, dx.as<int>(), dy.as<int>(), n2, s4, dresp.as<float>());
-        GD_CUDA(cudaGetLastError());
-        std::vector<float> hr((size_t)n2);
-        GD_CUDA(cudaMemcpy(hr.data(), dresp.p, sizeof(float) * n2, cudaMemcpyDeviceToHost));
-        retain_best_order(hr, nper[l], &perm);
-        const int n3 = (int)perm.size();
-        if (n3 == 0) continue;
-        std::vector<int> x3(n3), y3(n3);
-        for (int i = 0; i < n3; ++i) { x3[i] = x2[perm[i]]; y3[i] = y2[perm[i]]; }
-        GD_CUDA(cudaMemcpy(dx.p, x3.data(), sizeof(int) * n3, cudaMemcpyHostToDevice));
-        GD_CUDA(cudaMemcpy(dy.p, y3.data(), sizeof(int) * n3, cudaMemcpyHostToDevice));
-        k_gaussian7_float<<<dim3(cdiv(W, GF_W), cdiv(H, GF_H)), dim3(GF_W, GF_H)>>>(img, W, H, G, blur.as<uint8_t>());
-        GD_CUDA(cudaGetLastError());
-        GD_TRY(dang.alloc(sizeof(float) * n3));
-        GD_TRY(ddesc.alloc((size_t)32 * n3));
-        GD_TRY(orb_cv_describe(img, blur.as<uint8_t>(), W, dx.as<int>(), dy.as<int>(), n3, dang.as<float>(), ddesc.as<uint8_t>(), 0));
-        std::vector<float> ang((size_t)n3);
-        const size_t d0 = desc->size();
-        desc->resize(d0 + (size_t)32 * n3);
-        GD_CUDA(cudaMemcpy(ang.data(), dang.p, sizeof(float) * n3, cudaMemcpyDeviceToHost));
-        GD_CUDA(cudaMemcpy(desc->data() + d0, ddesc.p, (size_t)32 * n3, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < n3; ++i) {
-            gd_keypoint k;
-            k.x = (float)x3[i] * scale[l];
-            k.y = (float)y3[i] * scale[l];
-            k.size = 31.0f * scale[l];
-            k.angle = ang[i];
-            k.response = hr[perm[i]];
-            k.octave = l;
-            k.class_id = -1;
-            kps->push_back(k);
-        }
     }
+    {
+        LaunchScope ls(stats, s, "G2_cvorb_fast", 2);
+        GD_CUDA(cudaMemsetAsync(rowcnt.p, 0, rowcnt.bytes, s));
+        GD_TRY(orb_cv_fast_levels(py, pyr_bytes, pyr_args, batch, 20, GETRT_EDGE, score.as<uint8_t>(), kept.as<uint8_t>(), rowcnt.as<int>(),
+                                  (size_t)rows_total, s));
+    }
+    {
+        LaunchScope ls(stats, s, "G3_cvorb_select", 1);
+        SelArgs a;
+        a.nlevels = GETRT_LEVELS;
+        a.edge = GETRT_EDGE;
+        a.n2_cap = n2_cap;
+        a.sel_cap = sel_cap;
+        a.n1_cap_max = n1_cap;
+        a.s4 = harris_scale4();
+        for (int l = 0; l < GETRT_LEVELS; ++l) {
+            const CvLevelDev& L = pyr_args.lv[l];
+            const long long interior = (long long)std::max(0, L.w - 2 * GETRT_EDGE) * std::max(0, L.h - 2 * GETRT_EDGE);
+            a.lv[l] = {L.w, L.h, L.off, L.row_off, nper[l], (int)std::min<long long>((interior + 3) / 4 + 32, n1_cap)};
+        }
+        k_getrt_select<<<dim3(GETRT_LEVELS, batch), SEL_THREADS, select_smem, s>>>(py, kept.as<uint8_t>(), pyr_bytes, rowcnt.as<int>(),
+                                                                               (size_t)rows_total, a, sel.as<uint2>(), sel_n.as<int>(),
+                                                                               err.as<int>());
+        GD_CUDA(cudaGetLastError());
+    }
+    {
+        LaunchScope ls(stats, s, "G4_cvorb_blur", 1);
+        int tiles = 0;
+        for (int l = 0; l < GETRT_LEVELS; ++l) tiles = std::max(tiles, cdiv(pyr_args.lv[l].w, GF_W) * cdiv(pyr_args.lv[l].h, GF_H));
+        k_gaussian7_float_levels<<<dim3(tiles, GETRT_LEVELS, batch), dim3(GF_W, GF_H), 0, s>>>(py, pyr_bytes, pyr_args, gauss7_taps(),
+                                                                                          blur.as<uint8_t>());
+        GD_CUDA(cudaGetLastError());
+    }
+    {
+        LaunchScope ls(stats, s, "G5_cvorb_describe", 1);
+        GD_TRY(orb_cv_describe_sel(py, blur.as<uint8_t>(), pyr_bytes, pyr_args, batch, sel.as<uint2>(), sel_cap, sel_n.as<int>(), slot_kp(slot),
+                                   slot_desc(slot), slot_n(slot), feat_cap, s));
+    }
+    return GD_OK;
+}
+
+int GetRtCore::enqueue_match(int ref_slot, int cur_slot, const float* depth_ref, size_t depth_stride_b)
+{
+    GD_REQUIRE(ref_slot >= 0 && ref_slot < ring && cur_slot >= 0 && cur_slot < ring && depth_ref, "bad argument");
+    const cudaStream_t s = stream;
+    {
+        LaunchScope ls(stats, s, "G6_match", 1);
+        k_getrt_nn<<<dim3(cdiv(feat_cap, NN_THREADS), 2, batch), NN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(slot_desc(ref_slot)),
+                                                                                  reinterpret_cast<const uint4*>(slot_desc(cur_slot)),
+                                                                                  slot_n(ref_slot), slot_n(cur_slot), feat_cap, nn.as<int>(),
+                                                                                  dd.as<int>());
+        GD_CUDA(cudaGetLastError());
+    }
+    {
+        LaunchScope ls(stats, s, "G7_points", 1);
+        PointArgs a;
+        a.w = w; a.h = h; a.feat_cap = feat_cap; a.distorted = distorted ? 1 : 0;
+        a.fx = Kd[0]; a.fy = Kd[1]; a.cx = Kd[2]; a.cy = Kd[3];
+        for (int i = 0; i < 5; ++i) a.k[i] = dist[i];
+        for (int i = 0; i < 9; ++i) a.Ki[i] = cam.Ki[i];
+        k_getrt_points<<<batch, PT_THREADS, (size_t)feat_cap * 12, s>>>(slot_kp(ref_slot), slot_kp(cur_slot), slot_n(ref_slot), slot_n(cur_slot),
+                                                                      nn.as<int>(), dd.as<int>(), depth_ref, depth_stride_b, a,
+                                                                      out_obj.as<float>(), out_pix.as<float>(), out_cnt.as<int>());
+        GD_CUDA(cudaGetLastError());
+    }
+    return GD_OK;
+}
+
+int GetRtCore::enqueue_fetch()
+{
+    const cudaStream_t s = stream;
+    const size_t B = (size_t)batch;
+    float* hp = h_out.as<float>();
+    GD_CUDA(cudaMemcpyAsync(hp, out_obj.p, B * GETRT_TOP * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    GD_CUDA(cudaMemcpyAsync(hp + B * GETRT_TOP * 3, out_pix.p, B * GETRT_TOP * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    GD_CUDA(cudaMemcpyAsync(hp + B * GETRT_TOP * 5, out_cnt.p, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    GD_CUDA(cudaMemcpyAsync(reinterpret_cast<int*>(hp + B * GETRT_TOP * 5) + B, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     return GD_OK;
 }
 
@@ -297,6 +667,7 @@ static int cvorb_detect_and_compute(const uint8_t* gray, int w, int h, int nfeat
 
 using namespace gd;
 
+// ------------------------------------------------------------------------------------------------ stage entry points
 extern "C" {
 
 int gd_stage_resize_linear_exact(int device, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh)
@@ -312,8 +683,8 @@ int gd_stage_resize_linear_exact(int device, const uint8_t* src, int sw, int sh,
     GD_TRY(t.alloc(tab.size() * sizeof(ushort4)));
     GD_CUDA(cudaMemcpy(s.p, src, (size_t)sw * sh, cudaMemcpyHostToDevice));
     GD_CUDA(cudaMemcpy(t.p, tab.data(), tab.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
-    k_resize_linear_exact<<<dim3(cdiv(dw, 32), cdiv(dh, 8)), dim3(32, 8)>>>(s.as<uint8_t>(), sw, d.as<uint8_t>(), dw, dh, t.as<ushort4>(),
-                                                                          t.as<ushort4>() + dw);
+    k_resize_linear_exact<<<dim3(cdiv(dw, 32), cdiv(dh, 8), 1), dim3(32, 8)>>>(s.as<uint8_t>(), 0, sw, d.as<uint8_t>(), 0, dw, dh, t.as<ushort4>(),
+                                                                             t.as<ushort4>() + dw);
     GD_CUDA(cudaGetLastError());
     GD_CUDA(cudaMemcpy(dst, d.p, (size_t)dw * dh, cudaMemcpyDeviceToHost));
     return GD_OK;
@@ -323,21 +694,14 @@ int gd_stage_gaussian7_float(int device, const uint8_t* src, int w, int h, uint8
 {
     GD_REQUIRE(src && dst && w > 3 && h > 3, "bad argument");
     GD_TRY(select_device(device));
-    Gauss7 G;
-    {  // getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised in double, then rounded to float
-        double g[7], sum = 0;
-        for (int i = 0; i < 7; ++i) {
-            const double x = i - 3;
-            g[i] = std::exp(-(x * x) / (2.0 * 2.0 * 2.0));
-            sum += g[i];
-        }
-        for (int k = 0; k <= 3; ++k) G.g[k] = (float)(g[3 + k] / sum);
-    }
     DevBuf s, d;
     GD_TRY(s.alloc((size_t)w * h));
     GD_TRY(d.alloc((size_t)w * h));
     GD_CUDA(cudaMemcpy(s.p, src, (size_t)w * h, cudaMemcpyHostToDevice));
-    k_gaussian7_float<<<dim3(cdiv(w, GF_W), cdiv(h, GF_H)), dim3(GF_W, GF_H)>>>(s.as<uint8_t>(), w, h, G, d.as<uint8_t>());
+    CvPyrArgs a;
+    a.nlevels = 1;
+    a.lv[0] = {w, h, 0ull, 0, 1.0f};
+    k_gaussian7_float_levels<<<dim3(cdiv(w, GF_W) * cdiv(h, GF_H), 1, 1), dim3(GF_W, GF_H)>>>(s.as<uint8_t>(), 0, a, gauss7_taps(), d.as<uint8_t>());
     GD_CUDA(cudaGetLastError());
     GD_CUDA(cudaMemcpy(dst, d.p, (size_t)w * h, cudaMemcpyDeviceToHost));
     return GD_OK;
@@ -349,10 +713,6 @@ int gd_stage_harris(int device, const uint8_t* img, int w, int h, const int* xs,
     GD_TRY(select_device(device));
     if (n == 0) return GD_OK;
     for (int i = 0; i < n; ++i) GD_REQUIRE(xs[i] >= 4 && ys[i] >= 4 && xs[i] < w - 4 && ys[i] < h - 4, "keypoint too close to the border");
-    float scale = 1.0f / (float)((1 << 2) * 7 * 255.0f);
-    volatile float s4 = scale * scale;  // (s * s * s * s) as three individually rounded products
-    s4 = s4 * scale;
-    s4 = s4 * scale;
     DevBuf im, dx, dy, o;
     GD_TRY(im.alloc((size_t)w * h));
     GD_TRY(dx.alloc(sizeof(int) * n));
@@ -361,33 +721,37 @@ int gd_stage_harris(int device, const uint8_t* img, int w, int h, const int* xs,
     GD_CUDA(cudaMemcpy(im.p, img, (size_t)w * h, cudaMemcpyHostToDevice));
     GD_CUDA(cudaMemcpy(dx.p, xs, sizeof(int) * n, cudaMemcpyHostToDevice));
     GD_CUDA(cudaMemcpy(dy.p, ys, sizeof(int) * n, cudaMemcpyHostToDevice));
-    k_harris<<<cdiv(n, 128), 128>>>(im.as<uint8_t>(), w, dx.as<int>(), dy.as<int>(), n, s4, o.as<float>());
+    k_harris<<<cdiv(n, 128), 128>>>(im.as<uint8_t>(), w, dx.as<int>(), dy.as<int>(), n, harris_scale4(), o.as<float>());
     GD_CUDA(cudaGetLastError());
     GD_CUDA(cudaMemcpy(out, o.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
     return GD_OK;
 }
 
+// BFMatcher(NORM_HAMMING, crossCheck = true)->match on two host descriptor sets: the matching kernel of the resident stage
+// (both directions) + the cross check in query order on the host
 int gd_stage_hamming_crosscheck(int device, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int* query_idx, int* train_idx,
                                 int* distance, int capacity, int* n_matches)
 {
     GD_REQUIRE(d1 && d2 && query_idx && train_idx && distance && n_matches && n1 > 0 && n2 > 0, "bad argument");
     GD_TRY(select_device(device));
-    DevBuf a, b, nn12, nn21, dd12, dd21;
-    GD_TRY(a.alloc((size_t)n1 * 32));
-    GD_TRY(b.alloc((size_t)n2 * 32));
-    GD_TRY(nn12.alloc(sizeof(int) * n1));
-    GD_TRY(dd12.alloc(sizeof(int) * n1));
-    GD_TRY(nn21.alloc(sizeof(int) * n2));
-    GD_TRY(dd21.alloc(sizeof(int) * n2));
+    const int cap = std::max(n1, n2);
+    DevBuf a, b, cnt, dnn, ddd;
+    GD_TRY(a.alloc((size_t)cap * 32));
+    GD_TRY(b.alloc((size_t)cap * 32));
+    GD_TRY(cnt.alloc(2 * sizeof(int)));
+    GD_TRY(dnn.alloc(sizeof(int) * 2 * cap));
+    GD_TRY(ddd.alloc(sizeof(int) * 2 * cap));
     GD_CUDA(cudaMemcpy(a.p, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice));
     GD_CUDA(cudaMemcpy(b.p, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice));
-    k_hamming_nn<<<cdiv(n1, 128), 128>>>(a.as<uint4>(), n1, b.as<uint4>(), n2, nn12.as<int>(), dd12.as<int>());
-    k_hamming_nn<<<cdiv(n2, 128), 128>>>(b.as<uint4>(), n2, a.as<uint4>(), n1, nn21.as<int>(), dd21.as<int>());
+    const int hn[2] = {n1, n2};
+    GD_CUDA(cudaMemcpy(cnt.p, hn, sizeof(hn), cudaMemcpyHostToDevice));
+    k_getrt_nn<<<dim3(cdiv(cap, NN_THREADS), 2, 1), NN_THREADS>>>(a.as<uint4>(), b.as<uint4>(), cnt.as<int>(), cnt.as<int>() + 1, cap, dnn.as<int>(),
+                                                                 ddd.as<int>());
     GD_CUDA(cudaGetLastError());
     std::vector<int> h12(n1), hd(n1), h21(n2);
-    GD_CUDA(cudaMemcpy(h12.data(), nn12.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));
-    GD_CUDA(cudaMemcpy(hd.data(), dd12.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));
-    GD_CUDA(cudaMemcpy(h21.data(), nn21.p, sizeof(int) * n2, cudaMemcpyDeviceToHost));
+    GD_CUDA(cudaMemcpy(h12.data(), dnn.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));
+    GD_CUDA(cudaMemcpy(hd.data(), ddd.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));
+    GD_CUDA(cudaMemcpy(h21.data(), dnn.as<int>() + cap, sizeof(int) * n2, cudaMemcpyDeviceToHost));
     int m = 0;  // cross check, ordered by query index like BFMatcher returns them
     for (int q = 0; q < n1; ++q) {
         const int t = h12[q];
@@ -405,71 +769,63 @@ int gd_stage_hamming_crosscheck(int device, const uint8_t* d1, int n1, const uin
     return GD_OK;
 }
 
-
+// cv::ORB(2000, 1.2, 8, 31, 0, 2)->detectAndCompute of one host image through the resident stage (ring of one slot)
 int gd_stage_cvorb_detect_and_compute(int device, const uint8_t* gray, int w, int h, int nfeatures, gd_keypoint* kps, uint8_t* desc,
                                       int capacity, int* n)
 {
-    GD_REQUIRE(gray && kps && desc && n && w > 0 && h > 0 && nfeatures > 0, "bad argument");
+    GD_REQUIRE(gray && kps && desc && n && w > 0 && h > 0, "bad argument");
     GD_TRY(select_device(device));
-    std::vector<gd_keypoint> k;
-    std::vector<uint8_t> d;
-    GD_TRY(cvorb_detect_and_compute(gray, w, h, nfeatures, &k, &d));
-    *n = (int)k.size();
-    GD_REQUIRE(*n <= capacity, "keypoint capacity too small");
-    std::memcpy(kps, k.data(), sizeof(gd_keypoint) * k.size());
-    std::memcpy(desc, d.data(), d.size());
+    const float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    GetRtCore c;
+    GD_TRY(c.init(K, nullptr, 0, w, h, device, 1, 1, nfeatures));
+    DevBuf g;
+    GD_TRY(g.alloc((size_t)w * h));
+    GD_CUDA(cudaMemcpy(g.p, gray, (size_t)w * h, cudaMemcpyHostToDevice));
+    GD_TRY(c.enqueue_features(g.as<uint8_t>(), (size_t)w * h, 0));
+    GD_CUDA(cudaDeviceSynchronize());
+    int cnt = 0, e = 0;
+    GD_CUDA(cudaMemcpy(&cnt, c.slot_n(0), sizeof(int), cudaMemcpyDeviceToHost));
+    GD_CUDA(cudaMemcpy(&e, c.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e != 0) {
+        set_error("cv::ORB stage: capacity overflow of the selection lists (flags %d)", e);
+        return GD_EINTERNAL;
+    }
+    *n = cnt;
+    GD_REQUIRE(cnt <= capacity, "keypoint capacity too small");
+    GD_CUDA(cudaMemcpy(kps, c.slot_kp(0), sizeof(gd_keypoint) * cnt, cudaMemcpyDeviceToHost));
+    GD_CUDA(cudaMemcpy(desc, c.slot_desc(0), (size_t)32 * cnt, cudaMemcpyDeviceToHost));
     return GD_OK;
 }
 
-
+// GetRt up to solvePnPRansac for one host image pair (ring of two slots)
 int gd_getrt_points(int device, const uint8_t* gray_first, const uint8_t* gray_second, int w, int h, const float* depth_first_m,
                     const float K[9], const float* dist, int ndist, float* object_points, float* image_pixels, int* n_points)
 {
     GD_REQUIRE(gray_first && gray_second && depth_first_m && K && object_points && image_pixels && n_points, "null argument");
-    for (int i = 0; i < ndist; ++i) GD_REQUIRE(!dist || dist[i] == 0.f, "distorted cameras are not built for GetRt yet (undistortPoints on the matches)");
     GD_TRY(select_device(device));
     *n_points = 0;
-    std::vector<gd_keypoint> k1, k2;
-    std::vector<uint8_t> d1, d2;
-    GD_TRY(cvorb_detect_and_compute(gray_first, w, h, 2000, &k1, &d1));    // GeoMaskMaker.cc:82-90
-    GD_TRY(cvorb_detect_and_compute(gray_second, w, h, 2000, &k2, &d2));
-    if (k1.empty() || k2.empty()) return GD_OK;
-    const int n1 = (int)k1.size(), n2 = (int)k2.size();
-    std::vector<int> mq(n1), mt(n1), md(n1);
-    int nm = 0;
-    GD_TRY(gd_stage_hamming_crosscheck(device, d1.data(), n1, d2.data(), n2, mq.data(), mt.data(), md.data(), n1, &nm));  // :92-94
-    // sort(matches.begin(), matches.end()) (:95): DMatch::operator< looks at the distance only; the same libstdc++ introsort
-    // on the same sequence leaves equal distances in the same order as the reference
-    struct M {
-        float d;
-        int i;
-        bool operator<(const M& o) const { return d < o.d; }
-    };
-    std::vector<M> ms((size_t)nm);
-    for (int i = 0; i < nm; ++i) ms[i] = {(float)md[i], i};
-    std::sort(ms.begin(), ms.end());
-    const int ntop = std::min(nm, 100);  // the reference takes begin()+100 unconditionally (:97); fewer matches are undefined there
-    CamConst cam;
-    make_cam_const(K, &cam);
-    int n = 0;
-    for (int r = 0; r < ntop; ++r) {
-        const int i = ms[r].i;
-        const float x = k1[mq[i]].x, y = k1[mq[i]].y;      // undistortPoints with D = 0, P = K is the identity in f32
-        const int dx = (int)x, dy = (int)y;                 // :122-123
-        if (dx < 0 || dy < 0 || dx >= w || dy >= h) continue;
-        const float depth = depth_first_m[(size_t)dy * w + dx];
-        if (depth == 0.f) continue;                         // :125-128
-        for (int c = 0; c < 3; ++c) {                       // (inv(K) * [x y 1]^T) * depth, f32 gemm of inner length 3 (:133)
-            volatile float t = cam.Ki[3 * c] * x;
-            t = t + cam.Ki[3 * c + 1] * y;
-            t = t + cam.Ki[3 * c + 2] * 1.0f;
-            object_points[3 * n + c] = t * depth;
-        }
-        image_pixels[2 * n] = k2[mt[i]].x;                  // :139
-        image_pixels[2 * n + 1] = k2[mt[i]].y;
-        ++n;
+    GetRtCore c;
+    GD_TRY(c.init(K, dist, ndist, w, h, device, 1, 2));
+    DevBuf g, d;
+    const size_t n = (size_t)w * h;
+    GD_TRY(g.alloc(2 * n));
+    GD_TRY(d.alloc(n * sizeof(float)));
+    GD_CUDA(cudaMemcpy(g.p, gray_first, n, cudaMemcpyHostToDevice));
+    GD_CUDA(cudaMemcpy(g.as<uint8_t>() + n, gray_second, n, cudaMemcpyHostToDevice));
+    GD_CUDA(cudaMemcpy(d.p, depth_first_m, n * sizeof(float), cudaMemcpyHostToDevice));
+    GD_TRY(c.enqueue_features(g.as<uint8_t>(), n, 0));
+    GD_TRY(c.enqueue_features(g.as<uint8_t>() + n, n, 1));
+    GD_TRY(c.enqueue_match(0, 1, d.as<float>(), n));
+    GD_TRY(c.enqueue_fetch());
+    GD_CUDA(cudaDeviceSynchronize());
+    if (c.host_err() != 0) {
+        set_error("GetRt stage: capacity overflow of the selection lists (flags %d)", c.host_err());
+        return GD_EINTERNAL;
     }
-    *n_points = n;
+    const int cnt = c.host_cnt()[0];
+    std::memcpy(object_points, c.host_obj(0), sizeof(float) * 3 * cnt);
+    std::memcpy(image_pixels, c.host_pix(0), sizeof(float) * 2 * cnt);
+    *n_points = cnt;
     return GD_OK;
 }
 

@@ -474,6 +474,100 @@ int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_
     return GD_OK;
 }
 
+// ---- the same two kernels over all pyramid levels of `batch` streams in one launch each (resident GetRt stage).
+// Levels are dense (pitch = width) at byte offset lv[l].off inside a stream's pyramid; blockIdx = (tile, level, stream).
+// The NMS kernel also counts, per level row, the surviving corners inside the cv::ORB border (edge <= x < w - edge, same
+// for y: KeyPointsFilter::runByImageBorder): the selection kernel turns the counts into raster-ordered list positions.
+__global__ void __launch_bounds__(256) k_cv_fast_score_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a, int th,
+                                                              uint8_t* __restrict__ score)
+{
+    const CvLevelDev L = a.lv[blockIdx.y];
+    const int tiles_x = (L.w + FW_W - 1) / FW_W, tiles_y = (L.h + FW_H - 1) / FW_H;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    const int w = L.w, h = L.h, pitch = L.w;
+    const uint8_t* img = pyr + (size_t)blockIdx.z * stride_b + L.off;
+    uint8_t* sco = score + (size_t)blockIdx.z * stride_b + L.off;
+    __shared__ __align__(16) uint8_t tile[(FW_H + 6) * FW_P];
+    __shared__ __align__(16) uint8_t sc[FW_H * FW_W];
+    __shared__ unsigned short plist[FW_H * FW_W];
+    __shared__ int s_nlist;
+    const int X0 = FW_W * ((int)blockIdx.x % tiles_x), Y0 = FW_H * ((int)blockIdx.x / tiles_x);
+    const int tid = threadIdx.x;
+    for (int q = tid; q < (FW_H + 6) * FW_P; q += 256) {
+        const int row = q / FW_P, col = q - row * FW_P;
+        const int gy = Y0 - 3 + row, gx = X0 - 4 + col;
+        tile[q] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? img[(size_t)gy * pitch + gx] : (uint8_t)0;
+    }
+    reinterpret_cast<unsigned*>(sc)[tid] = 0u;
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    const int lane = tid & 31;
+#pragma unroll
+    for (int base = 0; base < FW_H * FW_W; base += 256) {
+        const int q = base + tid, ly = q >> 6, lx = q & 63;
+        const int gx = X0 + lx, gy = Y0 + ly;
+        bool qk = gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3;
+        if (qk) qk = fast_quick(tile + (ly + 3) * FW_P + lx + 4, FW_P, th);
+        const unsigned bal = __ballot_sync(0xffffffffu, qk);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)q;
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    for (int e = tid; e < nl; e += 256) {
+        const int q = plist[e], ly = q >> 6, lx = q & 63;
+        const int sv = fast_full(tile + (ly + 3) * FW_P + lx + 4, FW_P);
+        sc[q] = (uint8_t)(sv > th ? sv : 0);
+    }
+    __syncthreads();
+    for (int q = tid; q < FW_H * FW_W; q += 256) {
+        const int ly = q >> 6, lx = q & 63, gx = X0 + lx, gy = Y0 + ly;
+        if (gx < w && gy < h) sco[(size_t)gy * pitch + gx] = sc[q];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cv_fast_nms_levels(const uint8_t* __restrict__ score, size_t stride_b, CvPyrArgs a, int edge,
+                                                            uint8_t* __restrict__ kept, int* __restrict__ rowcnt, size_t rowcnt_stride)
+{
+    const CvLevelDev L = a.lv[blockIdx.y];
+    const int tiles_x = (L.w + 31) / 32, tiles_y = (L.h + 7) / 8;
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    const int w = L.w, h = L.h, pitch = L.w;
+    const int x = ((int)blockIdx.x % tiles_x) * 32 + threadIdx.x, y = ((int)blockIdx.x / tiles_x) * 8 + threadIdx.y;
+    const uint8_t* sco = score + (size_t)blockIdx.z * stride_b + L.off;
+    int out = 0;
+    if (x < w && y < h) {
+        const uint8_t* c = sco + (size_t)y * pitch + x;
+        const int s = c[0];
+        if (s > 0) {  // scored pixels are at least 3 from the border: the 8 neighbours exist
+            const int m0 = max(max(c[-pitch - 1], c[-pitch]), max(c[-pitch + 1], c[-1]));
+            const int m1 = max(max(c[pitch - 1], c[pitch]), max(c[pitch + 1], c[1]));
+            if (max(m0, m1) < s) out = s;
+        }
+        kept[(size_t)blockIdx.z * stride_b + L.off + (size_t)y * pitch + x] = (uint8_t)out;
+    }
+    const bool inside = out > 0 && x >= edge && x < w - edge && y >= edge && y < h - edge;
+    const unsigned bal = __ballot_sync(0xffffffffu, inside);  // one warp = one row segment
+    if (threadIdx.x == 0 && bal) atomicAdd(rowcnt + (size_t)blockIdx.z * rowcnt_stride + L.row_off + y, __popc(bal));
+}
+
+int orb_cv_fast_levels(const uint8_t* pyr, size_t stride_b, const CvPyrArgs& a, int batch, int th, int edge, uint8_t* score,
+                       uint8_t* kept, int* rowcnt, size_t rowcnt_stride, cudaStream_t s)
+{
+    int t_score = 0, t_nms = 0;
+    for (int l = 0; l < a.nlevels; ++l) {
+        t_score = std::max(t_score, cdiv(a.lv[l].w, FW_W) * cdiv(a.lv[l].h, FW_H));
+        t_nms = std::max(t_nms, cdiv(a.lv[l].w, 32) * cdiv(a.lv[l].h, 8));
+    }
+    k_cv_fast_score_levels<<<dim3(t_score, a.nlevels, batch), 256, 0, s>>>(pyr, stride_b, a, th, score);
+    GD_CUDA(cudaGetLastError());
+    k_cv_fast_nms_levels<<<dim3(t_nms, a.nlevels, batch), dim3(32, 8), 0, s>>>(score, stride_b, a, edge, kept, rowcnt, rowcnt_stride);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ K4c quadtree
 // DistributeOctTree restated for one CTA.  The reference keeps a std::list of nodes: every pass of its first loop
 // splits ALL nodes holding more than one key (children are push_front'ed, the parent erased); once another full pass
@@ -1072,6 +1166,95 @@ int orb_cv_describe(const uint8_t* d_img, const uint8_t* d_blur, int pitch, cons
     CvDescArgs a;
     for (int i = 0; i <= ORB_HALF; ++i) a.umax[i] = umax[i];
     k_cvorb_describe<<<cdiv(n, 8), 256, 0, s>>>(d_img, d_blur, pitch, d_xs, d_ys, n, a, d_angle, d_desc);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// IC_Angle + steered BRIEF for the keypoints the GetRt selection kernel kept (all levels, all streams, one launch): record g
+// of a stream = the g-th entry of the level-ordered concatenation of the per-level lists sel[level][0 .. sel_n[level]).
+// sel entry: .x = y * w + x at the level, .y = bits of the Harris response.  Output = cv::KeyPoint records in cv::ORB's
+// order (pt scaled to level 0, size 31 * scale, octave) and 32-byte descriptors.
+__global__ void __launch_bounds__(256) k_cv_describe_sel(const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, size_t stride_b,
+                                                         CvPyrArgs a, CvDescArgs da, const uint2* __restrict__ sel, int sel_cap,
+                                                         const int* __restrict__ sel_n, gd_keypoint* __restrict__ out_kp,
+                                                         uint8_t* __restrict__ out_desc, int* __restrict__ out_n, int feat_cap)
+{
+    const int lane = threadIdx.x & 31, b = blockIdx.y;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int l = -1, within = 0, total = 0;
+    for (int q = 0; q < a.nlevels; ++q) {
+        const int c = min(sel_n[b * a.nlevels + q], sel_cap);
+        if (l < 0 && g < total + c) {
+            l = q;
+            within = g - total;
+        }
+        total += c;
+    }
+    if (g == 0 && lane == 0) out_n[b] = min(total, feat_cap);
+    if (l < 0 || g >= feat_cap) return;
+    const CvLevelDev L = a.lv[l];
+    const uint2 e = sel[((size_t)b * a.nlevels + l) * sel_cap + within];
+    const int y = (int)(e.x / (unsigned)L.w), x = (int)(e.x - (unsigned)y * L.w), pitch = L.w;
+    const uint8_t* center = pyr + (size_t)b * stride_b + L.off + (size_t)y * pitch + x;
+    int m01 = 0, m10 = 0;
+    const int u = lane - ORB_HALF;
+    if (lane < 2 * ORB_HALF + 1) {
+        m10 = u * center[u];
+        const int au = abs(u);
+#pragma unroll
+        for (int v = 1; v <= ORB_HALF; ++v) {
+            if (au <= da.umax[v]) {
+                const int vp = center[u + v * pitch], vm = center[u - v * pitch];
+                m01 += v * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    const float angle = fast_atan2_dev((float)m01, (float)m10);
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ar = angle * factorPI;
+    const float ca = (float)cos((double)ar), sa = (float)sin((double)ar);
+    const uint8_t* bc = blur + (size_t)b * stride_b + L.off + (size_t)y * pitch + x;
+    int val = 0;
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2);
+    const int4 q1 = __ldg(reinterpret_cast<const int4*>(d_pattern) + lane * 2 + 1);
+    const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int wd = words[k];
+        const float x0 = (float)(signed char)(wd & 0xff), y0 = (float)(signed char)((wd >> 8) & 0xff),
+                    x1 = (float)(signed char)((wd >> 16) & 0xff), y1 = (float)(signed char)((wd >> 24) & 0xff);
+        const int t0 = bc[__float2int_rn(x0 * sa + y0 * ca) * pitch + __float2int_rn(x0 * ca - y0 * sa)];
+        const int t1 = bc[__float2int_rn(x1 * sa + y1 * ca) * pitch + __float2int_rn(x1 * ca - y1 * sa)];
+        val |= (t0 < t1) << k;
+    }
+    out_desc[((size_t)b * feat_cap + g) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        gd_keypoint k;
+        k.x = (float)x * L.scale;  // cv::ORB: pt *= scale for every level (scale of level 0 is 1)
+        k.y = (float)y * L.scale;
+        k.size = 31.0f * L.scale;
+        k.angle = angle;
+        k.response = __uint_as_float(e.y);
+        k.octave = l;
+        k.class_id = -1;
+        out_kp[(size_t)b * feat_cap + g] = k;
+    }
+}
+
+int orb_cv_describe_sel(const uint8_t* pyr, const uint8_t* blur, size_t stride_b, const CvPyrArgs& a, int batch, const uint2* sel,
+                        int sel_cap, const int* sel_n, gd_keypoint* out_kp, uint8_t* out_desc, int* out_n, int feat_cap, cudaStream_t s)
+{
+    static const int umax[ORB_HALF + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:456-469
+    CvDescArgs da;
+    for (int i = 0; i <= ORB_HALF; ++i) da.umax[i] = umax[i];
+    k_cv_describe_sel<<<dim3(cdiv(feat_cap, 8), batch), 256, 0, s>>>(pyr, blur, stride_b, a, da, sel, sel_cap, sel_n, out_kp, out_desc, out_n,
+                                                                    feat_cap);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

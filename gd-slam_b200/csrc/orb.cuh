@@ -90,4 +90,24 @@ int orb_cv_describe(const uint8_t* d_img, const uint8_t* d_blur, int pitch, cons
 // cv::FAST(th, nonmax) on a whole image (cv::ORB per level, GetRt): kept[y][x] = S' at surviving corners, else 0
 int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_t* d_score, uint8_t* d_kept, cudaStream_t s);
 
+// ---- batched cv::ORB blocks of the resident GetRt stage (getrt.cu): dense pyramid levels (pitch = width)
+struct CvLevelDev {
+    int w, h;
+    unsigned long long off;  // byte offset of the level inside one stream's pyramid
+    int row_off;             // offset of the level's rows inside the per-stream row-count array
+    float scale;             // (float)pow((double)1.2f, level)
+};
+struct CvPyrArgs {
+    int nlevels;
+    CvLevelDev lv[8];
+};
+// cv::FAST(th, nonmax) on every level of every stream: score map, then the NMS map (S' at surviving corners) and, per level
+// row, the number of survivors inside the `edge` border (rowcnt must be zero on entry)
+int orb_cv_fast_levels(const uint8_t* pyr, size_t stride_b, const CvPyrArgs& a, int batch, int th, int edge, uint8_t* score,
+                       uint8_t* kept, int* rowcnt, size_t rowcnt_stride, cudaStream_t s);
+// orientation + descriptors + cv::KeyPoint records for the selected keypoints (sel[b][level][sel_cap]: .x = y * w + x, .y = bits
+// of the Harris response), concatenated level by level
+int orb_cv_describe_sel(const uint8_t* pyr, const uint8_t* blur, size_t stride_b, const CvPyrArgs& a, int batch, const uint2* sel,
+                        int sel_cap, const int* sel_n, gd_keypoint* out_kp, uint8_t* out_desc, int* out_n, int feat_cap, cudaStream_t s);
+
 }  // namespace gd

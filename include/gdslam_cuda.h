@@ -53,7 +53,7 @@ extern "C" {
 #define GD_ECAPACITY (-5) /* an output buffer given by the caller is too small (results clamped, counts set) */
 #define GD_EINTERNAL (-6) /* an internal device-side capacity bound was exceeded (results truncated; reported once) */
 
-#define GD_ABI_VERSION 1
+#define GD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GD_API __attribute__((visibility("default")))
@@ -105,6 +105,12 @@ GD_API int gd_geomask_mask(gd_geomask_t* h, const float* R, const float* T, cons
                     size_t mask_step);
 /* number of frames pushed so far (image_count analogue) */
 GD_API int gd_geomask_frames(const gd_geomask_t* h);
+/* GeoMaskMaker::GetRt (GeoMaskMaker.cc:77-141) for the buffered pair (t-5, t): after gd_geomask_enable_getrt every pushed frame
+ * also gets its cv::ORB features (cached per ring slot); gd_geomask_getrt_points matches the pair and returns, per stream, the
+ * objectPoints (up to 100 x 3 floats) and imagePixels (100 x 2) of solvePnPRansac (:148) and their number.  The frames of the
+ * pair must have been pushed after the stage was enabled. */
+GD_API int gd_geomask_enable_getrt(gd_geomask_t* h);
+GD_API int gd_geomask_getrt_points(gd_geomask_t* h, float* const* object_points, float* const* image_pixels, int* n_points);
 
 /* intermediate products of the LAST gd_geomask_mask call of stream `stream`, for parity tests */
 enum gd_debug_what {
@@ -149,6 +155,7 @@ typedef struct gd_frontend_config {
     int orb_gray_order; /* 1: RGB2GRAY on the BGR bytes (Camera.RGB=1, Tracking.cc:219-225); 0: BGR2GRAY */
     int kp_capacity;    /* per-stream keypoint capacity of the result buffers (>= nfeatures + 3*nlevels) */
     int staged_slots;   /* number of device-resident input slots for gd_frontend_stage (0 = none) */
+    int getrt;          /* 1: run GeoMaskMaker::GetRt's feature / matching half (GeoMaskMaker.cc:77-141) as a stage of every step */
 } gd_frontend_config;
 
 GD_API int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg);
@@ -184,6 +191,19 @@ GD_API int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps,
  * keypoint indices of each cell in increasing order.  All output arrays must hold kp_capacity entries. */
 GD_API int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* depth, float* const* uright,
                                          int* const* cell_start, int* const* cell_items);
+/* SURVEY section 8 row (f)-1 — GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156) as a resident stage (config.getrt = 1): every
+ * step computes cv::ORB(2000, 1.2, 8, 31, 0, 2) features of the new frame once (kept per ring slot), matches them against the
+ * frame five steps back (BFMatcher NORM_HAMMING, crossCheck), sorts, keeps the first 100, undistorts, looks the depth up and
+ * back-projects: exactly the objectPoints / imagePixels the reference hands to cv::solvePnPRansac (:148).  That call and
+ * cv::Rodrigues stay with the caller (GD-SLAM links OpenCV):
+ *   - gd_frontend_fetch_getrt returns the points of the last step (up to 100 x 3 / 100 x 2 floats per stream; n_points[b] = 0
+ *     during the warm-up); GetRt returns false when n_points < 20 (:143-146);
+ *   - with a pose hook installed, a step called with R == NULL and T == NULL asks the hook for the pose of every stream with
+ *     at least 20 points (return non-zero when R (row-major 3x3) and T were written; zero = "no pose" = all-ones mask). */
+typedef int (*gd_pose_hook_fn)(void* user, int stream, const float* object_points, const float* image_pixels, int n_points,
+                               float R[9], float T[3]);
+GD_API int gd_frontend_set_pose_hook(gd_frontend_t* h, gd_pose_hook_fn hook, void* user);
+GD_API int gd_frontend_fetch_getrt(gd_frontend_t* h, float* const* object_points, float* const* image_pixels, int* n_points);
 GD_API int gd_frontend_sync(gd_frontend_t* h);
 /* CUDA-event timing on the handle's own stream: begin records an event, end records + synchronises and returns ms */
 GD_API int gd_frontend_timer_begin(gd_frontend_t* h);
@@ -223,18 +243,20 @@ GD_API int gd_stage_fast_cells(int device, const uint8_t* gray, int w, int h, in
 /* GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of an 8-bit image (ORBextractor.cc:1086) */
 GD_API int gd_stage_gaussian7(int device, const uint8_t* gray, int w, int h, uint8_t* out);
 
-/* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1: single kernels with host buffers,
- * each bit-exact against the cv2-pinned restatement oracle/getrt_proto.py.  The GetRt entry point itself is not built yet. */
-/* Everything GeoMaskMaker::GetRt does before solvePnPRansac (GeoMaskMaker.cc:82-141) for an undistorted camera: cv::ORB features
- * of both gray images and the Hamming cross-check matcher on the device, the reference's sort / first-100 / depth look-up /
- * back-projection on the host.  object_points: up to 100 x 3 floats (metres, first camera), image_pixels: up to 100 x 2 floats
- * (second image), in the reference's order.  GetRt then returns false when *n_points < 20 (:143-146) and otherwise calls
- * cv::solvePnPRansac(objectPoints, imagePixels, K, D, rvec, T) + cv::Rodrigues (:148-150), which stay in the caller. */
+/* ---- building blocks of GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156), SURVEY 8(f)-1, with host buffers: each bit-exact
+ * against the cv2-pinned restatement oracle/getrt_proto.py.  They run the kernels of the resident stage (gd_frontend getrt /
+ * gd_geomask_getrt_points) on a temporary one-stream instance. */
+/* Everything GeoMaskMaker::GetRt does before solvePnPRansac (GeoMaskMaker.cc:82-141) for one host image pair: cv::ORB features
+ * of both gray images, the Hamming cross-check matcher, the reference's sort / first-100 selection, undistortPoints (dist:
+ * k1 k2 p1 p2 [k3], may be all zero or NULL), depth look-up and back-projection, all on the device.  object_points: up to
+ * 100 x 3 floats (metres, first camera), image_pixels: up to 100 x 2 floats (second image), in the reference's order.  GetRt then
+ * returns false when *n_points < 20 (:143-146) and otherwise calls cv::solvePnPRansac(objectPoints, imagePixels, K, D, rvec, T) +
+ * cv::Rodrigues (:148-150), which stay in the caller. */
 GD_API int gd_getrt_points(int device, const uint8_t* gray_first, const uint8_t* gray_second, int w, int h, const float* depth_first_m,
                            const float K[9], const float* dist, int ndist, float* object_points, float* image_pixels, int* n_points);
 /* cv::ORB::create(nfeatures, 1.2f, 8, 31, 0, 2)->detectAndCompute(gray) of GeoMaskMaker.cc:82-90: keypoints (cv::KeyPoint layout) and
- * 32-byte descriptors in OpenCV's own order.  Pyramid, FAST, Harris, blur, orientation, descriptors on the device; the two
- * KeyPointsFilter::retainBest orderings (std::nth_element) on the host */
+ * 32-byte descriptors in OpenCV's own order.  Pyramid, FAST, the two KeyPointsFilter::retainBest orderings (libstdc++'s
+ * std::nth_element / std::partition restated for one device thread), Harris, blur, orientation, descriptors: all on the device */
 GD_API int gd_stage_cvorb_detect_and_compute(int device, const uint8_t* gray, int w, int h, int nfeatures, gd_keypoint* kps,
                                              uint8_t* desc, int capacity, int* n);
 /* cv::FAST(threshold, nonmaxSuppression) on a whole 8-bit image as cv::ORB runs it per level: kept[y*w+x] = S' (= response + 1)

@@ -158,19 +158,25 @@ def bf_match_hamming_crosscheck(d1: np.ndarray, d2: np.ndarray):
     return [(q, int(t), int(dist[q, t])) for q, t in enumerate(nn12) if nn21[t] == q]
 
 
-def back_project_matches(matches, kp1_xy, kp2_xy, depth1, K, ntop=100, sort_order=None):
-    """GeoMaskMaker.cc:95-141 for an undistorted camera: the `ntop` best matches (sort_order = pyoracle.sort_matches_order
-    gives the reference's std::sort order, otherwise a stable order), depth of the first image at the truncated pixel,
-    K^-1 [x y 1] * d in f32."""
+def back_project_matches(matches, kp1_xy, kp2_xy, depth1, K, ntop=100, sort_order=None, undistort=None):
+    """GeoMaskMaker.cc:95-141: the `ntop` best matches (sort_order = pyoracle.sort_matches_order gives the reference's
+    std::sort order, otherwise a stable order), undistortPoints on the first image's points (undistort: callable on an
+    (n, 2) f32 array = cv2.undistortPoints(pts, K, D, None, K); None = undistorted camera, where it is the identity in f32),
+    depth of the first image at the truncated pixel, K^-1 [x y 1] * d in f32."""
     if sort_order is not None:
         order = [int(i) for i in sort_order(np.asarray([m[2] for m in matches], np.float32))][:ntop]
     else:
         order = sorted(range(len(matches)), key=lambda i: (matches[i][2], i))[:ntop]
     Ki = np.linalg.inv(K.astype(np.float64)).astype(f32)  # cv::Mat::inv of a 3x3 f32: f64 cofactors (oracle gdo_inv3_f32)
     obj, pix = [], []
-    for i in order:
+    pts = np.array([[kp1_xy[matches[i][0]][0], kp1_xy[matches[i][0]][1]] for i in order], f32).reshape(-1, 2)
+    if undistort is not None and len(pts):
+        pts = np.asarray(undistort(pts), f32).reshape(-1, 2)
+    for r, i in enumerate(order):
         q, t, _ = matches[i]
-        x, y = f32(kp1_xy[q][0]), f32(kp1_xy[q][1])
+        x, y = f32(pts[r][0]), f32(pts[r][1])
+        if not (0 <= int(x) < depth1.shape[1] and 0 <= int(y) < depth1.shape[0]):
+            continue  # outside the image after undistortion: the reference would read out of bounds
         d = depth1[int(y), int(x)]
         if d == 0:
             continue

@@ -20,7 +20,7 @@ def test_header_symbols_all_exported_and_bound():
     unbound = [n for n in names if n not in capi.SYMBOLS]
     assert not unbound, unbound
     assert capi.missing_symbols() == []
-    assert L.gd_abi_version() == 1
+    assert L.gd_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -42,6 +42,33 @@ def test_depth_edge_bit_exact(capi, oracle, synth, pair, golden):
     assert np.array_equal(capi.stage_depth_edge(sub, K), oracle.depth_edge(sub, K))
 
 
+def test_depth_edge_interval_kernel_hard_cases(capi, oracle, synth, monkeypatch):
+    """The f32 interval kernel must hand every pixel it cannot decide to the exact f64 evaluation: surfaces whose
+    thres_edge sits right at 0.04 (a depth step swept across the threshold, plus noise), full resolution, both kernels."""
+    K = synth.intrinsics()
+    rs = np.random.RandomState(3)
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float32)
+    base = (1.0 + 0.0005 * xx + 0.0003 * yy).astype(np.float32)
+    # vertical stripes: every 8 columns a depth step growing from 3.0 cm to 5.0 cm down the image -> crosses 0.04 m
+    step = (0.030 + 0.020 * yy / 479.0).astype(np.float32)
+    d = (base + step * ((xx // 8) % 2)).astype(np.float32)
+    d += (rs.rand(480, 640).astype(np.float32) - 0.5) * 2e-4
+    d[100:110, 200:260] = 0.0       # holes
+    d[300:320, 50:80] = 3.6         # beyond the 3.5 m cut
+    d = np.round(d * 5000.0).astype(np.uint16).astype(np.float32) * np.float32(1.0 / 5000.0)
+    ref = oracle.depth_edge(d, K)
+    assert 0.05 < (ref == 255).mean() < 0.95
+    assert np.array_equal(capi.stage_depth_edge(d, K), ref)
+    monkeypatch.setenv("GD_EDGE_F64", "1")
+    assert np.array_equal(capi.stage_depth_edge(d, K), ref)
+    monkeypatch.delenv("GD_EDGE_F64")
+    # unquantised depth (arbitrary f32 values) and a tiny focal length (large error bound -> many undecided pixels)
+    d2 = (base + step * ((xx // 8) % 2) + (rs.rand(480, 640).astype(np.float32) - 0.5) * 1e-3).astype(np.float32)
+    assert np.array_equal(capi.stage_depth_edge(d2, K), oracle.depth_edge(d2, K))
+    K2 = np.array([[40.0, 0, 320.0], [0, 40.0, 240.0], [0, 0, 1]], np.float32)
+    assert np.array_equal(capi.stage_depth_edge(d2, K2), oracle.depth_edge(d2, K2))
+
+
 def test_mahalanobis_scatter_vs_oracle(capi, oracle, synth, pair):
     s, f0, f5 = pair
     K = synth.intrinsics()

@@ -150,5 +150,112 @@ def test_getrt_points_entry_point_and_final_pose(capi, proto, oracle, synth):
     assert np.array_equal(obj, seen["obj"]) and np.array_equal(pix, seen["pix"])
     R, T = solve(obj, pix, K)
     assert np.array_equal(np.asarray(R, np.float32), R_ref) and np.array_equal(np.asarray(T, np.float32).reshape(3), T_ref)
-    with pytest.raises(capi.GdError):  # distorted cameras: not built yet, rejected loudly
-        capi.getrt_points(g0, g5, f0.depth_m, K, np.array([0.1, 0, 0, 0], np.float32))
+
+
+def test_getrt_points_distorted_camera(capi, proto, oracle, synth):
+    """TUM1-like distortion: undistortPoints on the 100 matched points of the first image (GeoMaskMaker.cc:104-110), then the
+    depth look-up at the undistorted pixel.  Reference = the GPU features / matches (pinned above) + cv2.undistortPoints."""
+    import cv2
+
+    s = synth.SyntheticStream(1)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    D = np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)
+    g0, g5 = oracle.gray(f0.bgr, 0), oracle.gray(f5.bgr, 0)
+    k1, d1 = capi.stage_cvorb_detect_and_compute(g0, 2000)
+    k2, d2 = capi.stage_cvorb_detect_and_compute(g5, 2000)
+    m = capi.stage_hamming_crosscheck(d1, d2)
+
+    def und(p):
+        return cv2.undistortPoints(p.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+
+    obj_r, pix_r = proto.back_project_matches(m, list(zip(k1["x"], k1["y"])), list(zip(k2["x"], k2["y"])), f0.depth_m, K, 100,
+                                              oracle.sort_matches_order, undistort=und)
+    obj_p, _ = proto.back_project_matches(m, list(zip(k1["x"], k1["y"])), list(zip(k2["x"], k2["y"])), f0.depth_m, K, 100,
+                                          oracle.sort_matches_order)
+    for dist in (D, D[:4]):
+        obj, pix = capi.getrt_points(g0, g5, f0.depth_m, K, dist)
+        if len(dist) == 5:
+            assert len(obj) >= 20 and np.array_equal(obj, obj_r) and np.array_equal(pix, pix_r)
+            assert not np.array_equal(obj, obj_p[: len(obj)])  # the distortion does move the points
+        else:
+            und4 = lambda p: cv2.undistortPoints(p.reshape(-1, 1, 2), K, D[:4], None, K).reshape(-1, 2)  # noqa: E731
+            o4, p4 = proto.back_project_matches(m, list(zip(k1["x"], k1["y"])), list(zip(k2["x"], k2["y"])), f0.depth_m, K, 100,
+                                                oracle.sort_matches_order, undistort=und4)
+            assert np.array_equal(obj, o4) and np.array_equal(pix, p4)
+
+
+def test_getrt_resident_stage_in_the_frontend(capi, oracle, synth):
+    """config.getrt: every step computes the new frame's cv::ORB features once (ring-slot cache), matches against the frame five
+    steps back and returns the solvePnPRansac inputs.  They must equal the two-image entry point (which extracts both images)
+    for every stream of a batch, over more steps than the ring is deep, with graph replay and plain launches; with a pose hook
+    the mask equals the one computed from the same pose passed in."""
+    import cv2
+
+    K = synth.intrinsics()
+    B, NF = 3, 14
+    streams = [synth.SyntheticStream(s) for s in range(B)]
+    frames = [[st.frame(f) for f in range(NF)] for st in streams]
+    grays = [[oracle.gray(fr.bgr, 0) for fr in fs] for fs in frames]
+    fe = capi.Frontend(K, 640, 480, batch=B, getrt=True)         # batch <= 8: CUDA graph replay after two ring cycles
+    ref = capi.Frontend(K, 640, 480, batch=B)                     # no GetRt stage: masks from the pose passed in
+    hooked = capi.Frontend(K, 640, 480, batch=B, getrt=True)
+    poses = {}
+
+    def solve(stream, obj, pix):
+        ok, rvec, tvec, _ = cv2.solvePnPRansac(obj, pix, K, np.zeros((4, 1), np.float32))
+        if not ok:
+            return None
+        R, T = cv2.Rodrigues(rvec)[0].astype(np.float32), tvec.astype(np.float32).reshape(3)
+        poses[stream] = (R, T)
+        return R, T
+
+    hooked.set_pose_hook(solve)
+    for f in range(NF):
+        bgr = [frames[b][f].bgr for b in range(B)]
+        dep = [frames[b][f].depth_m for b in range(B)]
+        res = fe.step(bgr, dep)                                   # identity pose: only the GetRt points matter here
+        pts = fe.fetch_getrt()
+        poses.clear()
+        res_h = [(m.copy(), k.copy(), d.copy()) for m, k, d in hooked.step(bgr, dep, use_hook=True)]
+        for b in range(B):
+            if f < 5:
+                assert len(pts[b][0]) == 0
+                assert res_h[b][0].min() == 1                      # warm-up: all ones
+                continue
+            obj, pix = capi.getrt_points(grays[b][f - 5], grays[b][f], frames[b][f - 5].depth_m, K, np.zeros(4, np.float32))
+            assert len(obj) >= 20
+            assert np.array_equal(pts[b][0], obj) and np.array_equal(pts[b][1], pix), (f, b)
+        if f >= 5:
+            assert sorted(poses) == list(range(B))
+            R = np.stack([poses[b][0] for b in range(B)])
+            T = np.stack([poses[b][1] for b in range(B)])
+        else:
+            R = T = None
+        res_r = ref.step(bgr, dep, R, T)
+        for b in range(B):
+            assert np.array_equal(res_h[b][0], res_r[b][0]), (f, b)
+            assert np.array_equal(res_h[b][1], res_r[b][1]) and np.array_equal(res_h[b][2], res_r[b][2])
+            assert np.array_equal(res[b][1], res_r[b][1])          # ORB unaffected by the extra stage
+        if f >= 5:
+            assert (res_r[0][0] == 0).any()
+    for x in (fe, ref, hooked):
+        x.close()
+
+
+def test_geomask_handle_getrt_points(capi, oracle, synth):
+    """gd_geomask_getrt_points: what the drop-in GeoMaskMaker::GetRt calls before cv::solvePnPRansac."""
+    K = synth.intrinsics()
+    s = synth.SyntheticStream(2)
+    fr = [s.frame(f) for f in range(8)]
+    gm = capi.GeoMask(K, None, 5000.0, 640, 480, 0, batch=1)
+    gm.enable_getrt()
+    for f in range(8):
+        gm.add_new_image([fr[f].bgr], [fr[f].depth_m])
+        obj, pix = gm.getrt_points()[0]
+        if f < 5:
+            assert len(obj) == 0
+            continue
+        o2, p2 = capi.getrt_points(oracle.gray(fr[f - 5].bgr, 0), oracle.gray(fr[f].bgr, 0), fr[f - 5].depth_m, K)
+        assert len(obj) >= 20 and np.array_equal(obj, o2) and np.array_equal(pix, p2), f
+    gm.close()
