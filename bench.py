@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--e2e-handles", type=int, default=4, help="independent handles (host threads) the e2e leg drives per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the 8-streams-in-total (config 4 as written) side measurement")
+    ap.add_argument("--no-getrt", action="store_true", help="skip the side measurement with the GetRt stage enabled")
     ap.add_argument("--quick", action="store_true", help="device-resident leg and kernel profile only (A/B runs of kernel variants)")
     ap.add_argument("--probe-pcie", action="store_true",
                     help="only time bare pinned cudaMemcpyAsync H2D / D2H on all ranks at once and print the rates")
@@ -582,6 +583,36 @@ def main():
                   "ms_per_step": ms_s / K_, "scaling": "strong",
                   "note": "BASELINE configs[3] as written; per-step working set below the L2 size, not flushed"}
 
+    # ---- the same step with GeoMaskMaker::GetRt's GPU half included (cv::ORB features of the new frame, matching against the
+    #      frame five steps back, the 100 solvePnPRansac points fetched to the host); the pose itself is still the given one
+    #      (cv::solvePnPRansac is host OpenCV in the reference and stays with the caller)
+    with_getrt = None
+    if not args.no_getrt and not args.quick:
+        fg = capi.Frontend(K, W, H, batch=B, device=device, staged_slots=S, getrt=True)
+        for s in range(S):
+            fg.stage(s, hb[s], hd[s])
+        for k in range(6 + Wm):
+            fg.step_staged(k % S, Rs[k % S], Ts[k % S])
+        fg.sync()
+        barrier()
+        fg.timer_begin()
+        for k in range(K_):
+            fg.step_staged((6 + Wm + k) % S, Rs[(6 + Wm + k) % S], Ts[(6 + Wm + k) % S])
+        ms_g = max_over_ranks(fg.timer_end())
+        pts = fg.fetch_getrt()
+        npts = [len(p[0]) for p in pts]
+        fg.profile(True)
+        for k in range(2):
+            fg.step_staged((6 + Wm + K_ + k) % S, Rs[(6 + Wm + K_ + k) % S], Ts[(6 + Wm + K_ + k) % S])
+        fg.profile(False)
+        gfam = {n: ms / 2 for n, ms, _ in fg.profile_read() if n.startswith("G")}
+        fg.close()
+        with_getrt = {"value": world * B * K_ / (ms_g * 1e-3), "unit": "frames/s", "ms_per_step": ms_g / K_,
+                      "getrt_ms_per_frame_amortised": (ms_g - ms_total) / K_ / B,
+                      "points_per_stream_min_max": [int(min(npts)), int(max(npts))],
+                      "getrt_kernel_ms_per_step_serialised": gfam,
+                      "note": "GetRt up to solvePnPRansac on the GPU every step (features cached per ring slot); pose = given"}
+
     # ---- per-kernel-family device time (events on the handle's stream, serialised) -> dominant kernel + roofline
     fe.profile(True)
     PSTEPS = 3
@@ -651,6 +682,8 @@ def main():
         out["parity"] = parity
     if strong is not None:
         out["strong_scaling_8_streams"] = strong
+    if with_getrt is not None:
+        out["with_getrt_stage"] = with_getrt
 
     if args.quick:
         out["e2e"]["note"] = "--quick: 2 steps only, not a measurement"

@@ -94,6 +94,8 @@ SYMBOLS = {
     "gd_frontend_fetch_filtered": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), ip]),
     "gd_stage_erode_filter": (C.c_int, [C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "gd_frontend_fetch_stereo_grid": (C.c_int, [vp, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "gd_frontend_fetch_stereo_grid_un": (C.c_int, [vp, C.c_float, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                                   C.POINTER(vp)]),
     "gd_frontend_sync": (C.c_int, [vp]),
     "gd_frontend_timer_begin": (C.c_int, [vp]),
     "gd_frontend_timer_end": (C.c_int, [vp, fp]),
@@ -627,7 +629,10 @@ class Frontend:
         ur = [np.zeros(self.cap, np.float32) for _ in range(B)]
         cs = [np.zeros(64 * 48 + 1, np.int32) for _ in range(B)]
         ci = [np.zeros(self.cap, np.int32) for _ in range(B)]
-        check(lib().gd_frontend_fetch_stereo_grid(self._h, bf, _ptr_array(d), _ptr_array(ur), _ptr_array(cs), _ptr_array(ci)))
+        un = [np.zeros((self.cap, 2), np.float32) for _ in range(B)]
+        check(lib().gd_frontend_fetch_stereo_grid_un(self._h, bf, _ptr_array(d), _ptr_array(ur), _ptr_array(cs), _ptr_array(ci),
+                                                     _ptr_array(un)))
+        self.keys_un = un  # mvKeysUn positions of the filtered keypoints (rows beyond the count are unused)
         return [(d[b], ur[b], cs[b], ci[b][: cs[b][-1]].copy()) for b in range(B)]
 
     def results(self):

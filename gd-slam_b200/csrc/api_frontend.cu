@@ -23,7 +23,7 @@ struct gd_frontend {
     gd::DevBuf staged_depth;  // [slots][B][n_pad] f32
     gd::DevBuf l2_scratch;
     gd::DevBuf raw_depth;  // [B][n_pad] u16 staging of gd_frontend_step_u16
-    gd::DevBuf sg_depth, sg_uright, sg_start, sg_items;  // row f-3 outputs
+    gd::DevBuf sg_depth, sg_uright, sg_start, sg_items, sg_un;  // row f-3 outputs
     bool filtered_ready = false;
     gd::DevBuf keep, filt_kp, filt_desc, filt_n;  // Frame-ctor filter (row f-2): [B][cap] flags / records, [B] counts
     gd::PinnedBuf h_n;
@@ -514,6 +514,12 @@ int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_
 int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* depth, float* const* uright, int* const* cell_start,
                                   int* const* cell_items)
 {
+    return gd_frontend_fetch_stereo_grid_un(h, bf, depth, uright, cell_start, cell_items, nullptr);
+}
+
+int gd_frontend_fetch_stereo_grid_un(gd_frontend_t* h, float bf, float* const* depth, float* const* uright, int* const* cell_start,
+                                     int* const* cell_items, float* const* keys_un)
+{
     GD_REQUIRE(h, "null handle");
     GD_TRY(select_device(h->cfg.device));
     GD_REQUIRE(h->filtered_ready, "call gd_frontend_fetch_filtered first");
@@ -526,11 +532,14 @@ int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* dept
         GD_TRY(h->sg_uright.alloc(B * cap * sizeof(float)));
         GD_TRY(h->sg_start.alloc(B * ncell * sizeof(int)));
         GD_TRY(h->sg_items.alloc(B * cap * sizeof(int)));
+        GD_TRY(h->sg_un.alloc(B * cap * sizeof(float2)));
     }
+    UndistortArgs und;
+    make_undistort_args(h->cfg.K, h->cfg.dist, h->cfg.ndist, &und);
     const int cur = (g.frames - 1) % GD_RING;  // depth image of the newest frame
     GD_TRY(launch_stereo_grid(g.depth_slot_ptr(cur), g.depth_stride_b(), g.w, g.h, g.batch, h->filt_kp.as<gd_keypoint>(), cap,
-                              h->filt_n.as<int>(), bf, h->sg_depth.as<float>(), h->sg_uright.as<float>(), h->sg_start.as<int>(),
-                              h->sg_items.as<int>(), h->stream, &h->stats));
+                              h->filt_n.as<int>(), bf, und, h->sg_depth.as<float>(), h->sg_uright.as<float>(), h->sg_start.as<int>(),
+                              h->sg_items.as<int>(), h->sg_un.as<float2>(), h->stream, &h->stats));
     const int ucap = h->cfg.kp_capacity > 0 ? std::min(h->cfg.kp_capacity, o.plan.kp_capacity) : o.plan.kp_capacity;
     for (int b = 0; b < g.batch; ++b) {
         if (depth && depth[b])
@@ -541,6 +550,8 @@ int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* dept
             GD_CUDA(cudaMemcpyAsync(cell_start[b], h->sg_start.as<int>() + (size_t)b * ncell, sizeof(int) * ncell, cudaMemcpyDeviceToHost, h->stream));
         if (cell_items && cell_items[b])
             GD_CUDA(cudaMemcpyAsync(cell_items[b], h->sg_items.as<int>() + (size_t)b * cap, sizeof(int) * ucap, cudaMemcpyDeviceToHost, h->stream));
+        if (keys_un && keys_un[b])
+            GD_CUDA(cudaMemcpyAsync(keys_un[b], h->sg_un.as<float2>() + (size_t)b * cap, sizeof(float2) * ucap, cudaMemcpyDeviceToHost, h->stream));
     }
     GD_CUDA(cudaStreamSynchronize(h->stream));
     return GD_OK;

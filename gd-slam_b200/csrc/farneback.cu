@@ -1143,9 +1143,11 @@ int fb_prepare_flow_buffers(const FbPlan& plan, int batch, float* M0, float* M1,
     fb->fuse_next = M1 != nullptr && whole_batch && env_flag("GD_FLOW_NEXT", 1) != 0;
     fb->box_f32 = env_flag("GD_FLOW_BOX_F64", 0) == 0;
     fb->nbuf = env_flag("GD_FLOW_NBUF", 2);
-    fb->min_blocks = env_flag("GD_FLOW_MB", 2);
+    fb->min_blocks = env_flag("GD_FLOW_MB", 3);
     fb->use_tma = false;
-    if (!whole_batch || env_flag("GD_FLOW_TMA", 1) == 0) return GD_OK;
+    // the TMA tile load is built and tested but OFF by default: measured 2-5 % slower than the cp.async chunks on B200 for this
+    // tile (84-float box rows vs 80 needed, border fix-ups on all four sides, issue by a single thread) — profiles/README.md
+    if (!whole_batch || env_flag("GD_FLOW_TMA", 0) == 0) return GD_OK;
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return GD_OK;  // no driver entry point: the cp.async tile load is used
     for (int k = 0; k < plan.nlevels; ++k) {

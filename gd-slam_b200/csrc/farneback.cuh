@@ -58,7 +58,7 @@ struct FbFlowBuffers {
     size_t m_bytes = 0;
     bool fuse_next = false, use_tma = false;
     bool box_f32 = true;  // 15 x 15 box sums in f32 tree form (default) or f64 running sums like OpenCV (GD_FLOW_BOX_F64=1)
-    int min_blocks = 2;   // register budget of the f32 box kernel: 2 or 3 resident CTAs per SM (GD_FLOW_MB)
+    int min_blocks = 3;   // register budget of the f32 box kernel: 2 or 3 resident CTAs per SM (GD_FLOW_MB)
     int nbuf = 2;         // channel tiles a CTA of the box kernel keeps in flight (GD_FLOW_NBUF = 2 or 5)
     bool tmap_ok[FB_MAX_LEVELS][2] = {};
     alignas(64) CUtensorMap tmap[FB_MAX_LEVELS][2];

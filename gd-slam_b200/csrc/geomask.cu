@@ -75,6 +75,15 @@ void make_cam_const(const float K[9], CamConst* c)
     inv3_cv<double>(Kd, c->Kid);
 }
 
+void make_undistort_args(const float K[9], const float* dist, int ndist, UndistortArgs* a)
+{
+    a->fx = (double)K[0];
+    a->fy = (double)K[4];
+    a->cx = (double)K[2];
+    a->cy = (double)K[5];
+    for (int i = 0; i < 5; ++i) a->k[i] = (dist && i < ndist) ? (double)dist[i] : 0.0;
+}
+
 KeyFormat make_key_format(size_t n_px)
 {
     int idx_bits = 1;
@@ -181,8 +190,8 @@ int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w,
 //   v_f = h_f * d                 |v_f - v| <= 7 u S D =: ev
 //   diff_f = v_j - v_c            |.| <= 2 ev + 2 u S D = 16 u S D =: ed
 //   n_f = (dl - dc, dt - dc, 1) * (1 / sqrt(ss))   relative error <= 4.5 u per component -> en = 5 u
-//   phi_d_f = sum_i diff_i n_i    |.| <= 3 (2 S D en + ed) + 24 u S D = 102 u S D   -> E_D = 128 u S D
-//   phi_c_f = 1 - sum_i n_j,i n_c,i   |.| <= 6 en + 4 u = 34 u                      -> E_C = 40 u
+//   phi_d_f = v_j . n_c - v_c . n_c   each dot product within 45 u S D of the exact one        -> E_D = 192 u S D
+//   phi_c_f = 1 - sum_i n_j,i n_c,i   |.| <= 6 en + 4 u = 34 u                                  -> E_C = 40 u
 // ------------------------------------------------------------------------------------------------
 constexpr int ET_W = 32, ET_H = 16;
 
@@ -285,13 +294,17 @@ struct EdgeBounds {
     float e_c;    // bound on |phi_c_f32 - phi_c_f64|
 };
 
+// f32 interval form.  Per pixel two float4 in shared memory: A = (n0, n1, n2, v . n), B = (v0, v1, v2, -): with
+// phi_d = (v_j - v_c) . n_c = v_j . n_c - v_c . n_c a neighbour costs two vector loads, two 3-term dot products and the
+// interval bookkeeping.  Error bounds (fused multiply-adds only make them smaller):
+//   |v_j . n_c (f32) - exact| <= 3 (S D en + ev) + 9 u S D = 45 u S D, the same for v_c . n_c  -> E_D = 192 u S D (> 90 u S D)
 __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
                                                             CamConst cam, EdgeBounds eb, uint8_t* __restrict__ edge, size_t estride_b)
 {
     pdl_wait();
-    __shared__ float sd[ET_H + 4][ET_W + 4];      // clamped depth, halo 2
-    __shared__ float sn[ET_H + 2][ET_W + 2][3];   // f32 normals, halo 1
-    __shared__ float sv[ET_H + 2][ET_W + 2][3];   // f32 vertices, halo 1 (z == 0 <=> the reference's vertex is zero)
+    __shared__ float sd[ET_H + 4][ET_W + 4];       // clamped depth, halo 2
+    __shared__ float4 sA[ET_H + 2][ET_W + 2];      // (normal, v . n), halo 1
+    __shared__ float4 sB[ET_H + 2][ET_W + 2];      // (vertex, -), halo 1; z == 0 <=> the reference's vertex is zero
     __shared__ int s_todo[ET_W * ET_H];
     __shared__ int s_ntodo;
     const int b = blockIdx.z;
@@ -304,28 +317,27 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
     for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
         const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
         const int x = x0 + lx - 1, y = y0 + ly - 1;
-        float n0 = 0, n1 = 0, n2 = 0, v0 = 0, v1 = 0, v2 = 0;
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
         if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
             const float dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
             if (dc != 0.f && dt != 0.f && dl != 0.f) {
                 const float c0 = dl - dc, c1 = dt - dc;
-                float ss = c0 * c0;
-                ss = ss + c1 * c1;
-                ss = ss + 1.0f;
+                const float ss = fmaf(c0, c0, fmaf(c1, c1, 1.0f));
                 const float inv = 1.0f / sqrtf(ss);  // IEEE sqrt and division (this file is built without fast math)
-                n0 = c0 * inv;
-                n1 = c1 * inv;
-                n2 = inv;
+                A.x = c0 * inv;
+                A.y = c1 * inv;
+                A.z = inv;
                 const float px = (float)x, py = (float)y;
-                const float h0 = eb.Ki[0] * px + eb.Ki[1] * py + eb.Ki[2];
-                const float h1 = eb.Ki[3] * px + eb.Ki[4] * py + eb.Ki[5];
-                v0 = h0 * dc;
-                v1 = h1 * dc;
-                v2 = dc;  // third row of inv(K) is (0, 0, 1) on this path: z = depth exactly, like the reference's 1.0 * dc
+                const float h0 = fmaf(eb.Ki[0], px, fmaf(eb.Ki[1], py, eb.Ki[2]));
+                const float h1 = fmaf(eb.Ki[3], px, fmaf(eb.Ki[4], py, eb.Ki[5]));
+                B.x = h0 * dc;
+                B.y = h1 * dc;
+                B.z = dc;  // third row of inv(K) is (0, 0, 1) on this path: z = depth, like the reference's 1.0 * dc
+                A.w = fmaf(B.x, A.x, fmaf(B.y, A.y, B.z * A.z));
             }
         }
-        sn[ly][lx][0] = n0; sn[ly][lx][1] = n1; sn[ly][lx][2] = n2;
-        sv[ly][lx][0] = v0; sv[ly][lx][1] = v1; sv[ly][lx][2] = v2;
+        sA[ly][lx] = A;
+        sB[ly][lx] = B;
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -333,30 +345,23 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
     uint8_t e = 0;
     const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
     if (in_img && x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.f) {
-        const float cn0 = sn[ly][lx][0], cn1 = sn[ly][lx][1], cn2 = sn[ly][lx][2];
-        const float cv0 = sv[ly][lx][0], cv1 = sv[ly][lx][1], cv2 = sv[ly][lx][2];
+        const float4 Ac = sA[ly][lx];
+        const float cz = sB[ly][lx].z;
         bool zero_nb = false;
         float maxd = 0.f, c_lo = 0.f, c_hi = 0.f;  // all eight neighbours valid below -> both maxima are >= 0 in the reference
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int jx = lx + c_edge_nx[k], jy = ly + c_edge_ny[k];
-            const float z = sv[jy][jx][2];
-            if (z == 0.f) zero_nb = true;
-            float phi_d = (sv[jy][jx][0] - cv0) * cn0;
-            phi_d = phi_d + (sv[jy][jx][1] - cv1) * cn1;
-            phi_d = phi_d + (z - cv2) * cn2;
+            const float4 Aj = sA[jy][jx], Bj = sB[jy][jx];
+            zero_nb = zero_nb || Bj.z == 0.f;
+            const float phi_d = fmaf(Bj.x, Ac.x, fmaf(Bj.y, Ac.y, Bj.z * Ac.z)) - Ac.w;
+            const float phi_c = 1.0f - fmaf(Aj.x, Ac.x, fmaf(Aj.y, Ac.y, Aj.z * Ac.z));
             maxd = fmaxf(maxd, fabsf(phi_d));
-            float dot = sn[jy][jx][0] * cn0;
-            dot = dot + sn[jy][jx][1] * cn1;
-            dot = dot + sn[jy][jx][2] * cn2;
-            const float phi_c = 1.0f - dot;
             // contribution of this neighbour to max_phi_c: phi_c when phi_d >= 0, 0 when phi_d < 0; undecided sign -> both
-            const float lo = phi_d >= eb.e_d ? phi_c : (phi_d < -eb.e_d ? 0.f : fminf(0.f, phi_c));
-            const float hi = phi_d >= eb.e_d ? phi_c : (phi_d < -eb.e_d ? 0.f : fmaxf(0.f, phi_c));
-            c_lo = k == 0 ? lo : fmaxf(c_lo, lo);
-            c_hi = k == 0 ? hi : fmaxf(c_hi, hi);
+            c_hi = fmaxf(c_hi, phi_d >= -eb.e_d ? phi_c : 0.f);
+            c_lo = fmaxf(c_lo, phi_d >= eb.e_d ? phi_c : 0.f);
         }
-        if (zero_nb || cv2 == 0.f) {
+        if (zero_nb || cz == 0.f) {
             // a zero vertex among the neighbours: edge (:925-949).  A pixel with depth but without a normal (its top or left
             // neighbour has no depth): cn = cv = 0 -> phi_d = 0, phi_c = 1 for every valid neighbour -> 0.05 > 0.04: edge as well
             e = 255;
@@ -435,7 +440,7 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
         S = std::max(S, std::fabs(cam.Kid[3 * r]) * (w - 1) + std::fabs(cam.Kid[3 * r + 1]) * (h - 1) + std::fabs(cam.Kid[3 * r + 2]));
     S = std::max(S, 1.0);
     const double u = 5.9604644775390625e-08;  // 2^-24
-    const double e_d = 128.0 * u * S * 3.5;
+    const double e_d = 192.0 * u * S * 3.5;
     if (force_f64 || !plain_k || !(e_d < 1e-2)) {
         GD_CUDA(launch_pdl(k_depth_edge_f64, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
     } else {
@@ -910,14 +915,19 @@ int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth
 constexpr int SG_MAX = 4096;     // keypoints per stream the grid kernel sorts in shared memory
 constexpr int SG_CELLS = 64 * 48;
 
+struct GridBounds {
+    float minx, miny, inv_w, inv_h;  // mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv
+    int distorted;
+};
+
 __global__ void __launch_bounds__(512) k_stereo_grid(const float* __restrict__ depth, size_t dstride_b, int w, int h,
                                                      const gd_keypoint* __restrict__ kps, size_t cap, const int* __restrict__ n_kp,
-                                                     float bf, float* __restrict__ depth_out, float* __restrict__ uright,
-                                                     int* __restrict__ cell_start, int* __restrict__ cell_items)
+                                                     float bf, UndistortArgs und, GridBounds gb, float* __restrict__ depth_out,
+                                                     float* __restrict__ uright, int* __restrict__ cell_start,
+                                                     int* __restrict__ cell_items, float2* __restrict__ un_out)
 {
     __shared__ unsigned keys[SG_MAX];  // (cell << 12 | index), 0xFFFFFFFF = not in the grid / padding
     const int b = blockIdx.x, n = min(n_kp[b], SG_MAX);
-    const float inv_w = 64.f / (float)w, inv_h = 48.f / (float)h;  // mfGridElementWidthInv / HeightInv for bounds = image
     const float* dp = depth + (size_t)b * dstride_b;
     int npad = 1;
     while (npad < n) npad <<= 1;
@@ -925,15 +935,18 @@ __global__ void __launch_bounds__(512) k_stereo_grid(const float* __restrict__ d
         unsigned key = 0xFFFFFFFFu;
         if (i < n) {
             const gd_keypoint kp = kps[(size_t)b * cap + i];
-            const float d = dp[(size_t)(int)kp.y * w + (int)kp.x];
+            float ux = kp.x, uy = kp.y;  // mvKeysUn (Frame.cc:576-606)
+            if (gb.distorted) undistort_point_cv(und, kp.x, kp.y, &ux, &uy);
+            if (un_out) un_out[(size_t)b * cap + i] = make_float2(ux, uy);
+            const float d = dp[(size_t)(int)kp.y * w + (int)kp.x];  // depth at the DISTORTED keypoint (:826)
             float dv = -1.f, ur = -1.f;
             if (d > 0.f) {
                 dv = d;
-                ur = kp.x - bf / d;
+                ur = ux - bf / d;
             }
             depth_out[(size_t)b * cap + i] = dv;
             uright[(size_t)b * cap + i] = ur;
-            const int px = (int)roundf((kp.x - 0.f) * inv_w), py = (int)roundf((kp.y - 0.f) * inv_h);
+            const int px = (int)roundf((ux - gb.minx) * gb.inv_w), py = (int)roundf((uy - gb.miny) * gb.inv_h);
             if (px >= 0 && px < 64 && py >= 0 && py < 48) key = ((unsigned)(px * 48 + py) << 12) | (unsigned)i;
         }
         keys[i] = key;
@@ -973,12 +986,32 @@ __global__ void __launch_bounds__(512) k_stereo_grid(const float* __restrict__ d
 }
 
 int launch_stereo_grid(const float* depth, size_t depth_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
-                       const int* n_kp, float bf, float* depth_out, float* uright, int* cell_start, int* cell_items,
-                       cudaStream_t s, LaunchStats* st)
+                       const int* n_kp, float bf, const UndistortArgs& und, float* depth_out, float* uright, int* cell_start,
+                       int* cell_items, float2* un_out, cudaStream_t s, LaunchStats* st)
 {
     GD_REQUIRE(cap <= (size_t)SG_MAX, "keypoint capacity above 4096 is not supported by the grid kernel");
     LaunchScope ls(st, s, "F3_stereo_grid", 1);
-    k_stereo_grid<<<batch, 512, 0, s>>>(depth, depth_stride_b, w, h, kps, cap, n_kp, bf, depth_out, uright, cell_start, cell_items);
+    // Frame::ComputeImageBounds (Frame.cc:608-636): undistorted image corners when mDistCoef(0) != 0, else the image itself
+    GridBounds gb;
+    float minx = 0.f, maxx = (float)w, miny = 0.f, maxy = (float)h;
+    gb.distorted = und.k[0] != 0.0 ? 1 : 0;
+    if (gb.distorted) {
+        float c[4][2];
+        undistort_point_cv(und, 0.f, 0.f, &c[0][0], &c[0][1]);
+        undistort_point_cv(und, (float)w, 0.f, &c[1][0], &c[1][1]);
+        undistort_point_cv(und, 0.f, (float)h, &c[2][0], &c[2][1]);
+        undistort_point_cv(und, (float)w, (float)h, &c[3][0], &c[3][1]);
+        minx = std::min(c[0][0], c[2][0]);
+        maxx = std::max(c[1][0], c[3][0]);
+        miny = std::min(c[0][1], c[1][1]);
+        maxy = std::max(c[2][1], c[3][1]);
+    }
+    gb.minx = minx;
+    gb.miny = miny;
+    gb.inv_w = 64.f / (maxx - minx);
+    gb.inv_h = 48.f / (maxy - miny);
+    k_stereo_grid<<<batch, 512, 0, s>>>(depth, depth_stride_b, w, h, kps, cap, n_kp, bf, und, gb, depth_out, uright, cell_start, cell_items,
+                                        un_out);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }

@@ -36,6 +36,40 @@ struct CamConst {
     double Kid[9];  // inv((double)K)  (GeoMaskMaker.cc:888)
 };
 
+// cv::undistortPoints(pt, K, D, noArray(), K) for one f32 point: normalise (multiplying by 1/fx like OpenCV), 5 fixed-point
+// iterations (the default TermCriteria(COUNT, 5)), re-project, all in f64; D = k1 k2 p1 p2 k3.  Used by GetRt's matched
+// points (GeoMaskMaker.cc:104-110), Frame::UndistortKeyPoints and ComputeImageBounds (Frame.cc:576-636).  Compile the callers
+// without FMA contraction.
+struct UndistortArgs {
+    double fx, fy, cx, cy;
+    double k[5];
+};
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void undistort_point_cv(const UndistortArgs& a, float u, float v, float* ou, float* ov)
+{
+    const double ifx = 1.0 / a.fx, ify = 1.0 / a.fy;
+    double x = ((double)u - a.cx) * ifx, y = ((double)v - a.cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1 + ((a.k[4] * r2 + a.k[1]) * r2 + a.k[0]) * r2);
+        if (icdist < 0) {
+            x = ((double)u - a.cx) * ifx;
+            y = ((double)v - a.cy) * ify;
+            break;
+        }
+        const double dX = 2 * a.k[2] * x * y + a.k[3] * (r2 + 2 * x * x);
+        const double dY = a.k[2] * (r2 + 2 * y * y) + 2 * a.k[3] * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    *ou = (float)(a.fx * x + a.cx);
+    *ov = (float)(a.fy * y + a.cy);
+}
+void make_undistort_args(const float K[9], const float* dist, int ndist, UndistortArgs* a);
+
 void make_cam_const(const float K[9], CamConst* c);
 void make_pose(const float K[9], const float R[9], const float T[3], int valid, int epoch, PoseDev* p);
 
@@ -83,10 +117,12 @@ int launch_compact_keypoints(const gd_keypoint* kps, const uint8_t* desc, const 
 // "next" row (f)-4: raw 16-bit depth -> metres, (float)v * inv_factor (Tracking.cc:234-235)
 int launch_depth_u16_to_m(const uint16_t* raw, size_t raw_stride_b, float* depth, size_t depth_stride_b, size_t n, int batch,
                           float inv_factor, cudaStream_t s, LaunchStats* st);
-// "next" row (f)-3: ComputeStereoFromRGBD + AssignFeaturesToGrid (Frame.cc:815-837, 402-417, 553-565), one CTA per stream
+// "next" row (f)-3: UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD / AssignFeaturesToGrid (Frame.cc:576-636,
+// 815-837, 402-417, 553-565), one CTA per stream.  und: the camera (distorted iff und->k[0] != 0, the reference's own test);
+// un_out (optional): mvKeysUn positions (x, y) per keypoint.
 int launch_stereo_grid(const float* depth, size_t depth_stride_b, int w, int h, int batch, const gd_keypoint* kps, size_t cap,
-                       const int* n_kp, float bf, float* depth_out, float* uright, int* cell_start, int* cell_items,
-                       cudaStream_t s, LaunchStats* st);
+                       const int* n_kp, float bf, const UndistortArgs& und, float* depth_out, float* uright, int* cell_start,
+                       int* cell_items, float2* un_out, cudaStream_t s, LaunchStats* st);
 // all-ones mask (warm-up path)
 int launch_fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t s, LaunchStats* st);
 

@@ -330,9 +330,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_getrt_nn(const uint4* __restrict
 // ------------------------------------------------------------------------------------------------ matches -> points
 struct PointArgs {
     int w, h, feat_cap;
-    int distorted;
-    double fx, fy, cx, cy;  // (double) of the f32 K
-    double k[5];            // k1 k2 p1 p2 k3
+    UndistortArgs und;      // (double) of the f32 K and of k1 k2 p1 p2 k3
     float Ki[9];            // inv(K) in f32
 };
 struct MatchEntry {
@@ -340,29 +338,6 @@ struct MatchEntry {
     int i;
 };
 constexpr int PT_THREADS = 256;
-
-// cv::undistortPoints(pt, K, D, noArray(), K) for one float point: normalise, 5 fixed-point iterations, re-project (f64)
-__device__ __forceinline__ void undistort_point(const PointArgs& a, float u, float v, float* ou, float* ov)
-{
-    const double ifx = 1.0 / a.fx, ify = 1.0 / a.fy;
-    double x = ((double)u - a.cx) * ifx, y = ((double)v - a.cy) * ify;
-    const double x0 = x, y0 = y;
-    for (int it = 0; it < 5; ++it) {
-        const double r2 = x * x + y * y;
-        const double icdist = 1.0 / (1 + ((a.k[4] * r2 + a.k[1]) * r2 + a.k[0]) * r2);
-        if (icdist < 0) {
-            x = ((double)u - a.cx) * ifx;
-            y = ((double)v - a.cy) * ify;
-            break;
-        }
-        const double dX = 2 * a.k[2] * x * y + a.k[3] * (r2 + 2 * x * x);
-        const double dY = a.k[2] * (r2 + 2 * y * y) + 2 * a.k[3] * x * y;
-        x = (x0 - dX) * icdist;
-        y = (y0 - dY) * icdist;
-    }
-    *ou = (float)(a.fx * x + a.cx);
-    *ov = (float)(a.fy * y + a.cy);
-}
 
 // One CTA per stream.  Matches come out of BFMatcher ordered by query index; GetRt sorts them (std::sort on the distance,
 // unstable) and keeps the first 100; points whose depth is zero are dropped (GeoMaskMaker.cc:95-141).
@@ -425,7 +400,7 @@ __global__ void __launch_bounds__(PT_THREADS) k_getrt_points(const gd_keypoint* 
             const gd_keypoint k1 = kp_ref[(size_t)b * a.feat_cap + q];
             const gd_keypoint k2 = kp_cur[(size_t)b * a.feat_cap + t];
             float ux, uy;
-            undistort_point(a, k1.x, k1.y, &ux, &uy);  // :104-110 (D = 0: returns the point itself)
+            undistort_point_cv(a.und, k1.x, k1.y, &ux, &uy);  // :104-110 (D = 0: returns the point itself)
             const int dx = (int)ux, dy = (int)uy;      // :122-123
             if (dx >= 0 && dy >= 0 && dx < a.w && dy < a.h) {
                 const float depth = depth_ref[(size_t)b * depth_stride_b + (size_t)dy * a.w + dx];
@@ -639,9 +614,9 @@ int GetRtCore::enqueue_match(int ref_slot, int cur_slot, const float* depth_ref,
     {
         LaunchScope ls(stats, s, "G7_points", 1);
         PointArgs a;
-        a.w = w; a.h = h; a.feat_cap = feat_cap; a.distorted = distorted ? 1 : 0;
-        a.fx = Kd[0]; a.fy = Kd[1]; a.cx = Kd[2]; a.cy = Kd[3];
-        for (int i = 0; i < 5; ++i) a.k[i] = dist[i];
+        a.w = w; a.h = h; a.feat_cap = feat_cap;
+        a.und.fx = Kd[0]; a.und.fy = Kd[1]; a.und.cx = Kd[2]; a.und.cy = Kd[3];
+        for (int i = 0; i < 5; ++i) a.und.k[i] = dist[i];
         for (int i = 0; i < 9; ++i) a.Ki[i] = cam.Ki[i];
         k_getrt_points<<<batch, PT_THREADS, (size_t)feat_cap * 12, s>>>(slot_kp(ref_slot), slot_kp(cur_slot), slot_n(ref_slot), slot_n(cur_slot),
                                                                       nn.as<int>(), dd.as<int>(), depth_ref, depth_stride_b, a,

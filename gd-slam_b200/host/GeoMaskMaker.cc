@@ -38,6 +38,7 @@ void GeoMaskMaker::init(int width, int height, int device)
 {
     mimage_width = width;
     mimage_height = height;
+    device_ = device;
     float K[9];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) K[3 * r + c] = _inst_param.at<float>(r, c);
@@ -56,27 +57,16 @@ void GeoMaskMaker::AddNewImage(cv::Mat new_Image, cv::Mat new_Depth, cv::Mat /*l
         throw std::invalid_argument("GeoMaskMaker::AddNewImage: expects CV_8UC3 + CV_32FC1 (metres) of the configured size");
     const uint8_t* bgr = new_Image.ptr<uint8_t>(0);
     const float* dep = new_Depth.ptr<float>(0);
+#ifndef GD_SHIM_NO_OPENCV_GETRT
+    // GetRt() is the pose source unless a provider was installed: its cv::ORB features are computed once per pushed frame on
+    // the GPU and kept with the frame in the device ring (the reference re-extracts both images on every call, :82-90)
+    if (!pose_provider_ && !getrt_enabled_) {
+        gd_check(gd_geomask_enable_getrt(handle_), "gd_geomask_enable_getrt");
+        getrt_enabled_ = true;
+    }
+#endif
     gd_check(gd_geomask_push(handle_, &bgr, (size_t)new_Image.step, &dep, (size_t)new_Depth.step), "gd_geomask_push");
-    // host copies of the last six frames, only for GetRt() (GeoMaskMaker.cc:409-429): not kept while a pose provider is set
-    if (pose_provider_) {
-        if (++pushed_ > inter_frame_size) start_flag = true;
-        return;
-    }
-    ++pushed_;
-    cv::Mat rgb, depth;
-    new_Image.copyTo(rgb);
-    new_Depth.copyTo(depth);
-    host_rgb_.push_back(rgb);
-    host_depth_.push_back(depth);
-    if ((int)host_rgb_.size() > inter_frame_size) {
-        _firstImage = host_rgb_.front();
-        _firstDepth = host_depth_.front();
-        _secondImage = host_rgb_.back();
-        _secondDepth = host_depth_.back();
-        host_rgb_.erase(host_rgb_.begin());
-        host_depth_.erase(host_depth_.begin());
-        start_flag = true;
-    }
+    if (++pushed_ > inter_frame_size) start_flag = true;  // :419-428 (the device ring keeps the six frames)
 }
 
 void GeoMaskMaker::GetNoGMMmask(cv::Mat& mask)
@@ -118,7 +108,7 @@ cv::Mat GeoMaskMaker::GetEdge(cv::Mat arg_Depth_image)
     float K[9];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) K[3 * r + c] = _inst_param.at<float>(r, c);
-    gd_check(gd_stage_depth_edge(0, d.ptr<float>(0), d.cols, d.rows, K, e.ptr<uint8_t>(0)), "gd_stage_depth_edge");
+    gd_check(gd_stage_depth_edge(device_, d.ptr<float>(0), d.cols, d.rows, K, e.ptr<uint8_t>(0)), "gd_stage_depth_edge");
     return e;
 }
 
@@ -129,7 +119,35 @@ float GeoMaskMaker::depth2std(float depth)
 }
 
 #ifdef GD_SHIM_NO_OPENCV_GETRT
-// Build without OpenCV's features2d/calib3d (compile check, or deployments that feed Tracking's pose through
-// SetPoseProvider): no pose of our own -> the all-ones mask path of GeoMaskMaker.cc:179-185.
+// Build without OpenCV's calib3d (deployments that feed Tracking's pose through SetPoseProvider): no pose of our own -> the
+// all-ones mask path of GeoMaskMaker.cc:179-185.
 bool GeoMaskMaker::GetRt(cv::Mat&, cv::Mat&) { return false; }
+#else
+// GeoMaskMaker.cc:77-156.  Everything up to the solver input (:82-141) comes from the GPU in one call; the solver is the
+// reference's own: cv::solvePnPRansac with its default arguments and cv::Rodrigues, then the two convertTo (:148-152).
+bool GeoMaskMaker::GetRt(cv::Mat& R, cv::Mat& T)
+{
+    if (!getrt_enabled_) return false;  // frames were pushed while a pose provider was installed: no features to match
+    float obj[100 * 3], pix[100 * 2];
+    float* po = obj;
+    float* pp = pix;
+    int n = 0;
+    gd_check(gd_geomask_getrt_points(handle_, &po, &pp, &n), "gd_geomask_getrt_points");
+    if (n < 20) return false;  // :143-146
+    std::vector<cv::Point3f> objectPoints((size_t)n);
+    std::vector<cv::Point2f> imagePixels((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        objectPoints[i].x = obj[3 * i];
+        objectPoints[i].y = obj[3 * i + 1];
+        objectPoints[i].z = obj[3 * i + 2];
+        imagePixels[i].x = pix[2 * i];
+        imagePixels[i].y = pix[2 * i + 1];
+    }
+    cv::Mat rvec;
+    cv::solvePnPRansac(objectPoints, imagePixels, _inst_param, _DistCoefParam, rvec, T);  // :148
+    cv::Rodrigues(rvec, R);                                                               // :149
+    T.convertTo(T, CV_32FC1);
+    R.convertTo(R, CV_32FC1);
+    return true;
+}
 #endif

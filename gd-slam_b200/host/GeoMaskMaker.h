@@ -6,9 +6,11 @@
 //   void GetNoGMMmask(Mat& mask)
 // Everything behind them runs on the GPU through the C ABI of include/gdslam_cuda.h; the prototype code of the
 // reference header (graph / segmentation experiments that Tracking never calls) is not carried over.
-// GetRt() — the pose between the buffered pair — stays a host function: either keep the upstream body
-// (src/GeoMaskMaker.cc:77-156, OpenCV ORB + BFMatcher + solvePnPRansac) in your tree, or install a pose provider
-// with SetPoseProvider() (e.g. Tracking's own pose).  See INTEGRATION.md.
+// GetRt() — the pose between the buffered pair (src/GeoMaskMaker.cc:77-156) — runs its feature / matching half on the GPU
+// (gd_geomask_getrt_points: cv::ORB features cached per ring slot, cross-check matching, first-100 selection, undistortPoints,
+// depth look-up, back-projection) and calls cv::solvePnPRansac + cv::Rodrigues on the result, exactly like the reference
+// (:143-150).  Define GD_SHIM_NO_OPENCV_GETRT to build without OpenCV's calib3d (then install a pose provider with
+// SetPoseProvider(), e.g. Tracking's own pose, or every mask is all ones).  See INTEGRATION.md.
 #ifndef GEOMASKMAKER_H_
 #define GEOMASKMAKER_H_
 
@@ -28,8 +30,6 @@ public:
     int mimage_height;
     int mimage_width;
     int image_count = 0;
-    // newest pair kept on the host only for GetRt() (the GPU keeps its own copies in the device ring)
-    cv::Mat _firstImage, _secondImage, _firstDepth, _secondDepth;
 
     GeoMaskMaker(cv::Mat inst_param, cv::Mat DistCoef, float DepthMapFactor);
     // same as above with an explicit image size / device (the reference hard-codes 640x480)
@@ -40,9 +40,10 @@ public:
 
     void AddNewImage(cv::Mat new_RGB, cv::Mat new_Depth, cv::Mat label, cv::Mat originlabel);
     void GetNoGMMmask(cv::Mat& mask);
-    bool GetRt(cv::Mat& R, cv::Mat& T);  // host side; see the header comment
+    bool GetRt(cv::Mat& R, cv::Mat& T);  // GPU points + cv::solvePnPRansac; see the header comment
 
-    // optional: replaces GetRt() as the source of (R, T); return false for "no pose" (all-ones mask)
+    // optional: replaces GetRt() as the source of (R, T); return false for "no pose" (all-ones mask).  Install it before the
+    // first AddNewImage: with a provider the cv::ORB features of GetRt are not computed at all.
     typedef std::function<bool(cv::Mat& R, cv::Mat& T)> PoseProvider;
     void SetPoseProvider(PoseProvider p) { pose_provider_ = p; }
 
@@ -54,8 +55,9 @@ public:
 private:
     gd_geomask* handle_ = nullptr;
     PoseProvider pose_provider_;
-    std::vector<cv::Mat> host_rgb_, host_depth_;  // last six frames for GetRt() (not kept while a pose provider is set)
     int pushed_ = 0;
+    int device_ = 0;
+    bool getrt_enabled_ = false;
     void init(int width, int height, int device);
 };
 

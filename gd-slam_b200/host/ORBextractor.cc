@@ -53,7 +53,7 @@ void ORBextractor::ensure_handle(int w, int h)
     handle_ = nullptr;
     handle_w_ = w > handle_w_ ? w : handle_w_;
     handle_h_ = h > handle_h_ ? h : handle_h_;
-    int rc = gd_orb_create(&handle_, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, handle_w_, handle_h_, 0, 1);
+    int rc = gd_orb_create(&handle_, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, handle_w_, handle_h_, device, 1);
     if (rc != GD_OK) throw std::runtime_error(std::string("gd_orb_create: ") + gd_last_error());
 }
 

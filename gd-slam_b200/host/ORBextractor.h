@@ -37,6 +37,8 @@ public:
     // GrabImageRGBD_GD extracts twice from the identical gray image (src/Tracking.cc:238,252): serve the second
     // call from the first one's result (keyed on the exact image content: memcmp with a kept copy).
     bool memoizeLastImage = true;
+    // CUDA device of the extractor (set before the first call; the reference has no such notion)
+    int device = 0;
 
 protected:
     int nfeatures;

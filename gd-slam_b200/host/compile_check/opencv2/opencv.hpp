@@ -6,17 +6,24 @@
 #include <memory>
 #include <vector>
 
+#include <cmath>
+
 #define CV_8U 0
 #define CV_32F 5
+#define CV_64F 6
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << 3))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 
 namespace cv {
 struct Point2f {
     float x = 0, y = 0;
+};
+struct Point3f {
+    float x = 0, y = 0, z = 0;
 };
 struct KeyPoint {
     Point2f pt;
@@ -46,13 +53,25 @@ public:
     }
     int type() const { return type_; }
     bool empty() const { return !data || rows == 0 || cols == 0; }
-    size_t elem() const { return (size_t)(((type_ & 7) == CV_32F) ? 4 : 1) * ((type_ >> 3) + 1); }
+    size_t elem() const { return (size_t)(((type_ & 7) == CV_64F) ? 8 : ((type_ & 7) == CV_32F) ? 4 : 1) * ((type_ >> 3) + 1); }
+    // 32F / 64F single-channel conversions (what GetRt needs)
+    void convertTo(Mat& dst, int t) const
+    {
+        Mat out(rows, cols, t);
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const double v = (type_ & 7) == CV_64F ? at<double>(y, x) : (double)at<float>(y, x);
+                if ((t & 7) == CV_64F) out.at<double>(y, x) = v; else out.at<float>(y, x) = (float)v;
+            }
+        dst = out;
+    }
     template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step); }
     template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
     unsigned char* ptr(int y = 0) { return data + (size_t)y * step; }
     template <typename T> T& at(int y, int x) { return ((T*)(data + (size_t)y * step))[x]; }
     template <typename T> const T& at(int y, int x) const { return ((const T*)(data + (size_t)y * step))[x]; }
     template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     void copyTo(Mat& dst) const
     {
         if (empty()) { dst = Mat(); return; }
@@ -80,4 +99,29 @@ struct _OutputArray {
 };
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
+
+// calib3d stand-ins.  solvePnPRansac has no implementation here: the demo installs a function that plays the solver's role
+// (the parity tests use the real cv2.solvePnPRansac through the C ABI's pose hook).  Rodrigues: rotation vector -> matrix.
+typedef bool (*PnPRansacStandIn)(const std::vector<Point3f>& obj, const std::vector<Point2f>& pix, Mat& rvec, Mat& tvec);
+inline PnPRansacStandIn& pnp_stand_in()
+{
+    static PnPRansacStandIn f = nullptr;
+    return f;
+}
+inline bool solvePnPRansac(const std::vector<Point3f>& obj, const std::vector<Point2f>& pix, const Mat&, const Mat&, Mat& rvec, Mat& tvec)
+{
+    return pnp_stand_in() ? pnp_stand_in()(obj, pix, rvec, tvec) : false;
+}
+inline void Rodrigues(const Mat& rvec, Mat& R)
+{
+    const double rx = rvec.at<double>(0), ry = rvec.at<double>(1), rz = rvec.at<double>(2);
+    const double th = std::sqrt(rx * rx + ry * ry + rz * rz);
+    R.create(3, 3, CV_64FC1);
+    double k[3] = {0, 0, 0};
+    if (th > 0) { k[0] = rx / th; k[1] = ry / th; k[2] = rz / th; }
+    const double c = std::cos(th), s = std::sin(th), c1 = 1 - c;
+    const double Kx[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R.at<double>(i, j) = (i == j ? c : 0.0) + c1 * k[i] * k[j] + s * Kx[3 * i + j];
+}
 }  // namespace cv

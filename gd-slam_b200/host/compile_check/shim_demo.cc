@@ -2,17 +2,48 @@
 // ORB on the new gray image (twice, second call memoised), AddNewImage, GetNoGMMmask.  Reads a raw sequence file written by
 // tests/test_gpu_shim.py, writes masks / keypoints / descriptors for the test to compare with the oracle.
 //   file: int32 w, h, nframes; per frame: bgr (w*h*3 u8), gray (w*h u8), depth (w*h f32), R (9 f32), T (3 f32)
+// Third argument "getrt": no pose provider — GeoMaskMaker::GetRt() itself runs (GPU points + the solver).  The image has no
+// OpenCV SDK, so the stand-in solver below answers with the pose of the sequence file and logs the points it was given; the
+// test compares those with gd_getrt_points (and the real cv2.solvePnPRansac is exercised through the C ABI's pose hook).
 #include <chrono>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../GeoMaskMaker.h"
 #include "../ORBextractor.h"
 
+static float g_R[9], g_T[3];
+static std::vector<float> g_points;  // n, then n x 3 object points, n x 2 image pixels (of the last solver call)
+
+static bool demo_solver(const std::vector<cv::Point3f>& obj, const std::vector<cv::Point2f>& pix, cv::Mat& rvec, cv::Mat& tvec)
+{
+    g_points.clear();
+    g_points.push_back((float)obj.size());
+    for (const auto& p : obj) { g_points.push_back(p.x); g_points.push_back(p.y); g_points.push_back(p.z); }
+    for (const auto& p : pix) { g_points.push_back(p.x); g_points.push_back(p.y); }
+    // rotation matrix of the file -> rotation vector (what solvePnPRansac returns), f64 like OpenCV's outputs
+    const double tr = (double)g_R[0] + g_R[4] + g_R[8];
+    double c = (tr - 1) * 0.5;
+    c = c > 1 ? 1 : (c < -1 ? -1 : c);
+    const double th = std::acos(c);
+    double ax[3] = {(double)g_R[7] - g_R[5], (double)g_R[2] - g_R[6], (double)g_R[3] - g_R[1]};
+    const double s2 = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    rvec.create(3, 1, CV_64FC1);
+    tvec.create(3, 1, CV_64FC1);
+    for (int i = 0; i < 3; ++i) {
+        rvec.at<double>(i, 0) = s2 > 1e-12 ? ax[i] / s2 * th : 0.0;
+        tvec.at<double>(i, 0) = (double)g_T[i];
+    }
+    return true;
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3) return 2;
+    const bool use_getrt = argc > 3 && std::string(argv[3]) == "getrt";
     FILE* f = std::fopen(argv[1], "rb");
     FILE* o = std::fopen(argv[2], "wb");
     if (!f || !o) return 3;
@@ -22,15 +53,19 @@ int main(int argc, char** argv)
     float Kv[9] = {535.4f * w / 640, 0, 320.1f * w / 640, 0, 539.2f * w / 640, 247.6f * w / 640, 0, 0, 1};
     cv::Mat K(3, 3, CV_32FC1, Kv), D(4, 1, CV_32FC1);
     for (int i = 0; i < 4; ++i) D.at<float>(i) = 0.f;
-    float Rv[9], Tv[3];
+    float* Rv = g_R;
+    float* Tv = g_T;
     GeoMaskMaker gm(K, D, 5000.f, w, h, 0);
-    gm.SetPoseProvider([&](cv::Mat& R, cv::Mat& T) {
-        R.create(3, 3, CV_32FC1);
-        T.create(3, 1, CV_32FC1);
-        for (int i = 0; i < 9; ++i) R.at<float>(i / 3, i % 3) = Rv[i];
-        for (int i = 0; i < 3; ++i) T.at<float>(i, 0) = Tv[i];
-        return true;
-    });
+    if (use_getrt)
+        cv::pnp_stand_in() = demo_solver;
+    else
+        gm.SetPoseProvider([&](cv::Mat& R, cv::Mat& T) {
+            R.create(3, 3, CV_32FC1);
+            T.create(3, 1, CV_32FC1);
+            for (int i = 0; i < 9; ++i) R.at<float>(i / 3, i % 3) = Rv[i];
+            for (int i = 0; i < 3; ++i) T.at<float>(i, 0) = Tv[i];
+            return true;
+        });
     ORB_SLAM2::ORBextractor orb(1500, 1.2f, 8, 20, 7);
     std::vector<unsigned char> bgr((size_t)w * h * 3), gray((size_t)w * h);
     std::vector<float> depth((size_t)w * h);
@@ -52,6 +87,7 @@ int main(int argc, char** argv)
         const auto t1 = now();
         gm.AddNewImage(im, d, label, label);                                              // Tracking.cc:242
         const auto t2 = now();
+        g_points.clear();
         gm.GetNoGMMmask(mask);                                                            // Tracking.cc:245
         const auto t3 = now();
         orb(cv::_InputArray(g), cv::_InputArray(label), kps2, cv::_OutputArray(desc2));  // Frame(), Tracking.cc:252
@@ -70,6 +106,10 @@ int main(int argc, char** argv)
             std::fwrite(desc.ptr<unsigned char>(k), 1, 32, o);
         }
         for (int y = 0; y < h; ++y) std::fwrite(mask.ptr<unsigned char>(y), 1, (size_t)w, o);
+        if (use_getrt) {  // the solver's input of this frame (empty while GetRt is not called / returns early)
+            if (g_points.empty()) g_points.push_back(0.f);
+            std::fwrite(g_points.data(), 4, g_points.size(), o);
+        }
     }
     std::fclose(f);
     std::fclose(o);

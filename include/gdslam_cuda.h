@@ -184,13 +184,19 @@ GD_API int gd_frontend_fetch(gd_frontend_t* h, uint8_t* const* mask_out, size_t 
  * (src/Frame.cc:258-282) for the second Frame() of GrabImageRGBD_GD (src/Tracking.cc:252): erode(new mask, 31x31 ellipse),
  * keep keypoint i iff eroded((int)pt.y,(int)pt.x) == 1, order preserved.  Uses the mask and keypoints of the last step. */
 GD_API int gd_frontend_fetch_filtered(gd_frontend_t* h, gd_keypoint* const* kps, uint8_t* const* desc, int* n_kp);
-/* SURVEY section 8 row (f)-3 — Frame::ComputeStereoFromRGBD (src/Frame.cc:815-837) and AssignFeaturesToGrid / PosInGrid
- * (:402-417, :553-565) for the FILTERED keypoints of the last gd_frontend_fetch_filtered call, undistorted camera
- * (TUM3: mvKeysUn == mvKeys, image bounds = image).  depth[b][i] / uright[b][i]: mvDepth / mvuRight (-1 when d <= 0), bf =
- * Camera.bf.  Grid: cell = col * 48 + row (mGrid[col][row]); cell_start[b] has 64*48+1 entries, cell_items[b] lists the
- * keypoint indices of each cell in increasing order.  All output arrays must hold kp_capacity entries. */
+/* SURVEY section 8 row (f)-3 — Frame::UndistortKeyPoints + ComputeImageBounds (src/Frame.cc:576-636), ComputeStereoFromRGBD
+ * (:815-837) and AssignFeaturesToGrid / PosInGrid (:402-417, :553-565) for the FILTERED keypoints of the last
+ * gd_frontend_fetch_filtered call.  The camera is the handle's (K, dist); like the reference, it counts as distorted iff
+ * dist[0] != 0 (then mvKeysUn = cv::undistortPoints of the keypoints and the grid bounds are the undistorted image corners;
+ * otherwise mvKeysUn == mvKeys and the bounds are the image).  depth[b][i] / uright[b][i]: mvDepth / mvuRight (-1 when d <= 0;
+ * the depth is read at the distorted keypoint, uRight uses the undistorted x), bf = Camera.bf.  Grid: cell = col * 48 + row
+ * (mGrid[col][row]); cell_start[b] has 64*48+1 entries, cell_items[b] lists the keypoint indices of each cell in increasing
+ * order.  keys_un[b] (the _un variant, optional): mvKeysUn positions, 2 floats per keypoint.  All per-keypoint output arrays
+ * must hold kp_capacity entries. */
 GD_API int gd_frontend_fetch_stereo_grid(gd_frontend_t* h, float bf, float* const* depth, float* const* uright,
                                          int* const* cell_start, int* const* cell_items);
+GD_API int gd_frontend_fetch_stereo_grid_un(gd_frontend_t* h, float bf, float* const* depth, float* const* uright,
+                                            int* const* cell_start, int* const* cell_items, float* const* keys_un);
 /* SURVEY section 8 row (f)-1 — GeoMaskMaker::GetRt (src/GeoMaskMaker.cc:77-156) as a resident stage (config.getrt = 1): every
  * step computes cv::ORB(2000, 1.2, 8, 31, 0, 2) features of the new frame once (kept per ring slot), matches them against the
  * frame five steps back (BFMatcher NORM_HAMMING, crossCheck), sorts, keeps the first 100, undistorts, looks the depth up and

@@ -64,8 +64,9 @@ void gdo_erode31(const uint8_t* mask, int w, int h, uint8_t* out);
 int gdo_erode_filter(const uint8_t* mask, int w, int h, const float* kps, int n, uint8_t* keep);
 
 /* "next" row (f)-3, Frame::ComputeStereoFromRGBD + AssignFeaturesToGrid (src/Frame.cc:815-837, 402-417, 553-565), D = 0 */
-void gdo_stereo_grid(const float* depth_m, int w, int h, const float* kps, int n, float bf, float* depth_out, float* uright,
-                     int* cell_start, int* cell_items);
+void gdo_undistort_point(const float* K, const float* D, float u, float v, float* ou, float* ov);
+void gdo_stereo_grid(const float* depth_m, int w, int h, const float* kps, int n, float bf, const float* K, const float* D,
+                     float* depth_out, float* uright, int* cell_start, int* cell_items, float* un_out, float* bounds_out);
 
 /* depth2std (GeoMaskMaker.cc:1386-1391) */
 float gdo_depth2std(float depth, float fu);

@@ -396,25 +396,74 @@ int gdo_erode_filter(const uint8_t* mask, int w, int h, const float* kps, int n,
     return kept;
 }
 
-/* ---- "next" row (f)-3: Frame::ComputeStereoFromRGBD (src/Frame.cc:815-837) + AssignFeaturesToGrid / PosInGrid
- * (:402-417, :553-565) for an undistorted camera (TUM3: mvKeysUn == mvKeys, bounds = image, ComputeImageBounds :603-634).
- * cell = col * 48 + row (mGrid[col][row]); cell_start has 64*48+1 entries; items are keypoint indices in increasing order. */
-void gdo_stereo_grid(const float* depth_m, int w, int h, const float* kps, int n, float bf, float* depth_out, float* uright,
-                     int* cell_start, int* cell_items)
+/* ---- "next" row (f)-3: Frame::UndistortKeyPoints / ComputeImageBounds (src/Frame.cc:576-636), ComputeStereoFromRGBD
+ * (:815-837) and AssignFeaturesToGrid / PosInGrid (:402-417, :553-565).  K: 3x3 f32; D: k1 k2 p1 p2 k3 (f32, NULL = none).
+ * The reference tests mDistCoef(0) == 0 to decide whether anything is distorted (:578, :610).
+ * cell = col * 48 + row (mGrid[col][row]); cell_start has 64*48+1 entries; items are keypoint indices in increasing order.
+ * Pinned by tests/golden/stereo_grid.npz (literal Python transcription with cv2.undistortPoints). */
+void gdo_undistort_point(const float* K, const float* D, float u, float v, float* ou, float* ov)
+{
+    /* cv::undistortPoints(src, dst, K, D, noArray(), K): f64, 5 fixed-point iterations (default criteria), then K again */
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    double k[5] = {D[0], D[1], D[2], D[3], D[4]};
+    double x = ((double)u - cx) * ifx, y = ((double)v - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int it = 0; it < 5; ++it) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) {
+            x = ((double)u - cx) * ifx;
+            y = ((double)v - cy) * ify;
+            break;
+        }
+        const double dX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+        const double dY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+    }
+    *ou = (float)(fx * x + cx);
+    *ov = (float)(fy * y + cy);
+}
+
+void gdo_stereo_grid(const float* depth_m, int w, int h, const float* kps, int n, float bf, const float* K, const float* D,
+                     float* depth_out, float* uright, int* cell_start, int* cell_items, float* un_out, float* bounds_out)
 {
     enum { COLS = 64, ROWS = 48 };
-    const float inv_w = (float)COLS / (float)(w - 0), inv_h = (float)ROWS / (float)(h - 0);
+    const int distorted = D && D[0] != 0.0f;
+    float minx = 0.f, maxx = (float)w, miny = 0.f, maxy = (float)h;
+    if (distorted) { /* ComputeImageBounds: the four undistorted image corners */
+        float c[4][2];
+        gdo_undistort_point(K, D, 0.f, 0.f, &c[0][0], &c[0][1]);
+        gdo_undistort_point(K, D, (float)w, 0.f, &c[1][0], &c[1][1]);
+        gdo_undistort_point(K, D, 0.f, (float)h, &c[2][0], &c[2][1]);
+        gdo_undistort_point(K, D, (float)w, (float)h, &c[3][0], &c[3][1]);
+        minx = c[0][0] < c[2][0] ? c[0][0] : c[2][0];
+        maxx = c[1][0] > c[3][0] ? c[1][0] : c[3][0];
+        miny = c[0][1] < c[1][1] ? c[0][1] : c[1][1];
+        maxy = c[2][1] > c[3][1] ? c[2][1] : c[3][1];
+    }
+    if (bounds_out) {
+        bounds_out[0] = minx; bounds_out[1] = maxx; bounds_out[2] = miny; bounds_out[3] = maxy;
+    }
+    const float inv_w = (float)COLS / (maxx - minx), inv_h = (float)ROWS / (maxy - miny);
     int* cell = (int*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int));
     for (int i = 0; i < n; ++i) {
         const float u = kps[7 * i], v = kps[7 * i + 1];
-        const float d = depth_m[(size_t)(int)v * w + (int)u]; /* imDepth.at<float>(v,u): float -> int truncation */
+        float uu = u, vu = v; /* mvKeysUn */
+        if (distorted) gdo_undistort_point(K, D, u, v, &uu, &vu);
+        if (un_out) {
+            un_out[2 * i] = uu;
+            un_out[2 * i + 1] = vu;
+        }
+        const float d = depth_m[(size_t)(int)v * w + (int)u]; /* imDepth.at<float>(v,u) at the DISTORTED keypoint */
         depth_out[i] = -1.f;
         uright[i] = -1.f;
         if (d > 0) {
             depth_out[i] = d;
-            uright[i] = u - bf / d;
+            uright[i] = uu - bf / d;
         }
-        const int px = (int)roundf((u - 0.f) * inv_w), py = (int)roundf((v - 0.f) * inv_h);
+        const int px = (int)roundf((uu - minx) * inv_w), py = (int)roundf((vu - miny) * inv_h);
         cell[i] = (px < 0 || px >= COLS || py < 0 || py >= ROWS) ? -1 : px * ROWS + py;
     }
     int pos = 0;

@@ -341,8 +341,9 @@ def erode_filter(mask, kps):
     return keep
 
 
-def stereo_grid(depth_m, kps, bf):
-    """Frame::ComputeStereoFromRGBD + AssignFeaturesToGrid for D = 0: (depth, uright, cell_start[3073], cell_items)."""
+def stereo_grid(depth_m, kps, bf, K=None, D=None, want_undistorted=False):
+    """Frame::UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD / AssignFeaturesToGrid:
+    (depth, uright, cell_start[3073], cell_items) [+ (mvKeysUn xy, bounds)].  D = None / zeros: undistorted camera."""
     depth_m = _c(depth_m, np.float32)
     kps = np.ascontiguousarray(kps)
     n = len(kps)
@@ -350,7 +351,17 @@ def stereo_grid(depth_m, kps, bf):
     ur = np.empty(n, np.float32)
     cs = np.empty(64 * 48 + 1, np.int32)
     ci = np.empty(max(n, 1), np.int32)
+    un = np.empty((max(n, 1), 2), np.float32)
+    bounds = np.empty(4, np.float32)
+    Kf = _c(np.eye(3) if K is None else K, np.float32).reshape(-1)
+    Df = np.zeros(5, np.float32)
+    if D is not None:
+        Df[: len(np.ravel(D))] = np.ravel(D)
     L = lib()
-    L.gdo_stereo_grid.argtypes = [f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, f32p, f32p, i32p, i32p]
-    L.gdo_stereo_grid(depth_m.reshape(-1), depth_m.shape[1], depth_m.shape[0], kps.ctypes.data, n, bf, d, ur, cs, ci)
+    L.gdo_stereo_grid.argtypes = [f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, f32p, f32p, f32p, f32p, i32p, i32p,
+                                  f32p, f32p]
+    L.gdo_stereo_grid(depth_m.reshape(-1), depth_m.shape[1], depth_m.shape[0], kps.ctypes.data, n, bf, Kf, Df, d, ur, cs, ci,
+                      un.reshape(-1), bounds)
+    if want_undistorted:
+        return d, ur, cs, ci[: cs[-1]].copy(), un[:n].copy(), bounds
     return d, ur, cs, ci[: cs[-1]].copy()

@@ -282,6 +282,73 @@ def make_undistort():
                         lut_sum=np.float64(u.astype(np.float64).sum()))
 
 
+def make_stereo_grid():
+    """Row (f)-3: Frame::UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD / AssignFeaturesToGrid + PosInGrid
+    (src/Frame.cc:576-636, 815-837, 402-417, 553-565) transcribed literally (numpy f32 + cv2.undistortPoints) on the
+    reference-extracted keypoints of a synthetic frame, for TUM3 (no distortion) and TUM1 (distorted)."""
+    from oracle import pyoracle as po
+
+    s = synth.SyntheticStream(0)
+    fr = s.frame(5)
+    g = cv2.cvtColor(fr.bgr, cv2.COLOR_RGB2GRAY)
+    kp, _, _ = po.orbref_extract(g) if po.have_ref() else po.orb_extract(g)
+    out = {"kp": kp, "crc": np.uint64(synth.frame_crc(fr))}
+    bf = f32(40.0)
+    cams = {"tum3": (synth.intrinsics(), np.zeros(5, f32)),
+            "tum1": (np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], f32),
+                     np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], f32))}
+    h, w = fr.depth_m.shape
+    for name, (K, D) in cams.items():
+        N = len(kp)
+        # UndistortKeyPoints (:576-606)
+        if D[0] == 0.0:
+            un = np.stack([kp["x"], kp["y"]], 1).astype(f32)
+        else:
+            mat = np.stack([kp["x"], kp["y"]], 1).astype(f32).reshape(-1, 1, 2)
+            un = cv2.undistortPoints(mat, K, D, None, K).reshape(-1, 2).astype(f32)
+        # ComputeImageBounds (:608-636)
+        if D[0] != 0.0:
+            c = np.array([[0, 0], [w, 0], [0, h], [w, h]], f32).reshape(-1, 1, 2)
+            c = cv2.undistortPoints(c, K, D, None, K).reshape(-1, 2).astype(f32)
+            mnMinX, mnMaxX = min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0])
+            mnMinY, mnMaxY = min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])
+        else:
+            mnMinX, mnMaxX, mnMinY, mnMaxY = f32(0), f32(w), f32(0), f32(h)
+        winv = f32(f32(64) / f32(mnMaxX - mnMinX))
+        hinv = f32(f32(48) / f32(mnMaxY - mnMinY))
+        # ComputeStereoFromRGBD (:815-837): depth at the DISTORTED keypoint, uRight from the undistorted x
+        depth = np.full(N, -1, f32)
+        uright = np.full(N, -1, f32)
+        for i in range(N):
+            d = fr.depth_m[int(kp["y"][i]), int(kp["x"][i])]
+            if d > 0:
+                depth[i] = d
+                uright[i] = f32(un[i, 0] - f32(bf / d))
+        # AssignFeaturesToGrid + PosInGrid (:402-417, 553-565): C round() = half away from zero
+        grid = [[[] for _ in range(48)] for _ in range(64)]
+        for i in range(N):
+            fx_, fy_ = float(f32(f32(un[i, 0] - mnMinX) * winv)), float(f32(f32(un[i, 1] - mnMinY) * hinv))
+            px = int(np.floor(abs(fx_) + 0.5) * np.sign(fx_))
+            py = int(np.floor(abs(fy_) + 0.5) * np.sign(fy_))
+            if px < 0 or px >= 64 or py < 0 or py >= 48:
+                continue
+            grid[px][py].append(i)
+        start, items = [], []
+        for px in range(64):
+            for py in range(48):
+                start.append(len(items))
+                items += grid[px][py]
+        start.append(len(items))
+        out[name + "_K"], out[name + "_D"] = K, D
+        out[name + "_un"] = un
+        out[name + "_bounds"] = np.array([mnMinX, mnMaxX, mnMinY, mnMaxY], f32)
+        out[name + "_depth"], out[name + "_uright"] = depth, uright
+        out[name + "_cell_start"], out[name + "_cell_items"] = np.array(start, np.int32), np.array(items, np.int32)
+        print("stereo_grid", name, "keypoints", N, "in grid", len(items), "with depth", int((depth > 0).sum()),
+              "bounds", mnMinX, mnMaxX, mnMinY, mnMaxY)
+    np.savez_compressed(os.path.join(HERE, "stereo_grid.npz"), **out)
+
+
 def literal_get_edge_fast(depth, K, po):
     return po.depth_edge(depth, K)  # pinned bit-exact against literal_get_edge by geomask_small.npz
 
@@ -289,6 +356,9 @@ def literal_get_edge_fast(depth, K, po):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "erode":
         make_erode()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "stereo_grid":
+        make_stereo_grid()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "geomask_640":
         make_geomask_640()
@@ -298,4 +368,5 @@ if __name__ == "__main__":
     make_farneback()
     make_erode()
     make_undistort()
+    make_stereo_grid()
     print("cv2", cv2.__version__)

@@ -192,6 +192,29 @@ def test_stereo_from_rgbd_and_grid(capi, oracle, synth):
     fe.close()
 
 
+def test_stereo_grid_distorted_camera(capi, oracle, synth):
+    """Row (f)-3 with TUM1's distortion: mvKeysUn (UndistortKeyPoints), the undistorted image bounds (ComputeImageBounds),
+    depth at the distorted keypoint, uRight / grid cell from the undistorted one — against the golden-pinned oracle."""
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    D = np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)
+    s = synth.SyntheticStream(3)
+    fr = [s.frame(f) for f in range(6)]
+    fe = capi.Frontend(K, 640, 480, batch=1, dist=D)
+    for f in range(6):
+        R, T = s.pair_pose(max(f - 5, 0), f)
+        fe.step([fr[f].bgr], [fr[f].depth_m], R[None], T[None])
+    kp = fe.fetch_filtered()[0][0]
+    gd_, gur, gcs, gci = fe.fetch_stereo_grid(40.0)[0]
+    d, ur, cs, ci, un, bounds = oracle.stereo_grid(fr[5].depth_m, kp, 40.0, K, D, want_undistorted=True)
+    n = len(kp)
+    assert n > 100 and bounds[0] > 1.0  # the undistorted image is smaller than the sensor for this camera
+    assert np.array_equal(fe.keys_un[0][:n], un)
+    assert np.array_equal(gd_[:n], d) and np.array_equal(gur[:n], ur)
+    assert np.array_equal(gcs, cs) and np.array_equal(gci, ci)
+    assert not np.array_equal(un, np.stack([kp["x"], kp["y"]], 1))
+    fe.close()
+
+
 def test_cuda_graph_replay_equals_plain_launches(capi, synth, monkeypatch):
     """Small batches replay a CUDA graph of the per-frame launch sequence after two ring cycles: identical results."""
     K = synth.intrinsics(320, 240)

@@ -341,3 +341,37 @@ def test_fused_flow_form_still_matches_oracle(capi, oracle, synth, monkeypatch):
     assert nviol == 0, (nviol, dmax)
     assert (mask == mo).mean() >= 0.999
     gm.close()
+
+
+def test_flow_kernel_variants_within_tolerance(capi, oracle, synth, golden, monkeypatch):
+    """Every selectable form of the box-filter / solve kernel stays inside the flow tolerance against the oracle (f64 box sums
+    like OpenCV) and the cv2 goldens: f32 tree sums (default) vs f64 running sums, plain / fused-with-next-matrices, cp.async
+    chunks vs the rank-3 TMA tile (zero fill + border fix-ups on all four sides), prefetch depth 2 / 5, 2 / 3 CTAs per SM."""
+    gold = golden("farneback.npz")
+    s = synth.SyntheticStream(0)
+    g0, g5 = oracle.gray(s.frame(0).bgr), oracle.gray(s.frame(5).bgr)
+    ref640 = oracle.farneback(g0, g5)
+    small = oracle.gray(synth.SyntheticStream(1, 148, 100).frame(0).bgr), oracle.gray(synth.SyntheticStream(1, 148, 100).frame(5).bgr)
+    ref_small = oracle.farneback(*small)
+    variants = [dict(), dict(GD_FLOW_BOX_F64="1"), dict(GD_FLOW_NEXT="0"), dict(GD_FLOW_NEXT="0", GD_FLOW_BOX_F64="1"),
+                dict(GD_FLOW_TMA="1"), dict(GD_FLOW_TMA="1", GD_FLOW_NEXT="0"), dict(GD_FLOW_TMA="1", GD_FLOW_BOX_F64="1"),
+                dict(GD_FLOW_NBUF="5"), dict(GD_FLOW_NBUF="5", GD_FLOW_TMA="1"), dict(GD_FLOW_MB="2"),
+                dict(GD_FLOW_MB="2", GD_FLOW_NEXT="0")]
+    names = ("GD_FLOW_BOX_F64", "GD_FLOW_NEXT", "GD_FLOW_TMA", "GD_FLOW_NBUF", "GD_FLOW_MB")
+    worst = {}
+    for v in variants:
+        for n in names:
+            monkeypatch.delenv(n, raising=False)
+        for k, val in v.items():
+            monkeypatch.setenv(k, val)
+        for img, ref, tag in (((g0, g5), ref640, "640"), (small, ref_small, "148"),
+                              ((gold["gray_320_a"], gold["gray_320_b"]), gold["flow_320"], "cv2-320"),
+                              ((gold["gray_150_a"], gold["gray_150_b"]), gold["flow_150"], "cv2-150")):
+            flow = capi.stage_farneback(*img)
+            nviol, dmax = flow_tol_violations(flow, ref)
+            assert nviol == 0, (v, tag, nviol, dmax)
+            ratio = float((np.abs(flow.astype(np.float64) - ref) / (1e-4 * np.maximum(1.0, np.abs(ref)))).max())
+            worst[(tuple(sorted(v.items())), tag)] = ratio
+    # the f32 tree sums cost a small part of the tolerance (recorded in DESIGN.md): keep a margin
+    assert max(worst.values()) < 0.8, max(worst.items(), key=lambda kv: kv[1])
+    print("flow variants, worst |d| / tolerance:", {str(k): round(r, 3) for k, r in worst.items() if k[1] in ("640", "cv2-320")})

@@ -145,3 +145,19 @@ def test_erode_filter_vs_cv2_golden(oracle, golden):
     keep = oracle.erode_filter(mask, g["kp"])
     assert np.array_equal(keep, g["keep"])
     assert 0 < keep.sum() < len(keep)
+
+
+def test_stereo_grid_vs_literal_transcription(oracle, synth, golden):
+    """Row (f)-3 pinned: UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD, AssignFeaturesToGrid / PosInGrid
+    (src/Frame.cc:576-636, 815-837, 402-417, 553-565) against the literal numpy + cv2.undistortPoints transcription, for an
+    undistorted (TUM3) and a distorted (TUM1) camera."""
+    g = golden("stereo_grid.npz")
+    fr = synth.SyntheticStream(0).frame(5)
+    assert synth.frame_crc(fr) == int(g["crc"])
+    for cam in ("tum3", "tum1"):
+        d, ur, cs, ci, un, bounds = oracle.stereo_grid(fr.depth_m, g["kp"], 40.0, g[cam + "_K"], g[cam + "_D"], want_undistorted=True)
+        assert np.array_equal(un, g[cam + "_un"]), cam
+        assert np.array_equal(bounds, g[cam + "_bounds"]), cam
+        assert np.array_equal(d, g[cam + "_depth"]) and np.array_equal(ur, g[cam + "_uright"]), cam
+        assert np.array_equal(cs, g[cam + "_cell_start"]) and np.array_equal(ci, g[cam + "_cell_items"]), cam
+    assert not np.array_equal(g["tum1_un"], g["tum3_un"]) and not np.array_equal(g["tum1_cell_start"], g["tum3_cell_start"])
