@@ -54,8 +54,9 @@ FAMILY_BYTES = {
     "K1b_flow_upsample": (8 * 0.328125 / 4 + 8 * 0.328125) * N_PX,
     "K2a_depth_edge": 5 * N_PX,
     "K2b_mahalanobis": 22 * N_PX,
-    "K3a_minmax": 4 * N_PX,
-    "K3b_normalize_mask": 5 * N_PX,
+    "K3a_minmax": 8 * N_PX,                             # 64-bit scatter keys
+    "K3b_normalize_mask": 9 * N_PX,
+    "K3_minmax_mask": 9 * N_PX,                         # cluster form: keys read once, mask written once
     "K4a_pyramid_resize": 2 * 2.094 * N_PX,
     "K4b_fast_cells": 3.094 * N_PX,
     "K4c_quadtree": 8 * 8000 * 4,

@@ -184,10 +184,15 @@ int gd_stage_mahalanobis(int device, const float* flow, const float* depth_ref, 
     GD_TRY(launch_mahalanobis(dflow.as<float2>(), 0, dr.as<float>(), dc.as<float>(), 0, er.as<uint8_t>(), ec.as<uint8_t>(), 0,
                               lut ? dl.as<float2>() : nullptr, w, h, 1, cam, pose.as<PoseDev>(), kf,
                               keys.as<unsigned long long>(), 0, 0, nullptr));
-    GD_TRY(launch_minmax_reset(mm.as<unsigned>(), 1, 0));
-    GD_TRY(launch_minmax(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, mm.as<unsigned>(), 0, nullptr));
-    GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), 0, (int)n, 1, mm.as<unsigned>(), pose.as<PoseDev>(), kf,
-                                 dmask.as<uint8_t>(), 0, 0, nullptr));
+    bool clustered = false;
+    GD_TRY(launch_minmax_mask_cluster(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, mm.as<unsigned>(),
+                                      dmask.as<uint8_t>(), 0, 0, nullptr, &clustered));
+    if (!clustered) {
+        GD_TRY(launch_minmax_reset(mm.as<unsigned>(), 1, 0));
+        GD_TRY(launch_minmax(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, mm.as<unsigned>(), 0, nullptr));
+        GD_TRY(launch_normalize_mask(keys.as<unsigned long long>(), 0, (int)n, 1, mm.as<unsigned>(), pose.as<PoseDev>(), kf,
+                                     dmask.as<uint8_t>(), 0, 0, nullptr));
+    }
     GD_TRY(launch_resolve_dist(keys.as<unsigned long long>(), 0, (int)n, 1, pose.as<PoseDev>(), kf, ddist.as<float>(), 0, 0));
     GD_CUDA(cudaDeviceSynchronize());
     if (dist) GD_CUDA(cudaMemcpy(dist, ddist.p, n * 4, cudaMemcpyDeviceToHost));

@@ -12,6 +12,9 @@
 // no tensor-core work (largest matrix on the path is 6x6).
 #include "geomask.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -269,8 +272,9 @@ __device__ __forceinline__ uint8_t edge_decide_f64(NV nv)
     return 0;
 }
 
-__constant__ int c_edge_nx[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
-__constant__ int c_edge_ny[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// neighbour order of the reference (:905-906); compile-time functions so that the unrolled loops fold them into immediates
+__host__ __device__ constexpr int edge_nx(int k) { return k == 0 || k == 1 || k == 7 ? -1 : (k == 2 || k == 6 ? 0 : (k < 8 ? 1 : 0)); }
+__host__ __device__ constexpr int edge_ny(int k) { return k == 1 || k == 2 || k == 3 ? -1 : (k == 0 || k == 4 ? 0 : (k < 8 ? 1 : 0)); }
 
 __device__ __forceinline__ void load_depth_tile(const float* __restrict__ dp, int w, int h, int x0, int y0, int tid,
                                                 float (*sd)[ET_W + 4])
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
         float maxd = 0.f, c_lo = 0.f, c_hi = 0.f;  // all eight neighbours valid below -> both maxima are >= 0 in the reference
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int jx = lx + c_edge_nx[k], jy = ly + c_edge_ny[k];
+            const int jx = lx + edge_nx(k), jy = ly + edge_ny(k);
             const float4 Aj = sA[jy][jx], Bj = sB[jy][jx];
             zero_nb = zero_nb || Bj.z == 0.f;
             const float phi_d = fmaf(Bj.x, Ac.x, fmaf(Bj.y, Ac.y, Bj.z * Ac.z)) - Ac.w;
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restri
         const int ply = s_todo[t] >> 8, plx = s_todo[t] & 255;  // normal / vertex tile coordinates (halo 1)
         const int px = x0 + plx - 1, py = y0 + ply - 1;
         const uint8_t ex = edge_decide_f64([&](int k, double n[3], double v[3]) {
-            const int dx = k < 8 ? c_edge_nx[k] : 0, dy = k < 8 ? c_edge_ny[k] : 0;
+            const int dx = k < 8 ? edge_nx(k) : 0, dy = k < 8 ? edge_ny(k) : 0;
             edge_nv_f64(sd, ply + 1 + dy, plx + 1 + dx, px + dx, py + dy, w, h, cam, n, v);
         });
         edge[(size_t)b * estride_b + (size_t)py * w + px] = ex;
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge_f64(const float* __re
     const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
     if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.f)
         e = edge_decide_f64([&](int k, double n[3], double v[3]) {
-            const int jx = lx + (k < 8 ? c_edge_nx[k] : 0), jy = ly + (k < 8 ? c_edge_ny[k] : 0);
+            const int jx = lx + (k < 8 ? edge_nx(k) : 0), jy = ly + (k < 8 ? edge_ny(k) : 0);
             n[0] = sn[jy][jx][0]; n[1] = sn[jy][jx][1]; n[2] = sn[jy][jx][2];
             v[0] = sv[jy][jx][0]; v[1] = sv[jy][jx][1]; v[2] = sv[jy][jx][2];
         });
@@ -488,7 +492,9 @@ __device__ __forceinline__ float div_by(float x, float d, float r)
     return fmaf(rem, r, q);
 }
 
-__global__ void __launch_bounds__(256, 6) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
+// MB: resident CTAs per SM the register allocation aims at (6: 40 registers with ~140 bytes of spills, 4: 64 registers, none)
+template <int MB>
+__global__ void __launch_bounds__(256, MB) k_mahalanobis(const float2* __restrict__ flow, size_t fstride_b,
                                                      const float* __restrict__ depth_ref, const float* __restrict__ depth_cur,
                                                      size_t dstride_b, const uint8_t* __restrict__ edge_ref,
                                                      const uint8_t* __restrict__ edge_cur, size_t estride_b,
@@ -615,8 +621,13 @@ int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* de
 {
     LaunchScope ls(st, s, "K2b_mahalanobis", 1);
     dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), batch);
-    GD_CUDA(launch_pdl(k_mahalanobis, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
-                                          edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
+    const char* env = std::getenv("GD_MAHA_MB");
+    if (env && std::atoi(env) == 4)
+        GD_CUDA(launch_pdl(k_mahalanobis<4>, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
+                           edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
+    else
+        GD_CUDA(launch_pdl(k_mahalanobis<6>, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
+                           edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
@@ -765,6 +776,153 @@ int launch_normalize_mask(const unsigned long long* keys, size_t keys_stride_b, 
     dim3 grid(cdiv(cdiv(n_px, 4), 256), batch);
     GD_CUDA(launch_pdl(k_normalize_mask, grid, dim3(256), 0, s, keys, keys_stride_b, n_px, minmax_bits, poses, kf.shift, mask, mask_stride_b));
     GD_CUDA(cudaGetLastError());
+    return GD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3, single pass: a thread-block cluster of K3_CS CTAs per stream.  Every CTA resolves its slice of the key image into
+// shared memory (f32, 4 bytes per pixel) while it reduces min / max; the partial results are exchanged through distributed
+// shared memory, cluster.sync(), and each CTA normalises + thresholds its slice straight from shared memory.  The key image
+// is read ONCE (8 bytes per pixel) and the mask written once: 9 bytes per pixel, the algorithmic minimum for this layout
+// (the two-kernel form reads the keys twice: 17).  Used when a slice fits one CTA's shared memory (640 x 480: 150 KB).
+// ------------------------------------------------------------------------------------------------
+constexpr int K3_CS = 8;          // portable cluster size
+constexpr int K3_THREADS = 1024;
+
+__global__ void __cluster_dims__(K3_CS, 1, 1) __launch_bounds__(K3_THREADS, 1)
+    k_minmax_mask_cluster(const unsigned long long* __restrict__ keys, size_t kstride_b, int n_px, int slice,
+                          const PoseDev* __restrict__ poses, int key_shift, unsigned int* __restrict__ minmax_bits,
+                          uint8_t* __restrict__ mask, size_t mstride_b)
+{
+    extern __shared__ __align__(16) unsigned char k3_sm[];
+    unsigned* vals = reinterpret_cast<unsigned*>(k3_sm);  // [slice] resolved value bits of this CTA's pixels
+    __shared__ unsigned s_part[4];                        // min bits, max bits, poison flag (pixel 0 is NaN), -
+    __shared__ unsigned s_wmn[K3_THREADS / 32], s_wmx[K3_THREADS / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.y, rank = (int)cluster.block_rank(), tid = threadIdx.x;
+    const unsigned long long* kp = keys + (size_t)b * kstride_b;
+    const unsigned epoch = (unsigned)poses[b].epoch;
+    const int i0 = rank * slice, i1 = max(i0, min(n_px, i0 + slice));  // slice is a multiple of 4; empty for tiny images
+    unsigned mn = 0xFFFFFFFFu, mx = 0u, poison = 0u;
+    if (tid == 0) s_part[2] = 0u;
+    __syncthreads();
+    // pass 1: two keys (16 bytes) per load, four loads in flight per thread
+    const int npair = (i1 - i0) >> 1;
+    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(kp + i0);
+    for (int p = tid; p < npair; p += K3_THREADS * 4) {
+        ulonglong2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (p + u * K3_THREADS < npair) v[u] = __ldg(k2 + p + u * K3_THREADS);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = p + u * K3_THREADS;
+            if (q >= npair) break;
+            const unsigned a = key_value_bits(v[u].x, key_shift, epoch), c = key_value_bits(v[u].y, key_shift, epoch);
+            reinterpret_cast<uint2*>(vals)[q] = make_uint2(a, c);
+            if (!bits_is_nan(a)) {
+                mn = min(mn, a);
+                mx = max(mx, a);
+            } else if (i0 + 2 * q == 0) {
+                poison = 1u;
+            }
+            if (!bits_is_nan(c)) {
+                mn = min(mn, c);
+                mx = max(mx, c);
+            }
+        }
+    }
+    if (((i1 - i0) & 1) && tid == 0) {  // odd tail (only the last slice of an odd-sized image)
+        const unsigned a = key_value_bits(kp[i1 - 1], key_shift, epoch);
+        vals[i1 - 1 - i0] = a;
+        if (!bits_is_nan(a)) {
+            mn = min(mn, a);
+            mx = max(mx, a);
+        } else if (i1 - 1 == 0) {
+            poison = 1u;
+        }
+    }
+    if (poison) s_part[2] = 1u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((tid & 31) == 0) {
+        s_wmn[tid >> 5] = mn;
+        s_wmx[tid >> 5] = mx;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        mn = s_wmn[tid];
+        mx = s_wmx[tid];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (tid == 0) {
+            s_part[0] = mn;
+            s_part[1] = mx;
+        }
+    }
+    cluster.sync();  // every CTA's partial result is in its shared memory
+    unsigned gmn = 0xFFFFFFFFu, gmx = 0u, gpoison = 0u;
+#pragma unroll
+    for (int r = 0; r < K3_CS; ++r) {
+        const unsigned* rp = cluster.map_shared_rank(s_part, r);
+        gmn = min(gmn, rp[0]);
+        gmx = max(gmx, rp[1]);
+        gpoison |= rp[2];
+    }
+    cluster.sync();  // nobody leaves (and frees its shared memory) while a peer may still read it
+    if (rank == 0 && tid == 0) {  // same encoding as the two-kernel form (debug fetch)
+        minmax_bits[GD_MM_WORDS * b] = gmn;
+        minmax_bits[GD_MM_WORDS * b + 1] = ~gmx;
+        minmax_bits[GD_MM_WORDS * b + 2] = gpoison ? 0u : 0xFFFFFFFFu;
+    }
+    const bool valid = poses[b].valid != 0 && gpoison == 0u;
+    const double smin = (double)__uint_as_float(gmn), smax = (double)__uint_as_float(gmx);
+    const double scale = 255.0 * ((smax - smin) > 2.220446049250313e-16 ? 1.0 / (smax - smin) : 0.0);
+    const double shift = 0.0 - smin * scale;
+    const float a = (float)scale, bsh = (float)shift;
+    uint8_t* mp = mask + (size_t)b * mstride_b;
+    const int nquad = (i1 - i0) >> 2;
+    for (int q = tid; q < nquad; q += K3_THREADS) {
+        const uint4 v = reinterpret_cast<const uint4*>(vals)[q];
+        unsigned m = 0x01010101u;
+        if (valid)
+            m = mask_of(__uint_as_float(v.x), a, bsh) | (mask_of(__uint_as_float(v.y), a, bsh) << 8) |
+                (mask_of(__uint_as_float(v.z), a, bsh) << 16) | (mask_of(__uint_as_float(v.w), a, bsh) << 24);
+        *reinterpret_cast<unsigned*>(mp + i0 + 4 * q) = m;
+    }
+    for (int i = i0 + 4 * nquad + tid; i < i1; i += K3_THREADS)  // tail of an image whose size is not a multiple of 4
+        mp[i] = valid ? (uint8_t)mask_of(__uint_as_float(vals[i - i0]), a, bsh) : (uint8_t)1;
+}
+
+// returns GD_OK and sets *used when the cluster form fits (slice in shared memory, aligned strides); otherwise *used = false
+int launch_minmax_mask_cluster(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses,
+                               KeyFormat kf, unsigned int* minmax_bits, uint8_t* mask, size_t mask_stride_b, cudaStream_t s,
+                               LaunchStats* st, bool* used)
+{
+    *used = false;
+    const char* env = std::getenv("GD_K3_CLUSTER");
+    if (env && std::atoi(env) == 0) return GD_OK;
+    const int slice = (int)align_up((size_t)cdiv(n_px, K3_CS), 4);
+    const size_t smem = (size_t)slice * 4;
+    if (smem > 200 * 1024 || (mask_stride_b & 3) != 0 || (keys_stride_b & 1) != 0 || (slice & 1) != 0) return GD_OK;
+    static thread_local int attr_device = -1;
+    int dev = 0;
+    GD_CUDA(cudaGetDevice(&dev));
+    if (attr_device != dev) {
+        GD_CUDA(cudaFuncSetAttribute(k_minmax_mask_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_device = dev;
+    }
+    LaunchScope ls(st, s, "K3_minmax_mask", 1);
+    k_minmax_mask_cluster<<<dim3(K3_CS, batch), K3_THREADS, smem, s>>>(keys, keys_stride_b, n_px, slice, poses, kf.shift, minmax_bits, mask,
+                                                                      mask_stride_b);
+    GD_CUDA(cudaGetLastError());
+    *used = true;
     return GD_OK;
 }
 

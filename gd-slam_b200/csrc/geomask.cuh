@@ -100,6 +100,11 @@ int launch_minmax(const unsigned long long* keys, size_t keys_stride_b, int n_px
 int launch_normalize_mask(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch,
                           const unsigned int* minmax_bits, const PoseDev* poses, KeyFormat kf, uint8_t* mask,
                           size_t mask_stride_b, cudaStream_t s, LaunchStats* st);
+// K3 in one pass (thread-block cluster per stream, partial min/max exchanged through distributed shared memory); *used is
+// false when the image is too large for a slice to stay in shared memory: the caller then runs the two kernels above
+int launch_minmax_mask_cluster(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses,
+                               KeyFormat kf, unsigned int* minmax_bits, uint8_t* mask, size_t mask_stride_b, cudaStream_t s,
+                               LaunchStats* st, bool* used);
 // debug / parity only: the resolved f32 dist image of the last step (GeoMaskMaker.cc:269, before normalize)
 int launch_resolve_dist(const unsigned long long* keys, size_t keys_stride_b, int n_px, int batch, const PoseDev* poses,
                         KeyFormat kf, float* dist_out, size_t dist_stride_b, cudaStream_t s);

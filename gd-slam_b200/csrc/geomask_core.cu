@@ -254,6 +254,10 @@ int GeoMaskCore::enqueue_mask_tail()
                               edge.as<uint8_t>() + (size_t)ref * n_pad, edge.as<uint8_t>() + (size_t)cur * n_pad,
                               (size_t)GD_RING * n_pad, has_lut ? lut.as<float2>() : nullptr, w, h, batch, cam,
                               poses.as<PoseDev>(), keyfmt, keys.as<unsigned long long>(), n_pad, stream, stats));
+    bool clustered = false;
+    GD_TRY(launch_minmax_mask_cluster(keys.as<unsigned long long>(), n_pad, (int)n, batch, poses.as<PoseDev>(), keyfmt,
+                                      minmax.as<unsigned>(), mask.as<uint8_t>(), n_pad, stream, stats, &clustered));
+    if (clustered) return GD_OK;
     GD_TRY(launch_minmax_reset(minmax.as<unsigned>(), batch, stream));
     GD_TRY(launch_minmax(keys.as<unsigned long long>(), n_pad, (int)n, batch, poses.as<PoseDev>(), keyfmt, minmax.as<unsigned>(),
                          stream, stats));

@@ -90,9 +90,9 @@ def test_frontend_profile_families(capi, synth):
     fe.profile(False)
     fam = {n: (ms, ln) for n, ms, ln in fe.profile_read()}
     assert ("K1b_flow_iter" in fam) or ("K1b_matrices" in fam and "K1b_box_solve" in fam)  # fused or split flow form
-    for name in ("K0_gray", "K1a_polyexp", "K2a_depth_edge", "K2b_mahalanobis", "K3a_minmax",
-                 "K3b_normalize_mask", "K4a_pyramid_resize", "K4b_fast_cells", "K4c_quadtree", "K4e_blur7",
-                 "K4de_orient_describe"):
+    assert "K3_minmax_mask" in fam or ("K3a_minmax" in fam and "K3b_normalize_mask" in fam)  # cluster form or two kernels
+    for name in ("K0_gray", "K1a_polyexp", "K2a_depth_edge", "K2b_mahalanobis", "K4a_pyramid_resize", "K4b_fast_cells",
+                 "K4c_quadtree", "K4e_blur7", "K4de_orient_describe"):
         assert name in fam and fam[name][0] > 0, name
     fe.close()
 

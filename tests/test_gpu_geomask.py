@@ -375,3 +375,31 @@ def test_flow_kernel_variants_within_tolerance(capi, oracle, synth, golden, monk
     # the f32 tree sums cost a small part of the tolerance (recorded in DESIGN.md): keep a margin
     assert max(worst.values()) < 0.8, max(worst.items(), key=lambda kv: kv[1])
     print("flow variants, worst |d| / tolerance:", {str(k): round(r, 3) for k, r in worst.items() if k[1] in ("640", "cv2-320")})
+
+
+def test_k3_cluster_form_equals_two_kernel_form(capi, oracle, synth, monkeypatch):
+    """K3 as one thread-block-cluster kernel (partial min/max through distributed shared memory) vs the two-kernel form:
+    identical mask, min/max and dist, including an image size that is not a multiple of the slice and a NaN value."""
+    from test_oracle_geomask import nan_case
+
+    cases = []
+    s = synth.SyntheticStream(0)
+    f0, f5 = s.frame(0), s.frame(5)
+    K = synth.intrinsics()
+    R, T = s.pair_pose(0, 5)
+    flow = oracle.farneback(oracle.gray(f0.bgr), oracle.gray(f5.bgr))
+    e0, e5 = oracle.depth_edge(f0.depth_m, K), oracle.depth_edge(f5.depth_m, K)
+    cases.append((flow, f0.depth_m, f5.depth_m, e0, e5, K, R, T))
+    sub = (slice(0, 203), slice(0, 331))  # 203 x 331: odd size, ragged slices
+    cases.append((np.ascontiguousarray(flow[sub]), np.ascontiguousarray(f0.depth_m[sub]), np.ascontiguousarray(f5.depth_m[sub]),
+                  np.ascontiguousarray(e0[sub]), np.ascontiguousarray(e5[sub]), K, R, T))
+    fl, dr, dc, e, Kn, Rn, Tn, _ = nan_case(oracle, want_inputs=True)
+    cases.append((fl, dr, dc, e, e, Kn, Rn, Tn))
+    for c in cases:
+        monkeypatch.setenv("GD_K3_CLUSTER", "0")
+        d0, m0, mm0 = capi.stage_mahalanobis(*c)
+        monkeypatch.setenv("GD_K3_CLUSTER", "1")
+        d1, m1, mm1 = capi.stage_mahalanobis(*c)
+        assert np.array_equal(m0, m1) and np.array_equal(mm0, mm1, equal_nan=True) and np.array_equal(d0, d1, equal_nan=True)
+        do, _, _ = oracle.mahalanobis(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7])
+        assert np.array_equal(m1, oracle.normalize_threshold(do)[0])
