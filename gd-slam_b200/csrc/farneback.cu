@@ -308,6 +308,7 @@ __device__ __forceinline__ size_t align_up_dev(size_t v, size_t a);
 struct PolyArgs {
     int w, h;
     float g[2 * FB_POLY_N + 1], xg[2 * FB_POLY_N + 1], xxg[2 * FB_POLY_N + 1];
+    double gd[FB_POLY_N + 1], xxgd[FB_POLY_N + 1];  // (double)g[k], (double)xxg[k] for k >= 0: the two taps multiplied in f64
     double ig11, ig03, ig33, ig55;
 };
 
@@ -323,32 +324,45 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
     const int b = blockIdx.z;
     const float* Ip = I + (size_t)b * istride_b;
     const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
-    const int tid = threadIdx.y * PT_W + threadIdx.x;
-    for (int i = tid; i < (PT_H + 2 * PN) * (PT_W + 2 * PN); i += PT_NT) {
-        const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
-        const int x = min(max(x0 + lx - PN, 0), a.w - 1), y = min(max(y0 + ly - PN, 0), a.h - 1);
-        sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
-    }
-    __syncthreads();
-    // vertical pass for PT_H rows x (PT_W + 10) columns
+    // tile + 5-px halo (replicate border): warp = tile rows (stride 8), lane = tile column (two passes: 32 + 10 columns) — no
+    // per-element division, the clamped column is computed once per pass
     const float* g = a.g + PN;
     const float* xg = a.xg + PN;
     const float* xxg = a.xxg + PN;
-    for (int i = tid; i < PT_H * (PT_W + 2 * PN); i += PT_NT) {
-        const int ly = i / (PT_W + 2 * PN), lx = i - ly * (PT_W + 2 * PN);
-        const int cy = ly + PN;
-        float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
+    constexpr int TW = PT_W + 2 * PN;  // 42
 #pragma unroll
-        for (int k = 1; k <= PN; ++k) {
-            const float s0 = sI[cy - k][lx], s1 = sI[cy + k][lx];
-            const float p = s0 + s1;
-            t0 = t0 + g[k] * p;
-            t1 = t1 + xg[k] * (s1 - s0);
-            t2 = t2 + xxg[k] * p;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int lx = threadIdx.x + 32 * pass;
+        if (lx < TW) {
+            const int x = min(max(x0 + lx - PN, 0), a.w - 1);
+            for (int ly = threadIdx.y; ly < PT_H + 2 * PN; ly += PT_TY) {
+                const int y = min(max(y0 + ly - PN, 0), a.h - 1);
+                sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
+            }
         }
-        sR[0][ly][lx] = t0;
-        sR[1][ly][lx] = t1;
-        sR[2][ly][lx] = t2;
+    }
+    __syncthreads();
+    // vertical pass for PT_H rows x (PT_W + 10) columns, same thread mapping
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int lx = threadIdx.x + 32 * pass;
+        if (lx < TW) {
+            for (int ly = threadIdx.y; ly < PT_H; ly += PT_TY) {
+                const int cy = ly + PN;
+                float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int k = 1; k <= PN; ++k) {
+                    const float s0 = sI[cy - k][lx], s1 = sI[cy + k][lx];
+                    const float p = s0 + s1;
+                    t0 = t0 + g[k] * p;
+                    t1 = t1 + xg[k] * (s1 - s0);
+                    t2 = t2 + xxg[k] * p;
+                }
+                sR[0][ly][lx] = t0;
+                sR[1][ly][lx] = t1;
+                sR[2][ly][lx] = t2;
+            }
+        }
     }
     __syncthreads();
     const int x = x0 + threadIdx.x;
@@ -367,8 +381,8 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
 #pragma unroll
         for (int k = 1; k <= PN; ++k) {
             const double tg = r0[lx + k] + r0[lx - k];
-            b1 += tg * g[k];
-            b4 += tg * xxg[k];
+            b1 += tg * a.gd[k];
+            b4 += tg * a.xxgd[k];
             b2 += (r0[lx + k] - r0[lx - k]) * xg[k];
             b3 += (r1[lx + k] + r1[lx - k]) * g[k];
             b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
@@ -419,6 +433,10 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
             std::memcpy(po.xg, plan.xg, sizeof(po.xg));
             std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
             po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
+            for (int q = 0; q <= FB_POLY_N; ++q) {
+                po.gd[q] = (double)plan.g[FB_POLY_N + q];
+                po.xxgd[q] = (double)plan.xxg[FB_POLY_N + q];
+            }
             dim3 block(PT_W, PT_TY), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
             GD_CUDA(launch_pdl(k_fb_polyexp, grid, block, 0, s, scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b));
             GD_CUDA(cudaGetLastError());

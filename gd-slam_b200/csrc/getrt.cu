@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_resize_linear_exact(const uint8_t* __re
 struct Gauss7 {
     float g[4];  // g[0] = centre tap
 };
-constexpr int GF_W = 32, GF_H = 8;
+constexpr int GF_W = 32, GF_H = 16;
 
 __device__ __forceinline__ int reflect101_dev(int p, int len)
 {
@@ -204,6 +204,166 @@ __device__ int sel_block_scan(int* data, int n, int* s_total)
     return *s_total;
 }
 
+// ---- CTA-wide Hoare partition: the rank rule of stdalgo::rank_pair_swap evaluated with prefix sums ---------------------
+// Every thread owns a contiguous chunk of [lo, hi) (at most 128 elements: n <= 128 * SEL_THREADS) and keeps the left-stop /
+// right-stop flags of its elements, taken from the ORIGINAL values, in registers.  tmp: 2 * W elements of scratch (the values
+// of the swapped pairs travel through it in batches of W ranks).  s_cnt: 2 * SEL_THREADS ints; s_red: 8 ints.  All threads
+// call; returns (to every thread) the position std::__unguarded_partition would return; for std::partition the caller
+// derives its own return value from the predicate count.
+constexpr int PAR_MAX_CHUNK = 128;
+
+template <class T, class IsL, class IsR>
+__device__ int par_pair_swap(T* v, int lo, int hi, IsL is_l, IsR is_r, T* tmp, int W, int* s_cnt, int* s_red)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int m = hi - lo, chunk = (m + SEL_THREADS - 1) / SEL_THREADS;
+    const int c0 = min(hi, lo + tid * chunk), c1 = min(hi, c0 + chunk);
+    unsigned long long fl0 = 0, fl1 = 0, fr0 = 0, fr1 = 0;  // flags of chunk element j: bit j of (j < 64 ? x0 : x1)
+    int cl = 0, cr = 0;
+    for (int i = c0; i < c1; ++i) {
+        const T e = v[i];
+        const int j = i - c0;
+        const unsigned long long bit = 1ull << (j & 63);
+        if (is_l(e)) {
+            cl += 1;
+            if (j < 64) fl0 |= bit; else fl1 |= bit;
+        }
+        if (is_r(e)) {
+            cr += 1;
+            if (j < 64) fr0 |= bit; else fr1 |= bit;
+        }
+    }
+    s_cnt[tid] = cl;
+    s_cnt[SEL_THREADS + tid] = cr;
+    if (tid < 8) s_red[tid] = tid == 0 ? 0 : 0x7FFFFFFF;  // [0] K, [1] l_0, [2] l_K, [3] r_{K-1}
+    __syncthreads();
+    if (tid < 32) {  // exclusive prefix sums of both count arrays by warp 0; totals in s_red[4], s_red[5]
+        int carryL = 0, carryR = 0;
+        for (int base = 0; base < SEL_THREADS; base += 32) {
+            const int a = s_cnt[base + lane], b2 = s_cnt[SEL_THREADS + base + lane];
+            int xa = a, xb = b2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+                if (lane >= o) {
+                    xa += ya;
+                    xb += yb;
+                }
+            }
+            s_cnt[base + lane] = carryL + xa - a;
+            s_cnt[SEL_THREADS + base + lane] = carryR + xb - b2;
+            carryL += __shfl_sync(0xffffffffu, xa, 31);
+            carryR += __shfl_sync(0xffffffffu, xb, 31);
+        }
+        if (lane == 0) {
+            s_red[4] = carryL;
+            s_red[5] = carryR;
+        }
+    }
+    __syncthreads();
+    const int preL = s_cnt[tid];                                   // left stops left of my chunk
+    const int sufR = s_red[5] - s_cnt[SEL_THREADS + tid] - cr;     // right stops right of my chunk
+    auto flag = [](unsigned long long x0, unsigned long long x1, int j) -> bool { return ((j < 64 ? x0 : x1) >> (j & 63)) & 1ull; };
+    // decide: a left stop of rank L is swapped iff more than L right stops lie to its right (and symmetrically)
+    int myK = 0;
+    {
+        int L = preL, Rr = sufR + cr;
+        for (int i = c0; i < c1; ++i) {
+            const bool isl = flag(fl0, fl1, i - c0), isr = flag(fr0, fr1, i - c0);
+            if (isr) Rr -= 1;
+            if (isl) {
+                if (L == 0) atomicMin(&s_red[1], i);
+                if (Rr > L)
+                    myK += 1;
+                else
+                    atomicMin(&s_red[2], i);
+            }
+            if (isr && L > Rr) atomicMin(&s_red[3], i);
+            if (isl) L += 1;
+        }
+    }
+    if (myK) atomicAdd(&s_red[0], myK);
+    __syncthreads();
+    const int K = s_red[0];
+    for (int base = 0; base < K; base += W) {  // values of the pairs with rank in [base, base + W) through the scratch
+        for (int pass = 0; pass < 2; ++pass) {
+            int L = preL, Rr = sufR + cr;
+            for (int i = c0; i < c1; ++i) {
+                const bool isl = flag(fl0, fl1, i - c0), isr = flag(fr0, fr1, i - c0);
+                if (isr) Rr -= 1;
+                if (isl && Rr > L && L >= base && L < base + W) {
+                    if (pass == 0)
+                        tmp[L - base] = v[i];
+                    else
+                        v[i] = tmp[W + L - base];
+                } else if (isr && L > Rr && Rr >= base && Rr < base + W) {
+                    if (pass == 0)
+                        tmp[W + Rr - base] = v[i];
+                    else
+                        v[i] = tmp[Rr - base];
+                }
+                if (isl) L += 1;
+            }
+            __syncthreads();
+        }
+    }
+    const int l0 = s_red[1], lK = s_red[2], rK1 = s_red[3];
+    __syncthreads();
+    if (K == 0) return l0;
+    return (lK != 0x7FFFFFFF && lK < rK1) ? lK : rK1;
+}
+
+// std::nth_element by the whole CTA: libstdc++'s introselect loop with the partition above; ranges of at most SEQ_CUT
+// elements (and the heap fallback) are finished by thread 0 with the sequential restatement.  Less(a, b).
+constexpr int PAR_SEQ_CUT = 256;
+template <class T, class Less>
+__device__ void par_nth_element(T* v, int n, int nth, Less less, T* tmp, int W, int* s_cnt, int* s_red)
+{
+    int first = 0, last = n;
+    int depth = stdalgo::lg_((long)n) * 2;
+    while (last - first > 3) {
+        if (last - first <= PAR_SEQ_CUT || depth == 0) break;
+        --depth;
+        if (threadIdx.x == 0) stdalgo::move_median_to_first(v + first, v + first + 1, v + first + (last - first) / 2, v + last - 1, less);
+        __syncthreads();
+        const T pivot = v[first];
+        const int cut = par_pair_swap(v, first + 1, last, [pivot, less](const T& e) { return !less(e, pivot); },
+                                      [pivot, less](const T& e) { return !less(pivot, e); }, tmp, W, s_cnt, s_red);
+        if (cut <= nth)
+            first = cut;
+        else
+            last = cut;
+    }
+    if (threadIdx.x == 0) stdalgo::introselect(v + first, v + nth, v + last, depth, less);  // also covers last - first <= 3
+    __syncthreads();
+}
+
+// cv::KeyPointsFilter::retainBest by the whole CTA (see stdalgo::retain_best for the sequential statement); key(e) is the
+// response, larger first.  Returns the new size to every thread.
+template <class T, class Key>
+__device__ int par_retain_best(T* v, int n, int n_points, Key key, T* tmp, int W, int* s_cnt, int* s_red)
+{
+    if (n_points < 0 || n <= n_points) return n;
+    if (n_points == 0) return 0;
+    par_nth_element(v, n, n_points - 1, [key](const T& a, const T& b) { return key(a) > key(b); }, tmp, W, s_cnt, s_red);
+    const auto amb = key(v[n_points - 1]);
+    // std::partition(v + n_points, v + n, key >= amb): left pointer stops at !pred, right pointer at pred
+    const int m = n - n_points;
+    if (m <= PAR_SEQ_CUT) {
+        __shared__ int s_end;
+        if (threadIdx.x == 0) s_end = (int)(stdalgo::partition(v + n_points, v + n, [key, amb](const T& e) { return key(e) >= amb; }) - v);
+        __syncthreads();
+        const int r = s_end;
+        __syncthreads();
+        return r;
+    }
+    par_pair_swap(v, n_points, n, [key, amb](const T& e) { return !(key(e) >= amb); }, [key, amb](const T& e) { return key(e) >= amb; }, tmp, W,
+                  s_cnt, s_red);
+    const int npred = s_red[5];  // total number of right stops = elements with pred true (left there by par_pair_swap)
+    __syncthreads();
+    return n_points + npred;
+}
+
 // One CTA per (level, stream): cv::ORB's computeKeyPoints for that level after cv::FAST.
 //   list1 (u32: response << 24 | pixel index)  = the FAST output inside the 31-px border in raster order
 //   retainBest(list1, 2 N) by one thread, Harris responses by all, retainBest(list2, N) by one thread
@@ -216,7 +376,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __r
     unsigned* list1 = reinterpret_cast<unsigned*>(sel_sm);
     HarrisEntry* list2 = reinterpret_cast<HarrisEntry*>(sel_sm + (size_t)a.n1_cap_max * 4);
     int* rowoff = reinterpret_cast<int*>(list2);  // scratch until list2 is filled (h <= 2 * n2_cap ints)
-    __shared__ int s_total, s_n;
+    __shared__ int s_total, s_cnt[2 * SEL_THREADS], s_red[8];
     const int l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const SelLevel L = a.lv[l];
     const int edge = a.edge;
@@ -252,9 +412,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __r
         }
     }
     __syncthreads();
-    if (tid == 0) s_n = stdalgo::retain_best(list1, n1, 2 * L.N, [](unsigned e) { return e >> 24; });
-    __syncthreads();
-    int n2 = s_n;
+    // stage 1: the scratch of the partition lives in the (still unused) list2 region
+    int n2 = par_retain_best(list1, n1, 2 * L.N, [](const unsigned& e) { return e >> 24; }, reinterpret_cast<unsigned*>(list2), a.n2_cap, s_cnt,
+                             s_red);
     if (n2 > a.n2_cap) {
         if (tid == 0) atomicOr(err, 8);
         n2 = a.n2_cap;
@@ -269,9 +429,9 @@ __global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __r
         list2[i] = e;
     }
     __syncthreads();
-    if (tid == 0) s_n = stdalgo::retain_best(list2, n2, L.N, [](const HarrisEntry& e) { return e.r; });
-    __syncthreads();
-    int n3 = s_n;
+    // stage 2: list1 is no longer needed — its region is the scratch (n1_cap_max * 4 bytes >= 2 * W * 8)
+    int n3 = par_retain_best(list2, n2, L.N, [](const HarrisEntry& e) { return e.r; }, reinterpret_cast<HarrisEntry*>(list1), a.n1_cap_max / 4,
+                             s_cnt, s_red);
     if (n3 > a.sel_cap) {
         if (tid == 0) atomicOr(err, 16);
         n3 = a.sel_cap;

@@ -174,6 +174,26 @@ GD_HD void sort_heap_(T* first, T* last, Less less)
     }
 }
 
+// std::__introselect(first, nth, last, depth_limit, less): the loop of std::nth_element from a given state
+template <class T, class Less>
+GD_HD void introselect(T* first, T* nth, T* last, int depth_limit, Less less)
+{
+    while (last - first > 3) {
+        if (depth_limit == 0) {
+            heap_select(first, nth + 1, last, less);
+            swap_(*first, *nth);
+            return;
+        }
+        --depth_limit;
+        T* cut = unguarded_partition_pivot(first, last, less);
+        if (cut <= nth)
+            first = cut;
+        else
+            last = cut;
+    }
+    insertion_sort(first, last, less);
+}
+
 // std::nth_element(first, nth, last, less)
 template <class T, class Less>
 GD_HD void nth_element(T* first, T* nth, T* last, Less less)
@@ -304,6 +324,51 @@ GD_HD long sort_prefix(T* first, T* last, long k, Less less)
         stop = last;
     }
     return (long)(stop - first);
+}
+
+// ---- the Hoare partition as a data-parallel rule (what the CTA-wide selection kernel implements) ------------------------
+// std::__unguarded_partition and std::partition both run two pointers towards each other: the left one stops at elements
+// for which is_left_stop holds, the right one at is_right_stop, the two stopped elements are swapped, and the scan goes on
+// until the pointers meet.  The pointers only ever look at elements they have not visited, so with l_k = the k-th left
+// stop from the left and r_k = the k-th right stop from the right (in the ORIGINAL array) the result is: swap (l_k, r_k)
+// for every k with l_k < r_k, nothing else.  A left stop x of rank k is swapped iff more than k right stops lie to its
+// right; symmetrically for a right stop.  K = number of swapped pairs.  The position the unguarded variant returns is
+// l_K when that left stop lies before r_{K-1} (or K = 0), else r_{K-1}.  This sequential statement of the rule is compared
+// with the pointer loops above in tests/native/stdalgo_check.cpp; the kernel evaluates the same rule with prefix sums.
+template <class T, class IsL, class IsR>
+GD_HD long rank_pair_swap(T* v, long lo, long hi, IsL is_left_stop, IsR is_right_stop)
+{
+    long nR = 0;
+    for (long i = lo; i < hi; ++i) nR += is_right_stop(v[i]) ? 1 : 0;
+    // first pass: ranks on the original values; find K, l_K and r_{K-1}
+    long K = 0, lK = -1, rK1 = -1, l0 = -1;
+    {
+        long L = 0, R_right = nR;  // left stops strictly left of i / right stops strictly right of i
+        for (long i = lo; i < hi; ++i) {
+            const bool isr = is_right_stop(v[i]), isl = is_left_stop(v[i]);
+            if (isr) R_right -= 1;
+            if (isl) {
+                if (l0 < 0) l0 = i;
+                if (R_right > L) K += 1;                    // swapped left stop (rank L)
+                else if (lK < 0) lK = i;                    // first unswapped left stop = l_K
+            }
+            if (isr && L > R_right && rK1 < 0) rK1 = i;     // leftmost swapped right stop = r_{K-1}
+            if (isl) L += 1;
+        }
+    }
+    // second pass: exchange the values of the swapped pairs (pair k: left rank k <-> right rank k)
+    {
+        long li = lo, ri = hi - 1;
+        for (long k = 0; k < K; ++k) {
+            while (!is_left_stop(v[li])) ++li;
+            while (!is_right_stop(v[ri])) --ri;
+            swap_(v[li], v[ri]);
+            ++li;
+            --ri;
+        }
+    }
+    if (K == 0) return l0;
+    return (lK >= 0 && lK < rK1) ? lK : rK1;
 }
 
 // cv::KeyPointsFilter::retainBest(keypoints, n_points) on an array of n elements ordered by `greater` on the response:

@@ -69,6 +69,36 @@ static int check_sort_prefix(std::mt19937& rng, int n, int levels, int k)
     return 0;
 }
 
+// the data-parallel statement of the Hoare partition (rank_pair_swap) against the two pointer loops
+static int check_rank_rule(std::mt19937& rng, int n, int levels)
+{
+    if (n < 8) return 0;
+    std::vector<E> a(n), b;
+    for (int i = 0; i < n; ++i) a[i] = {(float)(rng() % levels), i};
+    // unguarded partition as introselect calls it: median of three to the front, range [first + 1, last), pivot = *first
+    auto less = [](const E& x, const E& y) { return x.r > y.r; };
+    gd::stdalgo::move_median_to_first(a.data(), a.data() + 1, a.data() + n / 2, a.data() + n - 1, less);
+    b = a;
+    const E pivot = a[0];
+    E* cut_a = gd::stdalgo::unguarded_partition(a.data() + 1, a.data() + n, a.data(), less);
+    const long cut_b = gd::stdalgo::rank_pair_swap(b.data(), 1L, (long)n, [pivot, less](const E& e) { return !less(e, pivot); },
+                                                   [pivot, less](const E& e) { return !less(pivot, e); });
+    int bad = (cut_a - a.data()) != cut_b;
+    for (int i = 0; i < n; ++i) bad += a[i].i != b[i].i;
+    // std::partition(first, last, pred)
+    std::vector<E> c(n), d;
+    for (int i = 0; i < n; ++i) c[i] = {(float)(rng() % levels), i};
+    d = c;
+    const float amb = (float)(rng() % levels);
+    auto pa = std::partition(c.begin(), c.end(), [amb](const E& e) { return e.r >= amb; });
+    long npred = 0;
+    for (int i = 0; i < n; ++i) npred += d[i].r >= amb;
+    gd::stdalgo::rank_pair_swap(d.data(), 0L, (long)n, [amb](const E& e) { return !(e.r >= amb); }, [amb](const E& e) { return e.r >= amb; });
+    bad += (pa - c.begin()) != npred;
+    for (int i = 0; i < n; ++i) bad += c[i].i != d[i].i;
+    return bad ? 1 : 0;
+}
+
 // adversarial input that drives introsort / introselect into the heap fallback (depth limit 0): median-of-3 killer sequence
 static std::vector<E> killer(int n)
 {
@@ -111,6 +141,8 @@ extern "C" int gd_stdalgo_selfcheck(int seed, int rounds)
         bad += check_retain_best(rng, n, levels, n_points);
         bad += check_sort(rng, n, levels, r % 4);
         bad += check_sort_prefix(rng, n, levels, 100);
+        bad += check_rank_rule(rng, n, levels);
+        bad += check_rank_rule(rng, n, 1 + (int)(rng() % 3));
         bad += check_sort_prefix(rng, n, 1 + (int)(rng() % 257), 16 + (int)(rng() % 300));
     }
     // sizes around the thresholds (3 / 16) and the FAST-like case: 20 000 small-integer responses, keep 868
