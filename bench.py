@@ -362,6 +362,8 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the 8-streams-in-total (config 4 as written) side measurement")
     ap.add_argument("--no-getrt", action="store_true", help="skip the side measurement with the GetRt stage enabled")
     ap.add_argument("--quick", action="store_true", help="device-resident leg and kernel profile only (A/B runs of kernel variants)")
+    ap.add_argument("--probe-handles", action="store_true",
+                    help="experiment: device-resident throughput with the streams split over 1 / 2 / 4 handles (host threads)")
     ap.add_argument("--probe-pcie", action="store_true",
                     help="only time bare pinned cudaMemcpyAsync H2D / D2H on all ranks at once and print the rates")
     ap.add_argument("--res", default="640x480", help="WxH of the synthetic streams (configs[4]: 1280x720, 1920x1080)")
@@ -496,6 +498,41 @@ def main():
     ms_total = max_over_ranks(ms_total)
     value = world * B * K_ / (ms_total * 1e-3)
 
+    if args.probe_handles:  # how much does interleaving independent groups of streams help? (wall clock, synchronised ends)
+        res = {}
+        for NHp in (1, 2, 4):
+            Bp = B // NHp
+            hs = [capi.Frontend(K, W, H, batch=Bp, device=device, staged_slots=S) for _ in range(NHp)]
+            for i, hnd in enumerate(hs):
+                for s in range(S):
+                    hnd.stage(s, hb[s, i * Bp:(i + 1) * Bp], hd[s, i * Bp:(i + 1) * Bp])
+
+            def loop(i, n, ev):
+                ev.wait()
+                for k in range(n):
+                    hs[i].step_staged(k % S, Rs[k % S, i * Bp:(i + 1) * Bp], Ts[k % S, i * Bp:(i + 1) * Bp])
+                hs[i].sync()
+
+            def run(n):
+                ev = threading.Event()
+                th = [threading.Thread(target=loop, args=(i, n, ev)) for i in range(NHp)]
+                for t in th:
+                    t.start()
+                t0 = time.perf_counter()
+                ev.set()
+                for t in th:
+                    t.join()
+                return time.perf_counter() - t0
+
+            run(6 + 12 + 5)
+            dt = run(K_)
+            res[NHp] = B * K_ / dt
+            for hnd in hs:
+                hnd.close()
+        print(json.dumps({"probe": "device-resident frames/s with the batch split over N handles", "streams": B,
+                          "single_handle_event_timed": value, "by_handles": res}), flush=True)
+        return
+
     # ---- parity of what was just timed: stream 0 (and the last stream) of the LAST timed step against the CPU oracle
     parity = None
     if rank == 0:
@@ -514,8 +551,12 @@ def main():
         fs = capi.Frontend(K, W, H, batch=bs, device=device, staged_slots=S)
         for s in range(S):
             fs.stage(s, hb[s, :bs], hd[s, :bs])
-        for k in range(6 + 2 * 6 + 40):  # ring, graph capture of the six ring phases, warm-up
-            fs.step_staged(k % S, Rs[k % S, :bs], Ts[k % S, :bs])
+        k, t_w = 0, time.perf_counter()
+        while k < 6 + 2 * 6 + 40 or time.perf_counter() - t_w < 0.6:  # ring, graph capture of the ring phases, then at least
+            fs.step_staged(k % S, Rs[k % S, :bs], Ts[k % S, :bs])     # 0.6 s of load: the GPU idled during the oracle check
+            k += 1                                                    # above and needs that long to be back at full clocks
+            if k % 64 == 0:
+                fs.sync()
         fs.sync()
         barrier()
         fs.timer_begin()
