@@ -188,13 +188,8 @@ int launch_gray(const uint8_t* bgr, size_t bgr_step, size_t bgr_stride_b, int w,
 // (nearly) idle.  k_depth_edge_f64 (the all-f64 kernel of round 1) stays as the path for cameras whose inv(K) has a
 // non-trivial third row, and as the in-tree cross-check (GD_EDGE_F64=1).
 //
-// Error bounds (u = 2^-24; S = max_i sum_j |Kinv_ij| * (W-1, H-1, 1); D = 3.5 m, the depth cut applied to interior pixels):
-//   h_f = Kinv_f * (x, y, 1)      |h_f - h| <= 6 u S            (constants rounded to f32, two products, two sums)
-//   v_f = h_f * d                 |v_f - v| <= 7 u S D =: ev
-//   diff_f = v_j - v_c            |.| <= 2 ev + 2 u S D = 16 u S D =: ed
-//   n_f = (dl - dc, dt - dc, 1) * (1 / sqrt(ss))   relative error <= 4.5 u per component -> en = 5 u
-//   phi_d_f = v_j . n_c - v_c . n_c   each dot product within 45 u S D of the exact one        -> E_D = 192 u S D
-//   phi_c_f = 1 - sum_i n_j,i n_c,i   |.| <= 6 en + 4 u = 34 u                                  -> E_C = 40 u
+// Notation of the error bounds stated at the kernel: u = 2^-24; S = max_i sum_j |Kinv_ij| * (W-1, H-1, 1) (>= 1); D = 3.5 m,
+// the depth cut applied to interior pixels.
 // ------------------------------------------------------------------------------------------------
 constexpr int ET_W = 32, ET_H = 16;
 
@@ -276,120 +271,231 @@ __device__ __forceinline__ uint8_t edge_decide_f64(NV nv)
 __host__ __device__ constexpr int edge_nx(int k) { return k == 0 || k == 1 || k == 7 ? -1 : (k == 2 || k == 6 ? 0 : (k < 8 ? 1 : 0)); }
 __host__ __device__ constexpr int edge_ny(int k) { return k == 1 || k == 2 || k == 3 ? -1 : (k == 0 || k == 4 ? 0 : (k < 8 ? 1 : 0)); }
 
-__device__ __forceinline__ void load_depth_tile(const float* __restrict__ dp, int w, int h, int x0, int y0, int tid,
+// depth tile with halo 2, interior pixels clamped like :870-874.  Thread (tx, ty) of the 32 x 16 block loads rows ty, ty + 16 and
+// columns tx, tx + 32 (no index divisions).  Returns true when a loaded value is NaN or infinite (the f32 interval form is
+// only used on finite depths).
+__device__ __forceinline__ bool load_depth_tile(const float* __restrict__ dp, int w, int h, int x0, int y0, int tx, int ty,
                                                 float (*sd)[ET_W + 4])
 {
-    for (int i = tid; i < (ET_H + 4) * (ET_W + 4); i += ET_W * ET_H) {
-        const int ly = i / (ET_W + 4), lx = i - ly * (ET_W + 4);
-        const int x = x0 + lx - 2, y = y0 + ly - 2;
-        float v = 0.f;
-        if (x >= 0 && y >= 0 && x < w && y < h) {
-            v = __ldg(dp + (size_t)y * w + x);
-            const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
-            if (interior && v > 3.5f) v = 0.f;  // :870-874 ((double)v > 3.5 <=> v > 3.5f: 3.5 is a float)
+    bool bad = false;
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int ly = ty + ry * ET_H;
+        if (ly >= ET_H + 4) break;
+        const int y = y0 + ly - 2;
+#pragma unroll
+        for (int rx = 0; rx < 2; ++rx) {
+            const int lx = tx + rx * ET_W;
+            if (lx >= ET_W + 4) break;
+            const int x = x0 + lx - 2;
+            float v = 0.f;
+            if (x >= 0 && y >= 0 && x < w && y < h) {
+                v = __ldg(dp + (size_t)y * w + x);
+                const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
+                if (interior && v > 3.5f) v = 0.f;  // :870-874 ((double)v > 3.5 <=> v > 3.5f: 3.5 is a float)
+                bad = bad || !(fabsf(v) <= 3.0e38f);
+            }
+            sd[ly][lx] = v;
         }
-        sd[ly][lx] = v;
     }
+    return bad;
 }
 
 struct EdgeBounds {
-    float Ki[9];  // inv(K) rounded to f32
+    float Ki[6];  // first two rows of inv(K) rounded to f32 (the third row is (0, 0, 1) on this path)
     float e_d;    // bound on |phi_d_f32 - phi_d_f64|
     float e_c;    // bound on |phi_c_f32 - phi_c_f64|
 };
 
-// f32 interval form.  Per pixel two float4 in shared memory: A = (n0, n1, n2, v . n), B = (v0, v1, v2, -): with
-// phi_d = (v_j - v_c) . n_c = v_j . n_c - v_c . n_c a neighbour costs two vector loads, two 3-term dot products and the
-// interval bookkeeping.  Error bounds (fused multiply-adds only make them smaller):
-//   |v_j . n_c (f32) - exact| <= 3 (S D en + ev) + 9 u S D = 45 u S D, the same for v_c . n_c  -> E_D = 192 u S D (> 90 u S D)
-__global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
-                                                            CamConst cam, EdgeBounds eb, uint8_t* __restrict__ edge, size_t estride_b)
+// f32 interval form.  Shared memory holds ONE float4 per pixel, A = (n0, n1, n2, depth); the vertex is never stored:
+// with h(x, y) = inv(K) (x, y, 1) and v = h * depth,
+//     phi_d = (v_j - v_c) . n_c = d_j * G_j - d_c * g,     g = h_c . n_c,   G_j = g + dx * gx + dy * gy,
+//     gx = Ki0 n0 + Ki3 n1,  gy = Ki1 n0 + Ki4 n1          (h_j - h_c = dx * column 0 + dy * column 1 of inv(K)),
+// so a neighbour costs one vector load, one fused multiply-add for phi_d, three for phi_c and the interval bookkeeping.
+// n2 = 1 / sqrt(ss) lies in [0.19, 1], so n2 == 0 marks "no normal / zero vertex" (border pixels, pixels whose own, top or
+// left depth is missing).  Error bounds (u = 2^-24, S >= 1 and D = 3.5 as above; the reference's own f64 rounding is below
+// 1e-15 and covered by the margins):
+//   n_f: c = dl - dc rounds once (u), ss = fma(c0, c0, fma(c1, c1, 1)) is within 4 u, MUFU.RSQ within 2 ulp = 4 u + 2 u from
+//        ss, the product one more: relative error <= 10 u                                             -> en = 12 u
+//   h_f: |h_f - h| <= 6 u S;   g_f: 2 (6 + 12) u S + 12 u inputs + 3 roundings of <= 3 u S            -> 57 u S
+//   gx_f, gy_f: <= 15 u (|Ki0| + |Ki3|) <= 30 u S each;  G_j: g, gx, gy and two roundings             -> 123 u S
+//   phi_d_f = fma(d_j, G_j, -d_c g): D 123 u S + D 57 u S + 3 u S D + 7 u S D = 190 u S D             -> E_D = 256 u S D
+//   phi_c_f = 1 - sum_i n_j,i n_c,i: 12 u sum_i (|n_c,i| + |n_j,i|) <= 42 u, + 4 u of roundings       -> E_C = 64 u
+//
+// Execution: the kernel is latency bound when every tile is its own CTA (ncu: barrier + long-scoreboard stalls, the depth
+// images come from DRAM), so it is PERSISTENT — 2 CTAs per SM walk the tile list, and the depth values of tile i+1 are
+// requested into registers right after tile i's values have been published to shared memory; they arrive while the normals
+// and the neighbour loop of tile i run.  The depth tile is double buffered (the exact f64 pass of stragglers may still read
+// the old one), the per-tile flags alternate between two slots, three barriers per tile.
+struct EdgeTiles {
+    int tiles_x, tiles_per_img, total;
+    unsigned magic_x, magic_img;  // ceil(2^32 / d): __umulhi(t, magic) == t / d for t * d < 2^32
+};
+
+__device__ __forceinline__ float edge_load_clamped(const float* __restrict__ dp, int x, int y, int w, int h)
+{
+    float v = 0.f;
+    if (x >= 0 && y >= 0 && x < w && y < h) {
+        v = __ldg(dp + (size_t)y * w + x);
+        const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
+        if (interior && v > 3.5f) v = 0.f;  // :870-874 ((double)v > 3.5 <=> v > 3.5f: 3.5 is a float)
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
+                                                               CamConst cam, EdgeBounds eb, EdgeTiles et, uint8_t* __restrict__ edge,
+                                                               size_t estride_b)
 {
     pdl_wait();
-    __shared__ float sd[ET_H + 4][ET_W + 4];       // clamped depth, halo 2
-    __shared__ float4 sA[ET_H + 2][ET_W + 2];      // (normal, v . n), halo 1
-    __shared__ float4 sB[ET_H + 2][ET_W + 2];      // (vertex, -), halo 1; z == 0 <=> the reference's vertex is zero
+    __shared__ float sd2[2][ET_H + 4][ET_W + 4];   // clamped depth, halo 2 (double buffered)
+    __shared__ float4 sA[ET_H + 2][ET_W + 2];      // (normal, clamped depth), halo 1
     __shared__ int s_todo[ET_W * ET_H];
-    __shared__ int s_ntodo;
-    const int b = blockIdx.z;
-    const float* dp = depth + (size_t)b * dstride_b;
-    const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
-    const int tid = threadIdx.y * ET_W + threadIdx.x;
-    if (tid == 0) s_ntodo = 0;
-    load_depth_tile(dp, w, h, x0, y0, tid, sd);
-    __syncthreads();
-    for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
-        const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
-        const int x = x0 + lx - 1, y = y0 + ly - 1;
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-        if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
-            const float dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
-            if (dc != 0.f && dt != 0.f && dl != 0.f) {
-                const float c0 = dl - dc, c1 = dt - dc;
-                const float ss = fmaf(c0, c0, fmaf(c1, c1, 1.0f));
-                const float inv = 1.0f / sqrtf(ss);  // IEEE sqrt and division (this file is built without fast math)
-                A.x = c0 * inv;
-                A.y = c1 * inv;
-                A.z = inv;
+    __shared__ int s_flags[2][2];                  // per tile parity: {number of undecided pixels, non-finite depth seen}
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * ET_W + tx;
+    if (tid < 4) (&s_flags[0][0])[tid] = 0;
+    // Besides its own element every thread of the first warps owns one element of the halo strips (no per-element divisions
+    // inside the tile loop): depth tile = rows 16..19 (4 x 36) + columns 32..35 of rows 0..15 (16 x 4) = 208 elements,
+    // normal tile = rows 16..17 (2 x 34) + columns 32..33 of rows 0..15 (16 x 2) = 100 elements.
+    int dly = -1, dlx = 0, nly = -1, nlx = 0;
+    if (tid < 4 * (ET_W + 4)) {
+        dly = ET_H + tid / (ET_W + 4);
+        dlx = tid % (ET_W + 4);
+    } else if (tid < 4 * (ET_W + 4) + ET_H * 4) {
+        const int k = tid - 4 * (ET_W + 4);
+        dly = k >> 2;
+        dlx = ET_W + (k & 3);
+    }
+    if (tid < 2 * (ET_W + 2)) {
+        nly = ET_H + tid / (ET_W + 2);
+        nlx = tid % (ET_W + 2);
+    } else if (tid < 2 * (ET_W + 2) + ET_H * 2) {
+        const int k = tid - 2 * (ET_W + 2);
+        nly = k >> 1;
+        nlx = ET_W + (k & 1);
+    }
+    int tile = blockIdx.x;
+    int b = 0, x0 = 0, y0 = 0;
+    auto decode = [&](int t, int& tb, int& tx0, int& ty0) {
+        tb = (int)__umulhi((unsigned)t, et.magic_img);
+        const int r = t - tb * et.tiles_per_img;
+        const int tyi = (int)__umulhi((unsigned)r, et.magic_x);
+        tx0 = (r - tyi * et.tiles_x) * ET_W;
+        ty0 = tyi * ET_H;
+    };
+    float v0 = 0.f, v1 = 0.f;
+    if (tile < et.total) {
+        decode(tile, b, x0, y0);
+        const float* dp = depth + (size_t)b * dstride_b;
+        v0 = edge_load_clamped(dp, x0 + tx - 2, y0 + ty - 2, w, h);
+        if (dly >= 0) v1 = edge_load_clamped(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
+    }
+    __syncthreads();  // flags zeroed
+    for (int it = 0; tile < et.total; ++it, tile += gridDim.x) {
+        const int par = it & 1;
+        float (*sd)[ET_W + 4] = sd2[par];
+        sd[ty][tx] = v0;
+        bool bad = !(fabsf(v0) <= 3.0e38f);
+        if (dly >= 0) {
+            sd[dly][dlx] = v1;
+            bad = bad || !(fabsf(v1) <= 3.0e38f);
+        }
+        if (bad) s_flags[par][1] = 1;
+        __syncthreads();
+        const int cb = b, cx0 = x0, cy0 = y0;  // the tile being evaluated
+        {
+            const int nt = tile + gridDim.x;
+            if (tid < 2) s_flags[par ^ 1][tid] = 0;  // last read before the barrier above, next written after the third one
+            if (nt < et.total) {
+                decode(nt, b, x0, y0);
+                const float* dp = depth + (size_t)b * dstride_b;
+                v0 = edge_load_clamped(dp, x0 + tx - 2, y0 + ty - 2, w, h);
+                if (dly >= 0) v1 = edge_load_clamped(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
+            }
+        }
+        auto normal_at = [&](int ly, int lx) {  // normal tile element (halo 1) from the depth tile (halo 2)
+            const int x = cx0 + lx - 1, y = cy0 + ly - 1;
+            float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x >= 1 && y >= 1 && x < w - 1 && y < h - 1) {
+                const float dc = sd[ly + 1][lx + 1], dt = sd[ly][lx + 1], dl = sd[ly + 1][lx];
+                A.w = dc;
+                if (dc != 0.f && dt != 0.f && dl != 0.f) {
+                    const float c0 = dl - dc, c1 = dt - dc;
+                    const float ss = fmaf(c0, c0, fmaf(c1, c1, 1.0f));
+                    float inv;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ss));
+                    A.x = c0 * inv;
+                    A.y = c1 * inv;
+                    A.z = inv;
+                }
+            }
+            sA[ly][lx] = A;
+        };
+        normal_at(ty, tx);
+        if (nly >= 0) normal_at(nly, nlx);
+        __syncthreads();
+        const int x = cx0 + tx, y = cy0 + ty;
+        const bool in_img = x < w && y < h;
+        uint8_t e = 0;
+        const int lx = tx + 1, ly = ty + 1;
+        const float4 Ac = sA[ly][lx];
+        if (in_img && x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && Ac.w != 0.f) {
+            if (Ac.z == 0.f) {
+                // a pixel with depth but without a normal (its top or left neighbour has no depth): cn = cv = 0 -> a zero vertex
+                // among the neighbours, or phi_d = 0 and phi_c = 1 for every neighbour -> 0.05 > 0.04: edge in both cases
+                e = 255;
+            } else if (s_flags[par][1]) {
+                s_todo[atomicAdd(&s_flags[par][0], 1)] = (ly << 8) | lx;
+            } else {
                 const float px = (float)x, py = (float)y;
                 const float h0 = fmaf(eb.Ki[0], px, fmaf(eb.Ki[1], py, eb.Ki[2]));
                 const float h1 = fmaf(eb.Ki[3], px, fmaf(eb.Ki[4], py, eb.Ki[5]));
-                B.x = h0 * dc;
-                B.y = h1 * dc;
-                B.z = dc;  // third row of inv(K) is (0, 0, 1) on this path: z = depth, like the reference's 1.0 * dc
-                A.w = fmaf(B.x, A.x, fmaf(B.y, A.y, B.z * A.z));
+                const float g = fmaf(h0, Ac.x, fmaf(h1, Ac.y, Ac.z));
+                const float gx = fmaf(eb.Ki[0], Ac.x, eb.Ki[3] * Ac.y);
+                const float gy = fmaf(eb.Ki[1], Ac.x, eb.Ki[4] * Ac.y);
+                const float ncw = -(Ac.w * g);
+                const float gxs[3] = {g - gx, g, g + gx};
+                float minz = 1.f, maxd = 0.f, c_lo = 0.f, c_hi = 0.f;  // eight valid neighbours -> both maxima are >= 0 in the reference
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int dx = edge_nx(k), dy = edge_ny(k);
+                    const float4 Aj = sA[ly + dy][lx + dx];
+                    const float G = dy == 0 ? gxs[dx + 1] : (dy < 0 ? gxs[dx + 1] - gy : gxs[dx + 1] + gy);
+                    minz = fminf(minz, Aj.z);
+                    const float phi_d = fmaf(Aj.w, G, ncw);
+                    const float phi_c = fmaf(-Aj.x, Ac.x, fmaf(-Aj.y, Ac.y, fmaf(-Aj.z, Ac.z, 1.0f)));
+                    maxd = fmaxf(maxd, fabsf(phi_d));
+                    // contribution of this neighbour to max_phi_c: phi_c when phi_d >= 0, 0 when phi_d < 0; undecided sign -> both
+                    if (phi_d >= -eb.e_d) c_hi = fmaxf(c_hi, phi_c);
+                    if (phi_d >= eb.e_d) c_lo = fmaxf(c_lo, phi_c);
+                }
+                if (minz == 0.f) {
+                    e = 255;  // a zero vertex among the neighbours (:925-949)
+                } else {
+                    const float slack = eb.e_d * 1.125f + 1e-6f;  // + rounding of the few f32 operations below
+                    const float t_lo = (maxd - slack) + 0.05f * (c_lo - eb.e_c);
+                    const float t_hi = (maxd + slack) + 0.05f * (c_hi + eb.e_c);
+                    if (t_lo > 0.04f)
+                        e = 255;
+                    else if (!(t_hi < 0.04f))
+                        s_todo[atomicAdd(&s_flags[par][0], 1)] = (ly << 8) | lx;  // undecided: exact f64 evaluation below
+                }
             }
         }
-        sA[ly][lx] = A;
-        sB[ly][lx] = B;
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool in_img = x < w && y < h;
-    uint8_t e = 0;
-    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
-    if (in_img && x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && sd[ly + 1][lx + 1] != 0.f) {
-        const float4 Ac = sA[ly][lx];
-        const float cz = sB[ly][lx].z;
-        bool zero_nb = false;
-        float maxd = 0.f, c_lo = 0.f, c_hi = 0.f;  // all eight neighbours valid below -> both maxima are >= 0 in the reference
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int jx = lx + edge_nx(k), jy = ly + edge_ny(k);
-            const float4 Aj = sA[jy][jx], Bj = sB[jy][jx];
-            zero_nb = zero_nb || Bj.z == 0.f;
-            const float phi_d = fmaf(Bj.x, Ac.x, fmaf(Bj.y, Ac.y, Bj.z * Ac.z)) - Ac.w;
-            const float phi_c = 1.0f - fmaf(Aj.x, Ac.x, fmaf(Aj.y, Ac.y, Aj.z * Ac.z));
-            maxd = fmaxf(maxd, fabsf(phi_d));
-            // contribution of this neighbour to max_phi_c: phi_c when phi_d >= 0, 0 when phi_d < 0; undecided sign -> both
-            c_hi = fmaxf(c_hi, phi_d >= -eb.e_d ? phi_c : 0.f);
-            c_lo = fmaxf(c_lo, phi_d >= eb.e_d ? phi_c : 0.f);
+        uint8_t* ep = edge + (size_t)cb * estride_b;
+        if (in_img) ep[(size_t)y * w + x] = e;
+        __syncthreads();
+        const int ntodo = s_flags[par][0];  // block-uniform
+        for (int t = tid; t < ntodo; t += ET_W * ET_H) {
+            const int ply = s_todo[t] >> 8, plx = s_todo[t] & 255;  // normal tile coordinates (halo 1)
+            const int px = cx0 + plx - 1, py = cy0 + ply - 1;
+            const uint8_t ex = edge_decide_f64([&](int k, double n[3], double v[3]) {
+                const int dx = k < 8 ? edge_nx(k) : 0, dy = k < 8 ? edge_ny(k) : 0;
+                edge_nv_f64(sd, ply + 1 + dy, plx + 1 + dx, px + dx, py + dy, w, h, cam, n, v);
+            });
+            ep[(size_t)py * w + px] = ex;
         }
-        if (zero_nb || cz == 0.f) {
-            // a zero vertex among the neighbours: edge (:925-949).  A pixel with depth but without a normal (its top or left
-            // neighbour has no depth): cn = cv = 0 -> phi_d = 0, phi_c = 1 for every valid neighbour -> 0.05 > 0.04: edge as well
-            e = 255;
-        } else {
-            const float slack = eb.e_d * 1.125f + 1e-6f;  // + rounding of the few f32 operations below
-            const float t_lo = (maxd - slack) + 0.05f * (c_lo - eb.e_c);
-            const float t_hi = (maxd + slack) + 0.05f * (c_hi + eb.e_c);
-            if (t_lo > 0.04f)
-                e = 255;
-            else if (!(t_hi < 0.04f))
-                s_todo[atomicAdd(&s_ntodo, 1)] = (ly << 8) | lx;  // undecided: exact f64 evaluation below
-        }
-    }
-    if (in_img) edge[(size_t)b * estride_b + (size_t)y * w + x] = e;
-    __syncthreads();
-    const int ntodo = s_ntodo;  // block-uniform
-    for (int t = tid; t < ntodo; t += ET_W * ET_H) {
-        const int ply = s_todo[t] >> 8, plx = s_todo[t] & 255;  // normal / vertex tile coordinates (halo 1)
-        const int px = x0 + plx - 1, py = y0 + ply - 1;
-        const uint8_t ex = edge_decide_f64([&](int k, double n[3], double v[3]) {
-            const int dx = k < 8 ? edge_nx(k) : 0, dy = k < 8 ? edge_ny(k) : 0;
-            edge_nv_f64(sd, ply + 1 + dy, plx + 1 + dx, px + dx, py + dy, w, h, cam, n, v);
-        });
-        edge[(size_t)b * estride_b + (size_t)py * w + px] = ex;
     }
 }
 
@@ -405,7 +511,7 @@ __global__ void __launch_bounds__(ET_W* ET_H) k_depth_edge_f64(const float* __re
     const float* dp = depth + (size_t)b * dstride_b;
     const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
     const int tid = threadIdx.y * ET_W + threadIdx.x;
-    load_depth_tile(dp, w, h, x0, y0, tid, sd);
+    load_depth_tile(dp, w, h, x0, y0, threadIdx.x, threadIdx.y, sd);
     __syncthreads();
     for (int i = tid; i < (ET_H + 2) * (ET_W + 2); i += ET_W * ET_H) {
         const int ly = i / (ET_W + 2), lx = i - ly * (ET_W + 2);
@@ -444,15 +550,34 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
         S = std::max(S, std::fabs(cam.Kid[3 * r]) * (w - 1) + std::fabs(cam.Kid[3 * r + 1]) * (h - 1) + std::fabs(cam.Kid[3 * r + 2]));
     S = std::max(S, 1.0);
     const double u = 5.9604644775390625e-08;  // 2^-24
-    const double e_d = 192.0 * u * S * 3.5;
+    const double e_d = 256.0 * u * S * 3.5;
     if (force_f64 || !plain_k || !(e_d < 1e-2)) {
         GD_CUDA(launch_pdl(k_depth_edge_f64, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
     } else {
         EdgeBounds eb;
-        for (int i = 0; i < 9; ++i) eb.Ki[i] = (float)cam.Kid[i];
+        for (int i = 0; i < 6; ++i) eb.Ki[i] = (float)cam.Kid[i];
         eb.e_d = (float)(e_d * 1.0000002);  // rounded up
-        eb.e_c = (float)(40.0 * u);
-        GD_CUDA(launch_pdl(k_depth_edge, grid, block, 0, s, depth, depth_stride_b, w, h, cam, eb, edge, edge_stride_b));
+        eb.e_c = (float)(64.0 * u);
+        EdgeTiles et;
+        et.tiles_x = (int)grid.x;
+        et.tiles_per_img = (int)(grid.x * grid.y);
+        et.total = et.tiles_per_img * batch;
+        auto magic = [](unsigned d) { return d <= 1u ? 0xFFFFFFFFu : (unsigned)(((1ull << 32) + d - 1) / d); };
+        et.magic_x = magic((unsigned)et.tiles_x);
+        et.magic_img = magic((unsigned)et.tiles_per_img);
+        const bool magic_ok = et.tiles_x > 1 && (unsigned long long)et.total * et.tiles_per_img < (1ull << 32);
+        if (!magic_ok) {
+            GD_CUDA(launch_pdl(k_depth_edge_f64, grid, block, 0, s, depth, depth_stride_b, w, h, cam, edge, edge_stride_b));
+        } else {
+            static int n_sm = 0;
+            if (!n_sm) {
+                int dev = 0;
+                GD_CUDA(cudaGetDevice(&dev));
+                GD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            }
+            const dim3 pgrid((unsigned)std::min(et.total, 2 * n_sm));
+            GD_CUDA(launch_pdl(k_depth_edge, pgrid, block, 0, s, depth, depth_stride_b, w, h, cam, eb, et, edge, edge_stride_b));
+        }
     }
     GD_CUDA(cudaGetLastError());
     return GD_OK;

@@ -100,6 +100,7 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
         GD_REQUIRE(L.nCols >= 1 && L.nRows >= 1, "level too small for one FAST cell");
         L.wCell = (int)std::ceil(width / L.nCols);
         L.hCell = (int)std::ceil(height / L.nRows);
+        GD_REQUIRE((long long)L.nCols * L.nRows * L.nCols < (1ll << 20), "too many FAST cells per level for the index split");
         L.cell_start = cells;
         cells += L.nCols * L.nRows;
         p->max_cells_level = std::max(p->max_cells_level, L.nCols * L.nRows);
@@ -122,12 +123,10 @@ int orb_make_plan(int nfeatures, float scale_factor, int nlevels, int ini_th, in
     p->pyr_bytes = off;
     p->total_cells = cells;
     p->cell_cap = ((p->tile_w - 6 + 1) / 2) * ((p->tile_h - 6 + 1) / 2);
-    GD_REQUIRE((p->tile_w - 9) * (p->tile_h - 6) <= 128 * 32, "FAST cell larger than the keep bitmap");
+    GD_REQUIRE(p->tile_w - 9 <= 64 && p->tile_h - 6 <= 64, "FAST cell larger than the keep bitmap (64 x 64)");
     p->cand_total = cand;
     p->kept_total = kept;
     GD_REQUIRE(p->max_N + 8 < 30000 && p->tile_w * p->tile_h * 2 < 200 * 1024, "plan exceeds kernel limits");
-    GD_REQUIRE((long long)(p->tile_w * p->tile_h + 8 * 64) * std::max(p->tile_w, p->tile_h) < (1ll << 20),
-               "FAST tile too large for the reciprocal-multiply index split");
     return GD_OK;
 }
 
@@ -188,6 +187,7 @@ struct FastLevelDev {
     int w, h, pitch;
     unsigned long long off;
     int nCols, nRows, wCell, hCell, cell_start;
+    unsigned inv_nCols;  // (1 << 20) / nCols + 1: (ci * inv) >> 20 == ci / nCols for ci * nCols < 2^20
 };
 struct FastArgs {
     int nlevels, total_cells, cell_cap, tile_w, tile_h, iniTh, minTh;
@@ -198,13 +198,19 @@ struct FastArgs {
 // negation DROPPED (verified on B200 with a 20-line repro: device returns max|d| where the host returns the FAST score).
 // The dark-arc score is therefore computed as a min over the negated differences (ring - v) — no negated min/max operand.
 // necessary condition for S' > th: a 9-arc contains at least two of the four compass points
+// Packed form (see fast_full for the offset packing): half = d + 256 + (0x2000 - (th + 257)) has bit 13 set exactly when
+// d > th (halves stay inside 0..0x3fff for th <= 255), the four masked flags add up without carries, and "at least two" is
+// bit 14 or 15 of a half.
 __device__ __forceinline__ bool fast_quick(const uint8_t* p, int tp, int th)
 {
+    th = max(-256, min(th, 255));  // outside this range the outcome no longer depends on th
     const int v = p[0];
-    const int r0 = p[3 * tp], r4 = p[3], r8 = p[-3 * tp], r12 = p[-3];
-    const int nb = (v - r0 > th) + (v - r4 > th) + (v - r8 > th) + (v - r12 > th);
-    const int nd = (r0 - v > th) + (r4 - v > th) + (r8 - v > th) + (r12 - v > th);
-    return nb >= 2 || nd >= 2;
+    const unsigned r0 = p[3 * tp], r4 = p[3], r8 = p[-3 * tp], r12 = p[-3];
+    unsigned C = (unsigned)(v + 0x2000 - 1 - th) + ((unsigned)(0x2000 - 1 - th - v) << 16);
+    asm("" : "+r"(C));
+    const unsigned M = 0x20002000u;
+    const unsigned s = ((r0 * 65535u + C) & M) + ((r4 * 65535u + C) & M) + ((r8 * 65535u + C) & M) + ((r12 * 65535u + C) & M);
+    return (s & 0xC000C000u) != 0u;
 }
 
 __device__ __forceinline__ int fast_full(const uint8_t* p, int tp)
@@ -227,34 +233,37 @@ __device__ __forceinline__ int fast_full(const uint8_t* p, int tp)
     r[13] = p[tp - 3];
     r[14] = p[2 * tp - 2];
     r[15] = p[3 * tp - 1];
-    // Both polarities at once with packed 16-bit SIMD min/max (VIMNMX.S16x2): low half = v - ring (centre brighter),
-    // high half = ring - v (centre darker); |values| <= 255 fit int16.
+    // Both polarities at once with packed 16-bit SIMD min/max (VIMNMX3.S16x2), on OFFSET differences so that one multiply-add
+    // packs a ring pixel: low half = (v - r) + 256 (centre brighter), high half = (r - v) + 256 (centre darker), both in
+    // 1..511;  r * 65535 + C = (r + 256 - v) * 65536 + (v + 256 - r)  with  C = (v + 256) + (256 - v) * 65536  (the low half
+    // is positive, so nothing borrows from the high half).  min / max commute with the offset.
+    unsigned C = (unsigned)(v + 256) + ((unsigned)(256 - v) << 16);
+    asm("" : "+r"(C));  // keep C as one register: the compiler otherwise rewrites r * 65535 + C as (r - v) * 65535 + const
     unsigned q[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int d = v - r[k];
-        q[k] = __byte_perm((unsigned)d, (unsigned)(-d), 0x5410);
-    }
-    unsigned q2[16], q4[16];
+    for (int k = 0; k < 16; ++k) q[k] = (unsigned)r[k] * 65535u + C;
+    // min over every 9-arc: q3[k] = min(q[k..k+2]), arc(k) = min(q3[k], q3[k+3], q3[k+6]); S' = max over the 16 arcs
+    unsigned q3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) q2[k] = __vmins2(q[k], q[(k + 1) & 15]);
+    for (int k = 0; k < 16; ++k) q3[k] = __vminu2(__vminu2(q[k], q[(k + 1) & 15]), q[(k + 2) & 15]);
+    unsigned a9[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) q4[k] = __vmins2(q2[k], q2[(k + 2) & 15]);
-    unsigned bestp = 0x80008000u;  // (-32768, -32768)
+    for (int k = 0; k < 16; ++k) a9[k] = __vminu2(__vminu2(q3[k], q3[(k + 3) & 15]), q3[(k + 6) & 15]);
+    unsigned m5[5];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const unsigned q9 = __vmins2(__vmins2(q4[k], q4[(k + 4) & 15]), q[(k + 8) & 15]);
-        bestp = __vmaxs2(bestp, q9);
-    }
-    const int blo = (int)(short)(bestp & 0xffffu), bhi = (int)(short)(bestp >> 16);
-    const int best = blo > bhi ? blo : bhi;
-    return best;  // S'
+    for (int k = 0; k < 5; ++k) m5[k] = __vmaxu2(__vmaxu2(a9[3 * k], a9[3 * k + 1]), a9[3 * k + 2]);
+    const unsigned bestp = __vmaxu2(__vmaxu2(__vmaxu2(m5[0], m5[1]), m5[2]), __vmaxu2(__vmaxu2(m5[3], m5[4]), a9[15]));
+    const int blo = (int)(bestp & 0xffffu), bhi = (int)(bestp >> 16);
+    return max(blo, bhi) - 256;  // S'
 }
 
 constexpr int FAST_THREADS = 256;
-constexpr int FAST_KEEP_WORDS = 128;  // keep bitmap: one bit per interior pixel of a cell (cells are < 60 x 60)
+constexpr int FAST_KEEP_WORDS = 128;  // keep bitmap: 64 bits per interior row of a cell (cells are < 60 x 60)
 constexpr int FAST_KW = FAST_KEEP_WORDS / 32;
 
+// All loops run over (row, column) with a warp per row, list entries are (y << 6 | x) and the keep bitmap is row aligned
+// (bit y * 64 + x): no index divisions anywhere.  ncu of the first form of this kernel: 23 % of the instructions were the
+// raster-ordered output replicated in all eight warps, 25 % the 4-point pass, 16 % the tile load, 8 % the prologue.
 __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __restrict__ pyr, size_t pyr_stride_b, FastArgs a,
                                                           int* __restrict__ cell_cnt, ushort4* __restrict__ slabs)
 {
@@ -266,11 +275,13 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     __shared__ unsigned s_keep[FAST_KEEP_WORDS];
     __shared__ int s_nlist;
     const int b = blockIdx.y;
-    int cell = blockIdx.x, l = 0;
-    while (l + 1 < a.nlevels && cell >= a.lv[l + 1].cell_start) ++l;
+    const int cell = blockIdx.x;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < ORB_MAX_LEVELS; ++k) l += (k < a.nlevels && cell >= a.lv[k].cell_start) ? 1 : 0;  // cell_start ascends
     const FastLevelDev& L = a.lv[l];
     const int ci = cell - L.cell_start;
-    const int i = ci / L.nCols, j = ci - i * L.nCols;
+    const int i = (int)(((unsigned)ci * L.inv_nCols) >> 20), j = ci - i * L.nCols;
     const int maxBX = L.w - ORB_EDGE + 3, maxBY = L.h - ORB_EDGE + 3;
     const int x0 = ORB_BORDER + j * L.wCell, y0 = ORB_BORDER + i * L.hCell;
     int x1 = x0 + L.wCell + 6, y1 = y0 + L.hCell + 6;
@@ -287,26 +298,26 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         if (threadIdx.x == 0) *cnt_out = 0;
         return;
     }
-    // t / d for t * d < 2^20 (tiles are <= ~45 x 45): multiply by ceil-ish reciprocal, exact in that range
-    const unsigned inv_iw = (1u << 20) / (unsigned)iw + 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = FAST_THREADS / 32;
     const int xo = x0 & 3;                         // the tile holds image columns [x0 - xo, x1)
-    const int nw = (cw + xo + 3) >> 2;             // 32-bit words per tile row
-    const unsigned inv_nw = (1u << 20) / (unsigned)nw + 1u;
+    const int nw = (cw + xo + 3) >> 2;             // 32-bit words per tile row (<= 17)
     const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off + (size_t)y0 * L.pitch + (x0 - xo);
-    for (int t = threadIdx.x; t < nw * ch; t += FAST_THREADS) {
-        const int y = (int)(((unsigned)t * inv_nw) >> 20), k = t - y * nw;
-        reinterpret_cast<unsigned*>(tile_base + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * L.pitch) + k);
+    // tile rows: half a warp per row, one word per lane (a second round only for the widest cells); score rows cleared alongside
+    for (int y = 2 * warp + (lane >> 4); y < ch; y += 2 * NW) {
+        const unsigned* src = reinterpret_cast<const unsigned*>(img + (size_t)y * L.pitch);
+        unsigned* dst = reinterpret_cast<unsigned*>(tile_base + y * tp);
+        unsigned* scd = reinterpret_cast<unsigned*>(sc_base + y * tp);
+        for (int k = lane & 15; k < nw; k += 16) {
+            dst[k] = __ldg(src + k);
+            scd[k] = 0u;
+        }
     }
-    for (int t = threadIdx.x; t < (tp * a.tile_h) >> 2; t += FAST_THREADS) reinterpret_cast<unsigned*>(sc_base)[t] = 0u;
     if (threadIdx.x < FAST_KEEP_WORDS) s_keep[threadIdx.x] = 0u;
     static_assert(FAST_KEEP_WORDS <= FAST_THREADS, "bitmap is cleared by one pass of the block");
     const uint8_t* tile = tile_base + xo;
     uint8_t* sc = sc_base + xo;
-    const int npix = iw * ih;
-    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h);  // raster indices of the survivors
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = FAST_THREADS / 32;
-    const int nwords = (npix + 31) >> 5;
+    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h);  // (y << 6 | x) of the survivors
     int tot = 0;
     unsigned kw[FAST_KW];  // keep words lane + 32 r (every warp holds the whole bitmap)
     // first pass at iniThFAST only, like the reference's first cv::FAST call; if no corner survives the NMS the cell is
@@ -314,30 +325,30 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     //   1. 4-point necessary test for every pixel, survivors appended to a shared list (warp-aggregated atomics)
     //   2. the 16-point network over the list (densely packed: in textured images nearly every warp holds a survivor)
     //   3. cell-local strict NMS over the listed corners only -> one keep bit per interior pixel
-    //   4. raster-ordered compaction straight from the bitmap
+    //   4. raster-ordered compaction straight from the bitmap (one warp)
     for (int pass = 0; pass < 2 && tot == 0; ++pass) {
         const int th = pass == 0 ? a.iniTh : a.minTh;
         if (threadIdx.x == 0) s_nlist = 0;
         __syncthreads();
-        for (int base = 0; base < npix; base += FAST_THREADS) {
-            const int t = base + threadIdx.x;
-            bool qk = false;
-            if (t < npix) {
-                const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
-                qk = fast_quick(tile + (y + 3) * tp + x + 3, tp, th);
+        for (int y = warp; y < ih; y += NW) {
+            const uint8_t* row = tile + (y + 3) * tp + 3;
+            for (int xb = 0; xb < iw; xb += 32) {
+                const int x = xb + lane;
+                const bool qk = x < iw && fast_quick(row + x, tp, th);
+                const unsigned bal = __ballot_sync(0xffffffffu, qk);
+                if (bal) {
+                    int wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_nlist, __popc(bal));
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((y << 6) | x);
+                }
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, qk);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)t;
         }
         __syncthreads();
         const int nl = s_nlist;
         for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
             const int t = plist[q];
-            const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
-            const int pp = (y + 3) * tp + x + 3;
+            const int pp = ((t >> 6) + 3) * tp + (t & 63) + 3;
             const int sv = fast_full(tile + pp, tp);
             sc[pp] = (uint8_t)(sv > th ? sv : 0);
         }
@@ -345,8 +356,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         // NMS: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th (sc is 0 otherwise)
         for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
             const int t = plist[q];
-            const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
-            const uint8_t* c = sc + (y + 3) * tp + x + 3;
+            const uint8_t* c = sc + ((t >> 6) + 3) * tp + (t & 63) + 3;
             const int sv = c[0];
             if (sv == 0) continue;
             const int m0 = max(max(c[-tp - 1], c[-tp]), max(c[-tp + 1], c[-1]));
@@ -362,40 +372,37 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         }
         tot = __reduce_add_sync(0xffffffffu, cnt);
     }
-    // exclusive prefix of the per-word counts (word k lives in lane k & 31, register k >> 5)
-    int ex[FAST_KW], run = 0;
+    if (warp != 0) return;
+    // raster order = ascending bit index.  Exclusive prefix of the per-word counts (word k lives in lane k & 31, register
+    // k >> 5), then every lane writes the corners of its own words.
+    ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
+    int run = 0;
 #pragma unroll
     for (int r = 0; r < FAST_KW; ++r) {
-        const int c = __popc(kw[r]);
+        if (16 * r >= ih) break;  // words 32 r .. 32 r + 31 hold rows 16 r .. 16 r + 15
+        unsigned word = kw[r];
+        const int c = __popc(word);
         int inc = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += v;
         }
-        ex[r] = run + inc - c;
+        int my = run + inc - c;
         run += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    ushort4* slab = slabs + ((size_t)b * a.total_cells + cell) * a.cell_cap;
-    for (int k = warp; k < nwords; k += NW) {
-        unsigned wsel = kw[0];
-        int esel = ex[0];
-#pragma unroll
-        for (int r = 1; r < FAST_KW; ++r)
-            if ((k >> 5) == r) { wsel = kw[r]; esel = ex[r]; }  // warp-uniform select
-        const unsigned word = __shfl_sync(0xffffffffu, wsel, k & 31);
-        const int off = __shfl_sync(0xffffffffu, esel, k & 31);
-        if ((word >> lane) & 1u) {
-            const int my = off + __popc(word & ((1u << lane) - 1));
+        const int tbase = (lane + 32 * r) * 32;
+        while (word) {
+            const int t = tbase + __ffs(word) - 1;
+            word &= word - 1;
             if (my < a.cell_cap) {
-                const int t = k * 32 + lane;
-                const int y = (int)(((unsigned)t * inv_iw) >> 20), x = t - y * iw;
+                const int y = t >> 6, x = t & 63;
                 slab[my] = make_ushort4((unsigned short)(x + 3 + j * L.wCell), (unsigned short)(y + 3 + i * L.hCell),
                                         (unsigned short)(sc[(y + 3) * tp + x + 3] - 1), 0);
             }
+            ++my;
         }
     }
-    if (threadIdx.x == 0) *cnt_out = min(tot, a.cell_cap);
+    if (lane == 0) *cnt_out = min(tot, a.cell_cap);
 }
 
 // ------------------------------------------------------------------------------------------------ whole-level FAST (GetRt)
@@ -1384,7 +1391,8 @@ int OrbCore::enqueue_extract()
         fa.tile_w = P.tile_w; fa.tile_h = P.tile_h; fa.iniTh = P.iniTh; fa.minTh = P.minTh;
         for (int l = 0; l < P.nlevels; ++l) {
             const OrbLevel& L = P.lv[l];
-            fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start};
+            fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start,
+                        (1u << 20) / (unsigned)L.nCols + 1u};
         }
         dim3 grid(P.total_cells, batch);
         GD_CUDA(launch_pdl(k_orb_fast, grid, dim3(FAST_THREADS), (size_t)P.tile_w * P.tile_h * 4, stream, py, P.pyr_bytes, fa, cell_cnt.as<int>(),
