@@ -332,15 +332,18 @@ struct EdgeTiles {
     unsigned magic_x, magic_img;  // ceil(2^32 / d): __umulhi(t, magic) == t / d for t * d < 2^32
 };
 
-__device__ __forceinline__ float edge_load_clamped(const float* __restrict__ dp, int x, int y, int w, int h)
+// raw depth (0 outside the image); the clamp of :870-874 is applied when the value is published to shared memory, so that
+// nothing depends on the load while the previous tile is being evaluated
+__device__ __forceinline__ float edge_load_raw(const float* __restrict__ dp, int x, int y, int w, int h)
 {
     float v = 0.f;
-    if (x >= 0 && y >= 0 && x < w && y < h) {
-        v = __ldg(dp + (size_t)y * w + x);
-        const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
-        if (interior && v > 3.5f) v = 0.f;  // :870-874 ((double)v > 3.5 <=> v > 3.5f: 3.5 is a float)
-    }
+    if (x >= 0 && y >= 0 && x < w && y < h) v = __ldg(dp + (size_t)y * w + x);
     return v;
+}
+__device__ __forceinline__ float edge_clamp(float v, int x, int y, int w, int h)
+{
+    const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
+    return interior && v > 3.5f ? 0.f : v;  // (double)v > 3.5 <=> v > 3.5f: 3.5 is a float
 }
 
 __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
@@ -388,16 +391,18 @@ __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __res
     if (tile < et.total) {
         decode(tile, b, x0, y0);
         const float* dp = depth + (size_t)b * dstride_b;
-        v0 = edge_load_clamped(dp, x0 + tx - 2, y0 + ty - 2, w, h);
-        if (dly >= 0) v1 = edge_load_clamped(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
+        v0 = edge_load_raw(dp, x0 + tx - 2, y0 + ty - 2, w, h);
+        if (dly >= 0) v1 = edge_load_raw(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
     }
     __syncthreads();  // flags zeroed
     for (int it = 0; tile < et.total; ++it, tile += gridDim.x) {
         const int par = it & 1;
         float (*sd)[ET_W + 4] = sd2[par];
+        v0 = edge_clamp(v0, x0 + tx - 2, y0 + ty - 2, w, h);
         sd[ty][tx] = v0;
         bool bad = !(fabsf(v0) <= 3.0e38f);
         if (dly >= 0) {
+            v1 = edge_clamp(v1, x0 + dlx - 2, y0 + dly - 2, w, h);
             sd[dly][dlx] = v1;
             bad = bad || !(fabsf(v1) <= 3.0e38f);
         }
@@ -410,8 +415,8 @@ __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __res
             if (nt < et.total) {
                 decode(nt, b, x0, y0);
                 const float* dp = depth + (size_t)b * dstride_b;
-                v0 = edge_load_clamped(dp, x0 + tx - 2, y0 + ty - 2, w, h);
-                if (dly >= 0) v1 = edge_load_clamped(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
+                v0 = edge_load_raw(dp, x0 + tx - 2, y0 + ty - 2, w, h);
+                if (dly >= 0) v1 = edge_load_raw(dp, x0 + dlx - 2, y0 + dly - 2, w, h);
             }
         }
         auto normal_at = [&](int ly, int lx) {  // normal tile element (halo 1) from the depth tile (halo 2)

@@ -11,6 +11,7 @@
 //   K4d/e k_orb_describe IC_Angle + computeOrbDescriptor :77-147, fix-up :837-847, scaling :1095-1101
 #include "orb.cuh"
 
+#include <climits>
 #include <cmath>
 
 namespace gd {
@@ -276,9 +277,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     __shared__ int s_nlist;
     const int b = blockIdx.y;
     const int cell = blockIdx.x;
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < ORB_MAX_LEVELS; ++k) l += (k < a.nlevels && cell >= a.lv[k].cell_start) ? 1 : 0;  // cell_start ascends
+    // level of the cell: binary search over the ascending cell_start table (unused levels hold INT_MAX)
+    static_assert(ORB_MAX_LEVELS == 16, "four search steps");
+    int l = cell >= a.lv[8].cell_start ? 8 : 0;
+    l += cell >= a.lv[l + 4].cell_start ? 4 : 0;
+    l += cell >= a.lv[l + 2].cell_start ? 2 : 0;
+    l += cell >= a.lv[l + 1].cell_start ? 1 : 0;
     const FastLevelDev& L = a.lv[l];
     const int ci = cell - L.cell_start;
     const int i = (int)(((unsigned)ci * L.inv_nCols) >> 20), j = ci - i * L.nCols;
@@ -303,14 +307,32 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     const int xo = x0 & 3;                         // the tile holds image columns [x0 - xo, x1)
     const int nw = (cw + xo + 3) >> 2;             // 32-bit words per tile row (<= 17)
     const uint8_t* img = pyr + (size_t)b * pyr_stride_b + L.off + (size_t)y0 * L.pitch + (x0 - xo);
-    // tile rows: half a warp per row, one word per lane (a second round only for the widest cells); score rows cleared alongside
-    for (int y = 2 * warp + (lane >> 4); y < ch; y += 2 * NW) {
-        const unsigned* src = reinterpret_cast<const unsigned*>(img + (size_t)y * L.pitch);
-        unsigned* dst = reinterpret_cast<unsigned*>(tile_base + y * tp);
-        unsigned* scd = reinterpret_cast<unsigned*>(sc_base + y * tp);
-        for (int k = lane & 15; k < nw; k += 16) {
-            dst[k] = __ldg(src + k);
-            scd[k] = 0u;
+    // tile rows: half a warp per row, one word per lane (+ word 16 for the widest cells); the loads of three rounds of rows
+    // are issued before the first store; score rows cleared alongside
+    {
+        const int k = lane & 15, yb = 2 * warp + (lane >> 4);
+        const bool k1 = k + 16 < nw;  // nw <= 17
+        auto ld = [&](int y, int kk) { return __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * L.pitch) + kk); };
+        auto st = [&](int y, int kk, unsigned v) {
+            reinterpret_cast<unsigned*>(tile_base + y * tp)[kk] = v;
+            reinterpret_cast<unsigned*>(sc_base + y * tp)[kk] = 0u;
+        };
+        unsigned v0[3], v1[3];
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int y = yb + 2 * NW * it;
+            v0[it] = (y < ch && k < nw) ? ld(y, k) : 0u;
+            v1[it] = (y < ch && k1) ? ld(y, k + 16) : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const int y = yb + 2 * NW * it;
+            if (y < ch && k < nw) st(y, k, v0[it]);
+            if (y < ch && k1) st(y, k + 16, v1[it]);
+        }
+        for (int y = yb + 6 * NW; y < ch; y += 2 * NW) {
+            if (k < nw) st(y, k, ld(y, k));
+            if (k1) st(y, k + 16, ld(y, k + 16));
         }
     }
     if (threadIdx.x < FAST_KEEP_WORDS) s_keep[threadIdx.x] = 0u;
@@ -319,6 +341,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     uint8_t* sc = sc_base + xo;
     unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h);  // (y << 6 | x) of the survivors
     int tot = 0;
+    const unsigned nlist_addr = (unsigned)__cvta_generic_to_shared(&s_nlist);
     unsigned kw[FAST_KW];  // keep words lane + 32 r (every warp holds the whole bitmap)
     // first pass at iniThFAST only, like the reference's first cv::FAST call; if no corner survives the NMS the cell is
     // redone at minThFAST (:812-816).  Per pass:
@@ -338,7 +361,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
                 const unsigned bal = __ballot_sync(0xffffffffu, qk);
                 if (bal) {
                     int wbase = 0;
-                    if (lane == 0) wbase = atomicAdd(&s_nlist, __popc(bal));
+                    if (lane == 0)  // plain atom.shared: the compiler wraps atomicAdd() in its own warp aggregation
+                        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(wbase) : "r"(nlist_addr), "r"(__popc(bal)) : "memory");
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
                     if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((y << 6) | x);
                 }
@@ -1393,6 +1417,10 @@ int OrbCore::enqueue_extract()
             const OrbLevel& L = P.lv[l];
             fa.lv[l] = {L.w, L.h, L.pitch, (unsigned long long)L.off, L.nCols, L.nRows, L.wCell, L.hCell, L.cell_start,
                         (1u << 20) / (unsigned)L.nCols + 1u};
+        }
+        for (int l = P.nlevels; l < ORB_MAX_LEVELS; ++l) {
+            fa.lv[l] = fa.lv[0];
+            fa.lv[l].cell_start = INT_MAX;
         }
         dim3 grid(P.total_cells, batch);
         GD_CUDA(launch_pdl(k_orb_fast, grid, dim3(FAST_THREADS), (size_t)P.tile_w * P.tile_h * 4, stream, py, P.pyr_bytes, fa, cell_cnt.as<int>(),
