@@ -970,16 +970,22 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
     for (int k = 0; k < 4; ++k) xr[k] = need ? reflect101i(x + k, w) : 0;
     const bool owner = lane >= 1 && lane <= 30 && x < w;
     unsigned hw[7][4];
-#pragma unroll
-    for (int r = 0; r < BT_H + 6; ++r) {
+    // the rows are requested BLUR_PF iterations ahead (the kernel is latency bound: one dependent load per row otherwise)
+    auto load_row = [&](int r) -> unsigned {
         const int yy = reflect101i(y0 + r - 3, h);
         const uint8_t* row = img + (size_t)yy * pitch;
-        unsigned B;
-        if (fast)
-            B = __ldg(reinterpret_cast<const unsigned*>(row + x));
-        else
-            B = (unsigned)__ldg(row + xr[0]) | ((unsigned)__ldg(row + xr[1]) << 8) | ((unsigned)__ldg(row + xr[2]) << 16) |
-                ((unsigned)__ldg(row + xr[3]) << 24);
+        if (fast) return __ldg(reinterpret_cast<const unsigned*>(row + x));
+        return (unsigned)__ldg(row + xr[0]) | ((unsigned)__ldg(row + xr[1]) << 8) | ((unsigned)__ldg(row + xr[2]) << 16) |
+               ((unsigned)__ldg(row + xr[3]) << 24);
+    };
+    constexpr int BLUR_PF = 6;
+    unsigned Bq[BLUR_PF];
+#pragma unroll
+    for (int r = 0; r < BLUR_PF; ++r) Bq[r] = load_row(r);
+#pragma unroll
+    for (int r = 0; r < BT_H + 6; ++r) {
+        const unsigned B = Bq[r % BLUR_PF];
+        if (r + BLUR_PF < BT_H + 6) Bq[r % BLUR_PF] = load_row(r + BLUR_PF);
         const unsigned A = __shfl_up_sync(0xffffffffu, B, 1), C = __shfl_down_sync(0xffffffffu, B, 1);
         // byte windows starting k pixels from the group start, split into 16-bit pairs P_k = (b[k], b[k+1])
         const unsigned wm3 = __funnelshift_r(A, B, 8), wm2 = __funnelshift_r(A, B, 16);
