@@ -362,50 +362,54 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
                                                             float* __restrict__ R, size_t rstride_b)
 {
     pdl_wait();
-    __shared__ float sI[PT_H + 2 * PN][PT_W + 2 * PN];
-    __shared__ float sR[3][PT_H][PT_W + 2 * PN];
+    constexpr int TW = PT_W + 2 * PN;  // 42
+    constexpr int TH = PT_H + 2 * PN;  // 26
+    __shared__ float sI[TH][TW];
+    __shared__ float4 sR[PT_H][TW];    // vertical sums (t0, t1, t2, -) of a column position: one vector load per tap
     const int b = blockIdx.z;
     const float* Ip = I + (size_t)b * istride_b;
     const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
-    // tile + 5-px halo (replicate border): warp = tile rows (stride 8), lane = tile column (two passes: 32 + 10 columns) — no
-    // per-element division, the clamped column is computed once per pass
+    const int tid = threadIdx.y * PT_W + threadIdx.x;
     const float* g = a.g + PN;
     const float* xg = a.xg + PN;
     const float* xxg = a.xxg + PN;
-    constexpr int TW = PT_W + 2 * PN;  // 42
+    // tile + 5-px halo (replicate border).  Columns 0..31: warp = tile rows (stride 8), lane = column.  The 10 halo columns
+    // 32..41 are a flat list (260 elements for the tile, 160 for the vertical pass) so that whole warps work on them.
+    {
+        const int lx = threadIdx.x;
+        const int x = min(max(x0 + lx - PN, 0), a.w - 1);
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int lx = threadIdx.x + 32 * pass;
-        if (lx < TW) {
-            const int x = min(max(x0 + lx - PN, 0), a.w - 1);
-            for (int ly = threadIdx.y; ly < PT_H + 2 * PN; ly += PT_TY) {
-                const int y = min(max(y0 + ly - PN, 0), a.h - 1);
-                sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
-            }
+        for (int ly = threadIdx.y; ly < TH; ly += PT_TY) {
+            const int y = min(max(y0 + ly - PN, 0), a.h - 1);
+            sI[ly][lx] = __ldg(Ip + (size_t)y * a.w + x);
+        }
+        for (int e = tid; e < 2 * PN * TH; e += PT_NT) {
+            const int ly = (e * 6554) >> 16, hx = PT_W + e - 10 * ly;  // e / 10 for e < 16384
+            static_assert(2 * PN == 10, "flat halo index split assumes 10 halo columns");
+            const int xx = min(max(x0 + hx - PN, 0), a.w - 1), y = min(max(y0 + ly - PN, 0), a.h - 1);
+            sI[ly][hx] = __ldg(Ip + (size_t)y * a.w + xx);
         }
     }
     __syncthreads();
-    // vertical pass for PT_H rows x (PT_W + 10) columns, same thread mapping
+    // vertical pass for PT_H rows x (PT_W + 10) columns
+    auto vertical = [&](int ly, int lx) {
+        const int cy = ly + PN;
+        float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int lx = threadIdx.x + 32 * pass;
-        if (lx < TW) {
-            for (int ly = threadIdx.y; ly < PT_H; ly += PT_TY) {
-                const int cy = ly + PN;
-                float t0 = sI[cy][lx] * g[0], t1 = 0.f, t2 = 0.f;
-#pragma unroll
-                for (int k = 1; k <= PN; ++k) {
-                    const float s0 = sI[cy - k][lx], s1 = sI[cy + k][lx];
-                    const float p = s0 + s1;
-                    t0 = t0 + g[k] * p;
-                    t1 = t1 + xg[k] * (s1 - s0);
-                    t2 = t2 + xxg[k] * p;
-                }
-                sR[0][ly][lx] = t0;
-                sR[1][ly][lx] = t1;
-                sR[2][ly][lx] = t2;
-            }
+        for (int k = 1; k <= PN; ++k) {
+            const float s0 = sI[cy - k][lx], s1 = sI[cy + k][lx];
+            const float p = s0 + s1;
+            t0 = t0 + g[k] * p;
+            t1 = t1 + xg[k] * (s1 - s0);
+            t2 = t2 + xxg[k] * p;
         }
+        sR[ly][lx] = make_float4(t0, t1, t2, 0.f);
+    };
+#pragma unroll
+    for (int ly = threadIdx.y; ly < PT_H; ly += PT_TY) vertical(ly, threadIdx.x);
+    if (tid < 2 * PN * PT_H) {
+        const int ly = (tid * 6554) >> 16;
+        vertical(ly, PT_W + tid - 10 * ly);
     }
     __syncthreads();
     const int x = x0 + threadIdx.x;
@@ -417,19 +421,19 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
     for (int rr = 0; rr < PT_H / PT_TY; ++rr) {
         const int ly = threadIdx.y + PT_TY * rr, y = y0 + ly;
         if (y >= a.h) break;
-        const float* r0 = sR[0][ly];
-        const float* r1 = sR[1][ly];
-        const float* r2 = sR[2][ly];
-        double b1 = r0[lx] * g[0], b2 = 0, b3 = r1[lx] * g[0], b4 = 0, b5 = r2[lx] * g[0], b6 = 0;
+        const float4* r = sR[ly];
+        const float4 c = r[lx];
+        double b1 = c.x * g[0], b2 = 0, b3 = c.y * g[0], b4 = 0, b5 = c.z * g[0], b6 = 0;
 #pragma unroll
         for (int k = 1; k <= PN; ++k) {
-            const double tg = r0[lx + k] + r0[lx - k];
+            const float4 p = r[lx + k], m = r[lx - k];
+            const double tg = p.x + m.x;
             b1 += tg * a.gd[k];
             b4 += tg * a.xxgd[k];
-            b2 += (r0[lx + k] - r0[lx - k]) * xg[k];
-            b3 += (r1[lx + k] + r1[lx - k]) * g[k];
-            b6 += (r1[lx + k] - r1[lx - k]) * xg[k];
-            b5 += (r2[lx + k] + r2[lx - k]) * g[k];
+            b2 += (p.x - m.x) * xg[k];
+            b3 += (p.y + m.y) * g[k];
+            b6 += (p.y - m.y) * xg[k];
+            b5 += (p.z + m.z) * g[k];
         }
         // R layout per level: float4 plane (channels 0..3) followed by a float plane (channel 4) -> the flow kernels'
         // bilinear gather needs 2 loads per tap instead of 5
