@@ -197,6 +197,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// The ordinary launch (full stream serialisation): for persistent kernels, whose CTAs would otherwise sit on every SM at
+// griddepcontrol.wait while the predecessor drains.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Replays a static launch sequence as a CUDA graph, one executable per key (small batches are launch bound).
 // enqueue() must only enqueue work on `s` (or on streams forked from and joined back into it), must give the same launches
 // for the same key, and must not advance host state.  Never used inside another capture: the batched front-end captures

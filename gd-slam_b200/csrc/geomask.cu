@@ -580,8 +580,15 @@ int launch_depth_edge(const float* depth, size_t depth_stride_b, int w, int h, i
                 GD_CUDA(cudaGetDevice(&dev));
                 GD_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
             }
-            const dim3 pgrid((unsigned)std::min(et.total, 2 * n_sm));
-            GD_CUDA(launch_pdl(k_depth_edge, pgrid, block, 0, s, depth, depth_stride_b, w, h, cam, eb, et, edge, edge_stride_b));
+            // persistent (2 CTAs per SM walking the tile list) only when every CTA gets at least 8 tiles; a small job runs
+            // one tile per CTA, so that the kernels of other streams and handles keep finding free SM resources
+            if (et.total >= 8 * 2 * n_sm) {
+                GD_CUDA(launch_plain(k_depth_edge, dim3((unsigned)(2 * n_sm)), block, 0, s, depth, depth_stride_b, w, h, cam, eb, et, edge,
+                                     edge_stride_b));
+            } else {
+                GD_CUDA(launch_pdl(k_depth_edge, dim3((unsigned)et.total), block, 0, s, depth, depth_stride_b, w, h, cam, eb, et, edge,
+                                   edge_stride_b));
+            }
         }
     }
     GD_CUDA(cudaGetLastError());
