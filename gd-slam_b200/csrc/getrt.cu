@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(256) k_resize_linear_exact(const uint8_t* __re
 struct Gauss7 {
     float g[4];  // g[0] = centre tap
 };
-constexpr int GF_W = 32, GF_H = 16;
 
 __device__ __forceinline__ int reflect101_dev(int p, int len)
 {
@@ -71,43 +70,49 @@ __device__ __forceinline__ int reflect101_dev(int p, int len)
     return p >= len ? 2 * len - 2 - p : p;
 }
 
-// blockIdx = (tile, level, stream); levels dense at lv[l].off of a stream's pyramid
-__global__ void __launch_bounds__(GF_W* GF_H) k_gaussian7_float_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a,
-                                                                       Gauss7 G, uint8_t* __restrict__ out)
+// blockIdx = (tile, level, stream); levels dense at lv[l].off of a stream's pyramid.  One warp filters a strip of GF_COLS
+// columns x GF_ROWS rows marching down: lane i owns column x0 - 3 + i (three halo lanes on either side), the row pass takes
+// its six neighbours from the adjacent lanes, the seven row results the column pass needs stay in registers.  Same products
+// and sums in the same order as the two-pass form (this file is built without FMA contraction).
+constexpr int GF_COLS = 26, GF_ROWS = 16, GF_WARPS = 8, GF_PF = 4;
+
+__global__ void __launch_bounds__(32 * GF_WARPS) k_gaussian7_float_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a,
+                                                                          Gauss7 G, uint8_t* __restrict__ out)
 {
     const CvLevelDev L = a.lv[blockIdx.y];
-    const int tiles_x = (L.w + GF_W - 1) / GF_W, tiles_y = (L.h + GF_H - 1) / GF_H;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
     const int w = L.w, h = L.h;
+    const int tiles_x = (w + GF_COLS - 1) / GF_COLS, tiles_y = (h + GF_ROWS * GF_WARPS - 1) / (GF_ROWS * GF_WARPS);
+    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
+    const int ty = (int)blockIdx.x / tiles_x, tx = (int)blockIdx.x - ty * tiles_x;
+    const int lane = threadIdx.x, x = tx * GF_COLS - 3 + lane, y0 = (ty * GF_WARPS + threadIdx.y) * GF_ROWS;
+    if (y0 >= h) return;  // warp-uniform
     const uint8_t* src = pyr + (size_t)blockIdx.z * stride_b + L.off;
     uint8_t* dst = out + (size_t)blockIdx.z * stride_b + L.off;
-    __shared__ float s_in[GF_H + 6][GF_W + 6];
-    __shared__ float s_row[GF_H + 6][GF_W];
-    const int x0 = ((int)blockIdx.x % tiles_x) * GF_W, y0 = ((int)blockIdx.x / tiles_x) * GF_H;
-    const int tid = threadIdx.y * GF_W + threadIdx.x;
-    for (int i = tid; i < (GF_H + 6) * (GF_W + 6); i += GF_W * GF_H) {
-        const int ly = i / (GF_W + 6), lx = i - ly * (GF_W + 6);
-        const int x = reflect101_dev(x0 + lx - 3, w), y = reflect101_dev(y0 + ly - 3, h);
-        s_in[ly][lx] = (float)src[(size_t)y * w + x];
-    }
-    __syncthreads();
-    for (int i = tid; i < (GF_H + 6) * GF_W; i += GF_W * GF_H) {
-        const int ly = i / GF_W, lx = i - ly * GF_W;
-        const float* p = &s_in[ly][lx + 3];
-        float r = G.g[0] * p[0];
+    const int xs = reflect101_dev(min(x, w + 2), w);        // lanes further right feed no owned column
+    const bool owner = lane >= 3 && lane < 3 + GF_COLS && x < w;
+    auto load_row = [&](int r) { return (float)__ldg(src + (size_t)reflect101_dev(min(y0 - 3 + r, h + 2), h) * w + xs); };
+    float pre[GF_PF];
 #pragma unroll
-        for (int k = 1; k <= 3; ++k) r = r + G.g[k] * (p[k] + p[-k]);
-        s_row[ly][lx] = r;
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const int ly = threadIdx.y + 3, lx = threadIdx.x;
-    float c = G.g[0] * s_row[ly][lx];
+    for (int r = 0; r < GF_PF; ++r) pre[r] = load_row(r);
+    float ring[7];
 #pragma unroll
-    for (int k = 1; k <= 3; ++k) c = c + G.g[k] * (s_row[ly + k][lx] + s_row[ly - k][lx]);
-    const int v = __float2int_rn(c);  // cvRound: round half to even
-    dst[(size_t)y * w + x] = (uint8_t)max(0, min(255, v));
+    for (int r = 0; r < GF_ROWS + 6; ++r) {
+        const float v = pre[r % GF_PF];
+        if (r + GF_PF < GF_ROWS + 6) pre[r % GF_PF] = load_row(r + GF_PF);
+        float rr = G.g[0] * v;
+#pragma unroll
+        for (int k = 1; k <= 3; ++k)
+            rr = rr + G.g[k] * (__shfl_down_sync(0xffffffffu, v, k) + __shfl_up_sync(0xffffffffu, v, k));
+        ring[r % 7] = rr;
+        if (r >= 6) {
+            const int y = y0 + r - 6;
+            float c = G.g[0] * ring[(r - 3) % 7];
+#pragma unroll
+            for (int k = 1; k <= 3; ++k) c = c + G.g[k] * (ring[(r - 3 + k) % 7] + ring[(r - 3 - k) % 7]);
+            const int vi = __float2int_rn(c);  // cvRound: round half to even
+            if (owner && y < h) dst[(size_t)y * w + x] = (uint8_t)max(0, min(255, vi));
+        }
+    }
 }
 
 static Gauss7 gauss7_taps()
@@ -442,49 +447,92 @@ __global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------ Hamming nearest neighbour
-// blockIdx = (query tile, direction, stream).  direction 0: queries = ref features, train = cur features; 1: the reverse.
-// One thread per query descriptor (eight words in registers); the train set goes through shared memory in tiles of 128.
-// Strict '<' keeps the smallest train index among equal distances, like cv::batchDistance.
-constexpr int NN_THREADS = 128;
+// Both directions of BFMatcher(crossCheck = true) from ONE pass over the distance matrix (ncu of the two-pass form: the
+// POPC pipe 97 % busy — the Hamming distances themselves are the bound, so each is computed once).
+// blockIdx = (tile of 128 ref features, stream).  One thread per ref descriptor (eight words in registers); the cur
+// descriptors go through shared memory in rounds of 512 (broadcast reads).  Per pair:
+//   direction 0 (query = ref i, train = cur j): running minimum in the thread, strict '<' in ascending j
+//   direction 1 (query = cur j, train = ref i): key = distance << 16 | i, minimum over the warp by one REDUX, over the CTA by a
+//     shared-memory atomicMin per warp, over the CTAs by a global atomicMin per cur feature -> smallest distance, then the
+//     smallest ref index: the element cv::batchDistance keeps.  The warp only reduces when one of its keys beats the bound
+//     already known for the column (seeded from the global keys).  k_getrt_nn_finish unpacks the keys.
+constexpr int NN_THREADS = 128, NN_TILE = 512;
 __global__ void __launch_bounds__(NN_THREADS) k_getrt_nn(const uint4* __restrict__ desc_ref, const uint4* __restrict__ desc_cur,
                                                          const int* __restrict__ n_ref, const int* __restrict__ n_cur, int feat_cap,
-                                                         int* __restrict__ nn, int* __restrict__ dd)
+                                                         int* __restrict__ nn, int* __restrict__ dd, unsigned* __restrict__ colkey)
 {
-    __shared__ uint4 tile[NN_THREADS * 2];
-    const int b = blockIdx.z, dir = blockIdx.y;
-    const int nq = min(dir == 0 ? n_ref[b] : n_cur[b], feat_cap), nt = min(dir == 0 ? n_cur[b] : n_ref[b], feat_cap);
+    __shared__ uint4 t0[NN_TILE], t1[NN_TILE];
+    __shared__ unsigned s_col[NN_TILE];
+    const int b = blockIdx.y;
+    const int nq = min(n_ref[b], feat_cap), nt = min(n_cur[b], feat_cap);
     if ((int)blockIdx.x * NN_THREADS >= nq) return;
-    const uint4* q = (dir == 0 ? desc_ref : desc_cur) + (size_t)b * feat_cap * 2;
-    const uint4* t = (dir == 0 ? desc_cur : desc_ref) + (size_t)b * feat_cap * 2;
-    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const uint4* q = desc_ref + (size_t)b * feat_cap * 2;
+    const uint4* t = desc_cur + (size_t)b * feat_cap * 2;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = i < nq;
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    if (i < nq) {
+    if (valid) {
         a0 = q[2 * i];
         a1 = q[2 * i + 1];
     }
+    const unsigned kinv = valid ? 0u : 0xFFFFFFFFu;  // rows past the end never win a column
     int best = 1 << 30, bi = -1;
-    for (int base = 0; base < nt; base += NN_THREADS) {
-        const int m = min(NN_THREADS, nt - base);
+    for (int base = 0; base < nt; base += NN_TILE) {
+        const int m = min(NN_TILE, nt - base);
+        unsigned* ck = colkey + (size_t)b * feat_cap + base;
         __syncthreads();
-        if ((int)threadIdx.x < m) {
-            tile[2 * threadIdx.x] = t[2 * (base + threadIdx.x)];
-            tile[2 * threadIdx.x + 1] = t[2 * (base + threadIdx.x) + 1];
+        for (int k = threadIdx.x; k < m; k += NN_THREADS) {
+            t0[k] = t[2 * (base + k)];
+            t1[k] = t[2 * (base + k) + 1];
+            s_col[k] = ck[k];  // what the other CTAs have found so far: an upper bound that makes most updates unnecessary
         }
         __syncthreads();
+#pragma unroll 2
         for (int j = 0; j < m; ++j) {
-            const uint4 b0 = tile[2 * j], b1 = tile[2 * j + 1];
+            const uint4 b0 = t0[j], b1 = t1[j];
             const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
                           __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
             if (d < best) {
                 best = d;
                 bi = base + j;
             }
+            const unsigned key = (((unsigned)d << 16) | (unsigned)i) | kinv;
+            if (__any_sync(0xffffffffu, key < s_col[j])) {  // (a stale bound only costs an unnecessary update)
+                const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+                if (lane == 0) atomicMin(&s_col[j], kmin);
+            }
         }
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += NN_THREADS) atomicMin(ck + k, s_col[k]);
     }
-    if (i < nq) {
-        nn[((size_t)b * 2 + dir) * feat_cap + i] = bi;
-        dd[((size_t)b * 2 + dir) * feat_cap + i] = best;
+    if (valid) {
+        nn[((size_t)b * 2 + 0) * feat_cap + i] = bi;
+        dd[((size_t)b * 2 + 0) * feat_cap + i] = best;
     }
+}
+
+// direction 1 from the column keys (0xFFFFFFFF: no ref feature at all -> index -1, distance 1 << 30 like an empty scan)
+__global__ void __launch_bounds__(256) k_getrt_nn_finish(const unsigned* __restrict__ colkey, const int* __restrict__ n_cur, int feat_cap,
+                                                         int* __restrict__ nn, int* __restrict__ dd)
+{
+    const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= min(n_cur[b], feat_cap)) return;
+    const unsigned key = colkey[(size_t)b * feat_cap + j];
+    const bool none = key == 0xFFFFFFFFu;
+    nn[((size_t)b * 2 + 1) * feat_cap + j] = none ? -1 : (int)(key & 0xFFFFu);
+    dd[((size_t)b * 2 + 1) * feat_cap + j] = none ? (1 << 30) : (int)(key >> 16);
+}
+
+static int launch_hamming_both(const uint4* desc_ref, const uint4* desc_cur, const int* n_ref, const int* n_cur, int feat_cap, int batch,
+                               int* nn, int* dd, unsigned* colkey, cudaStream_t s)
+{
+    GD_REQUIRE(feat_cap <= 65536, "ref feature index does not fit the column key");
+    GD_CUDA(cudaMemsetAsync(colkey, 0xFF, (size_t)batch * feat_cap * sizeof(unsigned), s));
+    k_getrt_nn<<<dim3(cdiv(feat_cap, NN_THREADS), batch), NN_THREADS, 0, s>>>(desc_ref, desc_cur, n_ref, n_cur, feat_cap, nn, dd, colkey);
+    GD_CUDA(cudaGetLastError());
+    k_getrt_nn_finish<<<dim3(cdiv(feat_cap, 256), batch), 256, 0, s>>>(colkey, n_cur, feat_cap, nn, dd);
+    GD_CUDA(cudaGetLastError());
+    return GD_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ matches -> points
@@ -689,6 +737,7 @@ int GetRtCore::init(const float K[9], const float* dist_coef, int ndist, int wid
     GD_TRY(feat_n.alloc((size_t)ring * B * sizeof(int)));
     GD_TRY(nn.alloc(B * 2 * feat_cap * sizeof(int)));
     GD_TRY(dd.alloc(B * 2 * feat_cap * sizeof(int)));
+    GD_TRY(colkey.alloc(B * feat_cap * sizeof(unsigned)));
     GD_TRY(out_obj.alloc(B * GETRT_TOP * 3 * sizeof(float)));
     GD_TRY(out_pix.alloc(B * GETRT_TOP * 2 * sizeof(float)));
     GD_TRY(out_cnt.alloc((B + 1) * sizeof(int)));
@@ -719,7 +768,7 @@ int GetRtCore::enqueue_features(const uint8_t* gray, size_t gray_stride_b, int s
         }
     }
     {
-        LaunchScope ls(stats, s, "G2_cvorb_fast", 2);
+        LaunchScope ls(stats, s, "G2_cvorb_fast", 1);
         GD_CUDA(cudaMemsetAsync(rowcnt.p, 0, rowcnt.bytes, s));
         GD_TRY(orb_cv_fast_levels(py, pyr_bytes, pyr_args, batch, 20, GETRT_EDGE, score.as<uint8_t>(), kept.as<uint8_t>(), rowcnt.as<int>(),
                                   (size_t)rows_total, s));
@@ -746,8 +795,9 @@ int GetRtCore::enqueue_features(const uint8_t* gray, size_t gray_stride_b, int s
     {
         LaunchScope ls(stats, s, "G4_cvorb_blur", 1);
         int tiles = 0;
-        for (int l = 0; l < GETRT_LEVELS; ++l) tiles = std::max(tiles, cdiv(pyr_args.lv[l].w, GF_W) * cdiv(pyr_args.lv[l].h, GF_H));
-        k_gaussian7_float_levels<<<dim3(tiles, GETRT_LEVELS, batch), dim3(GF_W, GF_H), 0, s>>>(py, pyr_bytes, pyr_args, gauss7_taps(),
+        for (int l = 0; l < GETRT_LEVELS; ++l)
+            tiles = std::max(tiles, cdiv(pyr_args.lv[l].w, GF_COLS) * cdiv(pyr_args.lv[l].h, GF_ROWS * GF_WARPS));
+        k_gaussian7_float_levels<<<dim3(tiles, GETRT_LEVELS, batch), dim3(32, GF_WARPS), 0, s>>>(py, pyr_bytes, pyr_args, gauss7_taps(),
                                                                                           blur.as<uint8_t>());
         GD_CUDA(cudaGetLastError());
     }
@@ -764,12 +814,9 @@ int GetRtCore::enqueue_match(int ref_slot, int cur_slot, const float* depth_ref,
     GD_REQUIRE(ref_slot >= 0 && ref_slot < ring && cur_slot >= 0 && cur_slot < ring && depth_ref, "bad argument");
     const cudaStream_t s = stream;
     {
-        LaunchScope ls(stats, s, "G6_match", 1);
-        k_getrt_nn<<<dim3(cdiv(feat_cap, NN_THREADS), 2, batch), NN_THREADS, 0, s>>>(reinterpret_cast<const uint4*>(slot_desc(ref_slot)),
-                                                                                  reinterpret_cast<const uint4*>(slot_desc(cur_slot)),
-                                                                                  slot_n(ref_slot), slot_n(cur_slot), feat_cap, nn.as<int>(),
-                                                                                  dd.as<int>());
-        GD_CUDA(cudaGetLastError());
+        LaunchScope ls(stats, s, "G6_match", 2);
+        GD_TRY(launch_hamming_both(reinterpret_cast<const uint4*>(slot_desc(ref_slot)), reinterpret_cast<const uint4*>(slot_desc(cur_slot)),
+                                   slot_n(ref_slot), slot_n(cur_slot), feat_cap, batch, nn.as<int>(), dd.as<int>(), colkey.as<unsigned>(), s));
     }
     {
         LaunchScope ls(stats, s, "G7_points", 1);
@@ -836,7 +883,7 @@ int gd_stage_gaussian7_float(int device, const uint8_t* src, int w, int h, uint8
     CvPyrArgs a;
     a.nlevels = 1;
     a.lv[0] = {w, h, 0ull, 0, 1.0f};
-    k_gaussian7_float_levels<<<dim3(cdiv(w, GF_W) * cdiv(h, GF_H), 1, 1), dim3(GF_W, GF_H)>>>(s.as<uint8_t>(), 0, a, gauss7_taps(), d.as<uint8_t>());
+    k_gaussian7_float_levels<<<dim3(cdiv(w, GF_COLS) * cdiv(h, GF_ROWS * GF_WARPS), 1, 1), dim3(32, GF_WARPS)>>>(s.as<uint8_t>(), 0, a, gauss7_taps(), d.as<uint8_t>());
     GD_CUDA(cudaGetLastError());
     GD_CUDA(cudaMemcpy(dst, d.p, (size_t)w * h, cudaMemcpyDeviceToHost));
     return GD_OK;
@@ -880,9 +927,11 @@ int gd_stage_hamming_crosscheck(int device, const uint8_t* d1, int n1, const uin
     GD_CUDA(cudaMemcpy(b.p, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice));
     const int hn[2] = {n1, n2};
     GD_CUDA(cudaMemcpy(cnt.p, hn, sizeof(hn), cudaMemcpyHostToDevice));
-    k_getrt_nn<<<dim3(cdiv(cap, NN_THREADS), 2, 1), NN_THREADS>>>(a.as<uint4>(), b.as<uint4>(), cnt.as<int>(), cnt.as<int>() + 1, cap, dnn.as<int>(),
-                                                                 ddd.as<int>());
-    GD_CUDA(cudaGetLastError());
+    DevBuf ck;
+    GD_TRY(ck.alloc(sizeof(unsigned) * cap));
+    GD_TRY(launch_hamming_both(a.as<uint4>(), b.as<uint4>(), cnt.as<int>(), cnt.as<int>() + 1, cap, 1, dnn.as<int>(), ddd.as<int>(),
+                               ck.as<unsigned>(), 0));
+    GD_CUDA(cudaDeviceSynchronize());
     std::vector<int> h12(n1), hd(n1), h21(n2);
     GD_CUDA(cudaMemcpy(h12.data(), dnn.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));
     GD_CUDA(cudaMemcpy(hd.data(), ddd.p, sizeof(int) * n1, cudaMemcpyDeviceToHost));

@@ -37,6 +37,7 @@ struct GetRtCore {
     DevBuf sel_n;                   // [B][levels] int
     DevBuf feat_kp, feat_desc, feat_n;  // [ring][B][feat_cap] cv::KeyPoint records / [..][32] descriptors / [ring][B] counts
     DevBuf nn, dd;                  // [B][2][feat_cap] nearest neighbour index / distance of both matching directions
+    DevBuf colkey;                  // [B][feat_cap] packed column minima of the distance matrix (direction 1)
     DevBuf out_obj, out_pix, out_cnt;   // [B][100][3] f32, [B][100][2] f32, [B] int: what GetRt hands to solvePnPRansac
     DevBuf err;                     // [1] int: capacity overflow flags of the selection kernel
     PinnedBuf h_out;                // pinned copy of out_obj | out_pix | out_cnt | err

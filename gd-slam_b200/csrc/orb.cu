@@ -505,96 +505,104 @@ int orb_fast_whole(const uint8_t* d_img, int w, int h, int pitch, int th, uint8_
     return GD_OK;
 }
 
-// ---- the same two kernels over all pyramid levels of `batch` streams in one launch each (resident GetRt stage).
+// ---- the same over all pyramid levels of `batch` streams in ONE launch (resident GetRt stage).
 // Levels are dense (pitch = width) at byte offset lv[l].off inside a stream's pyramid; blockIdx = (tile, level, stream).
 // The NMS kernel also counts, per level row, the surviving corners inside the cv::ORB border (edge <= x < w - edge, same
 // for y: KeyPointsFilter::runByImageBorder): the selection kernel turns the counts into raster-ordered list positions.
-__global__ void __launch_bounds__(256) k_cv_fast_score_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a, int th,
-                                                              uint8_t* __restrict__ score)
+// One kernel: a CTA scores the 66 x 18 pixels around its 64 x 16 output tile (the 1-pixel ring of scores the 8-neighbour
+// suppression needs is recomputed instead of being exchanged through a score map in HBM), suppresses and writes the map of
+// kept corners.  The image tile is assembled from ALIGNED 32-bit words (dense levels: rows start at any byte) with a funnel
+// shift; words that would lie outside the level are clamped to its first / last word — they only hold pixels outside the
+// image, which no scored pixel (3 <= x < w - 3, 3 <= y < h - 3) ever reads.
+constexpr int FK_TP = 80, FK_TR = FW_H + 8;   // tile: 24 rows x 80 bytes (19 words loaded), image (Y0 - 4 + r, X0 - 4 + c)
+constexpr int FK_SW = FW_W + 2, FK_SH = FW_H + 2, FK_SP = 68;  // scores: 18 rows x 66 (pitch 68), image (Y0 - 1 + sy, X0 - 1 + sx)
+
+__global__ void __launch_bounds__(256) k_cv_fast_kept_levels(const uint8_t* __restrict__ pyr, size_t stride_b, CvPyrArgs a, int th,
+                                                             int edge, uint8_t* __restrict__ kept, int* __restrict__ rowcnt,
+                                                             size_t rowcnt_stride)
 {
     const CvLevelDev L = a.lv[blockIdx.y];
     const int tiles_x = (L.w + FW_W - 1) / FW_W, tiles_y = (L.h + FW_H - 1) / FW_H;
     if ((int)blockIdx.x >= tiles_x * tiles_y) return;
     const int w = L.w, h = L.h, pitch = L.w;
-    const uint8_t* img = pyr + (size_t)blockIdx.z * stride_b + L.off;
-    uint8_t* sco = score + (size_t)blockIdx.z * stride_b + L.off;
-    __shared__ __align__(16) uint8_t tile[(FW_H + 6) * FW_P];
-    __shared__ __align__(16) uint8_t sc[FW_H * FW_W];
-    __shared__ unsigned short plist[FW_H * FW_W];
+    const uint8_t* img = pyr + (size_t)blockIdx.z * stride_b + L.off;  // 256-byte aligned
+    __shared__ __align__(16) uint8_t tile[FK_TR * FK_TP];
+    __shared__ __align__(16) uint8_t sc[FK_SH * FK_SP];
+    __shared__ unsigned short plist[FK_SH * FK_SW];
     __shared__ int s_nlist;
-    const int X0 = FW_W * ((int)blockIdx.x % tiles_x), Y0 = FW_H * ((int)blockIdx.x / tiles_x);
-    const int tid = threadIdx.x;
-    for (int q = tid; q < (FW_H + 6) * FW_P; q += 256) {
-        const int row = q / FW_P, col = q - row * FW_P;
-        const int gy = Y0 - 3 + row, gx = X0 - 4 + col;
-        tile[q] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? img[(size_t)gy * pitch + gx] : (uint8_t)0;
+    const int ty = (int)blockIdx.x / tiles_x;
+    const int X0 = FW_W * ((int)blockIdx.x - ty * tiles_x), Y0 = FW_H * ty;
+    const int tid = threadIdx.x, lane = tid & 31;
+    {
+        const int last = (w * h - 1) & ~3;
+        const unsigned* iw = reinterpret_cast<const unsigned*>(img);
+        for (int q = tid; q < FK_TR * 19; q += 256) {
+            const int r = (q * 3450) >> 16, k = q - 19 * r;  // q / 19 for q < 4681
+            const int gy = min(max(Y0 - 4 + r, 0), h - 1);
+            const int o = gy * pitch + X0 - 4 + 4 * k, m = o & 3, oa = o - m;
+            const unsigned w0 = __ldg(iw + (min(max(oa, 0), last) >> 2)), w1 = __ldg(iw + (min(max(oa + 4, 0), last) >> 2));
+            reinterpret_cast<unsigned*>(tile + r * FK_TP)[k] = __funnelshift_r(w0, w1, 8 * m);
+        }
+        for (int q = tid; q < FK_SH * FK_SP / 4; q += 256) reinterpret_cast<unsigned*>(sc)[q] = 0u;
+        if (tid == 0) s_nlist = 0;
     }
-    reinterpret_cast<unsigned*>(sc)[tid] = 0u;
-    if (tid == 0) s_nlist = 0;
     __syncthreads();
-    const int lane = tid & 31;
-#pragma unroll
-    for (int base = 0; base < FW_H * FW_W; base += 256) {
-        const int q = base + tid, ly = q >> 6, lx = q & 63;
-        const int gx = X0 + lx, gy = Y0 + ly;
-        bool qk = gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3;
-        if (qk) qk = fast_quick(tile + (ly + 3) * FW_P + lx + 4, FW_P, th);
+    const unsigned nlist_addr = (unsigned)__cvta_generic_to_shared(&s_nlist);
+    for (int base = 0; base < FK_SH * FK_SW; base += 256) {
+        const int q = base + tid;
+        const int sy = (q * 993) >> 16, sx = q - FK_SW * sy;  // q / 66 for q < 32768
+        const int gx = X0 - 1 + sx, gy = Y0 - 1 + sy;
+        bool qk = q < FK_SH * FK_SW && gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3;
+        if (qk) qk = fast_quick(tile + (sy + 3) * FK_TP + sx + 3, FK_TP, th);
         const unsigned bal = __ballot_sync(0xffffffffu, qk);
-        int wbase = 0;
-        if (lane == 0 && bal) wbase = atomicAdd(&s_nlist, __popc(bal));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)q;
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(wbase) : "r"(nlist_addr), "r"(__popc(bal)) : "memory");
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((sy << 7) | sx);
+        }
     }
     __syncthreads();
     const int nl = s_nlist;
     for (int e = tid; e < nl; e += 256) {
-        const int q = plist[e], ly = q >> 6, lx = q & 63;
-        const int sv = fast_full(tile + (ly + 3) * FW_P + lx + 4, FW_P);
-        sc[q] = (uint8_t)(sv > th ? sv : 0);
+        const int q = plist[e], sy = q >> 7, sx = q & 127;
+        const int sv = fast_full(tile + (sy + 3) * FK_TP + sx + 3, FK_TP);
+        sc[sy * FK_SP + sx] = (uint8_t)(sv > th ? sv : 0);
     }
     __syncthreads();
-    for (int q = tid; q < FW_H * FW_W; q += 256) {
-        const int ly = q >> 6, lx = q & 63, gx = X0 + lx, gy = Y0 + ly;
-        if (gx < w && gy < h) sco[(size_t)gy * pitch + gx] = sc[q];
-    }
-}
-
-__global__ void __launch_bounds__(256) k_cv_fast_nms_levels(const uint8_t* __restrict__ score, size_t stride_b, CvPyrArgs a, int edge,
-                                                            uint8_t* __restrict__ kept, int* __restrict__ rowcnt, size_t rowcnt_stride)
-{
-    const CvLevelDev L = a.lv[blockIdx.y];
-    const int tiles_x = (L.w + 31) / 32, tiles_y = (L.h + 7) / 8;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
-    const int w = L.w, h = L.h, pitch = L.w;
-    const int x = ((int)blockIdx.x % tiles_x) * 32 + threadIdx.x, y = ((int)blockIdx.x / tiles_x) * 8 + threadIdx.y;
-    const uint8_t* sco = score + (size_t)blockIdx.z * stride_b + L.off;
-    int out = 0;
-    if (x < w && y < h) {
-        const uint8_t* c = sco + (size_t)y * pitch + x;
-        const int s = c[0];
-        if (s > 0) {  // scored pixels are at least 3 from the border: the 8 neighbours exist
-            const int m0 = max(max(c[-pitch - 1], c[-pitch]), max(c[-pitch + 1], c[-1]));
-            const int m1 = max(max(c[pitch - 1], c[pitch]), max(c[pitch + 1], c[1]));
-            if (max(m0, m1) < s) out = s;
+    uint8_t* kp = kept + (size_t)blockIdx.z * stride_b + L.off;
+#pragma unroll
+    for (int base = 0; base < FW_H * FW_W; base += 256) {
+        const int q = base + tid, ly = q >> 6, lx = q & 63;
+        const int x = X0 + lx, y = Y0 + ly;
+        int out = 0;
+        if (x < w && y < h) {
+            const uint8_t* c = sc + (ly + 1) * FK_SP + lx + 1;
+            const int sv = c[0];
+            if (sv > 0) {
+                const int m0 = max(max(c[-FK_SP - 1], c[-FK_SP]), max(c[-FK_SP + 1], c[-1]));
+                const int m1 = max(max(c[FK_SP - 1], c[FK_SP]), max(c[FK_SP + 1], c[1]));
+                if (max(m0, m1) < sv) out = sv;
+            }
+            kp[(size_t)y * pitch + x] = (uint8_t)out;
         }
-        kept[(size_t)blockIdx.z * stride_b + L.off + (size_t)y * pitch + x] = (uint8_t)out;
+        const bool inside = out > 0 && x >= edge && x < w - edge && y >= edge && y < h - edge;
+        const unsigned bal = __ballot_sync(0xffffffffu, inside);  // one warp = 32 consecutive pixels of one row
+        if (lane == 0 && bal) atomicAdd(rowcnt + (size_t)blockIdx.z * rowcnt_stride + L.row_off + y, __popc(bal));
     }
-    const bool inside = out > 0 && x >= edge && x < w - edge && y >= edge && y < h - edge;
-    const unsigned bal = __ballot_sync(0xffffffffu, inside);  // one warp = one row segment
-    if (threadIdx.x == 0 && bal) atomicAdd(rowcnt + (size_t)blockIdx.z * rowcnt_stride + L.row_off + y, __popc(bal));
 }
 
 int orb_cv_fast_levels(const uint8_t* pyr, size_t stride_b, const CvPyrArgs& a, int batch, int th, int edge, uint8_t* score,
                        uint8_t* kept, int* rowcnt, size_t rowcnt_stride, cudaStream_t s)
 {
-    int t_score = 0, t_nms = 0;
+    (void)score;  // the score map stays on chip
+    int t_score = 0;
     for (int l = 0; l < a.nlevels; ++l) {
         t_score = std::max(t_score, cdiv(a.lv[l].w, FW_W) * cdiv(a.lv[l].h, FW_H));
-        t_nms = std::max(t_nms, cdiv(a.lv[l].w, 32) * cdiv(a.lv[l].h, 8));
+        GD_REQUIRE(((size_t)a.lv[l].off & 3) == 0 && a.lv[l].w >= 8 && a.lv[l].h >= 8, "cv::ORB level layout");
     }
-    k_cv_fast_score_levels<<<dim3(t_score, a.nlevels, batch), 256, 0, s>>>(pyr, stride_b, a, th, score);
-    GD_CUDA(cudaGetLastError());
-    k_cv_fast_nms_levels<<<dim3(t_nms, a.nlevels, batch), dim3(32, 8), 0, s>>>(score, stride_b, a, edge, kept, rowcnt, rowcnt_stride);
+    GD_REQUIRE((stride_b & 3) == 0 && ((uintptr_t)pyr & 3) == 0, "cv::ORB pyramid alignment");
+    k_cv_fast_kept_levels<<<dim3(t_score, a.nlevels, batch), 256, 0, s>>>(pyr, stride_b, a, th, edge, kept, rowcnt, rowcnt_stride);
     GD_CUDA(cudaGetLastError());
     return GD_OK;
 }
