@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "stdalgo.cuh"
@@ -511,6 +512,148 @@ __global__ void __launch_bounds__(NN_THREADS) k_getrt_nn(const uint4* __restrict
     }
 }
 
+// ---- the same on the tensor cores.  Hamming(a, b) = popc(a) + popc(b) - 2 <a, b> with the descriptors expanded to 256
+// bytes of 0 / 1: the inner products of a 32 x 8 block of (ref, cur) pairs are two m16n8k32 u8 MMAs per 32 bits of
+// descriptor (IMMA.16832.U8 in the SASS), the POPC pipe — the bound of the scalar form — is only used once per descriptor.
+// A CTA owns 128 ref features (one warp = 32 of them, their A fragments stay in registers: 2 x 8 x 4 words) and walks the
+// cur features in rounds of 128 that are expanded into shared memory.  The order of the k index inside an MMA is free as long
+// as A and B agree (a distance does not depend on the order of the bits): thread `tig` of a quad takes bytes 8 tig .. 8 tig + 7
+// of every 32-byte chunk, (a0, a2) / (a1, a3) / (b0, b1) are one 64-bit load each; the row pitch of 288 bytes makes those
+// loads conflict free.  Minima as in k_getrt_nn: rows in the thread (columns ascending, strict '<', quad merge by
+// (distance, index)), columns through packed keys with a rarely taken shared atomicMin.
+constexpr int HM_TILE = 128, HM_PITCH = 288, HM_THREADS = 128;
+
+__device__ __forceinline__ int hm_expand(uint8_t* dst, const uint4 lo, const uint4 hi)
+{
+    const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    int pc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        pc += __popc(w[k]);
+        unsigned o[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) o[n] = (((w[k] >> (4 * n)) & 15u) * 0x00204081u) & 0x01010101u;  // bit q of the nibble -> byte q
+        uint4* d4 = reinterpret_cast<uint4*>(dst + 32 * k);
+        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    return pc;
+}
+
+__device__ __forceinline__ void hm_mma(int (&c)[4], const unsigned (&a)[4], const uint2 b)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+__global__ void __launch_bounds__(HM_THREADS) k_getrt_nn_mma(const uint4* __restrict__ desc_ref, const uint4* __restrict__ desc_cur,
+                                                             const int* __restrict__ n_ref, const int* __restrict__ n_cur, int feat_cap,
+                                                             int* __restrict__ nn, int* __restrict__ dd, unsigned* __restrict__ colkey)
+{
+    __shared__ __align__(16) uint8_t hm[HM_TILE * HM_PITCH];
+    __shared__ int s_pc[HM_TILE];
+    __shared__ unsigned s_col[HM_TILE];
+    const int b = blockIdx.y;
+    const int nq = min(n_ref[b], feat_cap), nt = min(n_cur[b], feat_cap);
+    const int row0 = blockIdx.x * HM_TILE;
+    if (row0 >= nq) return;
+    const uint4* q = desc_ref + (size_t)b * feat_cap * 2;
+    const uint4* t = desc_cur + (size_t)b * feat_cap * 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    {   // the CTA's ref descriptors: expanded once, then only their fragments (registers) and popcounts are kept
+        const bool v = row0 + tid < nq;
+        s_pc[tid] = hm_expand(hm + tid * HM_PITCH, v ? q[2 * (row0 + tid)] : zero4, v ? q[2 * (row0 + tid) + 1] : zero4);
+    }
+    __syncthreads();
+    unsigned A[2][8][4];
+    int pa[4], rowi[4];
+    unsigned kinv[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const uint2 lo = *reinterpret_cast<const uint2*>(hm + (warp * 32 + 16 * mt + g) * HM_PITCH + 32 * ks + 8 * tig);
+            const uint2 hi = *reinterpret_cast<const uint2*>(hm + (warp * 32 + 16 * mt + g + 8) * HM_PITCH + 32 * ks + 8 * tig);
+            A[mt][ks][0] = lo.x; A[mt][ks][2] = lo.y;
+            A[mt][ks][1] = hi.x; A[mt][ks][3] = hi.y;
+        }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int lr = warp * 32 + g + 8 * r;  // r = 2 mt + half: rows g, g + 8 of m-tile 0, then of m-tile 1
+        pa[r] = s_pc[lr];
+        rowi[r] = row0 + lr;
+        kinv[r] = rowi[r] < nq ? 0u : 0xFFFFFFFFu;
+    }
+    int best[4], bj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        best[r] = 1 << 30;
+        bj[r] = -1;
+    }
+    for (int base = 0; base < nt; base += HM_TILE) {
+        const int m = min(HM_TILE, nt - base);
+        unsigned* ck = colkey + (size_t)b * feat_cap + base;
+        __syncthreads();  // fragments loaded / previous round done with the tile
+        {
+            const bool v = tid < m;
+            const int pc = hm_expand(hm + tid * HM_PITCH, v ? t[2 * (base + tid)] : zero4, v ? t[2 * (base + tid) + 1] : zero4);
+            s_pc[tid] = v ? pc : (1 << 30);  // a column past the end never beats a row minimum ...
+            s_col[tid] = v ? ck[tid] : 0u;   // ... and no key is below its bound
+        }
+        __syncthreads();
+        const int ntile = (m + 7) >> 3;
+        for (int n8 = 0; n8 < ntile; ++n8) {
+            int c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            const uint8_t* bp = hm + (8 * n8 + g) * HM_PITCH + 8 * tig;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const uint2 bb = *reinterpret_cast<const uint2*>(bp + 32 * ks);
+                hm_mma(c[0], A[0][ks], bb);
+                hm_mma(c[1], A[1][ks], bb);
+            }
+            const int col = 8 * n8 + 2 * tig;
+            const int pb0 = s_pc[col], pb1 = s_pc[col + 1];
+            const unsigned bound0 = s_col[col], bound1 = s_col[col + 1];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int d0 = pa[r] + pb0 - 2 * c[r >> 1][2 * (r & 1)], d1 = pa[r] + pb1 - 2 * c[r >> 1][2 * (r & 1) + 1];
+                if (d0 < best[r]) {
+                    best[r] = d0;
+                    bj[r] = base + col;
+                }
+                if (d1 < best[r]) {
+                    best[r] = d1;
+                    bj[r] = base + col + 1;
+                }
+                const unsigned key0 = (((unsigned)d0 << 16) | (unsigned)rowi[r]) | kinv[r];
+                const unsigned key1 = (((unsigned)d1 << 16) | (unsigned)rowi[r]) | kinv[r];
+                if (key0 < bound0) atomicMin(&s_col[col], key0);
+                if (key1 < bound1) atomicMin(&s_col[col + 1], key1);
+            }
+        }
+        __syncthreads();
+        if (tid < m) atomicMin(ck + tid, s_col[tid]);
+    }
+    // merge the four threads of a quad (they hold disjoint columns of the same rows)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int off = 1; off < 4; off <<= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best[r], off), oi = __shfl_xor_sync(0xffffffffu, bj[r], off);
+            if (ob < best[r] || (ob == best[r] && oi < bj[r])) {
+                best[r] = ob;
+                bj[r] = oi;
+            }
+        }
+        if (tig == 0 && rowi[r] < nq) {
+            nn[((size_t)b * 2 + 0) * feat_cap + rowi[r]] = bj[r];
+            dd[((size_t)b * 2 + 0) * feat_cap + rowi[r]] = best[r];
+        }
+    }
+}
+
 // direction 1 from the column keys (0xFFFFFFFF: no ref feature at all -> index -1, distance 1 << 30 like an empty scan)
 __global__ void __launch_bounds__(256) k_getrt_nn_finish(const unsigned* __restrict__ colkey, const int* __restrict__ n_cur, int feat_cap,
                                                          int* __restrict__ nn, int* __restrict__ dd)
@@ -528,7 +671,14 @@ static int launch_hamming_both(const uint4* desc_ref, const uint4* desc_cur, con
 {
     GD_REQUIRE(feat_cap <= 65536, "ref feature index does not fit the column key");
     GD_CUDA(cudaMemsetAsync(colkey, 0xFF, (size_t)batch * feat_cap * sizeof(unsigned), s));
-    k_getrt_nn<<<dim3(cdiv(feat_cap, NN_THREADS), batch), NN_THREADS, 0, s>>>(desc_ref, desc_cur, n_ref, n_cur, feat_cap, nn, dd, colkey);
+    static const bool scalar = [] {
+        const char* e = std::getenv("GD_GETRT_NN_SCALAR");  // the POPC form, kept for A/B runs and as the in-tree cross-check
+        return e && std::atoi(e) != 0;
+    }();
+    if (scalar)
+        k_getrt_nn<<<dim3(cdiv(feat_cap, NN_THREADS), batch), NN_THREADS, 0, s>>>(desc_ref, desc_cur, n_ref, n_cur, feat_cap, nn, dd, colkey);
+    else
+        k_getrt_nn_mma<<<dim3(cdiv(feat_cap, HM_TILE), batch), HM_THREADS, 0, s>>>(desc_ref, desc_cur, n_ref, n_cur, feat_cap, nn, dd, colkey);
     GD_CUDA(cudaGetLastError());
     k_getrt_nn_finish<<<dim3(cdiv(feat_cap, 256), batch), 256, 0, s>>>(colkey, n_cur, feat_cap, nn, dd);
     GD_CUDA(cudaGetLastError());
