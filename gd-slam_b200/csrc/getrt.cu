@@ -405,15 +405,27 @@ __global__ void __launch_bounds__(SEL_THREADS) k_getrt_select(const uint8_t* __r
         for (int r = warp; r < rows; r += SEL_THREADS / 32) {
             int pos = rowoff[r];
             const int y = edge + r;
-            for (int x0 = edge; x0 < L.w - edge; x0 += 32) {
-                const int x = x0 + lane;
-                const int v = x < L.w - edge ? (int)kp[(size_t)y * L.w + x] : 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, v > 0);
-                if (v > 0) {
-                    const int p = pos + __popc(bal & ((1u << lane) - 1));
-                    if (p < L.n1_cap) list1[p] = ((unsigned)(v - 1) << 24) | (unsigned)(y * L.w + x);
+            // six segments of 32 pixels per pass: their loads are in flight together (one dependent load per segment made
+            // this scan latency bound: 18 round trips to L2 / HBM per row)
+            constexpr int SEG = 6;
+            const uint8_t* row = kp + (size_t)y * L.w;
+            for (int x0 = edge; x0 < L.w - edge; x0 += 32 * SEG) {
+                int v[SEG];
+#pragma unroll
+                for (int u = 0; u < SEG; ++u) {
+                    const int x = x0 + 32 * u + lane;
+                    v[u] = x < L.w - edge ? (int)__ldg(row + x) : 0;
                 }
-                pos += __popc(bal);
+#pragma unroll
+                for (int u = 0; u < SEG; ++u) {
+                    const int x = x0 + 32 * u + lane;
+                    const unsigned bal = __ballot_sync(0xffffffffu, v[u] > 0);
+                    if (v[u] > 0) {
+                        const int p = pos + __popc(bal & ((1u << lane) - 1));
+                        if (p < L.n1_cap) list1[p] = ((unsigned)(v[u] - 1) << 24) | (unsigned)(y * L.w + x);
+                    }
+                    pos += __popc(bal);
+                }
             }
         }
     }
@@ -603,34 +615,42 @@ __global__ void __launch_bounds__(HM_THREADS) k_getrt_nn_mma(const uint4* __rest
             s_col[tid] = v ? ck[tid] : 0u;   // ... and no key is below its bound
         }
         __syncthreads();
+        // two column tiles per pass: four independent accumulator chains per thread (the tile always holds 16 column tiles;
+        // columns past the end are zero descriptors with an unreachable popcount)
         const int ntile = (m + 7) >> 3;
-        for (int n8 = 0; n8 < ntile; ++n8) {
-            int c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int n8 = 0; n8 < ntile; n8 += 2) {
+            int c[2][2][4] = {{{0, 0, 0, 0}, {0, 0, 0, 0}}, {{0, 0, 0, 0}, {0, 0, 0, 0}}};  // [column tile][m-tile][4]
             const uint8_t* bp = hm + (8 * n8 + g) * HM_PITCH + 8 * tig;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-                const uint2 bb = *reinterpret_cast<const uint2*>(bp + 32 * ks);
-                hm_mma(c[0], A[0][ks], bb);
-                hm_mma(c[1], A[1][ks], bb);
+                const uint2 b0 = *reinterpret_cast<const uint2*>(bp + 32 * ks);
+                const uint2 b1 = *reinterpret_cast<const uint2*>(bp + 8 * HM_PITCH + 32 * ks);
+                hm_mma(c[0][0], A[0][ks], b0);
+                hm_mma(c[0][1], A[1][ks], b0);
+                hm_mma(c[1][0], A[0][ks], b1);
+                hm_mma(c[1][1], A[1][ks], b1);
             }
-            const int col = 8 * n8 + 2 * tig;
-            const int pb0 = s_pc[col], pb1 = s_pc[col + 1];
-            const unsigned bound0 = s_col[col], bound1 = s_col[col + 1];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int d0 = pa[r] + pb0 - 2 * c[r >> 1][2 * (r & 1)], d1 = pa[r] + pb1 - 2 * c[r >> 1][2 * (r & 1) + 1];
-                if (d0 < best[r]) {
-                    best[r] = d0;
-                    bj[r] = base + col;
+            for (int u = 0; u < 2; ++u) {
+                const int col = 8 * (n8 + u) + 2 * tig;
+                const int pb0 = s_pc[col], pb1 = s_pc[col + 1];
+                const unsigned bound0 = s_col[col], bound1 = s_col[col + 1];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int d0 = pa[r] + pb0 - 2 * c[u][r >> 1][2 * (r & 1)], d1 = pa[r] + pb1 - 2 * c[u][r >> 1][2 * (r & 1) + 1];
+                    if (d0 < best[r]) {
+                        best[r] = d0;
+                        bj[r] = base + col;
+                    }
+                    if (d1 < best[r]) {
+                        best[r] = d1;
+                        bj[r] = base + col + 1;
+                    }
+                    const unsigned key0 = (((unsigned)d0 << 16) | (unsigned)rowi[r]) | kinv[r];
+                    const unsigned key1 = (((unsigned)d1 << 16) | (unsigned)rowi[r]) | kinv[r];
+                    if (key0 < bound0) atomicMin(&s_col[col], key0);
+                    if (key1 < bound1) atomicMin(&s_col[col + 1], key1);
                 }
-                if (d1 < best[r]) {
-                    best[r] = d1;
-                    bj[r] = base + col + 1;
-                }
-                const unsigned key0 = (((unsigned)d0 << 16) | (unsigned)rowi[r]) | kinv[r];
-                const unsigned key1 = (((unsigned)d1 << 16) | (unsigned)rowi[r]) | kinv[r];
-                if (key0 < bound0) atomicMin(&s_col[col], key0);
-                if (key1 < bound1) atomicMin(&s_col[col + 1], key1);
             }
         }
         __syncthreads();
