@@ -127,9 +127,12 @@ int fb_make_plan(int w, int h, double pyr_scale, int levels, int iterations, int
     plan->r_floats = r_off;
     plan->hrow_off = align_up(i_off, 64);
     {
-        size_t mx = 0;
-        for (int q = 0; q < plan->nlevels; ++q) mx = std::max(mx, (size_t)plan->lv[q].w);
-        plan->i_floats = align_up(plan->hrow_off + 2 * (size_t)h * mx, 64);  // + float2 row-pass scratch [h][max level width]
+        size_t mx = 0, sum = 0;  // the row-pass scratches of the resampled levels lie side by side (one launch for all levels)
+        for (int q = 0; q < plan->nlevels; ++q) {
+            mx = std::max(mx, (size_t)plan->lv[q].w);
+            if (q > 0) sum += (size_t)plan->lv[q].w;
+        }
+        plan->i_floats = align_up(plan->hrow_off + 2 * (size_t)h * std::max(mx, sum), 64);  // + float2 row-pass scratch [h][widths]
     }
     plan->f_float2 = f_off;
     plan->m_floats = 5 * align_up((size_t)plan->lv[0].w * plan->lv[0].h, 64);
@@ -282,6 +285,110 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize(const float2* __restr
     I[(size_t)b * istride_b + (size_t)dy * a.lw + dx] = r0 * b0 + r1 * b1;
 }
 
+// ---- all resampled levels in ONE launch each (the levels are independent: every level is blurred from the full-res image).
+// blockIdx.x walks the 32 x 8 tiles of all levels (tile_start), so the narrow levels do not cost a launch of their own —
+// at small batches the pyramid was 7 dependent launches of a few microseconds of work.  Same arithmetic as the per-level kernels.
+struct PyrLevelDev {
+    int lw, lh, ksize, tiles_x;
+    int tile_start_row, tile_start_col;  // first tile of this level in the row-pass / column-pass launch
+    double scale_x, scale_y;
+    unsigned long long hrow_off2, i_off;  // float2 offset of the level's row-pass scratch, float offset of its I plane
+    float taps[FB_MAX_KSIZE];
+};
+struct PyrMultiArgs {
+    int W, H, nl;
+    PyrLevelDev lv[FB_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) k_fb_rowblur_levels(const uint8_t* __restrict__ gray, size_t gstride_b, PyrMultiArgs a,
+                                                           float* __restrict__ scratch, size_t istride_b)
+{
+    pdl_wait();
+    int l = 0;
+    while (l + 1 < a.nl && (int)blockIdx.x >= a.lv[l + 1].tile_start_row) ++l;
+    const PyrLevelDev& L = a.lv[l];
+    const int t = (int)blockIdx.x - L.tile_start_row, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+    const int dx = tx * 32 + threadIdx.x, y = ty * 8 + threadIdx.y, b = blockIdx.y;
+    if (dx >= L.lw || y >= a.H) return;
+    float fx;
+    const int sx = fb_src_col(dx, L.scale_x, a.W, &fx);
+    const int r = L.ksize >> 1;
+    const uint8_t* row = gray + (size_t)b * gstride_b + (size_t)y * a.W;
+    const int x0 = sx - r;
+    float prev = (float)__ldg(row + reflect101_once(x0, a.W));
+    float nxt = (float)__ldg(row + reflect101_once(x0 + 1, a.W));
+    float acc0 = L.taps[0] * prev, acc1 = L.taps[0] * nxt;
+#pragma unroll 6
+    for (int i = 1; i < L.ksize; ++i) {
+        prev = nxt;
+        nxt = (float)__ldg(row + reflect101_once(x0 + i + 1, a.W));
+        acc0 = acc0 + L.taps[i] * prev;
+        acc1 = acc1 + L.taps[i] * nxt;
+    }
+    float2* Hrow = reinterpret_cast<float2*>(scratch + (size_t)b * istride_b) + L.hrow_off2;
+    Hrow[(size_t)y * L.lw + dx] = make_float2(acc0, acc1);
+}
+
+__global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a, float* __restrict__ scratch, size_t istride_b)
+{
+    pdl_wait();
+    int l = 0;
+    while (l + 1 < a.nl && (int)blockIdx.x >= a.lv[l + 1].tile_start_col) ++l;
+    const PyrLevelDev& L = a.lv[l];
+    const int t = (int)blockIdx.x - L.tile_start_col, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+    const int dx = tx * 32 + threadIdx.x, dy = ty * 8 + threadIdx.y, b = blockIdx.y;
+    if (dx >= L.lw || dy >= L.lh) return;
+    float fx;
+    (void)fb_src_col(dx, L.scale_x, a.W, &fx);
+    float fy = (float)((dy + 0.5) * L.scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    int sy1 = sy + 1;
+    sy = max(0, min(a.H - 1, sy));
+    sy1 = max(0, min(a.H - 1, sy1));
+    const int r = L.ksize >> 1;
+    float* sb = scratch + (size_t)b * istride_b;
+    const float2* hp = reinterpret_cast<const float2*>(sb) + L.hrow_off2 + dx;
+    float B00, B01, B10, B11;
+    const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < a.H;
+    if (interior && L.ksize == 19) {
+        fb_colblur_window<19>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+    } else if (interior && L.ksize == 9) {
+        fb_colblur_window<9>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+    } else if (interior && L.ksize == 3) {
+        fb_colblur_window<3>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+    } else {
+        const float2 c0 = __ldg(hp + (size_t)sy * L.lw);
+        B00 = L.taps[r] * c0.x;
+        B01 = L.taps[r] * c0.y;
+#pragma unroll 4
+        for (int i = 1; i <= r; ++i) {
+            const float tp = L.taps[r + i];
+            const float2 u = __ldg(hp + (size_t)reflect101(sy + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy - i, a.H) * L.lw);
+            B00 += tp * (u.x + d.x);
+            B01 += tp * (u.y + d.y);
+        }
+        B10 = B00;
+        B11 = B01;
+        if (sy1 != sy) {
+            const float2 c1 = __ldg(hp + (size_t)sy1 * L.lw);
+            B10 = L.taps[r] * c1.x;
+            B11 = L.taps[r] * c1.y;
+#pragma unroll 4
+            for (int i = 1; i <= r; ++i) {
+                const float tp = L.taps[r + i];
+                const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, a.H) * L.lw);
+                B10 += tp * (u.x + d.x);
+                B11 += tp * (u.y + d.y);
+            }
+        }
+    }
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const float r0 = B00 * a0 + B01 * a1;
+    const float r1 = B10 * a0 + B11 * a1;
+    sb[L.i_off + (size_t)dy * L.lw + dx] = r0 * b0 + r1 * b1;
+}
+
 // level 0: the level has the size of the image, cv::resize is a copy -> one 3x3 separable blur per pixel
 __global__ void __launch_bounds__(256) k_fb_blur3_same(const uint8_t* __restrict__ gray, size_t gstride_b, int W, int H, float t0,
                                                        float t1, float t2, float* __restrict__ I, size_t istride_b)
@@ -348,8 +455,13 @@ __global__ void __launch_bounds__(128) k_fb_blur3_same_v4(const uint8_t* __restr
 
 // ------------------------------------------------------------------------------------------------ K1a-2
 __device__ __forceinline__ size_t align_up_dev(size_t v, size_t a);
+struct PolyLevelDev {
+    int w, h, tiles_x, tile_start;
+    unsigned long long i_off, r_off;  // float offsets of the level's I plane / R planes inside a stream's scratch / R pyramid
+};
 struct PolyArgs {
-    int w, h;
+    int nl;
+    PolyLevelDev lv[FB_MAX_LEVELS];
     float g[2 * FB_POLY_N + 1], xg[2 * FB_POLY_N + 1], xxg[2 * FB_POLY_N + 1];
     double gd[FB_POLY_N + 1], xxgd[FB_POLY_N + 1];  // (double)g[k], (double)xxg[k] for k >= 0: the two taps multiplied in f64
     double ig11, ig03, ig33, ig55;
@@ -358,7 +470,8 @@ struct PolyArgs {
 constexpr int PT_W = 32, PT_H = 16, PT_TY = 8, PN = FB_POLY_N;  // 32x16 tile, 32x8 threads (2 rows per thread)
 constexpr int PT_NT = PT_W * PT_TY;
 
-__global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs a,
+// blockIdx.x walks the 32 x 16 tiles of ALL levels (independent of each other): one launch for the whole pyramid
+__global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ I, size_t istride_b, PolyArgs pa,
                                                             float* __restrict__ R, size_t rstride_b)
 {
     pdl_wait();
@@ -366,13 +479,19 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
     constexpr int TH = PT_H + 2 * PN;  // 26
     __shared__ float sI[TH][TW];
     __shared__ float4 sR[PT_H][TW];    // vertical sums (t0, t1, t2, -) of a column position: one vector load per tap
-    const int b = blockIdx.z;
-    const float* Ip = I + (size_t)b * istride_b;
-    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+    int lvl = 0;
+    while (lvl + 1 < pa.nl && (int)blockIdx.x >= pa.lv[lvl + 1].tile_start) ++lvl;
+    const PolyLevelDev& LV = pa.lv[lvl];
+    struct { int w, h; const float *g_, *xg_, *xxg_; const double *gd, *xxgd; double ig11, ig03, ig33, ig55; } a = {
+        LV.w, LV.h, pa.g, pa.xg, pa.xxg, pa.gd, pa.xxgd, pa.ig11, pa.ig03, pa.ig33, pa.ig55};
+    const int tile = (int)blockIdx.x - LV.tile_start, tyi = tile / LV.tiles_x, txi = tile - tyi * LV.tiles_x;
+    const int b = blockIdx.y;
+    const float* Ip = I + (size_t)b * istride_b + LV.i_off;
+    const int x0 = txi * PT_W, y0 = tyi * PT_H;
     const int tid = threadIdx.y * PT_W + threadIdx.x;
-    const float* g = a.g + PN;
-    const float* xg = a.xg + PN;
-    const float* xxg = a.xxg + PN;
+    const float* g = a.g_ + PN;
+    const float* xg = a.xg_ + PN;
+    const float* xxg = a.xxg_ + PN;
     // tile + 5-px halo (replicate border).  Columns 0..31: warp = tile rows (stride 8), lane = column.  The 10 halo columns
     // 32..41 are a flat list (260 elements for the tile, 160 for the vertical pass) so that whole warps work on them.
     {
@@ -416,7 +535,7 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
     if (x >= a.w) return;
     const int lx = threadIdx.x + PN;
     const size_t npad = align_up_dev((size_t)a.w * a.h, 64);
-    float* Rb = R + (size_t)b * rstride_b;
+    float* Rb = R + (size_t)b * rstride_b + LV.r_off;
 #pragma unroll
     for (int rr = 0; rr < PT_H / PT_TY; ++rr) {
         const int ly = threadIdx.y + PT_TY * rr, y = y0 + ly;
@@ -447,55 +566,75 @@ __global__ void __launch_bounds__(PT_NT) k_fb_polyexp(const float* __restrict__ 
 int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gray_stride_b, int batch, float* scratch_I,
                               size_t i_stride_b, float* R, size_t r_stride_b, cudaStream_t s, LaunchStats* st)
 {
+    // levels of the image size with a 3-tap blur (level 0): one 3x3 kernel; every other level: row pass + column pass /
+    // resize, ALL of them in one launch each
+    PyrMultiArgs ma;
+    ma.W = plan.w; ma.H = plan.h; ma.nl = 0;
+    int tiles_row = 0, tiles_col = 0, n_same = 0;
+    size_t hrow2 = plan.hrow_off / 2;  // float2 units (hrow_off is a multiple of 64 floats)
     for (int k = 0; k < plan.nlevels; ++k) {
         const FbLevel& L = plan.lv[k];
-        PyrArgs pa;
-        pa.W = plan.w; pa.H = plan.h; pa.lw = L.w; pa.lh = L.h; pa.ksize = L.ksize;
-        pa.scale_x = L.scale_x; pa.scale_y = L.scale_y;
-        std::memcpy(pa.taps, L.taps, sizeof(pa.taps));
-        {
-            LaunchScope ls(st, s, "K1a_blur_resample", (L.w == plan.w && L.h == plan.h && L.ksize == 3) ? 1 : 2);
-            // one thread per level column: the block width with the fewest idle lanes for this level (80 -> 96, 160 -> 160)
-            int bs = 128;
-            for (int c = 256, waste = 1 << 30; c >= 64; c -= 32)
-                if (cdiv(L.w, c) * c - L.w < waste) { waste = cdiv(L.w, c) * c - L.w; bs = c; }
-            dim3 block(bs), grid(cdiv(L.w, bs), L.h, batch);
+        if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
+            ++n_same;
+            continue;
+        }
+        PyrLevelDev& D = ma.lv[ma.nl++];
+        D.lw = L.w; D.lh = L.h; D.ksize = L.ksize; D.tiles_x = cdiv(L.w, 32);
+        D.tile_start_row = tiles_row; D.tile_start_col = tiles_col;
+        tiles_row += D.tiles_x * cdiv(plan.h, 8);
+        tiles_col += D.tiles_x * cdiv(L.h, 8);
+        D.scale_x = L.scale_x; D.scale_y = L.scale_y;
+        D.hrow_off2 = hrow2;
+        hrow2 += (size_t)plan.h * L.w;
+        D.i_off = L.i_off;
+        std::memcpy(D.taps, L.taps, sizeof(D.taps));
+    }
+    GD_REQUIRE(2 * hrow2 <= plan.i_floats, "row-pass scratch too small for the resampled levels");
+    {
+        LaunchScope ls(st, s, "K1a_blur_resample", n_same + (ma.nl ? 2 : 0));
+        for (int k = 0; k < plan.nlevels; ++k) {
+            const FbLevel& L = plan.lv[k];
+            if (!(L.w == plan.w && L.h == plan.h && L.ksize == 3)) continue;
             float* Ik = scratch_I + L.i_off;
-            if (L.w == plan.w && L.h == plan.h && L.ksize == 3) {
-                const bool v4 = plan.w % 4 == 0 && plan.h >= 2 && gray_stride_b % 4 == 0 && i_stride_b % 4 == 0 &&
-                                ((uintptr_t)gray & 3) == 0 && ((uintptr_t)Ik & 15) == 0;
-                if (v4) {
-                    constexpr int RY = 8;
-                    dim3 b4(32, 4), g4(cdiv(plan.w / 4, 32), cdiv(plan.h, 4 * RY), batch);
-                    GD_CUDA(launch_pdl(k_fb_blur3_same_v4<RY>, g4, b4, 0, s, gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b));
-                } else {
-                    GD_CUDA(launch_pdl(k_fb_blur3_same, grid, block, 0, s, gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b));
-                }
+            const bool v4 = plan.w % 4 == 0 && plan.h >= 2 && gray_stride_b % 4 == 0 && i_stride_b % 4 == 0 &&
+                            ((uintptr_t)gray & 3) == 0 && ((uintptr_t)Ik & 15) == 0;
+            if (v4) {
+                constexpr int RY = 8;
+                dim3 b4(32, 4), g4(cdiv(plan.w / 4, 32), cdiv(plan.h, 4 * RY), batch);
+                GD_CUDA(launch_pdl(k_fb_blur3_same_v4<RY>, g4, b4, 0, s, gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b));
             } else {
-                float2* Hrow = reinterpret_cast<float2*>(scratch_I + plan.hrow_off);
-                dim3 gridA(cdiv(L.w, bs), plan.h, batch);
-                GD_CUDA(launch_pdl(k_fb_rowblur, gridA, block, 0, s, gray, gray_stride_b, pa, Hrow, i_stride_b / 2));
-                GD_CUDA(cudaGetLastError());
-                GD_CUDA(launch_pdl(k_fb_colblur_resize, grid, block, 0, s, Hrow, i_stride_b / 2, pa, Ik, i_stride_b));
+                dim3 block(128), grid(cdiv(L.w, 128), L.h, batch);
+                GD_CUDA(launch_pdl(k_fb_blur3_same, grid, block, 0, s, gray, gray_stride_b, plan.w, plan.h, L.taps[0], L.taps[1], L.taps[2], Ik, i_stride_b));
             }
             GD_CUDA(cudaGetLastError());
         }
-        {
-            LaunchScope ls(st, s, "K1a_polyexp", 1);
-            PolyArgs po;
-            po.w = L.w; po.h = L.h;
-            std::memcpy(po.g, plan.g, sizeof(po.g));
-            std::memcpy(po.xg, plan.xg, sizeof(po.xg));
-            std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
-            po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
-            for (int q = 0; q <= FB_POLY_N; ++q) {
-                po.gd[q] = (double)plan.g[FB_POLY_N + q];
-                po.xxgd[q] = (double)plan.xxg[FB_POLY_N + q];
-            }
-            dim3 block(PT_W, PT_TY), grid(cdiv(L.w, PT_W), cdiv(L.h, PT_H), batch);
-            GD_CUDA(launch_pdl(k_fb_polyexp, grid, block, 0, s, scratch_I + L.i_off, i_stride_b, po, R + L.r_off, r_stride_b));
+        if (ma.nl) {
+            GD_CUDA(launch_pdl(k_fb_rowblur_levels, dim3(tiles_row, batch), dim3(32, 8), 0, s, gray, gray_stride_b, ma, scratch_I, i_stride_b));
+            GD_CUDA(cudaGetLastError());
+            GD_CUDA(launch_pdl(k_fb_colblur_resize_levels, dim3(tiles_col, batch), dim3(32, 8), 0, s, ma, scratch_I, i_stride_b));
             GD_CUDA(cudaGetLastError());
         }
+    }
+    {
+        LaunchScope ls(st, s, "K1a_polyexp", 1);
+        PolyArgs po;
+        po.nl = plan.nlevels;
+        int tiles = 0;
+        for (int k = 0; k < plan.nlevels; ++k) {
+            const FbLevel& L = plan.lv[k];
+            po.lv[k] = {L.w, L.h, cdiv(L.w, PT_W), tiles, (unsigned long long)L.i_off, (unsigned long long)L.r_off};
+            tiles += cdiv(L.w, PT_W) * cdiv(L.h, PT_H);
+        }
+        std::memcpy(po.g, plan.g, sizeof(po.g));
+        std::memcpy(po.xg, plan.xg, sizeof(po.xg));
+        std::memcpy(po.xxg, plan.xxg, sizeof(po.xxg));
+        po.ig11 = plan.ig11; po.ig03 = plan.ig03; po.ig33 = plan.ig33; po.ig55 = plan.ig55;
+        for (int q = 0; q <= FB_POLY_N; ++q) {
+            po.gd[q] = (double)plan.g[FB_POLY_N + q];
+            po.xxgd[q] = (double)plan.xxg[FB_POLY_N + q];
+        }
+        GD_CUDA(launch_pdl(k_fb_polyexp, dim3(tiles, batch), dim3(PT_W, PT_TY), 0, s, scratch_I, i_stride_b, po, R, r_stride_b));
+        GD_CUDA(cudaGetLastError());
     }
     return GD_OK;
 }
