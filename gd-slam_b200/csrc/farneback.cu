@@ -155,12 +155,6 @@ __device__ __forceinline__ int reflect101_once(int p, int len)
     return p >= len ? 2 * len - 2 - p : p;
 }
 
-struct PyrArgs {
-    int W, H, lw, lh, ksize;
-    double scale_x, scale_y;
-    float taps[FB_MAX_KSIZE];
-};
-
 // cv::resize source column of level column dx (and its interpolation weight)
 __device__ __forceinline__ int fb_src_col(int dx, double scale_x, int W, float* frac)
 {
@@ -171,34 +165,6 @@ __device__ __forceinline__ int fb_src_col(int dx, double scale_x, int W, float* 
     if (sx >= W - 1) { fx = 0; sx = W - 1; }
     *frac = fx;
     return sx;
-}
-
-// Pass A of blur+resample: the row pass of the separable Gaussian on the FULL-RES rows, evaluated only at the two source
-// columns (sx, sx+1) every level column interpolates between.  One thread = one (full-res row, level column).
-__global__ void __launch_bounds__(256) k_fb_rowblur(const uint8_t* __restrict__ gray, size_t gstride_b, PyrArgs a,
-                                                    float2* __restrict__ Hrow, size_t hstride_b)
-{
-    pdl_wait();
-    const int dx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (dx >= a.lw) return;
-    float fx;
-    const int sx = fb_src_col(dx, a.scale_x, a.W, &fx);
-    const int r = a.ksize >> 1;
-    const uint8_t* row = gray + (size_t)b * gstride_b + (size_t)y * a.W;
-    // one code path for interior and border columns (a divergent border branch would be taken by most warps of the narrow
-    // levels); the first tap is peeled so that the loop body is two FMAs per load
-    const int x0 = sx - r;
-    float prev = (float)__ldg(row + reflect101_once(x0, a.W));
-    float nxt = (float)__ldg(row + reflect101_once(x0 + 1, a.W));
-    float acc0 = a.taps[0] * prev, acc1 = a.taps[0] * nxt;
-#pragma unroll 6
-    for (int i = 1; i < a.ksize; ++i) {
-        prev = nxt;
-        nxt = (float)__ldg(row + reflect101_once(x0 + i + 1, a.W));
-        acc0 = acc0 + a.taps[i] * prev;
-        acc1 = acc1 + a.taps[i] * nxt;
-    }
-    Hrow[(size_t)b * hstride_b + (size_t)y * a.lw + dx] = make_float2(acc0, acc1);
 }
 
 // column pass for an interior level row: rows sy - r .. sy + 1 + r of the row-pass scratch, both windows from one set of loads
@@ -225,69 +191,15 @@ __device__ __forceinline__ void fb_colblur_window(const float2* __restrict__ hp,
     }
 }
 
-// Pass B: column pass (symmetric form, REFLECT_101) at the two source rows of every level pixel, then cv::resize's
-// bilinear combination (horizontal first, then vertical).  Reads of Hrow are coalesced across dx.
-__global__ void __launch_bounds__(256) k_fb_colblur_resize(const float2* __restrict__ Hrow, size_t hstride_b, PyrArgs a,
-                                                           float* __restrict__ I, size_t istride_b)
-{
-    pdl_wait();
-    const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y, b = blockIdx.z;
-    if (dx >= a.lw) return;
-    float fx;
-    (void)fb_src_col(dx, a.scale_x, a.W, &fx);
-    float fy = (float)((dy + 0.5) * a.scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= sy;
-    int sy1 = sy + 1;
-    sy = max(0, min(a.H - 1, sy));
-    sy1 = max(0, min(a.H - 1, sy1));
-    const int r = a.ksize >> 1;
-    const float2* hp = Hrow + (size_t)b * hstride_b + dx;
-    float B00, B01, B10, B11;
-    // interior rows (all but the first/last few level rows): the two windows centred on sy and sy + 1 share ksize - 1 of
-    // their rows; load the ksize + 1 rows once.  Same products and sums as the general path below.
-    const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < a.H;
-    if (interior && a.ksize == 19) {
-        fb_colblur_window<19>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
-    } else if (interior && a.ksize == 9) {
-        fb_colblur_window<9>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
-    } else if (interior && a.ksize == 3) {
-        fb_colblur_window<3>(hp, a.lw, sy, a.taps, B00, B01, B10, B11);
-    } else {
-    const float2 c0 = __ldg(hp + (size_t)sy * a.lw);
-    B00 = a.taps[r] * c0.x;
-    B01 = a.taps[r] * c0.y;
-#pragma unroll 4
-    for (int i = 1; i <= r; ++i) {
-        const float t = a.taps[r + i];
-        const float2 u = __ldg(hp + (size_t)reflect101(sy + i, a.H) * a.lw), d = __ldg(hp + (size_t)reflect101(sy - i, a.H) * a.lw);
-        B00 += t * (u.x + d.x);
-        B01 += t * (u.y + d.y);
-    }
-    B10 = B00;
-    B11 = B01;
-    if (sy1 != sy) {
-        const float2 c1 = __ldg(hp + (size_t)sy1 * a.lw);
-        B10 = a.taps[r] * c1.x;
-        B11 = a.taps[r] * c1.y;
-#pragma unroll 4
-        for (int i = 1; i <= r; ++i) {
-            const float t = a.taps[r + i];
-            const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, a.H) * a.lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, a.H) * a.lw);
-            B10 += t * (u.x + d.x);
-            B11 += t * (u.y + d.y);
-        }
-    }
-    }
-    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const float r0 = B00 * a0 + B01 * a1;
-    const float r1 = B10 * a0 + B11 * a1;
-    I[(size_t)b * istride_b + (size_t)dy * a.lw + dx] = r0 * b0 + r1 * b1;
-}
-
-// ---- all resampled levels in ONE launch each (the levels are independent: every level is blurred from the full-res image).
-// blockIdx.x walks the 32 x 8 tiles of all levels (tile_start), so the narrow levels do not cost a launch of their own —
-// at small batches the pyramid was 7 dependent launches of a few microseconds of work.  Same arithmetic as the per-level kernels.
+// Blur + resample of all resampled levels in ONE launch per pass (the levels are independent: every level is blurred from
+// the full-res image).  blockIdx.x walks the 32 x 8 tiles of all levels (tile_start), so the narrow levels do not cost a
+// launch of their own — at small batches the pyramid was 7 dependent launches of a few microseconds of work.
+// Pass A (k_fb_rowblur_levels): the row pass of the separable Gaussian on the FULL-RES rows, evaluated only at the two source
+// columns (sx, sx + 1) every level column interpolates between; one thread = one (full-res row, level column); one code path
+// for interior and border columns, the first tap peeled so that the loop body is two FMAs per load.
+// Pass B (k_fb_colblur_resize_levels): column pass (symmetric form, REFLECT_101) at the two source rows of every level
+// pixel, then cv::resize's bilinear combination (horizontal first, then vertical); interior rows load the ksize + 1 rows of
+// the two overlapping windows once.
 struct PyrLevelDev {
     int lw, lh, ksize, tiles_x;
     int tile_start_row, tile_start_col;  // first tile of this level in the row-pass / column-pass launch

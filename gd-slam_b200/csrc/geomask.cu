@@ -661,7 +661,9 @@ __global__ void __launch_bounds__(256, MB) k_mahalanobis(const float2* __restric
         const float2 a = __ldg(lut + i);
         rx = a.x; ry = a.y;
     }
-    const int rix = (int)rx, riy = (int)ry;
+    // without a LUT the undistorted positions are the integer pixel positions themselves: no float <-> int round trips
+    // (they run on the conversion pipe, which bounds this kernel)
+    const int rix = lut ? (int)rx : x, riy = lut ? (int)ry : y;
     const bool ref_in = rix >= 0 && riy >= 0 && rix < w && riy < h;
     const size_t ri = ref_in ? (size_t)riy * w + rix : 0;
     const float ref_depth = __ldg(depth_ref + (size_t)b * dstride_b + ri);
@@ -676,13 +678,13 @@ __global__ void __launch_bounds__(256, MB) k_mahalanobis(const float2* __restric
         const float2 c = __ldg(lut + (size_t)icy * w + icx);
         cx = c.x; cy = c.y;
     }
-    const int cix = (int)cx, ciy = (int)cy;
+    const int cix = lut ? (int)cx : icx, ciy = lut ? (int)cy : icy;
     if (!ref_in || cix < 0 || ciy < 0 || cix >= w || ciy >= h) return;
     const size_t ci = (size_t)ciy * w + cix;
     const float cur_depth = __ldg(depth_cur + (size_t)b * dstride_b + ci);
     const uint8_t cur_edge = __ldg(edge_cur + (size_t)b * estride_b + ci);
     if (ref_edge == 255 || cur_edge == 255) return;
-    if (cur_depth == 0.f || (double)cur_depth > 3.5 || ref_depth == 0.f || (double)ref_depth > 3.5) return;
+    if (cur_depth == 0.f || cur_depth > 3.5f || ref_depth == 0.f || ref_depth > 3.5f) return;  // (double)d > 3.5 <=> d > 3.5f
 
     const float fu = cam.fu, fv = cam.fv, cu = cam.cu;
     const float U0 = dot3f(P->RK[0], rx, P->RK[1], ry, P->RK[2], 1.0f);
