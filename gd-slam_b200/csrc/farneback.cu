@@ -212,6 +212,8 @@ struct PyrMultiArgs {
     PyrLevelDev lv[FB_MAX_LEVELS];
 };
 
+constexpr int RB_ROWS = 8;  // full-res rows per thread of the row pass: the per-column set-up (source column in f64, level
+                            // look-up) is paid once for eight rows — it was two thirds of the instructions with one row per thread
 __global__ void __launch_bounds__(256) k_fb_rowblur_levels(const uint8_t* __restrict__ gray, size_t gstride_b, PyrMultiArgs a,
                                                            float* __restrict__ scratch, size_t istride_b)
 {
@@ -219,26 +221,58 @@ __global__ void __launch_bounds__(256) k_fb_rowblur_levels(const uint8_t* __rest
     int l = 0;
     while (l + 1 < a.nl && (int)blockIdx.x >= a.lv[l + 1].tile_start_row) ++l;
     const PyrLevelDev& L = a.lv[l];
-    const int t = (int)blockIdx.x - L.tile_start_row, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
-    const int dx = tx * 32 + threadIdx.x, y = ty * 8 + threadIdx.y, b = blockIdx.y;
-    if (dx >= L.lw || y >= a.H) return;
-    float fx;
-    const int sx = fb_src_col(dx, L.scale_x, a.W, &fx);
-    const int r = L.ksize >> 1;
-    const uint8_t* row = gray + (size_t)b * gstride_b + (size_t)y * a.W;
-    const int x0 = sx - r;
-    float prev = (float)__ldg(row + reflect101_once(x0, a.W));
-    float nxt = (float)__ldg(row + reflect101_once(x0 + 1, a.W));
-    float acc0 = L.taps[0] * prev, acc1 = L.taps[0] * nxt;
-#pragma unroll 6
-    for (int i = 1; i < L.ksize; ++i) {
-        prev = nxt;
-        nxt = (float)__ldg(row + reflect101_once(x0 + i + 1, a.W));
-        acc0 = acc0 + L.taps[i] * prev;
-        acc1 = acc1 + L.taps[i] * nxt;
+    // the level is only known at run time: the taps go through shared memory instead of indexed constant-bank reads
+    __shared__ float taps[FB_MAX_KSIZE];
+    {
+        const int tl = threadIdx.y * 32 + threadIdx.x;
+        if (tl < L.ksize) taps[tl] = L.taps[tl];
     }
-    float2* Hrow = reinterpret_cast<float2*>(scratch + (size_t)b * istride_b) + L.hrow_off2;
-    Hrow[(size_t)y * L.lw + dx] = make_float2(acc0, acc1);
+    __syncthreads();
+    const int lw = L.lw, ksize = L.ksize, W = a.W, H = a.H;
+    const int t = (int)blockIdx.x - L.tile_start_row, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
+    const int dx = tx * 32 + threadIdx.x, ybase = (ty * 8 + threadIdx.y) * RB_ROWS, b = blockIdx.y;
+    if (dx >= lw || ybase >= H) return;
+    float fx;
+    const int sx = fb_src_col(dx, L.scale_x, W, &fx);
+    const int x0 = sx - (ksize >> 1);
+    const uint8_t* g = gray + (size_t)b * gstride_b;
+    int rowoff[RB_ROWS];  // rows past the image end read the last row (results discarded)
+#pragma unroll
+    for (int j = 0; j < RB_ROWS; ++j) rowoff[j] = min(ybase + j, H - 1) * W;
+    // source columns x0 .. x0 + ksize ascending; column c feeds tap c of the window at sx and tap c - 1 of the one at sx + 1:
+    // per accumulator the same products and sums in the same order as a per-row loop
+    float acc0[RB_ROWS], acc1[RB_ROWS];
+    {
+        const int c0 = reflect101_once(x0, W), c1 = reflect101_once(x0 + 1, W);
+        const float t0 = taps[0], t1 = taps[1];
+#pragma unroll
+        for (int j = 0; j < RB_ROWS; ++j) {
+            const float v0 = (float)__ldg(g + rowoff[j] + c0), v1 = (float)__ldg(g + rowoff[j] + c1);
+            acc0[j] = t0 * v0;
+            acc0[j] = acc0[j] + t1 * v1;
+            acc1[j] = t0 * v1;
+        }
+    }
+    for (int c = 2; c < ksize; ++c) {
+        const int col = reflect101_once(x0 + c, W);
+        const float tA = taps[c], tB = taps[c - 1];
+#pragma unroll
+        for (int j = 0; j < RB_ROWS; ++j) {
+            const float v = (float)__ldg(g + rowoff[j] + col);
+            acc0[j] = acc0[j] + tA * v;
+            acc1[j] = acc1[j] + tB * v;
+        }
+    }
+    {
+        const int col = reflect101_once(x0 + ksize, W);
+        const float tB = taps[ksize - 1];
+#pragma unroll
+        for (int j = 0; j < RB_ROWS; ++j) acc1[j] = acc1[j] + tB * (float)__ldg(g + rowoff[j] + col);
+    }
+    float2* Hrow = reinterpret_cast<float2*>(scratch + (size_t)b * istride_b) + L.hrow_off2 + (size_t)ybase * lw + dx;
+#pragma unroll
+    for (int j = 0; j < RB_ROWS; ++j)
+        if (ybase + j < H) Hrow[(size_t)j * lw] = make_float2(acc0[j], acc1[j]);
 }
 
 __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a, float* __restrict__ scratch, size_t istride_b)
@@ -247,6 +281,12 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a
     int l = 0;
     while (l + 1 < a.nl && (int)blockIdx.x >= a.lv[l + 1].tile_start_col) ++l;
     const PyrLevelDev& L = a.lv[l];
+    __shared__ float taps[FB_MAX_KSIZE];
+    {
+        const int tl = threadIdx.y * 32 + threadIdx.x;
+        if (tl < L.ksize) taps[tl] = L.taps[tl];
+    }
+    __syncthreads();
     const int t = (int)blockIdx.x - L.tile_start_col, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
     const int dx = tx * 32 + threadIdx.x, dy = ty * 8 + threadIdx.y, b = blockIdx.y;
     if (dx >= L.lw || dy >= L.lh) return;
@@ -264,18 +304,18 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a
     float B00, B01, B10, B11;
     const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < a.H;
     if (interior && L.ksize == 19) {
-        fb_colblur_window<19>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+        fb_colblur_window<19>(hp, L.lw, sy, taps, B00, B01, B10, B11);
     } else if (interior && L.ksize == 9) {
-        fb_colblur_window<9>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+        fb_colblur_window<9>(hp, L.lw, sy, taps, B00, B01, B10, B11);
     } else if (interior && L.ksize == 3) {
-        fb_colblur_window<3>(hp, L.lw, sy, L.taps, B00, B01, B10, B11);
+        fb_colblur_window<3>(hp, L.lw, sy, taps, B00, B01, B10, B11);
     } else {
         const float2 c0 = __ldg(hp + (size_t)sy * L.lw);
-        B00 = L.taps[r] * c0.x;
-        B01 = L.taps[r] * c0.y;
+        B00 = taps[r] * c0.x;
+        B01 = taps[r] * c0.y;
 #pragma unroll 4
         for (int i = 1; i <= r; ++i) {
-            const float tp = L.taps[r + i];
+            const float tp = taps[r + i];
             const float2 u = __ldg(hp + (size_t)reflect101(sy + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy - i, a.H) * L.lw);
             B00 += tp * (u.x + d.x);
             B01 += tp * (u.y + d.y);
@@ -284,11 +324,11 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a
         B11 = B01;
         if (sy1 != sy) {
             const float2 c1 = __ldg(hp + (size_t)sy1 * L.lw);
-            B10 = L.taps[r] * c1.x;
-            B11 = L.taps[r] * c1.y;
+            B10 = taps[r] * c1.x;
+            B11 = taps[r] * c1.y;
 #pragma unroll 4
             for (int i = 1; i <= r; ++i) {
-                const float tp = L.taps[r + i];
+                const float tp = taps[r + i];
                 const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, a.H) * L.lw);
                 B10 += tp * (u.x + d.x);
                 B11 += tp * (u.y + d.y);
@@ -493,7 +533,7 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
         PyrLevelDev& D = ma.lv[ma.nl++];
         D.lw = L.w; D.lh = L.h; D.ksize = L.ksize; D.tiles_x = cdiv(L.w, 32);
         D.tile_start_row = tiles_row; D.tile_start_col = tiles_col;
-        tiles_row += D.tiles_x * cdiv(plan.h, 8);
+        tiles_row += D.tiles_x * cdiv(plan.h, 8 * RB_ROWS);
         tiles_col += D.tiles_x * cdiv(L.h, 8);
         D.scale_x = L.scale_x; D.scale_y = L.scale_y;
         D.hrow_off2 = hrow2;

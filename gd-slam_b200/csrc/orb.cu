@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     l += cell >= a.lv[l + 4].cell_start ? 4 : 0;
     l += cell >= a.lv[l + 2].cell_start ? 2 : 0;
     l += cell >= a.lv[l + 1].cell_start ? 1 : 0;
-    const FastLevelDev& L = a.lv[l];
+    const FastLevelDev L = a.lv[l];  // by value: the level is a run-time index, every later use would be an indexed constant read
     const int ci = cell - L.cell_start;
     const int i = (int)(((unsigned)ci * L.inv_nCols) >> 20), j = ci - i * L.nCols;
     const int maxBX = L.w - ORB_EDGE + 3, maxBY = L.h - ORB_EDGE + 3;
