@@ -77,6 +77,7 @@ using namespace gd;
 static int frontend_enqueue_head(gd_frontend* h, const uint8_t* bgr_dev, size_t bgr_stride_b, bool* forked)
 {
     GeoMaskCore& g = h->geo;
+    PdlScope pdl_scope(g.batch);
     OrbCore& o = h->orb;
     // K0: both grays in one pass over the BGR bytes (BGR2GRAY for the flow, cfg.orb_gray_order for ORB level 0)
     GD_TRY(launch_gray(bgr_dev, (size_t)g.w * 3, bgr_stride_b, g.w, g.h, g.batch, g.gray.as<uint8_t>(), g.n_pad, o.level0(0),
@@ -117,6 +118,7 @@ static int frontend_enqueue_head(gd_frontend* h, const uint8_t* bgr_dev, size_t 
 static int frontend_enqueue_tail(gd_frontend* h, bool forked)
 {
     GeoMaskCore& g = h->geo;
+    PdlScope pdl_scope(g.batch);
     if (forked) GD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
     GD_TRY(g.enqueue_mask_tail());
     if (forked) {

@@ -172,14 +172,25 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
-inline bool pdl_enabled()
+// GD_PDL: 1 = always, 0 = never, unset = automatic: on for handles with more than one stream.  (Measured on B200: with a
+// single 640x480 stream the early-launched grids cost 26 us per frame — 0.311 vs 0.285 ms — from two streams on they pay.)
+inline int pdl_mode()
 {
-    static const bool on = [] {
+    static const int mode = [] {
         const char* e = std::getenv("GD_PDL");
-        return e ? std::atoi(e) != 0 : true;
+        return e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
     }();
-    return on;
+    return mode;
 }
+inline thread_local bool g_pdl_auto_on = true;  // set by PdlScope around the enqueue calls of a handle
+struct PdlScope {
+    bool prev;
+    explicit PdlScope(int batch) : prev(g_pdl_auto_on) { g_pdl_auto_on = batch > 1; }
+    ~PdlScope() { g_pdl_auto_on = prev; }
+    PdlScope(const PdlScope&) = delete;
+    PdlScope& operator=(const PdlScope&) = delete;
+};
+inline bool pdl_enabled() { return pdl_mode() < 0 ? g_pdl_auto_on : pdl_mode() == 1; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)

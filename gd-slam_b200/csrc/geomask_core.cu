@@ -137,6 +137,7 @@ int GeoMaskCore::push_resident(bool gray_done)
 
 int GeoMaskCore::enqueue_push(int slot, bool gray_done)
 {
+    PdlScope pdl_scope(batch);
     // K0: gray for the flow (the batched front-end computes it together with the ORB gray)
     if (!gray_done)
         GD_TRY(launch_gray(bgr.as<uint8_t>(), (size_t)w * 3, n_pad * 3, w, h, batch, gray.as<uint8_t>(), n_pad, nullptr, 0, 0, 0,
@@ -222,12 +223,14 @@ int GeoMaskCore::upload_poses(const float* Rm, const float* Tm, const int* pose_
 // device half: everything GetNoGMMmask enqueues on the stream (capturable into a CUDA graph)
 int GeoMaskCore::enqueue_mask()
 {
+    PdlScope pdl_scope(batch);
     GD_TRY(enqueue_flow());
     return enqueue_mask_tail();
 }
 
 int GeoMaskCore::enqueue_flow()
 {
+    PdlScope pdl_scope(batch);
     const bool started = frames >= GD_RING;
     if (!started) {
         last_flow = nullptr;
@@ -245,6 +248,7 @@ int GeoMaskCore::enqueue_flow()
 
 int GeoMaskCore::enqueue_mask_tail()
 {
+    PdlScope pdl_scope(batch);
     const bool started = frames >= GD_RING;
     if (!started) {  // warm-up: all-ones mask (:171-175)
         return launch_fill_u8(mask.as<uint8_t>(), (size_t)batch * n_pad, 1, stream, stats);

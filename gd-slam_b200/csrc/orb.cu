@@ -1411,6 +1411,7 @@ int OrbCore::extract_resident()
 
 int OrbCore::enqueue_extract()
 {
+    PdlScope pdl_scope(batch);
     const OrbPlan& P = plan;
     uint8_t* py = pyr.as<uint8_t>();
     // K4a: pyramid chain
