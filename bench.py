@@ -87,6 +87,17 @@ FAMILY_LIMITER = {
 }
 
 
+def _load_limiter_util():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "limiters.json")))
+        return {k: v for k, v in d.items() if not k.startswith("_")}
+    except Exception:
+        return {}
+
+
+LIMITER_UTIL = _load_limiter_util()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -675,6 +686,8 @@ def main():
         families[name] = {"ms_per_step": ms / PSTEPS, "launches_per_step": ln / PSTEPS, "share": ms / tot_ms,
                           "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak if gbs else None,
                           "limiter": FAMILY_LIMITER.get(name)}
+        if name in LIMITER_UTIL:  # ncu: how busy the limiting resource is (static, from profiles/limiters.json)
+            families[name]["limiter_util"] = LIMITER_UTIL[name]
     dom = max(fam, key=lambda x: x[1])
     dom_name, dom_ms, dom_ln = dom
     dom_bytes_per_launch = FAMILY_BYTES.get(dom_name, 0.0) * B * PSTEPS / max(1, dom_ln)
