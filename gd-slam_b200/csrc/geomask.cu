@@ -340,10 +340,15 @@ __device__ __forceinline__ float edge_load_raw(const float* __restrict__ dp, int
     if (x >= 0 && y >= 0 && x < w && y < h) v = __ldg(dp + (size_t)y * w + x);
     return v;
 }
-__device__ __forceinline__ float edge_clamp(float v, int x, int y, int w, int h)
+// `bad`: the value leaves the range the f32 error bounds assume — interior pixels |d| <= D = 3.5 after the clamp (a NaN, an
+// infinity or a large negative depth fails), border pixels (never clamped, they only enter the normals of their neighbours)
+// |d| <= 1e4 so that no f32 intermediate overflows.  A tile with a bad value is evaluated by the f64 arithmetic throughout.
+__device__ __forceinline__ float edge_clamp(float v, int x, int y, int w, int h, bool& bad)
 {
     const bool interior = x >= 1 && y >= 1 && x < w - 1 && y < h - 1;
-    return interior && v > 3.5f ? 0.f : v;  // (double)v > 3.5 <=> v > 3.5f: 3.5 is a float
+    v = interior && v > 3.5f ? 0.f : v;  // (double)v > 3.5 <=> v > 3.5f: 3.5 is a float
+    bad = bad || !(fabsf(v) <= (interior ? 3.5f : 1.0e4f));
+    return v;
 }
 
 __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __restrict__ depth, size_t dstride_b, int w, int h,
@@ -398,13 +403,12 @@ __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __res
     for (int it = 0; tile < et.total; ++it, tile += gridDim.x) {
         const int par = it & 1;
         float (*sd)[ET_W + 4] = sd2[par];
-        v0 = edge_clamp(v0, x0 + tx - 2, y0 + ty - 2, w, h);
+        bool bad = false;
+        v0 = edge_clamp(v0, x0 + tx - 2, y0 + ty - 2, w, h, bad);
         sd[ty][tx] = v0;
-        bool bad = !(fabsf(v0) <= 3.0e38f);
         if (dly >= 0) {
-            v1 = edge_clamp(v1, x0 + dlx - 2, y0 + dly - 2, w, h);
+            v1 = edge_clamp(v1, x0 + dlx - 2, y0 + dly - 2, w, h, bad);
             sd[dly][dlx] = v1;
-            bad = bad || !(fabsf(v1) <= 3.0e38f);
         }
         if (bad) s_flags[par][1] = 1;
         __syncthreads();
@@ -446,12 +450,12 @@ __global__ void __launch_bounds__(ET_W* ET_H, 2) k_depth_edge(const float* __res
         const int lx = tx + 1, ly = ty + 1;
         const float4 Ac = sA[ly][lx];
         if (in_img && x >= 1 && y >= 1 && x < w - 1 && y < h - 1 && Ac.w != 0.f) {
-            if (Ac.z == 0.f) {
+            if (s_flags[par][1]) {
+                s_todo[atomicAdd(&s_flags[par][0], 1)] = (ly << 8) | lx;  // tile with a value outside the bounds' range: all exact
+            } else if (Ac.z == 0.f) {
                 // a pixel with depth but without a normal (its top or left neighbour has no depth): cn = cv = 0 -> a zero vertex
-                // among the neighbours, or phi_d = 0 and phi_c = 1 for every neighbour -> 0.05 > 0.04: edge in both cases
+                // among the neighbours, or phi_d = 0 and phi_c = 1 for every (finite) neighbour -> 0.05 > 0.04: edge in both cases
                 e = 255;
-            } else if (s_flags[par][1]) {
-                s_todo[atomicAdd(&s_flags[par][0], 1)] = (ly << 8) | lx;
             } else {
                 const float px = (float)x, py = (float)y;
                 const float h0 = fmaf(eb.Ki[0], px, fmaf(eb.Ki[1], py, eb.Ki[2]));

@@ -69,6 +69,24 @@ def test_depth_edge_interval_kernel_hard_cases(capi, oracle, synth, monkeypatch)
     assert np.array_equal(capi.stage_depth_edge(d2, K2), oracle.depth_edge(d2, K2))
 
 
+def test_depth_edge_non_finite_depth(capi, oracle, synth, pair):
+    """NaN / +-Inf / negative depth values (reference: NaN > 3.5 and NaN == 0 are both false, so such pixels take part in the
+    normals): tiles that hold one are evaluated entirely by the f64 arithmetic of the reference — same bits as the oracle."""
+    _, f0, _ = pair
+    K = synth.intrinsics()
+    d = f0.depth_m.copy()
+    d[50, 60] = np.nan
+    d[51:53, 300:303] = np.inf
+    d[200, 10] = -np.inf
+    d[0, 5] = np.inf          # image border: never clamped, feeds the normal of the pixel below
+    d[479, 630] = np.nan
+    d[240, 639] = -1.0
+    d[120:124, 400:404] = -0.5
+    with np.errstate(all="ignore"):
+        ref = oracle.depth_edge(d, K)
+    assert np.array_equal(capi.stage_depth_edge(d, K), ref)
+
+
 def test_mahalanobis_scatter_vs_oracle(capi, oracle, synth, pair):
     s, f0, f5 = pair
     K = synth.intrinsics()
