@@ -244,7 +244,14 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
     h->cfg = *cfg;
     int r = GD_OK;
     do {
-        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        int main_prio = 0;
+        {  // GD_MAIN_PRIO=1: the flow stream at the highest stream priority (A/B switch)
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char* e = std::getenv("GD_MAIN_PRIO");
+            if (e && std::atoi(e) > 0) main_prio = hi;
+        }
+        if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, main_prio) != cudaSuccess) {
             set_error("cudaStreamCreate failed");
             r = GD_ECUDA;
             break;
@@ -269,7 +276,19 @@ int gd_frontend_create(gd_frontend_t** out, const gd_frontend_config* cfg)
             const char* e = std::getenv("GD_OVERLAP");
             h->overlap = e ? std::atoi(e) != 0 : true;
         }
-        if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        // GD_AUX_PRIO: stream priority of the auxiliary (depth edges + ORB) stream relative to the flow stream: 1 = higher,
+        // -1 = lower, 0 / unset = same (A/B switch)
+        int aux_prio = 0;
+        {
+            int lo = 0, hi = 0;  // lo = numerically largest = least priority
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            const char* e = std::getenv("GD_AUX_PRIO");
+            const int want = e ? std::atoi(e) : 0;
+            aux_prio = want > 0 ? hi : (want < 0 ? lo : 0);
+            if (aux_prio < hi) aux_prio = hi;
+            if (aux_prio > lo) aux_prio = lo;
+        }
+        if (cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, aux_prio) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
