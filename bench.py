@@ -82,7 +82,7 @@ FAMILY_LIMITER = {
     "K4a_pyramid_resize": "issue slots (byte gathers), L2 resident",
     "K4b_fast_cells": "issue slots (90 % busy: 4-point pass, 16-point network, cell bookkeeping), L2 resident",
     "K4c_quadtree": "latency (one CTA per level and stream)",
-    "K4e_blur7": "latency / issue slots (rows requested six iterations ahead), L2 resident",
+    "K4e_blur7": "latency / issue slots (rows requested seven iterations ahead), L2 resident",
     "K4de_orient_describe": "latency / gathers",
 }
 

@@ -944,11 +944,11 @@ struct BlurArgs {
     int nlevels, total_tiles;
     BlurLevelDev lv[ORB_MAX_LEVELS];
 };
-// One warp blurs a 120 x 32 block: lane i owns the 4-pixel group at x0 - 4 + 4 i (lanes 0 and 31 only supply halo words),
-// marches down 32 + 6 rows with the 7-row window of horizontal sums in registers.  Horizontal pass on packed 16-bit
+// One warp blurs a 120 x 36 block: lane i owns the 4-pixel group at x0 - 4 + 4 i (lanes 0 and 31 only supply halo words),
+// marches down 36 + 6 rows with the 7-row window of horizontal sums in registers.  Horizontal pass on packed 16-bit
 // pairs (sums <= 255 * 256 fit a lane), vertical pass in 32 bit, one rounding at the end: the integer arithmetic is
 // order independent, so the result equals the row-then-column cv::GaussianBlur fixed-point path bit for bit.
-constexpr int BT_W = 120, BT_H = 32;
+constexpr int BT_W = 120, BT_H = 36;  // BT_H + 6 = 42 rows = six passes of the seven-row body
 
 __device__ __forceinline__ int reflect101i(int p, int len)
 {
@@ -956,7 +956,7 @@ __device__ __forceinline__ int reflect101i(int p, int len)
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ out, size_t stride_b,
+__global__ void __launch_bounds__(256, 4) k_orb_blur(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ out, size_t stride_b,
                                                   BlurArgs a)
 {
     pdl_wait();
@@ -986,44 +986,51 @@ __global__ void __launch_bounds__(256) k_orb_blur(const uint8_t* __restrict__ py
         return (unsigned)__ldg(row + xr[0]) | ((unsigned)__ldg(row + xr[1]) << 8) | ((unsigned)__ldg(row + xr[2]) << 16) |
                ((unsigned)__ldg(row + xr[3]) << 24);
     };
-    constexpr int BLUR_PF = 6;
+    // Seven rows (the period of the window ring and of the prefetch ring) are unrolled, the six passes over them are a real
+    // loop: the fully unrolled 38-row form spent more stall cycles on instruction fetch than on memory (ncu: no_instruction).
+    constexpr int BLUR_PF = 7;
+    static_assert((BT_H + 6) % 7 == 0, "whole passes of seven rows");
     unsigned Bq[BLUR_PF];
 #pragma unroll
     for (int r = 0; r < BLUR_PF; ++r) Bq[r] = load_row(r);
+#pragma unroll 1
+    for (int rb = 0; rb < BT_H + 6; rb += 7) {
 #pragma unroll
-    for (int r = 0; r < BT_H + 6; ++r) {
-        const unsigned B = Bq[r % BLUR_PF];
-        if (r + BLUR_PF < BT_H + 6) Bq[r % BLUR_PF] = load_row(r + BLUR_PF);
-        const unsigned A = __shfl_up_sync(0xffffffffu, B, 1), C = __shfl_down_sync(0xffffffffu, B, 1);
-        // byte windows starting k pixels from the group start, split into 16-bit pairs P_k = (b[k], b[k+1])
-        const unsigned wm3 = __funnelshift_r(A, B, 8), wm2 = __funnelshift_r(A, B, 16);
-        const unsigned wp1 = __funnelshift_r(B, C, 8), wp2 = __funnelshift_r(B, C, 16), wp3 = __funnelshift_r(B, C, 24);
-        const unsigned Pm3 = __byte_perm(wm3, 0u, 0x4140), Pm1 = __byte_perm(wm3, 0u, 0x4342);
-        const unsigned Pm2 = __byte_perm(wm2, 0u, 0x4140), P0 = __byte_perm(wm2, 0u, 0x4342);
-        const unsigned P1 = __byte_perm(wp1, 0u, 0x4140), P3 = __byte_perm(wp1, 0u, 0x4342);
-        const unsigned P2 = __byte_perm(wp2, 0u, 0x4140), P4 = __byte_perm(wp2, 0u, 0x4342);
-        const unsigned P5 = __byte_perm(wp3, 0u, 0x4342);
-        const unsigned h01 = 18u * (Pm3 + P3) + 34u * (Pm2 + P2) + 48u * (Pm1 + P1) + 56u * P0;
-        const unsigned h23 = 18u * (Pm1 + P5) + 34u * (P0 + P4) + 48u * (P1 + P3) + 56u * P2;
-        unsigned* hn = hw[r % 7];
-        hn[0] = h01 & 0xffffu; hn[1] = h01 >> 16; hn[2] = h23 & 0xffffu; hn[3] = h23 >> 16;
-        if (r >= 6) {
-            const int y = y0 + r - 6;
-            unsigned o[4];
+        for (int rr = 0; rr < 7; ++rr) {
+            const int r = rb + rr;  // r % 7 == rr
+            const unsigned B = Bq[rr];
+            if (r + BLUR_PF < BT_H + 6) Bq[rr] = load_row(r + BLUR_PF);
+            const unsigned A = __shfl_up_sync(0xffffffffu, B, 1), C = __shfl_down_sync(0xffffffffu, B, 1);
+            // byte windows starting k pixels from the group start, split into 16-bit pairs P_k = (b[k], b[k+1])
+            const unsigned wm3 = __funnelshift_r(A, B, 8), wm2 = __funnelshift_r(A, B, 16);
+            const unsigned wp1 = __funnelshift_r(B, C, 8), wp2 = __funnelshift_r(B, C, 16), wp3 = __funnelshift_r(B, C, 24);
+            const unsigned Pm3 = __byte_perm(wm3, 0u, 0x4140), Pm1 = __byte_perm(wm3, 0u, 0x4342);
+            const unsigned Pm2 = __byte_perm(wm2, 0u, 0x4140), P0 = __byte_perm(wm2, 0u, 0x4342);
+            const unsigned P1 = __byte_perm(wp1, 0u, 0x4140), P3 = __byte_perm(wp1, 0u, 0x4342);
+            const unsigned P2 = __byte_perm(wp2, 0u, 0x4140), P4 = __byte_perm(wp2, 0u, 0x4342);
+            const unsigned P5 = __byte_perm(wp3, 0u, 0x4342);
+            const unsigned h01 = 18u * (Pm3 + P3) + 34u * (Pm2 + P2) + 48u * (Pm1 + P1) + 56u * P0;
+            const unsigned h23 = 18u * (Pm1 + P5) + 34u * (P0 + P4) + 48u * (P1 + P3) + 56u * P2;
+            unsigned* hn = hw[rr];
+            hn[0] = h01 & 0xffffu; hn[1] = h01 >> 16; hn[2] = h23 & 0xffffu; hn[3] = h23 >> 16;
+            if (r >= 6) {
+                const int y = y0 + r - 6;
+                unsigned o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned acc = 18u * (hw[(r + 1) % 7][j] + hw[r % 7][j]) + 34u * (hw[(r + 2) % 7][j] + hw[(r + 6) % 7][j]) +
-                                     48u * (hw[(r + 3) % 7][j] + hw[(r + 5) % 7][j]) + 56u * hw[(r + 4) % 7][j];
-                o[j] = (acc + 32768u) >> 16;
-            }
-            if (owner && y < h) {
-                uint8_t* q = dst + (size_t)y * pitch + x;
-                if (x + 3 < w) {
-                    *reinterpret_cast<unsigned*>(q) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
-                } else {
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned acc = 18u * (hw[(rr + 1) % 7][j] + hw[rr][j]) + 34u * (hw[(rr + 2) % 7][j] + hw[(rr + 6) % 7][j]) +
+                                         48u * (hw[(rr + 3) % 7][j] + hw[(rr + 5) % 7][j]) + 56u * hw[(rr + 4) % 7][j];
+                    o[j] = (acc + 32768u) >> 16;
+                }
+                if (owner && y < h) {
+                    uint8_t* q = dst + (size_t)y * pitch + x;
+                    if (x + 3 < w) {
+                        *reinterpret_cast<unsigned*>(q) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (x + j < w) q[j] = (uint8_t)o[j];
+                        for (int j = 0; j < 4; ++j)
+                            if (x + j < w) q[j] = (uint8_t)o[j];
+                    }
                 }
             }
         }
