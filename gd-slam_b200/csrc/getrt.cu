@@ -3,7 +3,7 @@
 //
 //   per frame (enqueue_features)   cv::ORB::create(2000, 1.2f, 8, 31, 0, 2)->detectAndCompute(gray)            :82-90
 //     k_resize_linear_exact          pyramid: every level from the previous one, INTER_LINEAR_EXACT (8.8 fixed point)
-//     k_cv_fast_score/nms_levels     cv::FAST(20, nonmax) on every level + per-row corner counts          (orb.cu)
+//     k_cv_fast_kept_levels          cv::FAST(20, nonmax) on every level + per-row corner counts          (orb.cu)
 //     k_getrt_select                 raster-ordered corner list, retainBest(2 N_l) on the FAST response, Harris responses,
 //                                    retainBest(N_l): std::nth_element / std::partition run as libstdc++ runs them, by one
 //                                    thread per (level, stream) on lists in shared memory (stdalgo.cuh)
@@ -884,6 +884,7 @@ int GetRtCore::init(const float K[9], const float* dist_coef, int ndist, int wid
     for (int l = 0; l < GETRT_LEVELS; ++l) {
         const CvLevelDev& L = pyr_args.lv[l];
         const long long interior = (long long)std::max(0, L.w - 2 * GETRT_EDGE) * std::max(0, L.h - 2 * GETRT_EDGE);
+        // (34816 entries would let one CTA of the flow's box kernel share the SM with a selection CTA: measured, no gain)
         n1_cap = std::max<long long>(n1_cap, std::min<long long>((interior + 3) / 4 + 32, 36864));
     }
     n2_cap = 2 * max_n + 4096;
@@ -895,7 +896,6 @@ int GetRtCore::init(const float K[9], const float* dist_coef, int ndist, int wid
     GD_REQUIRE((size_t)feat_cap * 12 <= 48 * 1024, "match list larger than the default shared memory");
     const size_t B = (size_t)batch;
     GD_TRY(pyr.alloc(B * pyr_bytes));
-    GD_TRY(score.alloc(B * pyr_bytes));
     GD_TRY(kept.alloc(B * pyr_bytes));
     GD_TRY(blur.alloc(B * pyr_bytes));
     GD_TRY(rowcnt.alloc(B * rows_total * sizeof(int)));
@@ -940,7 +940,7 @@ int GetRtCore::enqueue_features(const uint8_t* gray, size_t gray_stride_b, int s
     {
         LaunchScope ls(stats, s, "G2_cvorb_fast", 1);
         GD_CUDA(cudaMemsetAsync(rowcnt.p, 0, rowcnt.bytes, s));
-        GD_TRY(orb_cv_fast_levels(py, pyr_bytes, pyr_args, batch, 20, GETRT_EDGE, score.as<uint8_t>(), kept.as<uint8_t>(), rowcnt.as<int>(),
+        GD_TRY(orb_cv_fast_levels(py, pyr_bytes, pyr_args, batch, 20, GETRT_EDGE, nullptr, kept.as<uint8_t>(), rowcnt.as<int>(),
                                   (size_t)rows_total, s));
     }
     {

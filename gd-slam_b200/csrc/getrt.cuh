@@ -29,7 +29,7 @@ struct GetRtCore {
     int n1_cap = 0, n2_cap = 0, sel_cap = 0, feat_cap = 0;
     size_t select_smem = 0;
 
-    DevBuf pyr, score, kept, blur;  // [B][pyr_bytes]
+    DevBuf pyr, kept, blur;         // [B][pyr_bytes]
     DevBuf rowcnt;                  // [B][rows_total] int
     DevBuf tabs;                    // cv::resize(INTER_LINEAR_EXACT) tables of levels 1..7: x table then y table (ushort4)
     int tab_x[GETRT_LEVELS] = {0}, tab_y[GETRT_LEVELS] = {0};
