@@ -765,7 +765,10 @@ int launch_mahalanobis(const float2* flow, size_t flow_stride_b, const float* de
     LaunchScope ls(st, s, "K2b_mahalanobis", 1);
     dim3 block(32, 8), grid(cdiv(w, 32), cdiv(h, 8), batch);
     const char* env = std::getenv("GD_MAHA_MB");
-    if (env && std::atoi(env) == 4)
+    if (env && std::atoi(env) == 5)
+        GD_CUDA(launch_pdl(k_mahalanobis<5>, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
+                           edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
+    else if (env && std::atoi(env) == 4)
         GD_CUDA(launch_pdl(k_mahalanobis<4>, grid, block, 0, s, flow, flow_stride_b, depth_ref, depth_cur, depth_stride_b, edge_ref, edge_cur,
                            edge_stride_b, lut, w, h, cam, poses, kf.shift, keys, keys_stride_b));
     else
