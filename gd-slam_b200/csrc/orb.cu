@@ -274,7 +274,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     uint8_t* tile_base = sm;                       // [tile_h][tp], rows start at the 4-byte aligned column below x0
     uint8_t* sc_base = sm + tp * a.tile_h;         // S' of the pixels that pass the 4-point test and the threshold, else 0
     __shared__ unsigned s_keep[FAST_KEEP_WORDS];
-    __shared__ int s_nlist;
     const int b = blockIdx.y;
     const int cell = blockIdx.x;
     // level of the cell: binary search over the ascending cell_start table (unused levels hold INT_MAX)
@@ -339,38 +338,34 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
     static_assert(FAST_KEEP_WORDS <= FAST_THREADS, "bitmap is cleared by one pass of the block");
     const uint8_t* tile = tile_base + xo;
     uint8_t* sc = sc_base + xo;
-    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h);  // (y << 6 | x) of the survivors
+    // survivors of the 4-point test as (y << 6 | x), one private list segment per warp (a warp owns the rows y = warp mod 8:
+    // no atomics, and the 16-point pass of a warp only needs its own list).  A segment holds ceil(ih / 8) * iw entries at most,
+    // which is below tp * tile_h / 8 for every cell.
+    unsigned short* plist = reinterpret_cast<unsigned short*>(sm + 2 * tp * a.tile_h) + warp * ((tp * a.tile_h) / NW);
     int tot = 0;
-    const unsigned nlist_addr = (unsigned)__cvta_generic_to_shared(&s_nlist);
     unsigned kw[FAST_KW];  // keep words lane + 32 r (every warp holds the whole bitmap)
     // first pass at iniThFAST only, like the reference's first cv::FAST call; if no corner survives the NMS the cell is
     // redone at minThFAST (:812-816).  Per pass:
-    //   1. 4-point necessary test for every pixel, survivors appended to a shared list (warp-aggregated atomics)
-    //   2. the 16-point network over the list (densely packed: in textured images nearly every warp holds a survivor)
+    //   1. 4-point necessary test for every pixel of the warp's rows, survivors appended to the warp's list
+    //   2. the 16-point network over the list (densely packed lanes whatever the pass rate of the 4-point test)
     //   3. cell-local strict NMS over the listed corners only -> one keep bit per interior pixel
     //   4. raster-ordered compaction straight from the bitmap (one warp)
     for (int pass = 0; pass < 2 && tot == 0; ++pass) {
         const int th = pass == 0 ? a.iniTh : a.minTh;
-        if (threadIdx.x == 0) s_nlist = 0;
-        __syncthreads();
+        __syncthreads();  // tile / cleared scores visible (first pass); the previous pass is done with the bitmap
+        int nl = 0;       // warp-uniform
         for (int y = warp; y < ih; y += NW) {
             const uint8_t* row = tile + (y + 3) * tp + 3;
             for (int xb = 0; xb < iw; xb += 32) {
                 const int x = xb + lane;
                 const bool qk = x < iw && fast_quick(row + x, tp, th);
                 const unsigned bal = __ballot_sync(0xffffffffu, qk);
-                if (bal) {
-                    int wbase = 0;
-                    if (lane == 0)  // plain atom.shared: the compiler wraps atomicAdd() in its own warp aggregation
-                        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(wbase) : "r"(nlist_addr), "r"(__popc(bal)) : "memory");
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((y << 6) | x);
-                }
+                if (qk) plist[nl + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((y << 6) | x);
+                nl += __popc(bal);
             }
         }
-        __syncthreads();
-        const int nl = s_nlist;
-        for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
+        __syncwarp();
+        for (int q = lane; q < nl; q += 32) {
             const int t = plist[q];
             const int pp = ((t >> 6) + 3) * tp + (t & 63) + 3;
             const int sv = fast_full(tile + pp, tp);
@@ -378,7 +373,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_orb_fast(const uint8_t* __rest
         }
         __syncthreads();
         // NMS: keep iff S' > th and S' > S'_nb for every neighbour that is itself a corner at th (sc is 0 otherwise)
-        for (int q = threadIdx.x; q < nl; q += FAST_THREADS) {
+        for (int q = lane; q < nl; q += 32) {
             const int t = plist[q];
             const uint8_t* c = sc + ((t >> 6) + 3) * tp + (t & 63) + 3;
             const int sv = c[0];
@@ -528,11 +523,11 @@ __global__ void __launch_bounds__(256) k_cv_fast_kept_levels(const uint8_t* __re
     const uint8_t* img = pyr + (size_t)blockIdx.z * stride_b + L.off;  // 256-byte aligned
     __shared__ __align__(16) uint8_t tile[FK_TR * FK_TP];
     __shared__ __align__(16) uint8_t sc[FK_SH * FK_SP];
-    __shared__ unsigned short plist[FK_SH * FK_SW];
-    __shared__ int s_nlist;
+    constexpr int FK_ITERS = (FK_SH * FK_SW + 255) / 256;        // 5 rounds of 256 positions
+    __shared__ unsigned short plist[8][FK_ITERS * 32];           // one private survivor list per warp: no atomics
     const int ty = (int)blockIdx.x / tiles_x;
     const int X0 = FW_W * ((int)blockIdx.x - ty * tiles_x), Y0 = FW_H * ty;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const int last = (w * h - 1) & ~3;
         const unsigned* iw = reinterpret_cast<const unsigned*>(img);
@@ -544,28 +539,24 @@ __global__ void __launch_bounds__(256) k_cv_fast_kept_levels(const uint8_t* __re
             reinterpret_cast<unsigned*>(tile + r * FK_TP)[k] = __funnelshift_r(w0, w1, 8 * m);
         }
         for (int q = tid; q < FK_SH * FK_SP / 4; q += 256) reinterpret_cast<unsigned*>(sc)[q] = 0u;
-        if (tid == 0) s_nlist = 0;
     }
     __syncthreads();
-    const unsigned nlist_addr = (unsigned)__cvta_generic_to_shared(&s_nlist);
-    for (int base = 0; base < FK_SH * FK_SW; base += 256) {
+    int nl = 0;  // warp-uniform
+    unsigned short* wl = plist[warp];
+#pragma unroll
+    for (int base = 0; base < FK_ITERS * 256; base += 256) {
         const int q = base + tid;
         const int sy = (q * 993) >> 16, sx = q - FK_SW * sy;  // q / 66 for q < 32768
         const int gx = X0 - 1 + sx, gy = Y0 - 1 + sy;
         bool qk = q < FK_SH * FK_SW && gx >= 3 && gx < w - 3 && gy >= 3 && gy < h - 3;
         if (qk) qk = fast_quick(tile + (sy + 3) * FK_TP + sx + 3, FK_TP, th);
         const unsigned bal = __ballot_sync(0xffffffffu, qk);
-        if (bal) {
-            int wbase = 0;
-            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(wbase) : "r"(nlist_addr), "r"(__popc(bal)) : "memory");
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (qk) plist[wbase + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((sy << 7) | sx);
-        }
+        if (qk) wl[nl + __popc(bal & ((1u << lane) - 1))] = (unsigned short)((sy << 7) | sx);
+        nl += __popc(bal);
     }
-    __syncthreads();
-    const int nl = s_nlist;
-    for (int e = tid; e < nl; e += 256) {
-        const int q = plist[e], sy = q >> 7, sx = q & 127;
+    __syncwarp();
+    for (int e = lane; e < nl; e += 32) {
+        const int q = wl[e], sy = q >> 7, sx = q & 127;
         const int sv = fast_full(tile + (sy + 3) * FK_TP + sx + 3, FK_TP);
         sc[sy * FK_SP + sx] = (uint8_t)(sv > th ? sv : 0);
     }
