@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(256) k_fb_rowblur_levels(const uint8_t* __rest
         if (ybase + j < H) Hrow[(size_t)j * lw] = make_float2(acc0[j], acc1[j]);
 }
 
+constexpr int CB_ROWS = 4;  // level rows per thread of the column pass (the per-column set-up is paid once)
 __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a, float* __restrict__ scratch, size_t istride_b)
 {
     pdl_wait();
@@ -287,58 +288,69 @@ __global__ void __launch_bounds__(256) k_fb_colblur_resize_levels(PyrMultiArgs a
         if (tl < L.ksize) taps[tl] = L.taps[tl];
     }
     __syncthreads();
+    const int lw = L.lw, lh = L.lh, ksize = L.ksize, H = a.H;
     const int t = (int)blockIdx.x - L.tile_start_col, ty = t / L.tiles_x, tx = t - ty * L.tiles_x;
-    const int dx = tx * 32 + threadIdx.x, dy = ty * 8 + threadIdx.y, b = blockIdx.y;
-    if (dx >= L.lw || dy >= L.lh) return;
+    const int dx = tx * 32 + threadIdx.x, dy0 = (ty * 8 + threadIdx.y) * CB_ROWS, b = blockIdx.y;
+    if (dx >= lw || dy0 >= lh) return;
     float fx;
     (void)fb_src_col(dx, L.scale_x, a.W, &fx);
-    float fy = (float)((dy + 0.5) * L.scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= sy;
-    int sy1 = sy + 1;
-    sy = max(0, min(a.H - 1, sy));
-    sy1 = max(0, min(a.H - 1, sy1));
-    const int r = L.ksize >> 1;
+    const double scale_y = L.scale_y;
+    const int r = ksize >> 1;
     float* sb = scratch + (size_t)b * istride_b;
     const float2* hp = reinterpret_cast<const float2*>(sb) + L.hrow_off2 + dx;
-    float B00, B01, B10, B11;
-    const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < a.H;
-    if (interior && L.ksize == 19) {
-        fb_colblur_window<19>(hp, L.lw, sy, taps, B00, B01, B10, B11);
-    } else if (interior && L.ksize == 9) {
-        fb_colblur_window<9>(hp, L.lw, sy, taps, B00, B01, B10, B11);
-    } else if (interior && L.ksize == 3) {
-        fb_colblur_window<3>(hp, L.lw, sy, taps, B00, B01, B10, B11);
-    } else {
-        const float2 c0 = __ldg(hp + (size_t)sy * L.lw);
-        B00 = taps[r] * c0.x;
-        B01 = taps[r] * c0.y;
-#pragma unroll 4
-        for (int i = 1; i <= r; ++i) {
-            const float tp = taps[r + i];
-            const float2 u = __ldg(hp + (size_t)reflect101(sy + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy - i, a.H) * L.lw);
-            B00 += tp * (u.x + d.x);
-            B01 += tp * (u.y + d.y);
-        }
-        B10 = B00;
-        B11 = B01;
-        if (sy1 != sy) {
-            const float2 c1 = __ldg(hp + (size_t)sy1 * L.lw);
-            B10 = taps[r] * c1.x;
-            B11 = taps[r] * c1.y;
+    float* out = sb + L.i_off + dx;
+    const float a0 = 1.f - fx, a1 = fx;
+#pragma unroll 1
+    for (int j = 0; j < CB_ROWS; ++j) {
+        const int dy = dy0 + j;
+        if (dy >= lh) break;
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        int sy1 = sy + 1;
+        sy = max(0, min(H - 1, sy));
+        sy1 = max(0, min(H - 1, sy1));
+        float B00, B01, B10, B11;
+        // interior rows (all but the first / last few level rows): the two windows centred on sy and sy + 1 share ksize - 1 of
+        // their rows; load the ksize + 1 rows once.  Same products and sums as the general path below.
+        const bool interior = sy1 == sy + 1 && sy - r >= 0 && sy1 + r < H;
+        if (interior && ksize == 19) {
+            fb_colblur_window<19>(hp, lw, sy, taps, B00, B01, B10, B11);
+        } else if (interior && ksize == 9) {
+            fb_colblur_window<9>(hp, lw, sy, taps, B00, B01, B10, B11);
+        } else if (interior && ksize == 3) {
+            fb_colblur_window<3>(hp, lw, sy, taps, B00, B01, B10, B11);
+        } else {
+            const float2 c0 = __ldg(hp + (size_t)sy * lw);
+            B00 = taps[r] * c0.x;
+            B01 = taps[r] * c0.y;
 #pragma unroll 4
             for (int i = 1; i <= r; ++i) {
                 const float tp = taps[r + i];
-                const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, a.H) * L.lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, a.H) * L.lw);
-                B10 += tp * (u.x + d.x);
-                B11 += tp * (u.y + d.y);
+                const float2 u = __ldg(hp + (size_t)reflect101(sy + i, H) * lw), d = __ldg(hp + (size_t)reflect101(sy - i, H) * lw);
+                B00 += tp * (u.x + d.x);
+                B01 += tp * (u.y + d.y);
+            }
+            B10 = B00;
+            B11 = B01;
+            if (sy1 != sy) {
+                const float2 c1 = __ldg(hp + (size_t)sy1 * lw);
+                B10 = taps[r] * c1.x;
+                B11 = taps[r] * c1.y;
+#pragma unroll 4
+                for (int i = 1; i <= r; ++i) {
+                    const float tp = taps[r + i];
+                    const float2 u = __ldg(hp + (size_t)reflect101(sy1 + i, H) * lw), d = __ldg(hp + (size_t)reflect101(sy1 - i, H) * lw);
+                    B10 += tp * (u.x + d.x);
+                    B11 += tp * (u.y + d.y);
+                }
             }
         }
+        const float b0 = 1.f - fy, b1 = fy;
+        const float r0 = B00 * a0 + B01 * a1;
+        const float r1 = B10 * a0 + B11 * a1;
+        out[(size_t)dy * lw] = r0 * b0 + r1 * b1;
     }
-    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
-    const float r0 = B00 * a0 + B01 * a1;
-    const float r1 = B10 * a0 + B11 * a1;
-    sb[L.i_off + (size_t)dy * L.lw + dx] = r0 * b0 + r1 * b1;
 }
 
 // level 0: the level has the size of the image, cv::resize is a copy -> one 3x3 separable blur per pixel
@@ -534,7 +546,7 @@ int fb_launch_pyramid_polyexp(const FbPlan& plan, const uint8_t* gray, size_t gr
         D.lw = L.w; D.lh = L.h; D.ksize = L.ksize; D.tiles_x = cdiv(L.w, 32);
         D.tile_start_row = tiles_row; D.tile_start_col = tiles_col;
         tiles_row += D.tiles_x * cdiv(plan.h, 8 * RB_ROWS);
-        tiles_col += D.tiles_x * cdiv(L.h, 8);
+        tiles_col += D.tiles_x * cdiv(L.h, 8 * CB_ROWS);
         D.scale_x = L.scale_x; D.scale_y = L.scale_y;
         D.hrow_off2 = hrow2;
         hrow2 += (size_t)plan.h * L.w;
