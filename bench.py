@@ -620,7 +620,7 @@ def main():
         return time.perf_counter() - t0
 
     Ke = 2 if args.quick else K_
-    run_host(6 + 3, True)  # fill the rings of the e2e handles + warm-up
+    run_host(6 + 3 + min(K_, 24), True)  # fill the rings of the e2e handles + warm-up (copy engines, host threads, clocks)
     barrier()
     e2e_s = run_host(Ke, True) * (K_ / Ke)
     barrier()
